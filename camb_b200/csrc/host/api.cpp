@@ -1,0 +1,160 @@
+// api.cpp -- extern "C" surface of the stand-in host (include/cambb200_host.h).
+#include <cstring>
+#include <exception>
+
+#include "../../../include/cambb200_host.h"
+#include "camb_host.h"
+
+using namespace cbh;
+
+struct cbh_state {
+    HostState S;
+    bool have_bessel = false;
+    std::vector<double> tight_A, nuapp_A, tight_T, nuapp_T, q_extra;
+};
+
+extern "C" {
+
+void cb_params_set_defaults(cb_params* p) {
+    std::memset(p, 0, sizeof(*p));
+    p->WantCls = 1; p->WantTransfer = 0; p->WantScalars = 1; p->WantTensors = 0; p->WantVectors = 0;
+    p->WantDerivedParameters = 1; p->Want_CMB = 1; p->Want_CMB_lensing = 1; p->DoLensing = 1; p->NonLinear = 0;
+    p->Min_l = 2; p->Max_l = 2500; p->Max_l_tensor = 600; p->lens_output_margin = 200;
+    p->Max_eta_k = 6250; p->Max_eta_k_tensor = 1200;
+    p->H0 = 67.0; p->TCMB = 2.7255; p->Yhe = 0.24; p->Num_Nu_massless = 3.044;
+    p->transfer_kmax = 0.9; p->transfer_PK_num_redshifts = 1;
+    p->As = 2e-9; p->ns = 0.96; p->pivot_scalar = 0.05; p->pivot_tensor = 0.05; p->At = 1; p->tensor_parameterization = 2;
+    p->de_model = CB_DE_FLUID; p->w = -1; p->wa = 0; p->cs2_lam = 1;
+    p->Reionization = 1; p->use_optical_depth = 0; p->include_helium_fullreion = 1;
+    p->redshift = 10; p->fraction = -1; p->delta_redshift = 0.5;
+    p->helium_redshift = 3.5; p->helium_delta_redshift = 0.4; p->helium_redshiftstart = 5.5;
+    p->tau_solve_accuracy_boost = 1; p->timestep_boost = 1; p->max_redshift = 50;
+    p->RECFAST_fudge = 1.105 + 0.02; p->RECFAST_fudge_He = 0.8472367977;
+    p->RECFAST_Hswitch = 1; p->RECFAST_He_rate_correction = 1; p->RECFAST_Nz = 2046; p->RECFAST_use_rosenbrock = 1;
+    p->AGauss1 = -0.1395272483; p->AGauss2 = 0.0729891952; p->zGauss1 = 7.2813061282; p->zGauss2 = 6.7667038679;
+    p->wGauss1 = 0.1638966410; p->wGauss2 = 0.2785834127;
+    p->rosenbrock_handoff_xH = 0.976; p->rosenbrock_tol = 3e-4;
+    p->Scalar_initial_condition = 1; p->DoLateRadTruncation = 1; p->MassiveNuMethod = 3;
+    p->AccuracyTarget = 1; p->use_cl_spline_template = 1; p->min_l_logl_sampling = 5000; p->Alens = 1;
+    cb_accuracy& a = p->Accuracy;
+    a.AccuracyBoost = a.lSampleBoost = a.lAccuracyBoost = 1;
+    a.AccuratePolarization = 1; a.AccurateBB = 0; a.AccurateReionization = 1;
+    a.TimeStepBoost = a.BackgroundTimeStepBoost = a.TimeSwitchBoost = a.IntTolBoost = 1;
+    a.SourcekAccuracyBoost = a.IntkAccuracyBoost = a.TransferkBoost = a.NonFlatIntAccuracyBoost = 1;
+    a.BessIntBoost = a.LensingBoost = a.NonlinSourceBoost = a.BesselBoost = a.LimberBoost = 1;
+    a.SourceLimberBoost = a.KmaxBoost = a.neutrino_q_boost = 1;
+}
+
+cbh_state* cbh_create(const cb_params* pin, int* err, char* errmsg, int errmsg_len) {
+    cbh_state* st = new cbh_state();
+    HostState& S = st->S;
+    int e = 0;
+    try {
+        cb_params P = *pin;
+        // CAMB_GetResults scalar-pass overrides, camb.f90:122-131
+        if (P.WantCls && P.WantScalars) {
+            P.Max_eta_k = std::fmax(std::min(P.Max_l, 3000) * 2.5, P.Max_eta_k);
+            if ((P.NonLinear == 2 || P.NonLinear == 3) && P.DoLensing) P.WantTransfer = 1;
+        }
+        e = S.SetParams(P);
+        if (!e) e = S.InitVars();
+        if (!e) {
+            S.tau_regions_c.clear();
+            for (int i = 0; i < S.TimeSteps.count; i++) {
+                const TRange& r = S.TimeSteps.R[i];
+                S.tau_regions_c.push_back(cb_range{r.start_index, r.steps, r.IsLog ? 1 : 0, r.Low, r.High, r.delta});
+            }
+            if (S.CP.WantCls) {
+                S.SetkValuesForSources();
+                S.lSamplesInit(S.CP.Min_l, S.maximum_l);
+                S.SetkValuesForInt();
+            }
+            if (S.CP.WantTransfer) S.InitTransfer();
+            if (S.CP.WantCls) S.PerModeLookups(S.Evolve_q.points, st->tight_A, st->nuapp_A);
+            if (S.CP.WantTransfer) {
+                st->q_extra.assign(S.q_trans.begin() + S.n_source_points, S.q_trans.end());
+                S.PerModeLookups(st->q_extra, st->tight_T, st->nuapp_T);
+            }
+        }
+    } catch (const std::exception& ex) {
+        e = CB_ERR_UNSUPPORTED_PARAMS;
+        S.error_msg = ex.what();
+    }
+    if (e) {
+        if (err) *err = e;
+        if (errmsg && errmsg_len > 0) { std::strncpy(errmsg, S.error_msg.c_str(), errmsg_len - 1); errmsg[errmsg_len - 1] = 0; }
+        delete st;
+        return nullptr;
+    }
+    if (err) *err = 0;
+    return st;
+}
+
+void cbh_destroy(cbh_state* s) { delete s; }
+
+int cbh_get_model(cbh_state* s, cb_model* out) { s->S.fill_model(*out); return 0; }
+
+int cbh_get_modes(cbh_state* s, cb_modes* out, int transfer_only) {
+    HostState& S = s->S;
+    if (!transfer_only) {
+        out->n_k = S.Evolve_q.npoints; out->q = S.Evolve_q.points.data();
+        out->tight_switchoff = s->tight_A.data(); out->nu_massive_approx_time = s->nuapp_A.data();
+    } else {
+        out->n_k = (int)s->q_extra.size(); out->q = s->q_extra.data();
+        out->tight_switchoff = s->tight_T.data(); out->nu_massive_approx_time = s->nuapp_T.data();
+    }
+    out->transfer_only = transfer_only;
+    return 0;
+}
+
+int cbh_get_bessel(cbh_state* s, cb_bessel* out) {
+    HostState& S = s->S;
+    try {
+        if (!s->have_bessel) { S.GenerateBessels(S.maximum_qeta); s->have_bessel = true; }
+    } catch (const std::exception& ex) { S.error_msg = ex.what(); return CB_ERR_UNSUPPORTED_PARAMS; }
+    out->n_l = (int)S.ls.size(); out->l = S.ls.data();
+    out->nx = S.BessRanges.npoints; out->x = S.BessRanges.points.data();
+    out->n_regions = (int)S.bess_regions_c.size(); out->regions = S.bess_regions_c.data();
+    out->horner = S.bessel_horner.data();
+    return 0;
+}
+
+int cbh_get_qint(cbh_state* s, int* n_q, const double** q, const double** dq) {
+    *n_q = s->S.q_int.npoints; *q = s->S.q_int.points.data(); *dq = s->S.q_int.dpoints.data();
+    return 0;
+}
+int cbh_get_ls(cbh_state* s, int* n_l, const int** l) { *n_l = (int)s->S.ls.size(); *l = s->S.ls.data(); return 0; }
+
+int cbh_get_pows(cbh_state* s, int tensor, double* pows) {
+    const HostState& S = s->S;
+    for (int i = 0; i < S.q_int.npoints; i++) pows[i] = tensor ? S.TensorPower(S.q_int.points[i]) : S.ScalarPower(S.q_int.points[i]);
+    return 0;
+}
+
+int cbh_get_derived(cbh_state* s, double out[13]) {
+    const Derived& D = s->S.derived;
+    if (!s->S.has_derived) return 1;
+    double v[13] = {D.age, D.zstar, D.rstar, D.thetastar, D.DAstar, D.zdrag, D.rdrag, D.kD, D.thetaD, D.zEQ, D.keq, D.thetaEQ, D.theta_rs_EQ};
+    std::memcpy(out, v, sizeof(v));
+    return 0;
+}
+
+int cbh_get_background(cbh_state* s, double out[16]) {
+    const HostState& S = s->S;
+    double v[16] = {S.tau0, S.taurst, S.taurend, S.tau_maxvis, S.dtaurec, S.scale, S.th.tight_tau, S.th.matter_verydom_tau,
+                    S.reion_redshift, S.th.actual_opt_depth, S.nu_masses[0], S.adotrad, S.qmin, S.qmax, S.max_etak_scalar,
+                    (double)S.th.nthermo};
+    std::memcpy(out, v, sizeof(v));
+    return 0;
+}
+
+int cbh_interp_cl(cbh_state* s, const double* iCl, double* all_Cl) {
+    const HostState& S = s->S;
+    InterpolateClArr(S.ls, iCl, S.CP.Min_l, all_Cl, (int)S.ls.size());
+    return 0;
+}
+
+double cbh_dtauda(cbh_state* s, double a) { return s->S.dtauda(a); }
+double cbh_xe(cbh_state* s, double a) { return s->S.rec.x_e(a); }
+
+}  // extern "C"

@@ -1,0 +1,163 @@
+/* cambb200.h -- C-ABI of the B200 per-k-mode Boltzmann path.
+ *
+ * This is the seam that replaces four OpenMP loops of the reference's
+ * fortran/cmbmain.f90 (there is no FFI seam in the reference today; the Fortran
+ * `interface ... bind(C)` block a maintainer adds is shown in INTEGRATION.md):
+ *
+ *   cb_evolve   <- loop A  cmbmain.f90:205-209 (DoSourcek -> CalcScalarSources :998-1074,
+ *                          CalcTensorSources :1076-1103) and loop A' :1147-1163 (GetTransfer)
+ *   cb_project  <- InitSourceInterpolation :1249-1265 + loop B :287-291
+ *                          (SourceToTransfers :543-562 -> InterpolateSources :1351-1480,
+ *                          DoSourceIntegration :1491-1523, DoFlatIntegration :1639-1862)
+ *   cb_cl       <- loop C  CalcScalCls :3179-3343 / CalcTensCls :3424-3476
+ *
+ * All pointers are HOST pointers to contiguous column-major (Fortran order) arrays
+ * with the reference's shapes; extents are explicit; every function returns 0 or a
+ * CAMB error id (fortran/config.f90:62-72, see cambb200_params.h).  The calling
+ * convention mirrors the reference: blocking calls from one master thread
+ * (cmbmain.f90:7-8 "not thread-safe").  There is NO CPU fallback: without a CUDA
+ * device every compute entry point returns CB_ERR_NO_DEVICE.
+ */
+#ifndef CAMBB200_H
+#define CAMBB200_H
+
+#include "cambb200_params.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One uniform or log-spaced region of a TRanges grid (forutils/RangeUtils.f90:13-22).
+ * start_index is 1-based like the reference. */
+typedef struct cb_range {
+    int start_index, steps, is_log;
+    double low, high, delta;
+} cb_range;
+
+/* Read-only boundary data of one cosmology: everything the hot path reads from
+ * CAMBdata/CAMBParams/TThermoData (SURVEY.md section 8(b) "Inputs to marshal").
+ * Built by the Fortran host in the real integration; by camb_b200/csrc/host here. */
+typedef struct cb_model {
+    /* ---- CAMBdata scalars (results.f90:184-227) ---- */
+    double grhog, grhor, grhornomass, grhob, grhoc, grhov, grhok;
+    double adotrad, tau0, tau_maxvis, taurst, taurend, akthom, fHe;
+    double H0, TCMB, Yhe, omch2, ombh2;
+    int    Nu_mass_eigenstates, Num_Nu_massive;
+    double grhormass[CB_MAX_NU], nu_masses[CB_MAX_NU];
+    /* ---- CAMBParams flags & accuracy ---- */
+    int    WantCls, WantTransfer, Want_CMB, WantTensors, WantScalars, DoLensing;
+    int    DoLateRadTruncation, Scalar_initial_condition, MassiveNuMethod;
+    int    transfer_high_precision, transfer_accurate_massive_neutrinos;
+    int    AccuratePolarization, AccurateReionization, AccuracyTarget;
+    double AccuracyBoost, lAccuracyBoost, IntTolBoost, TimeSwitchBoost, BessIntBoost, LimberBoost;
+    double Alens;
+    /* ---- dark energy (DarkEnergyInterface.f90:85-105,200-268) ---- */
+    int    de_is_cosmological_constant, de_model, de_num_perturb_equations;
+    double de_w, de_wa, de_cs2, de_c_gamma_ppf;
+    /* ---- TThermoData (results.f90:71-101) ---- */
+    int    nthermo;
+    double tauminn, dlntau, tight_tau, matter_verydom_tau;
+    const double* thermo_horner;   /* [nthermo][16] = cs2b(4), opacity(4), a(4), dopacity(4) */
+    const double* cs2;             /* [nthermo] */
+    const double* dotmu;           /* [nthermo] */
+    const double* ddotmu;          /* [nthermo] */
+    const double* dddotmu;         /* [nthermo] */
+    const double* ddddotmu;        /* [nthermo] */
+    const double* emmu;            /* [nthermo] */
+    const double* demmu;           /* [nthermo] */
+    /* ---- TimeSteps (TRanges) ---- */
+    int    n_tau;
+    const double* tau;             /* TimeSteps%points  [n_tau] */
+    const double* dtau;            /* TimeSteps%dpoints [n_tau] */
+    int    n_tau_regions;
+    const cb_range* tau_regions;
+    double tau_lowest, tau_highest;
+    /* ---- massive-neutrino momentum grid (massive_neutrinos.f90:120-178) and
+     *      switch times (equations.f90:197-198, 558-581) ---- */
+    int    nqmax;
+    double nu_q[CB_MAX_NQ], nu_int_kernel[CB_MAX_NQ];
+    double nu_tau_notmassless[CB_MAX_NQ * CB_MAX_NU];   /* (nqmax, max_nu), column-major */
+    double nu_tau_nonrelativistic[CB_MAX_NU];
+    double nu_tau_nonrelativistic_physical[CB_MAX_NU];
+    double nu_tau_massive[CB_MAX_NU];
+    /* ---- transfer output times (results.f90 transfer_times(1:num_transfer_redshifts)) ---- */
+    int    num_transfer_redshifts;
+    const double* transfer_times;  /* [num_transfer_redshifts] increasing */
+    /* ---- cmbmain module scalars (cmbmain.f90:96-105, 785-815) ---- */
+    double max_etak_scalar, max_etak_tensor, qmin, qmax;
+    int    WantLateTime;           /* cmbmain.f90:139 */
+    int    n_src;                  /* ThisSources%SourceNum, cmbmain.f90:755-773 */
+} cb_model;
+
+/* Per-call mode list for loop A / A'.  The two per-k host look-ups that the
+ * reference performs inside `initial` (equations.f90:1950 OpacityToTime and
+ * :2101-2102 DeltaTime) are hoisted to the host and passed per mode. */
+typedef struct cb_modes {
+    int    n_k;                    /* number of modes */
+    const double* q;               /* [n_k] */
+    const double* tight_switchoff; /* [n_k] EV%TightSwitchoffTime from `initial` */
+    const double* nu_massive_approx_time; /* [n_k*CB_MAX_NU] EV%MassiveNuApproxTime */
+    int    transfer_only;          /* 1: loop A' (GetTransfer), no sources */
+} cb_modes;
+
+/* Spherical-Bessel spline table + x grid (bessels.f90:20-41,168-182). */
+typedef struct cb_bessel {
+    int    n_l;
+    const int* l;                  /* ls%l [n_l] */
+    int    nx;                     /* BessRanges%npoints */
+    const double* x;               /* BessRanges%points [nx] */
+    int    n_regions;
+    const cb_range* regions;
+    const double* horner;          /* bessel_horner(4, nx-1, n_l) column-major */
+} cb_bessel;
+
+typedef struct cb_ctx cb_ctx;      /* one per device/process: streams, device buffers */
+typedef struct cb_dmodel cb_dmodel;/* device-resident copy of one cb_model + its work buffers */
+
+/* ---- lifetime ---- */
+int  cb_create(int device, cb_ctx** out);
+void cb_destroy(cb_ctx* ctx);
+const char* cb_last_error(const cb_ctx* ctx);
+int  cb_device_count(void);
+
+/* Upload (once; cosmology independent, cached across calls like bessels.f90:83-103). */
+int  cb_set_bessel(cb_ctx* ctx, const cb_bessel* b);
+
+/* Upload one cosmology's boundary data.  The cb_model and the arrays it points to
+ * may be freed after the call. */
+int  cb_model_create(cb_ctx* ctx, const cb_model* m, cb_dmodel** out);
+void cb_model_destroy(cb_ctx* ctx, cb_dmodel* dm);
+
+/* Loop A / A' for a batch of n_models cosmologies (n_models = 1 is the reference's
+ * call).  Outputs, each may be NULL to leave the result device-resident only:
+ *   LinearSrc[i]    double (n_k, n_src, n_tau)   k fastest  (cmbmain.f90:777)
+ *   TransferData[i] float  (13, n_k, n_z)        (results.f90:4208)
+ * stats[i] (may be NULL): int64[2*n_k] = {derivs evaluations, accepted steps} per mode. */
+int  cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* modes,
+               double* const* LinearSrc, float* const* TransferData, long long* const* stats);
+
+/* Replace the device-resident sources (e.g. after the host's non-linear scaling,
+ * cmbmain.f90:1190-1247) -- optional. ScaledSrc has LinearSrc's shape. */
+int  cb_set_sources(cb_ctx* ctx, cb_dmodel* dm, int n_k, const double* q, const double* ScaledSrc);
+
+/* Spline-in-k + loop B.  q_int/dq: ThisCT%q%points/dpoints [n_q].
+ *   Delta_p_l_k[i]  double (n_src, n_l, n_q)  source fastest (results.f90:3118-3119); may be NULL. */
+int  cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q,
+                const double* const* q_int, const double* const* dq,
+                double* const* Delta_p_l_k);
+
+/* Loop C.  pows[i] = P_R(k) at q_int (host evaluates InitPower, cmbmain.f90:3199).
+ *   iCl[i] double (n_l, n_cl) column-major, n_cl = 3 (n_src==2) or 6; tensor: 4. */
+int  cb_cl(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, int tensor,
+           const double* const* pows, double* const* iCl);
+
+/* Kernel timing of the last call of each stage, ms, measured with CUDA events on
+ * the launching stream: [0] evolve, [1] spline-k, [2] LOS, [3] C_l. */
+int  cb_last_timings(const cb_ctx* ctx, double ms[4]);
+/* Number of kernels this library launched since the context was created. */
+long long cb_launch_count(const cb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,42 @@
+/* cambb200_host.h -- C API of the stand-in host (libcambhost.so).
+ *
+ * In the real integration the reference's Fortran host (CAMBdata%SetParams,
+ * cmbmain's InitVars / SetkValuesForSources / InitTransfer / SetkValuesForInt,
+ * InitSpherBessels) produces the boundary arrays; this library stands in for it
+ * because the build image has no Fortran compiler.  It runs on the CPU and is
+ * never inside a timed region of bench.py.
+ */
+#ifndef CAMBB200_HOST_H
+#define CAMBB200_HOST_H
+#include "cambb200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cbh_state cbh_state;
+
+/* SetParams (results.f90:332-627) + InitVars (cmbmain.f90:785-862) + k/l grids.
+ * Applies CAMB_GetResults' scalar-pass overrides (camb.f90:122-131).  Returns NULL
+ * and sets *err on failure. */
+cbh_state* cbh_create(const cb_params* p, int* err, char* errmsg, int errmsg_len);
+void cbh_destroy(cbh_state* s);
+
+/* Boundary structs; pointers stay owned by (and valid for the life of) the state. */
+int cbh_get_model(cbh_state* s, cb_model* out);
+int cbh_get_modes(cbh_state* s, cb_modes* out, int transfer_only);
+int cbh_get_bessel(cbh_state* s, cb_bessel* out);             /* builds the table on first use */
+int cbh_get_qint(cbh_state* s, int* n_q, const double** q, const double** dq);
+int cbh_get_ls(cbh_state* s, int* n_l, const int** l);
+int cbh_get_pows(cbh_state* s, int tensor, double* pows);     /* InitPower at q_int [n_q] */
+int cbh_get_derived(cbh_state* s, double out[13]);            /* ThermoDerivedParams order */
+int cbh_get_background(cbh_state* s, double out[16]);         /* tau0,taurst,taurend,tau_maxvis,dtaurec,scale,... */
+/* InterpolateClArr (results.f90:1706-1743): iCl[n_l] -> all_Cl[lmin..ls(n_l)] */
+int cbh_interp_cl(cbh_state* s, const double* iCl, double* all_Cl);
+double cbh_dtauda(cbh_state* s, double a);
+double cbh_xe(cbh_state* s, double a);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
