@@ -1,0 +1,175 @@
+"""ctypes wrapper of libcambhost.so, the stand-in for the reference's Fortran host.
+
+It produces the boundary data (`cb_model`, `cb_modes`, `cb_bessel`, integration k grid,
+l samples, primordial power) that the reference's `cmbmain` would hand to the GPU path:
+`InitVars` (fortran/cmbmain.f90:785-862), `SetkValuesForSources` (:864-936),
+`InitTransfer` (:564-704), `SetkValuesForInt` (:1267-1349), `lSamples_init`
+(fortran/results.f90:1505-1704), `InitSpherBessels` (fortran/bessels.f90:64-113).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._cdefs import (cb_bessel, cb_model, cb_modes, cb_params, c_double_p, c_int_p)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+class CAMBError(Exception):
+    """Mirror of camb.baseconfig.CAMBError; `.code` is the CAMB error id (config.f90:62-72)."""
+
+    def __init__(self, msg, code=-1):
+        super().__init__(msg)
+        self.code = code
+
+
+def load_host_lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, "libcambhost.so")
+        if not os.path.exists(path):
+            raise ImportError(f"{path} not built; run `make host` (or __graft_entry__.build())")
+        lib = C.CDLL(path)
+        lib.cb_params_set_defaults.argtypes = [C.POINTER(cb_params)]
+        lib.cbh_create.restype = C.c_void_p
+        lib.cbh_create.argtypes = [C.POINTER(cb_params), c_int_p, C.c_char_p, C.c_int]
+        lib.cbh_destroy.argtypes = [C.c_void_p]
+        lib.cbh_get_model.argtypes = [C.c_void_p, C.POINTER(cb_model)]
+        lib.cbh_get_modes.argtypes = [C.c_void_p, C.POINTER(cb_modes), C.c_int]
+        lib.cbh_get_bessel.argtypes = [C.c_void_p, C.POINTER(cb_bessel)]
+        lib.cbh_get_qint.argtypes = [C.c_void_p, c_int_p, C.POINTER(c_double_p), C.POINTER(c_double_p)]
+        lib.cbh_get_ls.argtypes = [C.c_void_p, c_int_p, C.POINTER(c_int_p)]
+        lib.cbh_get_pows.argtypes = [C.c_void_p, C.c_int, c_double_p]
+        lib.cbh_get_derived.argtypes = [C.c_void_p, C.c_double * 13]
+        lib.cbh_get_background.argtypes = [C.c_void_p, C.c_double * 16]
+        lib.cbh_interp_cl.argtypes = [C.c_void_p, c_double_p, c_double_p]
+        lib.cbh_dtauda.restype = C.c_double
+        lib.cbh_dtauda.argtypes = [C.c_void_p, C.c_double]
+        lib.cbh_xe.restype = C.c_double
+        lib.cbh_xe.argtypes = [C.c_void_p, C.c_double]
+        _lib = lib
+    return _lib
+
+
+def default_params():
+    p = cb_params()
+    load_host_lib().cb_params_set_defaults(C.byref(p))
+    return p
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+DERIVED_NAMES = ["age", "zstar", "rstar", "thetastar", "DAstar", "zdrag", "rdrag", "kd", "thetad", "zeq", "keq",
+                 "thetaeq", "thetarseq"]
+
+
+class HostState:
+    """One cosmology's host-side state (the part of CAMBdata the hot path reads)."""
+
+    def __init__(self, params: cb_params):
+        lib = load_host_lib()
+        err = C.c_int(0)
+        msg = C.create_string_buffer(1024)
+        self._h = lib.cbh_create(C.byref(params), C.byref(err), msg, 1024)
+        if not self._h:
+            raise CAMBError(msg.value.decode() or "host setup failed", err.value)
+        self._lib = lib
+        self.params = params
+        self.model = cb_model()
+        lib.cbh_get_model(self._h, C.byref(self.model))
+        m = self.model
+        self.n_tau, self.n_src, self.nthermo = m.n_tau, m.n_src, m.nthermo
+        self.tau = np.ctypeslib.as_array(m.tau, shape=(m.n_tau,))
+        self.dtau = np.ctypeslib.as_array(m.dtau, shape=(m.n_tau,))
+        self._bessel = None
+        nl = C.c_int()
+        lp = c_int_p()
+        lib.cbh_get_ls(self._h, C.byref(nl), C.byref(lp))
+        self.ls = np.ctypeslib.as_array(lp, shape=(nl.value,)).copy() if nl.value else np.zeros(0, np.int32)
+        nq = C.c_int()
+        q = c_double_p()
+        dq = c_double_p()
+        lib.cbh_get_qint(self._h, C.byref(nq), C.byref(q), C.byref(dq))
+        if nq.value:
+            self.q_int = np.ctypeslib.as_array(q, shape=(nq.value,))
+            self.dq_int = np.ctypeslib.as_array(dq, shape=(nq.value,))
+        else:
+            self.q_int = self.dq_int = np.zeros(0)
+
+    def modes(self, transfer_only=False):
+        md = cb_modes()
+        self._lib.cbh_get_modes(self._h, C.byref(md), 1 if transfer_only else 0)
+        return md
+
+    def source_q(self):
+        md = self.modes(False)
+        return np.ctypeslib.as_array(md.q, shape=(md.n_k,))
+
+    def transfer_q(self):
+        md = self.modes(True)
+        return np.ctypeslib.as_array(md.q, shape=(md.n_k,)) if md.n_k else np.zeros(0)
+
+    def bessel(self):
+        if self._bessel is None:
+            b = cb_bessel()
+            e = self._lib.cbh_get_bessel(self._h, C.byref(b))
+            if e:
+                raise CAMBError("Bessel table generation failed", e)
+            self._bessel = b
+        return self._bessel
+
+    def scalar_power(self):
+        out = np.zeros(len(self.q_int))
+        self._lib.cbh_get_pows(self._h, 0, _dp(out))
+        return out
+
+    def tensor_power(self):
+        out = np.zeros(len(self.q_int))
+        self._lib.cbh_get_pows(self._h, 1, _dp(out))
+        return out
+
+    def derived(self):
+        d = (C.c_double * 13)()
+        if self._lib.cbh_get_derived(self._h, d):
+            return {}
+        return dict(zip(DERIVED_NAMES, list(d)))
+
+    def background(self):
+        b = (C.c_double * 16)()
+        self._lib.cbh_get_background(self._h, b)
+        names = ["tau0", "taurst", "taurend", "tau_maxvis", "dtaurec", "scale", "tight_tau", "matter_verydom_tau",
+                 "zre", "reion_opt_depth", "nu_mass0", "adotrad", "qmin", "qmax", "max_etak_scalar", "nthermo"]
+        return dict(zip(names, list(b)))
+
+    def interp_cl(self, iCl):
+        """results.f90:1706-1743 InterpolateClArr for each column of iCl (n_l, n_cl) -> (lmax+1, n_cl)."""
+        iCl = np.asarray(iCl, dtype=np.float64)
+        lmin, lmax = int(self.params.Min_l), int(self.ls[-1])
+        out = np.zeros((lmax + 1, iCl.shape[1]))
+        for c in range(iCl.shape[1]):
+            col = np.ascontiguousarray(iCl[:, c])
+            tmp = np.zeros(lmax - lmin + 1)
+            self._lib.cbh_interp_cl(self._h, _dp(col), _dp(tmp))
+            out[lmin:, c] = tmp
+        return out
+
+    def dtauda(self, a):
+        return self._lib.cbh_dtauda(self._h, float(a))
+
+    def x_e(self, a):
+        return self._lib.cbh_xe(self._h, float(a))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cbh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

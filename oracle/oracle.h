@@ -1,0 +1,32 @@
+/* oracle.h -- TEST INFRASTRUCTURE, NOT PRODUCT.  CPU restatement of the hot path
+ * (see oracle_evolve.c / oracle_project.c headers for the reference line ranges).
+ * PARITY UNPINNED against the Fortran reference (no Fortran compiler in the image).
+ */
+#ifndef ORACLE_H
+#define ORACLE_H
+#include "../include/cambb200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* loop A / A': LinearSrc (n_k, n_src, n_tau) k fastest; TransferData float (13, n_k, n_z);
+ * stats int64[2*n_k] = {derivs evaluations, accepted steps of the last DP45 segment}. */
+int oracle_evolve(const cb_model* M, const cb_modes* modes, double* LinearSrc, float* TransferData, long long* stats,
+                  int nthreads);
+
+/* InitSourceInterpolation: natural-spline second derivatives along k for every (src, tau). */
+int oracle_spline_k(int n_k, int n_src, int n_tau, const double* q_src, const double* ScaledSrc, double* ddScaledSrc);
+
+/* loop B: Delta_p_l_k (n_src, n_l, n_q), source fastest. */
+int oracle_project(const cb_model* M, const cb_bessel* B, int n_k, const double* q_src, const double* ScaledSrc,
+                   const double* ddScaledSrc, int n_q, const double* q_int, double* Delta_p_l_k, int nthreads);
+
+/* loop C: iCl (n_l, n_cl) column-major; n_cl = 3 (n_src == 2) or 6. */
+int oracle_cl(const cb_model* M, const cb_bessel* B, int n_q, const double* q_int, const double* dq, const double* pows,
+              const double* Delta_p_l_k, double* iCl);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,94 @@
+"""Test-side ctypes wrapper of oracle/liboracle.so (the CPU restatement used as checker).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from camb_b200._cdefs import cb_bessel, cb_model, cb_modes, c_double_p, c_float_p
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_lib = None
+c_ll_p = C.POINTER(C.c_longlong)
+
+
+def load():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_ROOT, "oracle", "liboracle.so")
+        if not os.path.exists(path):
+            raise ImportError(f"{path} not built; run `make oracle`")
+        lib = C.CDLL(path)
+        lib.oracle_evolve.argtypes = [C.POINTER(cb_model), C.POINTER(cb_modes), c_double_p, c_float_p, c_ll_p, C.c_int]
+        lib.oracle_spline_k.argtypes = [C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]
+        lib.oracle_project.argtypes = [C.POINTER(cb_model), C.POINTER(cb_bessel), C.c_int, c_double_p, c_double_p,
+                                       c_double_p, C.c_int, c_double_p, c_double_p, C.c_int]
+        lib.oracle_cl.argtypes = [C.POINTER(cb_model), C.POINTER(cb_bessel), C.c_int, c_double_p, c_double_p,
+                                  c_double_p, c_double_p, c_double_p]
+        _lib = lib
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def evolve(hs, transfer_only=False, nthreads=1, modes=None):
+    """Returns LinearSrc with shape (n_tau, n_src, n_k) (C order == Fortran (k, src, tau)),
+    TransferData (n_z, n_k, 13) float32, stats (n_k, 2) int64."""
+    lib = load()
+    md = modes if modes is not None else hs.modes(transfer_only)
+    m = hs.model
+    src = np.zeros((m.n_tau, m.n_src, md.n_k))
+    nz = max(1, m.num_transfer_redshifts)
+    tr = np.zeros((nz, md.n_k, 13), dtype=np.float32)
+    stats = np.zeros((md.n_k, 2), dtype=np.int64)
+    e = lib.oracle_evolve(C.byref(m), C.byref(md), _dp(src), tr.ctypes.data_as(c_float_p),
+                          stats.ctypes.data_as(c_ll_p), nthreads)
+    if e:
+        raise RuntimeError(f"oracle_evolve error {e}")
+    return src, tr, stats
+
+
+def spline_k(q_src, src):
+    lib = load()
+    n_tau, n_src, n_k = src.shape
+    dd = np.zeros_like(src)
+    q_src = np.ascontiguousarray(q_src)
+    lib.oracle_spline_k(n_k, n_src, n_tau, _dp(q_src), _dp(src), _dp(dd))
+    return dd
+
+
+def project(hs, q_src, src, dd, nthreads=1):
+    """Delta_p_l_k with shape (n_q, n_l, n_src) (C order == Fortran (src, l, q))."""
+    lib = load()
+    b = hs.bessel()
+    q_src = np.ascontiguousarray(q_src)
+    qi = np.ascontiguousarray(hs.q_int)
+    out = np.zeros((len(qi), b.n_l, hs.model.n_src))
+    lib.oracle_project(C.byref(hs.model), C.byref(b), len(q_src), _dp(q_src), _dp(src), _dp(dd), len(qi), _dp(qi),
+                       _dp(out), nthreads)
+    return out
+
+
+def cl(hs, delta, pows=None):
+    """iCl with shape (n_l, n_cl)."""
+    lib = load()
+    b = hs.bessel()
+    qi = np.ascontiguousarray(hs.q_int)
+    dq = np.ascontiguousarray(hs.dq_int)
+    if pows is None:
+        pows = hs.scalar_power()
+    n_cl = 6 if hs.model.n_src > 2 else 3
+    out = np.zeros((n_cl, b.n_l))
+    lib.oracle_cl(C.byref(hs.model), C.byref(b), len(qi), _dp(qi), _dp(dq), _dp(pows), _dp(delta), _dp(out))
+    return out.T.copy()
+
+
+def cls_from_params(hs, nthreads=1):
+    src, tr, stats = evolve(hs, nthreads=nthreads)
+    q_src = hs.source_q()
+    dd = spline_k(q_src, src)
+    delta = project(hs, q_src, src, dd, nthreads=nthreads)
+    return cl(hs, delta), dict(src=src, dd=dd, delta=delta, stats=stats, transfer=tr)
