@@ -1,0 +1,451 @@
+// cabi.cu -- extern "C" entry points of libcambb200.so (include/cambb200.h): context and
+// device-buffer management, host<->device marshalling, launch orchestration and timing.
+// No torch types cross this boundary; there is no CPU fallback (every compute entry point
+// fails with CB_ERR_NO_DEVICE when no CUDA device is usable).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dmodel.cuh"
+
+// evolve.cu
+size_t cb_evolve_smem_per_warp(int nv, int maxl);
+void cb_mode_size(const DModel& M, double q, int transfer_only, int* nvar, int* maxl);
+int cb_evolve_warps_per_block();
+void cb_evolve_launch(const DModel*, const DModeItem*, int, int, int, unsigned int*, int*, int, size_t, cudaStream_t);
+cudaError_t cb_evolve_set_smem(size_t smem);
+int cb_evolve_max_blocks_per_sm(size_t smem);
+// project.cu
+void cb_spline_k_launch(const DModel*, int, int, double* const*, cudaStream_t);
+size_t cb_los_smem(int, int);
+cudaError_t cb_los_set_smem(size_t);
+void cb_los_launch(const DModel*, int, const DBessel&, int, int, size_t, cudaStream_t);
+void cb_cl_launch(const DModel*, int, const DBessel&, cudaStream_t);
+
+struct cb_dmodel {
+    DModel h;                      // host copy with device pointers
+    std::vector<void*> owned;      // table allocations freed with the model
+    // per-call buffers (grown on demand)
+    double *d_q_src = nullptr, *d_src = nullptr, *d_dd = nullptr, *d_scratch = nullptr, *d_delta = nullptr, *d_icl = nullptr;
+    double *d_q_int = nullptr, *d_dq_int = nullptr, *d_pows = nullptr;
+    float* d_transfer = nullptr;
+    long long* d_stats = nullptr;
+    size_t cap_src = 0, cap_k = 0, cap_q = 0, cap_delta = 0, cap_tr = 0, cap_icl = 0;
+    int n_cl = 3;
+};
+
+struct cb_ctx {
+    int device = 0, n_sm = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    DBessel bess{};
+    std::vector<void*> bess_owned;
+    bool have_bessel = false;
+    double ms[4] = {0, 0, 0, 0};
+    long long launches = 0;
+    DModel* d_models = nullptr;    size_t cap_models = 0;
+    DModeItem* d_items = nullptr;  size_t cap_items = 0;
+    double** d_scratch_ptrs = nullptr; size_t cap_scr = 0;
+    unsigned int* d_counter = nullptr;
+    int* d_error = nullptr;
+};
+
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                        \
+            return CB_ERR_CUDA;                                                                   \
+        }                                                                                         \
+    } while (0)
+
+template <class T>
+static int upload(cb_ctx* ctx, const T* src, size_t n, T** dst, std::vector<void*>* owned) {
+    *dst = nullptr;
+    if (!src || n == 0) return 0;
+    CK(cudaMalloc((void**)dst, n * sizeof(T)));
+    if (owned) owned->push_back(*dst);
+    CK(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+template <class T>
+static int ensure(cb_ctx* ctx, T** p, size_t* cap, size_t n) {
+    if (n <= *cap && *p) return 0;
+    if (*p) CK(cudaFree(*p));
+    *p = nullptr;
+    CK(cudaMalloc((void**)p, n * sizeof(T)));
+    *cap = n;
+    return 0;
+}
+
+extern "C" {
+
+int cb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int cb_create(int device, cb_ctx** out) {
+    *out = nullptr;
+    int n = cb_device_count();
+    if (n <= 0 || device >= n) return CB_ERR_NO_DEVICE;
+    cb_ctx* ctx = new cb_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return CB_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return CB_ERR_NO_DEVICE; }
+    ctx->n_sm = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CB_ERR_CUDA; }
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+    if (cudaMalloc((void**)&ctx->d_counter, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_error, sizeof(int)) != cudaSuccess) { delete ctx; return CB_ERR_CUDA; }
+    *out = ctx;
+    return 0;
+}
+
+void cb_destroy(cb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (void* p : ctx->bess_owned) cudaFree(p);
+    if (ctx->d_models) cudaFree(ctx->d_models);
+    if (ctx->d_items) cudaFree(ctx->d_items);
+    if (ctx->d_scratch_ptrs) cudaFree(ctx->d_scratch_ptrs);
+    if (ctx->d_counter) cudaFree(ctx->d_counter);
+    if (ctx->d_error) cudaFree(ctx->d_error);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* cb_last_error(const cb_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int cb_set_bessel(cb_ctx* ctx, const cb_bessel* b) {
+    if (!ctx) return CB_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    for (void* p : ctx->bess_owned) cudaFree(p);
+    ctx->bess_owned.clear();
+    DBessel& B = ctx->bess;
+    B.n_l = b->n_l; B.nx = b->nx; B.n_regions = b->n_regions;
+    if (b->n_regions > 8) { ctx->err = "too many Bessel x regions"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    for (int i = 0; i < b->n_regions; i++) B.regions[i] = b->regions[i];
+    B.xmax = b->x[b->nx - 1];
+    int* dl; double *dx, *dh;
+    if (int e = upload(ctx, b->l, (size_t)b->n_l, &dl, &ctx->bess_owned)) return e;
+    if (int e = upload(ctx, b->x, (size_t)b->nx, &dx, &ctx->bess_owned)) return e;
+    if (int e = upload(ctx, b->horner, (size_t)4 * (b->nx - 1) * b->n_l, &dh, &ctx->bess_owned)) return e;
+    B.l = dl; B.x = dx; B.horner = dh;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_bessel = true;
+    return 0;
+}
+
+int cb_model_create(cb_ctx* ctx, const cb_model* m, cb_dmodel** out) {
+    *out = nullptr;
+    if (!ctx) return CB_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    // things the device path does not implement are errors, never a fallback
+    if (m->grhok != 0) { ctx->err = "non-flat models are not supported by the GPU path"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    if (m->Scalar_initial_condition != 1) { ctx->err = "only adiabatic initial conditions are supported"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    if (m->n_tau_regions > 8) { ctx->err = "too many time-step regions"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    if (m->n_src > 3) { ctx->err = "source windows / custom sources are not supported"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    if (!m->WantScalars) { ctx->err = "tensor/vector modes are not supported yet"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    cb_dmodel* dm = new cb_dmodel();
+    DModel& D = dm->h;
+    memset(&D, 0, sizeof(D));
+    D.grhog = m->grhog; D.grhornomass = m->grhornomass; D.grhob = m->grhob; D.grhoc = m->grhoc; D.grhov = m->grhov; D.grhok = m->grhok;
+    D.adotrad = m->adotrad; D.tau0 = m->tau0; D.tau_maxvis = m->tau_maxvis; D.taurst = m->taurst; D.taurend = m->taurend; D.H0 = m->H0;
+    D.Nu_mass_eigenstates = m->Nu_mass_eigenstates; D.Num_Nu_massive = m->Num_Nu_massive;
+    for (int i = 0; i < CB_MAX_NU; i++) { D.grhormass[i] = m->grhormass[i]; D.nu_masses[i] = m->nu_masses[i]; }
+    D.WantCls = m->WantCls; D.WantTransfer = m->WantTransfer; D.Want_CMB = m->Want_CMB; D.WantTensors = m->WantTensors;
+    D.DoLateRadTruncation = m->DoLateRadTruncation; D.MassiveNuMethod = m->MassiveNuMethod;
+    D.transfer_high_precision = m->transfer_high_precision; D.transfer_accurate_massive_neutrinos = m->transfer_accurate_massive_neutrinos;
+    D.AccuratePolarization = m->AccuratePolarization; D.AccurateReionization = m->AccurateReionization; D.AccuracyTarget = m->AccuracyTarget;
+    D.AccuracyBoost = m->AccuracyBoost; D.lAccuracyBoost = m->lAccuracyBoost; D.IntTolBoost = m->IntTolBoost;
+    D.TimeSwitchBoost = m->TimeSwitchBoost; D.BessIntBoost = m->BessIntBoost; D.LimberBoost = m->LimberBoost; D.Alens = m->Alens;
+    D.de_is_cc = m->de_is_cosmological_constant; D.de_model = m->de_model; D.de_nperturb = m->de_num_perturb_equations;
+    D.de_w = m->de_w; D.de_wa = m->de_wa; D.de_cs2 = m->de_cs2; D.de_c_gamma_ppf = m->de_c_gamma_ppf;
+    D.nthermo = m->nthermo; D.tauminn = m->tauminn; D.dlntau = m->dlntau; D.dlntau_inv = 1.0 / m->dlntau;
+    D.matter_verydom_tau = m->matter_verydom_tau;
+    D.n_tau = m->n_tau; D.n_tau_regions = m->n_tau_regions;
+    for (int i = 0; i < m->n_tau_regions; i++) D.tau_regions[i] = m->tau_regions[i];
+    D.tau_lowest = m->tau_lowest; D.tau_highest = m->tau_highest;
+    D.nqmax = m->nqmax;
+    for (int i = 0; i < CB_MAX_NQ; i++) { D.nu_q[i] = m->nu_q[i]; D.nu_int_kernel[i] = m->nu_int_kernel[i]; }
+    for (int i = 0; i < CB_MAX_NQ * CB_MAX_NU; i++) D.nu_tau_notmassless[i] = m->nu_tau_notmassless[i];
+    for (int i = 0; i < CB_MAX_NU; i++) {
+        D.nu_tau_nonrelativistic[i] = m->nu_tau_nonrelativistic[i];
+        D.nu_tau_nonrelativistic_physical[i] = m->nu_tau_nonrelativistic_physical[i];
+    }
+    D.num_transfer_redshifts = m->WantTransfer ? m->num_transfer_redshifts : 0;
+    D.max_etak_scalar = m->max_etak_scalar; D.max_etak_tensor = m->max_etak_tensor;
+    D.WantLateTime = m->WantLateTime; D.n_src = m->n_src;
+    dm->n_cl = m->n_src > 2 ? 6 : 3;
+    int e = 0;
+    double* p;
+    size_t nt = (size_t)m->nthermo;
+#define UP(field, src, n) do { if ((e = upload(ctx, (src), (n), &p, &dm->owned))) { cb_model_destroy(ctx, dm); return e; } D.field = p; } while (0)
+    UP(thermo_horner, m->thermo_horner, nt * 16);
+    UP(cs2, m->cs2, nt); UP(dotmu, m->dotmu, nt); UP(ddotmu, m->ddotmu, nt); UP(dddotmu, m->dddotmu, nt);
+    UP(ddddotmu, m->ddddotmu, nt); UP(emmu, m->emmu, nt); UP(demmu, m->demmu, nt);
+    UP(tau, m->tau, (size_t)m->n_tau); UP(dtau, m->dtau, (size_t)m->n_tau);
+    if (D.num_transfer_redshifts > 0) UP(transfer_times, m->transfer_times, (size_t)D.num_transfer_redshifts);
+#undef UP
+    CK(cudaStreamSynchronize(ctx->stream));
+    *out = dm;
+    return 0;
+}
+
+void cb_model_destroy(cb_ctx* ctx, cb_dmodel* dm) {
+    if (!dm) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    for (void* p : dm->owned) cudaFree(p);
+    void* bufs[] = {dm->d_q_src, dm->d_src, dm->d_dd, dm->d_scratch, dm->d_delta, dm->d_icl, dm->d_q_int, dm->d_dq_int,
+                    dm->d_pows, dm->d_transfer, dm->d_stats};
+    for (void* p : bufs) if (p) cudaFree(p);
+    delete dm;
+}
+
+static int push_models(cb_ctx* ctx, int n_models, cb_dmodel* const* dm) {
+    if (int e = ensure(ctx, &ctx->d_models, &ctx->cap_models, (size_t)n_models)) return e;
+    std::vector<DModel> hm(n_models);
+    for (int i = 0; i < n_models; i++) hm[i] = dm[i]->h;
+    CK(cudaMemcpyAsync(ctx->d_models, hm.data(), sizeof(DModel) * n_models, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // hm is a stack temporary
+    return 0;
+}
+
+int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* modes, double* const* LinearSrc,
+              float* const* TransferData, long long* const* stats) {
+    if (!ctx) return CB_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<DModeItem> items;
+    int nv = 0, maxl = 0;
+    for (int m = 0; m < n_models; m++) {
+        cb_dmodel* d = dm[m];
+        const cb_modes& md = modes[m];
+        DModel& D = d->h;
+        const int n_k = md.n_k, nz = D.num_transfer_redshifts;
+        if (!md.transfer_only) {
+            if (int e = ensure(ctx, &d->d_q_src, &d->cap_k, (size_t)n_k)) return e;
+            size_t ns = (size_t)n_k * D.n_src * D.n_tau;
+            if (ns > d->cap_src) {
+                size_t c1 = 0, c2 = 0, c3 = 0;
+                if (d->d_src) { cudaFree(d->d_src); d->d_src = nullptr; }
+                if (d->d_dd) { cudaFree(d->d_dd); d->d_dd = nullptr; }
+                if (d->d_scratch) { cudaFree(d->d_scratch); d->d_scratch = nullptr; }
+                if (int e = ensure(ctx, &d->d_src, &c1, ns)) return e;
+                if (int e = ensure(ctx, &d->d_dd, &c2, ns)) return e;
+                if (int e = ensure(ctx, &d->d_scratch, &c3, ns)) return e;
+                d->cap_src = ns;
+            }
+            CK(cudaMemcpyAsync(d->d_q_src, md.q, sizeof(double) * n_k, cudaMemcpyHostToDevice, ctx->stream));
+            // row j = 1 is never written by the reference (allocated zero, cmbmain.f90:777-778)
+            CK(cudaMemsetAsync(d->d_src, 0, sizeof(double) * (size_t)n_k * D.n_src, ctx->stream));
+            D.n_k = n_k; D.q_src = d->d_q_src; D.LinearSrc = d->d_src; D.ddSrc = d->d_dd;
+        } else {
+            D.n_k = n_k;
+        }
+        if (nz > 0) {
+            size_t ntr = (size_t)13 * n_k * nz;
+            if (ntr > d->cap_tr) { if (d->d_transfer) cudaFree(d->d_transfer); d->d_transfer = nullptr; d->cap_tr = 0; }
+            if (int e = ensure(ctx, &d->d_transfer, &d->cap_tr, ntr)) return e;
+            D.TransferData = d->d_transfer;
+        } else D.TransferData = nullptr;
+        {
+            if (d->d_stats) { cudaFree(d->d_stats); d->d_stats = nullptr; }
+            size_t cs = 0;
+            if (int e = ensure(ctx, &d->d_stats, &cs, (size_t)2 * n_k)) return e;
+            D.stats = d->d_stats;
+        }
+        for (int i = 0; i < n_k; i++) {
+            DModeItem it;
+            memset(&it, 0, sizeof(it));
+            it.model = m; it.q_ix = i; it.transfer_only = md.transfer_only; it.q = md.q[i];
+            it.tight_switchoff = md.tight_switchoff[i];
+            for (int j = 0; j < CB_MAX_NU; j++) it.nu_massive_approx_time[j] = md.nu_massive_approx_time[(size_t)i * CB_MAX_NU + j];
+            int ml;
+            cb_mode_size(D, it.q, it.transfer_only, &it.nvar, &ml);
+            nv = std::max(nv, it.nvar);
+            maxl = std::max(maxl, ml);
+            items.push_back(it);
+        }
+    }
+    const int n_items = (int)items.size();
+    if (n_items == 0) return 0;
+    if (maxl > CBD_MAX_L_EVOLVE) { ctx->err = "Need to increase max_l_evolve"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    // largest k first (cmbmain.f90:205-206: descending q with dynamic scheduling)
+    std::stable_sort(items.begin(), items.end(), [](const DModeItem& a, const DModeItem& b) { return a.q > b.q; });
+    if (int e = push_models(ctx, n_models, dm)) return e;
+    if (int e = ensure(ctx, &ctx->d_items, &ctx->cap_items, (size_t)n_items)) return e;
+    CK(cudaMemcpyAsync(ctx->d_items, items.data(), sizeof(DModeItem) * n_items, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_error, 0, sizeof(int), ctx->stream));
+    const int wpb = cb_evolve_warps_per_block();
+    const size_t smem = cb_evolve_smem_per_warp(nv, maxl) * wpb;
+    if (smem > 227 * 1024) { ctx->err = "evolve: shared-memory slab too large"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    CK(cb_evolve_set_smem(smem));
+    int bps = cb_evolve_max_blocks_per_sm(smem);
+    if (bps < 1) bps = 1;
+    int grid = std::min((n_items + wpb - 1) / wpb, ctx->n_sm * bps);
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    cb_evolve_launch(ctx->d_models, ctx->d_items, n_items, nv, maxl, ctx->d_counter, ctx->d_error, grid, smem, ctx->stream);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    int herr = 0;
+    CK(cudaMemcpyAsync(&herr, ctx->d_error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    for (int m = 0; m < n_models; m++) {
+        cb_dmodel* d = dm[m];
+        const DModel& D = d->h;
+        if (LinearSrc && LinearSrc[m] && !modes[m].transfer_only)
+            CK(cudaMemcpyAsync(LinearSrc[m], d->d_src, sizeof(double) * (size_t)D.n_k * D.n_src * D.n_tau, cudaMemcpyDeviceToHost, ctx->stream));
+        if (TransferData && TransferData[m] && D.num_transfer_redshifts > 0)
+            CK(cudaMemcpyAsync(TransferData[m], d->d_transfer, sizeof(float) * (size_t)13 * D.n_k * D.num_transfer_redshifts, cudaMemcpyDeviceToHost, ctx->stream));
+        if (stats && stats[m])
+            CK(cudaMemcpyAsync(stats[m], d->d_stats, sizeof(long long) * 2 * (size_t)D.n_k, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->ms[0] = ms;
+    if (herr) { ctx->err = "RungeKuttaDP45 error: step size underflow in the device integrator"; return herr; }
+    return 0;
+}
+
+int cb_set_sources(cb_ctx* ctx, cb_dmodel* d, int n_k, const double* q, const double* ScaledSrc) {
+    if (!ctx) return CB_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    DModel& D = d->h;
+    size_t ns = (size_t)n_k * D.n_src * D.n_tau;
+    if (ns > d->cap_src || !d->d_src) {
+        size_t c1 = 0, c2 = 0, c3 = 0;
+        if (d->d_src) { cudaFree(d->d_src); d->d_src = nullptr; }
+        if (d->d_dd) { cudaFree(d->d_dd); d->d_dd = nullptr; }
+        if (d->d_scratch) { cudaFree(d->d_scratch); d->d_scratch = nullptr; }
+        if (int e = ensure(ctx, &d->d_src, &c1, ns)) return e;
+        if (int e = ensure(ctx, &d->d_dd, &c2, ns)) return e;
+        if (int e = ensure(ctx, &d->d_scratch, &c3, ns)) return e;
+        d->cap_src = ns;
+    }
+    if (int e = ensure(ctx, &d->d_q_src, &d->cap_k, (size_t)n_k)) return e;
+    CK(cudaMemcpyAsync(d->d_q_src, q, sizeof(double) * n_k, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d->d_src, ScaledSrc, sizeof(double) * ns, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    D.n_k = n_k; D.q_src = d->d_q_src; D.LinearSrc = d->d_src; D.ddSrc = d->d_dd;
+    return 0;
+}
+
+int cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q, const double* const* q_int,
+               const double* const* dq, double* const* Delta_p_l_k) {
+    if (!ctx) return CB_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->have_bessel) { ctx->err = "cb_set_bessel must be called before cb_project"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    const int n_l = ctx->bess.n_l;
+    int max_cols = 0, max_nq = 0, max_ntau = 0, max_nsrc = 0;
+    std::vector<double*> scr(n_models);
+    for (int m = 0; m < n_models; m++) {
+        cb_dmodel* d = dm[m];
+        DModel& D = d->h;
+        if (!d->d_src || D.n_k <= 0) { ctx->err = "cb_project: no sources (call cb_evolve or cb_set_sources first)"; return CB_ERR_UNSUPPORTED_PARAMS; }
+        const int nq = n_q[m];
+        if ((size_t)nq > d->cap_q) {
+            if (d->d_q_int) cudaFree(d->d_q_int);
+            if (d->d_dq_int) cudaFree(d->d_dq_int);
+            if (d->d_pows) cudaFree(d->d_pows);
+            d->d_q_int = d->d_dq_int = d->d_pows = nullptr;
+            size_t c1 = 0, c2 = 0, c3 = 0;
+            if (int e = ensure(ctx, &d->d_q_int, &c1, (size_t)nq)) return e;
+            if (int e = ensure(ctx, &d->d_dq_int, &c2, (size_t)nq)) return e;
+            if (int e = ensure(ctx, &d->d_pows, &c3, (size_t)nq)) return e;
+            d->cap_q = nq;
+        }
+        size_t nd = (size_t)D.n_src * n_l * nq;
+        if (nd > d->cap_delta) { if (d->d_delta) cudaFree(d->d_delta); d->d_delta = nullptr; d->cap_delta = 0; }
+        if (int e = ensure(ctx, &d->d_delta, &d->cap_delta, nd)) return e;
+        CK(cudaMemcpyAsync(d->d_q_int, q_int[m], sizeof(double) * nq, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d->d_dq_int, dq[m], sizeof(double) * nq, cudaMemcpyHostToDevice, ctx->stream));
+        D.n_q = nq; D.q_int = d->d_q_int; D.dq_int = d->d_dq_int; D.pows = d->d_pows; D.Delta = d->d_delta;
+        max_cols = std::max(max_cols, D.n_src * D.n_tau);
+        max_nq = std::max(max_nq, nq); max_ntau = std::max(max_ntau, D.n_tau); max_nsrc = std::max(max_nsrc, D.n_src);
+        scr[m] = d->d_scratch;
+    }
+    if (int e = push_models(ctx, n_models, dm)) return e;
+    if (int e = ensure(ctx, &ctx->d_scratch_ptrs, &ctx->cap_scr, (size_t)n_models)) return e;
+    CK(cudaMemcpyAsync(ctx->d_scratch_ptrs, scr.data(), sizeof(double*) * n_models, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    cb_spline_k_launch(ctx->d_models, n_models, max_cols, ctx->d_scratch_ptrs, ctx->stream);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->ms[1] = ms;
+    const size_t smem = cb_los_smem(max_nsrc, max_ntau);
+    if (smem > 227 * 1024) { ctx->err = "LOS: too many time steps for shared memory"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    CK(cb_los_set_smem(smem));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    cb_los_launch(ctx->d_models, n_models, ctx->bess, max_nq, max_ntau, smem, ctx->stream);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    for (int m = 0; m < n_models; m++) {
+        const DModel& D = dm[m]->h;
+        if (Delta_p_l_k && Delta_p_l_k[m])
+            CK(cudaMemcpyAsync(Delta_p_l_k[m], dm[m]->d_delta, sizeof(double) * (size_t)D.n_src * n_l * D.n_q, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->ms[2] = ms;
+    return 0;
+}
+
+int cb_cl(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, int tensor, const double* const* pows, double* const* iCl) {
+    if (!ctx) return CB_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    if (tensor) { ctx->err = "tensor C_l are not supported yet"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    const int n_l = ctx->bess.n_l;
+    for (int m = 0; m < n_models; m++) {
+        cb_dmodel* d = dm[m];
+        DModel& D = d->h;
+        if (!d->d_delta || D.n_q <= 0) { ctx->err = "cb_cl: no transfer functions (call cb_project first)"; return CB_ERR_UNSUPPORTED_PARAMS; }
+        size_t nc = (size_t)n_l * d->n_cl;
+        if (nc > d->cap_icl) { if (d->d_icl) cudaFree(d->d_icl); d->d_icl = nullptr; d->cap_icl = 0; }
+        if (int e = ensure(ctx, &d->d_icl, &d->cap_icl, nc)) return e;
+        CK(cudaMemcpyAsync(d->d_pows, pows[m], sizeof(double) * D.n_q, cudaMemcpyHostToDevice, ctx->stream));
+        D.iCl = d->d_icl;
+    }
+    if (int e = push_models(ctx, n_models, dm)) return e;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    cb_cl_launch(ctx->d_models, n_models, ctx->bess, ctx->stream);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    for (int m = 0; m < n_models; m++)
+        if (iCl && iCl[m]) CK(cudaMemcpyAsync(iCl[m], dm[m]->d_icl, sizeof(double) * (size_t)n_l * dm[m]->n_cl, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->ms[3] = ms;
+    return 0;
+}
+
+int cb_last_timings(const cb_ctx* ctx, double ms[4]) {
+    if (!ctx) return CB_ERR_NO_DEVICE;
+    for (int i = 0; i < 4; i++) ms[i] = ctx->ms[i];
+    return 0;
+}
+
+long long cb_launch_count(const cb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

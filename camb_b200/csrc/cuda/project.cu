@@ -1,0 +1,292 @@
+// project.cu -- source interpolation in k, flat line-of-sight Bessel projection and
+// the k-integration to C_l on B200.
+//
+// What it replaces:
+//   cb_spline_k_kernel  InitSourceInterpolation  cmbmain.f90:1249-1265 (+ forutils spline :919-964)
+//   cb_los_kernel       loop B: SourceToTransfers :543-562 -> InterpolateSources :1351-1480,
+//                       DoSourceIntegration :1491-1523, DoFlatIntegration :1639-1862
+//   cb_cl_kernel        loop C: CalcScalCls :3179-3343
+//
+// B200 mapping: one CTA per integration wavenumber q.  The CTA first evaluates the cubic
+// spline in k for every time step into shared memory (Source_q, the Bessel-table index and
+// the interpolation weight are per-q, so they are computed once and shared by all l), then
+// its 8 warps walk the l list; inside a warp the time steps of the [tmin,tmax] window are
+// lane-strided, each step gathers one 32-byte Horner record of bessel_horner(:, ix, l)
+// (two 16-byte read-only loads; the 26 MB table is L2-resident) and the partial sums are
+// combined with a fixed-order shuffle tree, so results are deterministic run to run.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "dmodel.cuh"
+
+#define FULL 0xffffffffu
+#define LOS_THREADS 256
+
+namespace {
+
+__device__ __forceinline__ int ranges_index_of(const cb_range* R, int count, int npoints, double highest, double tau) {
+    for (int i = 0; i < count; i++) {
+        if (tau < R[i].high && tau >= R[i].low) {
+            if (R[i].is_log) return R[i].start_index + (int)(log(tau / R[i].low) / R[i].delta);
+            return R[i].start_index + (int)((tau - R[i].low) / R[i].delta);
+        }
+    }
+    if (tau >= highest) return npoints;
+    return -1;
+}
+
+// TRanges_IndexOfOrdered (RangeUtils.f90:539-666): reciprocal-delta form
+__device__ __forceinline__ int ranges_index_of_ordered(const cb_range* R, int count, int npoints, double highest, double tau) {
+    if (tau >= highest) return npoints;
+    for (int i = 0; i < count; i++) {
+        double lim = (i < count - 1) ? R[i].high : highest;
+        if (tau >= R[i].low && tau < lim) {
+            double inv_delta = 1.0 / R[i].delta;
+            if (R[i].is_log) return R[i].start_index + (int)(log(tau / R[i].low) * inv_delta);
+            return R[i].start_index + (int)((tau - R[i].low) * inv_delta);
+        }
+    }
+    return -1;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+}  // namespace
+
+// One thread per (source, time step) column: natural-spline second derivatives along k.
+// `u` is scratch of the same shape as dd.
+__global__ void cb_spline_k_kernel(const DModel* __restrict__ models, int n_models, double* const* __restrict__ scratch) {
+    const int m = blockIdx.y;
+    const DModel& M = models[m];
+    const int n_k = M.n_k, ncol = M.n_src * M.n_tau;
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncol) return;
+    const double* x = M.q_src;
+    const double* y = M.LinearSrc + (size_t)n_k * col;
+    double* d2 = M.ddSrc + (size_t)n_k * col;
+    double* u = scratch[m] + (size_t)n_k * col;
+    double d1r = (y[1] - y[0]) / (x[1] - x[0]), d1l;
+    d2[0] = 0; u[0] = 0;
+    for (int i = 1; i < n_k - 1; i++) {
+        d1l = d1r;
+        d1r = (y[i + 1] - y[i]) / (x[i + 1] - x[i]);
+        double xxdiv = 1.0 / (x[i + 1] - x[i - 1]);
+        double sig = (x[i] - x[i - 1]) * xxdiv;
+        double xp = 1.0 / (sig * d2[i - 1] + 2.0);
+        d2[i] = (sig - 1.0) * xp;
+        u[i] = (6.0 * (d1r - d1l) * xxdiv - sig * u[i - 1]) * xp;
+    }
+    d2[n_k - 1] = 0.0;
+    for (int i = n_k - 2; i >= 0; i--) d2[i] = d2[i] * d2[i + 1] + u[i];
+}
+
+// grid = (max n_q, n_models); dynamic smem: Source_q[n_src*n_tau] + left_weight[n_tau] + dtau[n_tau] + bes_index[n_tau]
+__global__ void __launch_bounds__(LOS_THREADS)
+cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
+    const DModel& M = models[blockIdx.y];
+    const int iq = blockIdx.x;
+    if (iq >= M.n_q) return;
+    extern __shared__ __align__(16) double sm[];
+    const int ntime = M.n_tau, nsrc = M.n_src, n_k = M.n_k, n_l = B.n_l;
+    double* Source_q = sm;                       // [nsrc][ntime]
+    double* left_weight = Source_q + (size_t)nsrc * max_n_tau;
+    double* dtau_s = left_weight + max_n_tau;
+    int* bes_index = reinterpret_cast<int*>(dtau_s + max_n_tau);
+    __shared__ int s_firstfail;
+    __shared__ cb_range s_tau_regions[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = LOS_THREADS / 32;
+    const double q = M.q_int[iq], tau0 = M.tau0;
+    const double* TimePoints = M.tau;
+    if (tid == 0) s_firstfail = ntime + 1;
+    if (tid < M.n_tau_regions) s_tau_regions[tid] = M.tau_regions[tid];
+    __syncthreads();
+    // ---- InterpolateSources, cmbmain.f90:1351-1480 ----
+    const bool ignore_etak = M.WantLateTime != 0;
+    const double max_etak = ignore_etak ? 0.0 : M.max_etak_scalar;
+    const double* qs = M.q_src;
+    int klo;
+    if (q <= qs[0]) klo = 1;
+    else if (q >= qs[n_k - 1]) klo = n_k - 1;
+    else {
+        int lo = 1, hi = n_k;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) / 2;
+            if (q >= qs[mid - 1]) lo = mid; else hi = mid;
+        }
+        klo = lo;
+    }
+    const int khi = klo + 1;
+    const double ho = qs[khi - 1] - qs[klo - 1];
+    const double a0 = (qs[khi - 1] - q) / ho, b0 = (q - qs[klo - 1]) / ho, ho2o6 = ho * ho / 6.0;
+    const double a03 = a0 * a0 * a0 - a0, b03 = b0 * b0 * b0 - b0;
+    for (int i = 2 + tid; i <= ntime; i += LOS_THREADS) {
+        const double tau = TimePoints[i - 1];
+        const bool pass = (ignore_etak || q * tau < max_etak) && (q * (tau0 - tau) > 1.e-8);
+        if (!pass) atomicMin(&s_firstfail, i);
+    }
+    __syncthreads();
+    const int SourceSteps = max(2, s_firstfail - 1);
+    for (int i = 1 + tid; i <= ntime; i += LOS_THREADS) {
+        const bool live = (i >= 2 && i < s_firstfail);
+        for (int j = 0; j < nsrc; j++) {
+            double v = 0.0;
+            if (live) {
+                const size_t off = (size_t)n_k * (j + (size_t)nsrc * (i - 1));
+                const double* S = M.LinearSrc + off;
+                const double* D = M.ddSrc + off;
+                v = a0 * S[klo - 1] + b0 * S[khi - 1] + (a03 * D[klo - 1] + b03 * D[khi - 1]) * ho2o6;
+            }
+            Source_q[(size_t)j * max_n_tau + (i - 1)] = v;
+        }
+        dtau_s[i - 1] = M.dtau[i - 1];
+        // ---- DoFlatIntegration preamble, cmbmain.f90:1680-1692 ----
+        if (i <= SourceSteps) {
+            const double xf = fabs(q * (tau0 - TimePoints[i - 1]));
+            int bes_ix = ranges_index_of_ordered(B.regions, B.n_regions, B.nx, B.xmax, xf);
+            if (bes_ix >= B.nx) bes_ix = B.nx - 1;
+            const double x_hi = B.x[bes_ix], dx = x_hi - B.x[bes_ix - 1];
+            left_weight[i - 1] = (x_hi - xf) / dx;
+            bes_index[i - 1] = bes_ix;
+        }
+    }
+    __syncthreads();
+    // ---- DoSourceIntegration: llmax (flat), cmbmain.f90:1516-1521 ----
+    int llmax = (int)llround(q * tau0);
+    if (llmax < 15) llmax = 17;
+    else llmax = (int)llround(q * (tau0 + 6.0 * 3.1415926535897932384626433832795 / q));
+    const double BessIntBoost = M.AccuracyBoost * M.BessIntBoost;
+    double* Dout = M.Delta + (size_t)nsrc * n_l * iq;
+    for (int j = 1 + warp; j <= n_l; j += nwarp) {
+        const int l = B.l[j - 1];
+        double s0 = 0, s1 = 0, s2 = 0;
+        bool active = l <= llmax;
+        double tmin = 0, tmax = 0;
+        if (active) {
+            const double xlim = fmax(0.0, l - 4.2 * pow((double)l, 1.0 / 3.0));
+            const double xlmax1 = 80 * l * BessIntBoost;
+            tmin = fmax(TimePoints[1], tau0 - xlmax1 / q);
+            tmax = tau0 - xlim / q;
+            if (tmax < TimePoints[1]) active = false;
+        }
+        if (active) {
+            const double* H = B.horner + (size_t)4 * (B.nx - 1) * (j - 1);
+            const int n1 = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, tmin);
+            int n2 = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, tmax);
+            if (n2 > SourceSteps) n2 = SourceSteps;
+            bool DoInt = true;
+            if (nsrc > 2) {
+                const double qmax_int = (l > 850 ? l : 850) * 3 * BessIntBoost / tau0 * 1.2;
+                DoInt = q < qmax_int;
+            }
+            if (DoInt) {
+                for (int n = n1 + lane; n <= n2; n += 32) {
+                    const double a2 = left_weight[n - 1];
+                    const double2* h = reinterpret_cast<const double2*>(H + 4 * (size_t)(bes_index[n - 1] - 1));
+                    const double2 h0 = __ldg(h), h1 = __ldg(h + 1);
+                    double J_l = h0.x + a2 * (h0.y + a2 * (h1.x + a2 * h1.y));
+                    J_l = J_l * dtau_s[n - 1];
+                    s0 = s0 + Source_q[n - 1] * J_l;
+                    s1 = s1 + Source_q[max_n_tau + n - 1] * J_l;
+                    if (nsrc > 2) s2 = s2 + Source_q[2 * (size_t)max_n_tau + n - 1] * J_l;
+                }
+                s0 = warp_sum(s0); s1 = warp_sum(s1);
+                if (nsrc > 2) s2 = warp_sum(s2);
+            }
+            if (nsrc > 2) {  // UseLimber, cmbmain.f90:1619-1636, 1821-1832
+                const bool limber = l > 400 * pow(M.AccuracyBoost * M.LimberBoost, 0.5);
+                if (!DoInt || limber) {
+                    double xf = tau0 - (l + 0.5) / q;
+                    if (xf < M.tau_highest && xf > M.tau_lowest) {
+                        const int n = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, xf);
+                        xf = (xf - TimePoints[n - 1]) / (TimePoints[n] - TimePoints[n - 1]);
+                        s2 = (Source_q[2 * (size_t)max_n_tau + n - 1] * (1 - xf) + xf * Source_q[2 * (size_t)max_n_tau + n]) *
+                             sqrt(3.1415926535897932384626433832795 / 2 / (l + 0.5)) / q;
+                    } else s2 = 0;
+                }
+            }
+        }
+        if (lane == 0) {
+            double* o = Dout + (size_t)nsrc * (j - 1);
+            o[0] = s0; o[1] = s1;
+            if (nsrc > 2) o[2] = s2;
+        }
+    }
+}
+
+// grid = (n_l, n_models), one CTA per l: deterministic block reduction over q.
+__global__ void __launch_bounds__(256) cb_cl_kernel(const DModel* __restrict__ models, DBessel B) {
+    const DModel& M = models[blockIdx.y];
+    const int j = blockIdx.x, n_l = B.n_l, nsrc = M.n_src, n_q = M.n_q;
+    const int ncl = nsrc > 2 ? 6 : 3;
+    double c[6] = {0, 0, 0, 0, 0, 0};
+    for (int iq = threadIdx.x; iq < n_q; iq += blockDim.x) {
+        const double dlnk = M.dq_int[iq] / M.q_int[iq], ap = M.pows[iq];
+        const double* D = M.Delta + (size_t)nsrc * (j + (size_t)n_l * iq);
+        const double d0 = D[0], d1 = D[1];
+        c[0] += ap * (d0 * d0) * dlnk;
+        c[1] += ap * (d1 * d1) * dlnk;
+        c[2] += ap * d0 * d1 * dlnk;
+        if (nsrc > 2) {
+            const double d2 = D[2];
+            c[3] += ap * (d2 * d2) * dlnk;
+            c[4] += ap * d2 * d0 * dlnk;
+            c[5] += ap * d2 * d1 * dlnk;
+        }
+    }
+    __shared__ double red[6][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t = 0; t < ncl; t++) {
+        double v = warp_sum(c[t]);
+        if (lane == 0) red[t][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s[6];
+        for (int t = 0; t < ncl; t++) {
+            double v = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += red[t][w];
+            s[t] = v;
+        }
+        const double ell = (double)B.l[j];
+        const double fourpi = 4 * 3.1415926535897932384626433832795, twopi = 2 * 3.1415926535897932384626433832795;
+        const double ctnorm = (ell * ell - 1) * (ell + 2) * ell;
+        const double dbletmp = (ell * (ell + 1)) / twopi * fourpi;
+        double* out = M.iCl;
+        out[j + n_l * 0] = s[0] * dbletmp;
+        out[j + n_l * 1] = s[1] * dbletmp * ctnorm;
+        out[j + n_l * 2] = s[2] * dbletmp * sqrt(ctnorm);
+        if (nsrc > 2) {
+            out[j + n_l * 3] = M.Alens * s[3] * fourpi * (ell * ell * ell * ell);
+            out[j + n_l * 4] = sqrt(M.Alens) * s[4] * fourpi * (ell * ell * ell);
+            out[j + n_l * 5] = sqrt(M.Alens) * s[5] * fourpi * (ell * ell * ell) * sqrt(ctnorm);
+        }
+    }
+}
+
+// ---------------- launch wrappers (called from cabi.cu) ----------------
+void cb_spline_k_launch(const DModel* d_models, int n_models, int max_cols, double* const* d_scratch, cudaStream_t st) {
+    dim3 grid((max_cols + 127) / 128, n_models);
+    cb_spline_k_kernel<<<grid, 128, 0, st>>>(d_models, n_models, d_scratch);
+}
+
+size_t cb_los_smem(int max_nsrc, int max_n_tau) {
+    return sizeof(double) * ((size_t)max_nsrc * max_n_tau + 2 * (size_t)max_n_tau) + sizeof(int) * (size_t)max_n_tau + 16;
+}
+
+cudaError_t cb_los_set_smem(size_t smem) {
+    return cudaFuncSetAttribute(cb_los_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+void cb_los_launch(const DModel* d_models, int n_models, const DBessel& B, int max_n_q, int max_n_tau, size_t smem, cudaStream_t st) {
+    dim3 grid(max_n_q, n_models);
+    cb_los_kernel<<<grid, LOS_THREADS, smem, st>>>(d_models, B, max_n_tau);
+}
+
+void cb_cl_launch(const DModel* d_models, int n_models, const DBessel& B, cudaStream_t st) {
+    dim3 grid(B.n_l, n_models);
+    cb_cl_kernel<<<grid, 256, 0, st>>>(d_models, B);
+}

@@ -1,0 +1,181 @@
+"""ctypes binding of libcambb200.so -- the C-ABI of the B200 Boltzmann path
+(include/cambb200.h).  This is the call a maintainer's Fortran `bind(C)` interface makes
+(INTEGRATION.md); Python goes through exactly the same entry points.
+
+The product path fails loudly when the CUDA library or a device is missing: there is no
+CPU fallback here (the CPU restatement under oracle/ is test infrastructure only).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._cdefs import cb_bessel, cb_model, cb_modes, c_double_p, c_float_p, c_int_p
+from .host import CAMBError
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+c_ll_p = C.POINTER(C.c_longlong)
+c_void_pp = C.POINTER(C.c_void_p)
+
+SYMBOLS = ["cb_create", "cb_destroy", "cb_last_error", "cb_device_count", "cb_set_bessel", "cb_model_create",
+           "cb_model_destroy", "cb_evolve", "cb_set_sources", "cb_project", "cb_cl", "cb_last_timings",
+           "cb_launch_count"]
+
+
+def load_gpu_lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, "libcambb200.so")
+        if not os.path.exists(path):
+            raise ImportError(f"{path} not built: run `make cuda` (or __graft_entry__.build()). "
+                              "camb_b200 has no CPU fallback.")
+        lib = C.CDLL(path)
+        lib.cb_create.argtypes = [C.c_int, c_void_pp]
+        lib.cb_destroy.argtypes = [C.c_void_p]
+        lib.cb_last_error.restype = C.c_char_p
+        lib.cb_last_error.argtypes = [C.c_void_p]
+        lib.cb_set_bessel.argtypes = [C.c_void_p, C.POINTER(cb_bessel)]
+        lib.cb_model_create.argtypes = [C.c_void_p, C.POINTER(cb_model), c_void_pp]
+        lib.cb_model_destroy.argtypes = [C.c_void_p, C.c_void_p]
+        lib.cb_evolve.argtypes = [C.c_void_p, C.c_int, c_void_pp, C.POINTER(cb_modes), C.POINTER(c_double_p),
+                                  C.POINTER(c_float_p), C.POINTER(c_ll_p)]
+        lib.cb_set_sources.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_double_p, c_double_p]
+        lib.cb_project.argtypes = [C.c_void_p, C.c_int, c_void_pp, c_int_p, C.POINTER(c_double_p),
+                                   C.POINTER(c_double_p), C.POINTER(c_double_p)]
+        lib.cb_cl.argtypes = [C.c_void_p, C.c_int, c_void_pp, C.c_int, C.POINTER(c_double_p), C.POINTER(c_double_p)]
+        lib.cb_last_timings.argtypes = [C.c_void_p, C.c_double * 4]
+        lib.cb_launch_count.restype = C.c_longlong
+        lib.cb_launch_count.argtypes = [C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+class GpuContext:
+    """One per process and device (cmbmain.f90:7-8: the reference is not re-entrant either)."""
+
+    def __init__(self, device=0):
+        self._lib = load_gpu_lib()
+        h = C.c_void_p()
+        e = self._lib.cb_create(device, C.byref(h))
+        if e:
+            raise CAMBError(f"cb_create failed with error {e}: no usable CUDA device "
+                            "(camb_b200 has no CPU fallback)", e)
+        self._h = h
+        self.device = device
+        self._bessel_key = None
+
+    def _check(self, e):
+        if e:
+            raise CAMBError(self._lib.cb_last_error(self._h).decode(), e)
+
+    def set_bessel(self, hs):
+        b = hs.bessel()
+        key = (b.n_l, b.nx, tuple(hs.ls.tolist()))
+        if key != self._bessel_key:
+            self._check(self._lib.cb_set_bessel(self._h, C.byref(b)))
+            self._bessel_key = key
+        self.n_l = b.n_l
+
+    def create_model(self, hs):
+        dm = C.c_void_p()
+        self._check(self._lib.cb_model_create(self._h, C.byref(hs.model), C.byref(dm)))
+        return dm
+
+    def destroy_model(self, dm):
+        self._lib.cb_model_destroy(self._h, dm)
+
+    # ---- the three loops, batched over cosmologies ----
+    def evolve(self, hss, dms, transfer_only=False, want_sources=True, want_stats=True):
+        n = len(hss)
+        dm_arr = (C.c_void_p * n)(*dms)
+        md_arr = (cb_modes * n)()
+        mds = [hs.modes(transfer_only) for hs in hss]
+        for i, md in enumerate(mds):
+            md_arr[i] = md
+        src, tr, st = [], [], []
+        src_p = (c_double_p * n)()
+        tr_p = (c_float_p * n)()
+        st_p = (c_ll_p * n)()
+        for i, hs in enumerate(hss):
+            m = hs.model
+            n_k = mds[i].n_k
+            if want_sources and not transfer_only:
+                a = np.zeros((m.n_tau, m.n_src, n_k))
+                src.append(a)
+                src_p[i] = _dp(a)
+            else:
+                src.append(None)
+            if m.WantTransfer and m.num_transfer_redshifts > 0:
+                t = np.zeros((m.num_transfer_redshifts, n_k, 13), dtype=np.float32)
+                tr.append(t)
+                tr_p[i] = t.ctypes.data_as(c_float_p)
+            else:
+                tr.append(None)
+            if want_stats:
+                s = np.zeros((n_k, 2), dtype=np.int64)
+                st.append(s)
+                st_p[i] = s.ctypes.data_as(c_ll_p)
+            else:
+                st.append(None)
+        self._check(self._lib.cb_evolve(self._h, n, dm_arr, md_arr, src_p, tr_p, st_p))
+        return src, tr, st
+
+    def set_sources(self, dm, q_src, src):
+        q_src = np.ascontiguousarray(q_src)
+        src = np.ascontiguousarray(src)
+        self._check(self._lib.cb_set_sources(self._h, dm, len(q_src), _dp(q_src), _dp(src)))
+
+    def project(self, hss, dms, want_delta=True):
+        n = len(hss)
+        dm_arr = (C.c_void_p * n)(*dms)
+        nq = (C.c_int * n)(*[len(hs.q_int) for hs in hss])
+        qs = [np.ascontiguousarray(hs.q_int) for hs in hss]
+        dqs = [np.ascontiguousarray(hs.dq_int) for hs in hss]
+        q_p = (c_double_p * n)(*[_dp(a) for a in qs])
+        dq_p = (c_double_p * n)(*[_dp(a) for a in dqs])
+        out, out_p = [], (c_double_p * n)()
+        for i, hs in enumerate(hss):
+            if want_delta:
+                a = np.zeros((len(hs.q_int), self.n_l, hs.model.n_src))
+                out.append(a)
+                out_p[i] = _dp(a)
+            else:
+                out.append(None)
+        self._check(self._lib.cb_project(self._h, n, dm_arr, nq, q_p, dq_p, out_p))
+        return out
+
+    def cl(self, hss, dms, pows=None):
+        n = len(hss)
+        dm_arr = (C.c_void_p * n)(*dms)
+        if pows is None:
+            pows = [hs.scalar_power() for hs in hss]
+        pows = [np.ascontiguousarray(p) for p in pows]
+        p_p = (c_double_p * n)(*[_dp(a) for a in pows])
+        out = [np.zeros((6 if hs.model.n_src > 2 else 3, self.n_l)) for hs in hss]
+        o_p = (c_double_p * n)(*[_dp(a) for a in out])
+        self._check(self._lib.cb_cl(self._h, n, dm_arr, 0, p_p, o_p))
+        return [o.T.copy() for o in out]
+
+    def timings_ms(self):
+        t = (C.c_double * 4)()
+        self._lib.cb_last_timings(self._h, t)
+        return dict(evolve=t[0], spline_k=t[1], los=t[2], cl=t[3])
+
+    def launch_count(self):
+        return int(self._lib.cb_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
