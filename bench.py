@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the per-k-mode Boltzmann path on B200 (BASELINE.json metric:
+LCDM C_l sets/sec at lmax 2500, with Boltzmann k-modes/sec alongside).
+
+A "step" is one pass of the hot path (evolve -> spline-in-k -> LOS projection -> C_l) over one
+batch of `--batch` synthetic LCDM parameter sets per GPU (planck_2018.ini cosmology box,
+massless neutrinos, T/E/lensing-potential sources, lmax 2500: BASELINE.json configs[1] without the
+host-side lensing of C_l, which SURVEY.md 8(f) lists as "next").  Parameter sets shard whole
+across GPUs with no data-path collective ("scaling": "weak").
+
+  value   device time (CUDA events on the library's stream), boundary tables resident in HBM
+  e2e     the same batch through the C-ABI with HOST buffers: per step every cosmology's
+          boundary tables are copied host->device from page-locked memory, and LinearSrc-free
+          results (iCl) are read back; wall clock bracketed by device synchronisation
+  roofline      dominant kernel (the ODE kernel): algorithmic FP64 flops / its CUDA-event time
+                against the FP64 FMA peak measured live; the LOS kernel's HBM figure is beside it
+  cpu_baseline  the oracle (CPU restatement, OpenMP over k-modes) on this box's host cores
+
+`--impl reference` times the CPU implementation of the path (the oracle port: the reference is
+Fortran and cannot be built in this image) on the same workload."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "lcdm_cl_sets_per_sec_lmax2500"
+UNIT = "C_l sets/s"
+WORKLOAD = "planck2018_lcdm_box_massless_nu_T+E+phi_lmax2500_keta6250"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_batch(n, seed):
+    from camb_b200.host import HostState
+    from camb_b200.workloads import synthetic_lcdm_batch
+    ps = synthetic_lcdm_batch(n, seed=seed, lmax=2500, lensing=True, massless=True)
+    return [HostState(p) for p in ps]
+
+
+def oracle_cl_sets(hss, nthreads, budget_s, min_sets=1):
+    """Time the oracle chain on a bounded sample of the batch; returns (sets, seconds, k_modes)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    t0 = time.perf_counter()
+    n = modes = 0
+    for hs in hss:
+        O.cls_from_params(hs, nthreads=nthreads)
+        n += 1
+        modes += len(hs.source_q())
+        if time.perf_counter() - t0 > budget_s and n >= min_sets:
+            break
+    return n, time.perf_counter() - t0, modes
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU implementation of the path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = max(1, min(args.batch, 4))
+    hss = build_batch(per_step, seed=20261017)
+    for hs in hss:
+        hs.bessel()
+    for _ in range(args.warmup):
+        oracle_cl_sets(hss, cores, 1e9)
+    t0 = time.perf_counter()
+    sets = modes = 0
+    for _ in range(args.steps):
+        n, _, m = oracle_cl_sets(hss, cores, 1e9)
+        sets += n
+        modes += m
+    dt = time.perf_counter() - t0
+    v = sets / dt
+    sample = f"{per_step} of the batch's parameter sets per step, OpenMP over k-modes, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sets_per_step": per_step,
+                   "note": "CPU restatement of the reference path (oracle port); the Fortran reference cannot be built in this image"},
+        "k_modes_per_sec": modes / dt,
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def model_h2d_bytes(hs):
+    m = hs.model
+    return 8 * (m.nthermo * (16 + 7) + 2 * m.n_tau) + 8 * max(0, m.num_transfer_redshifts)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=env_int("CAMB_B200_BATCH", 64), help="parameter sets per GPU per step")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from camb_b200.gpu import GpuContext
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; camb_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = GpuContext(local)
+    B = args.batch
+    hss = build_batch(B, seed=20261017 + 1000 * rank)       # every rank its own parameter sets
+    ctx.set_bessel(hss[0])
+    dms = [ctx.create_model(hs) for hs in hss]
+    n_modes = sum(len(hs.source_q()) for hs in hss)
+
+    def step(want_stats=False):
+        _, _, st = ctx.evolve(hss, dms, want_sources=False, want_stats=want_stats)
+        t_ev = ctx.timings_ms()["evolve"]
+        ctx.project(hss, dms, want_delta=False)
+        icl = ctx.cl(hss, dms)
+        return icl, st, t_ev, ctx.timings_ms()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fp64_peak = ctx.fp64_peak_tflops()
+    for _ in range(args.warmup):
+        icl, st, _, _ = step(True)
+    # algorithmic work of the ODE kernel from the integrator's own counters
+    evals = sum(int(s[:, 0].sum()) for s in st)
+    neq_evals = sum(int(s[:, 2].sum()) for s in st)
+    attempts = sum(int(s[:, 3].sum()) for s in st)
+    neq_attempts = neq_evals / 6.0                       # 6 integrator derivs calls per attempt (FSAL)
+    ode_flops = 5.0 * neq_evals + 200.0 * evals + 70.0 * neq_attempts
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    ctx.timer_start()
+    t_ev = t_los = t_spl = t_cl = 0.0
+    for _ in range(args.steps):
+        icl, _, tev, tm = step(False)
+        t_ev += tev; t_los += tm["los"]; t_spl += tm["spline_k"]; t_cl += tm["cl"]
+    ms = ctx.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # ---- e2e: host buffers -> C-ABI -> host results, copies inside the timed region ----
+    h2d = sum(model_h2d_bytes(hs) for hs in hss) + sum(8 * (3 * len(hs.q_int) + len(hs.source_q())) for hs in hss)
+    d2h = sum(8 * len(hs.ls) * 6 for hs in hss)
+
+    def e2e_step():
+        d = [ctx.create_model(hs) for hs in hss]
+        ctx.evolve(hss, d, want_sources=False, want_stats=False)
+        ctx.project(hss, d, want_delta=False)
+        out = ctx.cl(hss, d)
+        for x in d:
+            ctx.destroy_model(x)
+        return out
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = e2e_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert np.array_equal(out[0], icl[0]), "e2e path and resident path disagree"
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(t.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        ev_ms = t_ev / args.steps
+        los_ms = t_los / args.steps
+        ach = ode_flops / (ev_ms * 1e-3) / 1e12
+        # LOS: compulsory bytes per launch = Bessel table + per cosmology (Src + dd + Delta out)
+        b = hss[0].bessel()
+        los_bytes = 32.0 * (b.nx - 1) * b.n_l + sum(
+            8.0 * (2 * len(hs.source_q()) * hs.n_src * hs.n_tau + hs.n_src * len(hs.ls) * len(hs.q_int)) for hs in hss)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sets_per_gpu_per_step": B, "k_modes_per_set": n_modes / B,
+                       "l2": "inputs larger than L2 (per-step working set %.0f MB)" % (
+                           (los_bytes + sum(model_h2d_bytes(hs) for hs in hss)) / 1e6)},
+            "k_modes_per_sec": world * n_modes * args.steps / (ms_max * 1e-3),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "kernel": "cb_evolve_kernel", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": ach / fp64_peak if fp64_peak else None, "traffic": None,
+                         "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                         "ms_per_launch": ev_ms, "share_of_step": t_ev / (t_ev + t_los + t_spl + t_cl),
+                         "derivs_evals_per_launch": evals, "algorithmic_flops_per_launch": ode_flops},
+            "roofline_los": {"bound": "hbm", "kernel": "cb_los_kernel", "achieved": los_bytes / (los_ms * 1e-3) / 1e9,
+                             "peak": hbm_peak, "unit": "GB/s", "frac": los_bytes / (los_ms * 1e-3) / 1e9 / hbm_peak,
+                             "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",
+                             "ms_per_launch": los_ms, "share_of_step": t_los / (t_ev + t_los + t_spl + t_cl)},
+            "stage_ms_per_step": {"evolve": ev_ms, "spline_k": t_spl / args.steps, "los": los_ms, "cl": t_cl / args.steps},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            n, secs, m = oracle_cl_sets(hss, cores, args.cpu_budget)
+            line["cpu_baseline"] = {"value": n / secs, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"first {n} parameter sets of the batch, {secs:.1f} s, OpenMP over k-modes",
+                                    "k_modes_per_sec": m / secs}
+        print(json.dumps(line))
+    for dm in dms:
+        ctx.destroy_model(dm)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -25,6 +25,8 @@ size_t cb_los_smem(int, int);
 cudaError_t cb_los_set_smem(size_t);
 void cb_los_launch(const DModel*, int, const DBessel&, int, int, size_t, cudaStream_t);
 void cb_cl_launch(const DModel*, int, const DBessel&, cudaStream_t);
+// peak.cu
+double cb_fp64_peak_measure(int n_sm, cudaStream_t st, int reps);
 
 struct cb_dmodel {
     DModel h;                      // host copy with device pointers
@@ -34,14 +36,14 @@ struct cb_dmodel {
     double *d_q_int = nullptr, *d_dq_int = nullptr, *d_pows = nullptr;
     float* d_transfer = nullptr;
     long long* d_stats = nullptr;
-    size_t cap_src = 0, cap_k = 0, cap_q = 0, cap_delta = 0, cap_tr = 0, cap_icl = 0;
+    size_t cap_src = 0, cap_k = 0, cap_q = 0, cap_delta = 0, cap_tr = 0, cap_icl = 0, cap_stats = 0;
     int n_cl = 3;
 };
 
 struct cb_ctx {
     int device = 0, n_sm = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
     std::string err;
     DBessel bess{};
     std::vector<void*> bess_owned;
@@ -105,6 +107,8 @@ int cb_create(int device, cb_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CB_ERR_CUDA; }
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
+    cudaEventCreate(&ctx->evt0);
+    cudaEventCreate(&ctx->evt1);
     if (cudaMalloc((void**)&ctx->d_counter, sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_error, sizeof(int)) != cudaSuccess) { delete ctx; return CB_ERR_CUDA; }
     *out = ctx;
@@ -122,6 +126,8 @@ void cb_destroy(cb_ctx* ctx) {
     if (ctx->d_error) cudaFree(ctx->d_error);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->evt0) cudaEventDestroy(ctx->evt0);
+    if (ctx->evt1) cudaEventDestroy(ctx->evt1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -260,12 +266,8 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
             if (int e = ensure(ctx, &d->d_transfer, &d->cap_tr, ntr)) return e;
             D.TransferData = d->d_transfer;
         } else D.TransferData = nullptr;
-        {
-            if (d->d_stats) { cudaFree(d->d_stats); d->d_stats = nullptr; }
-            size_t cs = 0;
-            if (int e = ensure(ctx, &d->d_stats, &cs, (size_t)2 * n_k)) return e;
-            D.stats = d->d_stats;
-        }
+        if (int e = ensure(ctx, &d->d_stats, &d->cap_stats, (size_t)4 * n_k)) return e;
+        D.stats = d->d_stats;
         for (int i = 0; i < n_k; i++) {
             DModeItem it;
             memset(&it, 0, sizeof(it));
@@ -311,7 +313,7 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
         if (TransferData && TransferData[m] && D.num_transfer_redshifts > 0)
             CK(cudaMemcpyAsync(TransferData[m], d->d_transfer, sizeof(float) * (size_t)13 * D.n_k * D.num_transfer_redshifts, cudaMemcpyDeviceToHost, ctx->stream));
         if (stats && stats[m])
-            CK(cudaMemcpyAsync(stats[m], d->d_stats, sizeof(long long) * 2 * (size_t)D.n_k, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(stats[m], d->d_stats, sizeof(long long) * 4 * (size_t)D.n_k, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
@@ -447,5 +449,66 @@ int cb_last_timings(const cb_ctx* ctx, double ms[4]) {
 }
 
 long long cb_launch_count(const cb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int cb_timer_start(cb_ctx* ctx) {
+    if (!ctx) return CB_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->evt0, ctx->stream));
+    return 0;
+}
+
+int cb_timer_stop(cb_ctx* ctx, double* ms) {
+    if (!ctx) return CB_ERR_NO_DEVICE;
+    CK(cudaEventRecord(ctx->evt1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->evt1));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, ctx->evt0, ctx->evt1));
+    *ms = f;
+    return 0;
+}
+
+int cb_fp64_peak(cb_ctx* ctx, double* tflops) {
+    if (!ctx) return CB_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    *tflops = cb_fp64_peak_measure(ctx->n_sm, ctx->stream, 5);
+    ctx->launches += 6;
+    return *tflops > 0 ? 0 : CB_ERR_CUDA;
+}
+
+void* cb_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void cb_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int cb_device_buffer(cb_ctx* ctx, cb_dmodel* dm, int which, void** ptr, size_t* bytes) {
+    if (!ctx || !dm) return CB_ERR_NO_DEVICE;
+    const DModel& D = dm->h;
+    const size_t n_l = (size_t)ctx->bess.n_l;
+    switch (which) {
+        case CB_BUF_LINEARSRC: *ptr = dm->d_src; *bytes = sizeof(double) * (size_t)D.n_k * D.n_src * D.n_tau; return 0;
+        case CB_BUF_DELTA: *ptr = dm->d_delta; *bytes = sizeof(double) * (size_t)D.n_src * n_l * D.n_q; return 0;
+        case CB_BUF_ICL: *ptr = dm->d_icl; *bytes = sizeof(double) * n_l * dm->n_cl; return 0;
+        case CB_BUF_TRANSFER: *ptr = dm->d_transfer; *bytes = sizeof(float) * (size_t)13 * D.n_k * D.num_transfer_redshifts; return 0;
+    }
+    ctx->err = "cb_device_buffer: unknown buffer id";
+    return CB_ERR_UNSUPPORTED_PARAMS;
+}
+
+size_t cb_abi_sizeof(int which) {
+    switch (which) {
+        case 0: return sizeof(cb_params);
+        case 1: return sizeof(cb_model);
+        case 2: return sizeof(cb_modes);
+        case 3: return sizeof(cb_bessel);
+        case 4: return sizeof(cb_range);
+        case 5: return sizeof(cb_accuracy);
+    }
+    return 0;
+}
 
 }  // extern "C"

@@ -58,7 +58,7 @@ struct DModel {
     double* LinearSrc;       // (n_k, n_src, n_tau)
     double* ddSrc;           // same shape
     float* TransferData;     // (13, n_k, n_z)
-    long long* stats;        // [2*n_k]
+    long long* stats;        // [4*n_k]
     int n_q;
     const double* q_int;
     const double* dq_int;

@@ -747,7 +747,7 @@ __device__ __forceinline__ double warp_max(double v) {
 struct RK {
     double max_step_size, current_step_size, estimated_error, previous_xend;
     int xend_reached, first_derivative_valid, successive_failures;
-    long long steps;
+    long long steps, attempts, neq_evals;   // accepted steps, attempted steps, sum over derivs calls of neq
 };
 
 // One call of RungeKuttaDP45 (RungeKuttaDP45.f90:94-408) for this warp's mode.
@@ -768,8 +768,10 @@ __device__ void dp45(const DModel& M, EVs& E, const double* denlk, const double*
     for (;;) {
         if (ind != 6) {
             if (s.first_derivative_valid) s.first_derivative_valid = 0;  // reuse_first_derivative is always on (equations.f90:223)
-            else derivs<false>(M, E, denlk, denlk2, polfack, x, y, k1, lane, nullptr, nullptr, nderivs);
+            else { derivs<false>(M, E, denlk, denlk2, polfack, x, y, k1, lane, nullptr, nullptr, nderivs); s.neq_evals += n; }
         }
+        s.attempts++;
+        s.neq_evals += 6 * n;
         double temp = 0;
         for (int i = lane; i < n; i += 32) temp = fmax(temp, fabs(y[i]));
         temp = warp_max(temp);
@@ -1081,7 +1083,7 @@ cb_evolve_kernel(const DModel* __restrict__ models, const DModeItem* __restrict_
         __syncwarp();
         RK rk;
         rk.max_step_size = 0; rk.current_step_size = 0; rk.estimated_error = 0; rk.previous_xend = 0;
-        rk.xend_reached = 0; rk.first_derivative_valid = 0; rk.successive_failures = 0; rk.steps = 0;
+        rk.xend_reached = 0; rk.first_derivative_valid = 0; rk.successive_failures = 0; rk.steps = 0; rk.attempts = 0; rk.neq_evals = 0;
         double tau = taustart;
         int ind = 1, itf = 1;
         double tol1 = 1.0e-4 / exp(M.AccuracyBoost * M.IntTolBoost - 1);
@@ -1147,7 +1149,7 @@ cb_evolve_kernel(const DModel* __restrict__ models, const DModeItem* __restrict_
         }
         if (lane == 0) {
             if (failed) atomicExch(error_flag, CB_ERR_EVOLUTION);
-            if (M.stats) { M.stats[2 * q_ix] = nderivs; M.stats[2 * q_ix + 1] = rk.steps; }
+            if (M.stats) { M.stats[4 * q_ix] = nderivs; M.stats[4 * q_ix + 1] = rk.steps; M.stats[4 * q_ix + 2] = rk.neq_evals; M.stats[4 * q_ix + 3] = rk.attempts; }
         }
         __syncwarp();
     }

@@ -20,7 +20,8 @@ c_void_pp = C.POINTER(C.c_void_p)
 
 SYMBOLS = ["cb_create", "cb_destroy", "cb_last_error", "cb_device_count", "cb_set_bessel", "cb_model_create",
            "cb_model_destroy", "cb_evolve", "cb_set_sources", "cb_project", "cb_cl", "cb_last_timings",
-           "cb_launch_count"]
+           "cb_launch_count", "cb_abi_sizeof", "cb_timer_start", "cb_timer_stop", "cb_fp64_peak",
+           "cb_host_alloc", "cb_host_free", "cb_device_buffer"]
 
 
 def load_gpu_lib():
@@ -47,6 +48,15 @@ def load_gpu_lib():
         lib.cb_last_timings.argtypes = [C.c_void_p, C.c_double * 4]
         lib.cb_launch_count.restype = C.c_longlong
         lib.cb_launch_count.argtypes = [C.c_void_p]
+        lib.cb_timer_start.argtypes = [C.c_void_p]
+        lib.cb_timer_stop.argtypes = [C.c_void_p, c_double_p]
+        lib.cb_fp64_peak.argtypes = [C.c_void_p, c_double_p]
+        lib.cb_host_alloc.restype = C.c_void_p
+        lib.cb_host_alloc.argtypes = [C.c_size_t]
+        lib.cb_host_free.argtypes = [C.c_void_p]
+        lib.cb_device_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_void_pp, C.POINTER(C.c_size_t)]
+        lib.cb_abi_sizeof.restype = C.c_size_t
+        lib.cb_abi_sizeof.argtypes = [C.c_int]
         _lib = lib
     return _lib
 
@@ -117,7 +127,7 @@ class GpuContext:
             else:
                 tr.append(None)
             if want_stats:
-                s = np.zeros((n_k, 2), dtype=np.int64)
+                s = np.zeros((n_k, 4), dtype=np.int64)
                 st.append(s)
                 st_p[i] = s.ctypes.data_as(c_ll_p)
             else:
@@ -160,6 +170,25 @@ class GpuContext:
         o_p = (c_double_p * n)(*[_dp(a) for a in out])
         self._check(self._lib.cb_cl(self._h, n, dm_arr, 0, p_p, o_p))
         return [o.T.copy() for o in out]
+
+    def timer_start(self):
+        self._check(self._lib.cb_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(self._lib.cb_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def fp64_peak_tflops(self):
+        t = C.c_double()
+        self._check(self._lib.cb_fp64_peak(self._h, C.byref(t)))
+        return t.value
+
+    def device_buffer(self, dm, which):
+        """(device pointer, bytes) of a result buffer: 0 LinearSrc, 1 Delta_p_l_k, 2 iCl, 3 TransferData."""
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self._lib.cb_device_buffer(self._h, dm, which, C.byref(p), C.byref(n)))
+        return p.value, n.value
 
     def timings_ms(self):
         t = (C.c_double * 4)()

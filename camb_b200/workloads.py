@@ -1,0 +1,114 @@
+"""Parameter sets of the benchmark / parity configurations (BASELINE.json `configs`,
+SURVEY.md section 8(d)).  Values are those of the reference's ini files
+(inifiles/planck_2018.ini, inifiles/params.ini) with the overrides SURVEY.md lists."""
+import numpy as np
+
+from .host import default_params
+
+
+def planck2018_params(lmax=2500, lensing=True, massless=True, k_eta_max=None, accuracy_boost=1.0,
+                      de="lcdm", w=-1.0, wa=0.0, want_transfer=False):
+    """inifiles/planck_2018.ini:38-110 cosmology + recombination/reionization settings.
+    `massless=True` is BASELINE.json config 2's "massless neutrinos" override
+    (omnuh2=0, massive_neutrinos=0, massless_neutrinos=3.046)."""
+    p = default_params()
+    p.H0 = 67.32117
+    p.ombh2 = 0.0223828
+    p.omch2 = 0.1201075
+    p.Yhe = 0.2454006
+    p.TCMB = 2.7255
+    if massless:
+        p.omnuh2 = 0.0
+        p.Num_Nu_massive = 0
+        p.Nu_mass_eigenstates = 0
+        p.Num_Nu_massless = 3.046
+    else:
+        p.omnuh2 = 0.6451439E-03
+        p.Num_Nu_massless = 2.046
+        p.Num_Nu_massive = 1
+        p.Nu_mass_eigenstates = 1
+        p.share_delta_neff = 1
+        p.Nu_mass_fractions[0] = 1.0
+        p.Nu_mass_numbers[0] = 0
+    p.As = 2.100549e-9
+    p.ns = 0.9660499
+    p.use_optical_depth = 1
+    p.optical_depth = 0.05430842
+    p.delta_redshift = 0.5
+    p.helium_redshift = 3.5
+    p.helium_delta_redshift = 0.5
+    p.helium_redshiftstart = 3.5 + 5 * 0.5
+    p.RECFAST_fudge = 1.125
+    p.RECFAST_fudge_He = 0.86
+    p.RECFAST_He_rate_correction = 0
+    p.AGauss1, p.AGauss2 = -0.14, 0.079
+    p.zGauss1, p.zGauss2 = 7.28, 6.73
+    p.wGauss1, p.wGauss2 = 0.18, 0.33
+    p.de_model = 1  # ppf, as the ini file
+    p.w, p.wa = (w, wa) if de != "lcdm" else (-1.0, 0.0)
+    p.DoLensing = 1 if lensing else 0
+    p.Max_l = int(lmax)
+    p.Max_eta_k = float(k_eta_max) if k_eta_max else 2.5 * lmax
+    p.Accuracy.AccuracyBoost = float(accuracy_boost)
+    p.WantTransfer = 1 if want_transfer else 0
+    return p
+
+
+def params_ini_config1():
+    """inifiles/params.ini:33-60 with SURVEY.md 8(d) config-1 overrides (lmax 2500,
+    k_eta_max 6250, no lensing, no transfer): flat LCDM, one massive neutrino, n_src = 2."""
+    p = default_params()
+    p.H0 = 67.5
+    p.ombh2 = 0.022
+    p.omch2 = 0.122
+    p.omnuh2 = 0.00064
+    p.Yhe = 0.24
+    p.Num_Nu_massless = 2.046
+    p.Num_Nu_massive = 1
+    p.Nu_mass_eigenstates = 1
+    p.share_delta_neff = 1
+    p.Nu_mass_fractions[0] = 1.0
+    p.Nu_mass_numbers[0] = 0
+    p.As = 2e-9
+    p.ns = 0.965
+    p.use_optical_depth = 1
+    p.optical_depth = 0.06
+    p.DoLensing = 0
+    p.Max_l = 2500
+    p.Max_eta_k = 6250
+    return p
+
+
+def synthetic_lcdm_batch(n, seed=20261017, lmax=2500, lensing=True, massless=True, extended=False):
+    """Synthetic parameter sets (SURVEY.md 8(d) config 5 box; the reference defines no
+    distribution).  `extended` adds mnu and w0wa (PPF)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        ombh2 = rng.uniform(0.0205, 0.0240)
+        omch2 = rng.uniform(0.105, 0.135)
+        H0 = rng.uniform(60.0, 76.0)
+        tau = rng.uniform(0.03, 0.09)
+        ns = rng.uniform(0.92, 1.00)
+        lnAs = rng.uniform(2.9, 3.2)
+        mnu = rng.uniform(0.0, 0.3)
+        w0 = rng.uniform(-1.3, -0.7)
+        wa = rng.uniform(-0.5, 0.5)
+        if w0 + wa >= 0:
+            wa = -w0 - 0.05
+        p = planck2018_params(lmax=lmax, lensing=lensing, massless=massless and not extended)
+        p.ombh2, p.omch2, p.H0, p.optical_depth, p.ns = ombh2, omch2, H0, tau, ns
+        p.As = np.exp(lnAs) * 1e-10
+        if extended:
+            # one massive eigenstate; omnuh2 = mnu / 93.14 eV (3 species share Neff, results.f90 SetParams)
+            p.omnuh2 = mnu / 93.14
+            p.Num_Nu_massless = 2.046
+            p.Num_Nu_massive = 1
+            p.Nu_mass_eigenstates = 1
+            p.share_delta_neff = 1
+            p.Nu_mass_fractions[0] = 1.0
+            p.Nu_mass_numbers[0] = 0
+            p.de_model = 1
+            p.w, p.wa = w0, wa
+        out.append(p)
+    return out

@@ -21,6 +21,8 @@
 #ifndef CAMBB200_H
 #define CAMBB200_H
 
+#include <stddef.h>
+
 #include "cambb200_params.h"
 
 #ifdef __cplusplus
@@ -132,7 +134,9 @@ void cb_model_destroy(cb_ctx* ctx, cb_dmodel* dm);
  * call).  Outputs, each may be NULL to leave the result device-resident only:
  *   LinearSrc[i]    double (n_k, n_src, n_tau)   k fastest  (cmbmain.f90:777)
  *   TransferData[i] float  (13, n_k, n_z)        (results.f90:4208)
- * stats[i] (may be NULL): int64[2*n_k] = {derivs evaluations, accepted steps} per mode. */
+ * stats[i] (may be NULL): int64[4*n_k] = {derivs evaluations, accepted steps, sum over the
+ * integrator's derivs calls of the number of equations, attempted steps} per mode -- the inputs of
+ * the algorithmic-FLOP figure in DESIGN.md. */
 int  cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* modes,
                double* const* LinearSrc, float* const* TransferData, long long* const* stats);
 
@@ -156,6 +160,24 @@ int  cb_cl(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, int tensor,
 int  cb_last_timings(const cb_ctx* ctx, double ms[4]);
 /* Number of kernels this library launched since the context was created. */
 long long cb_launch_count(const cb_ctx* ctx);
+/* Device-time bracket on the library's stream (CUDA events): start, run any sequence of
+ * cb_* calls, stop -> elapsed ms.  This is what bench.py times its steps with. */
+int  cb_timer_start(cb_ctx* ctx);
+int  cb_timer_stop(cb_ctx* ctx, double* ms);
+/* FP64 FMA throughput of this device in TFLOP/s, measured live (DFMA microbenchmark,
+ * timed alone, best of 5): the roofline denominator of the ODE stage. */
+int  cb_fp64_peak(cb_ctx* ctx, double* tflops);
+/* Page-locked host memory for the boundary arrays (what a Fortran host would get with
+ * cudaHostRegister on its allocatables): makes the H2D/D2H copies of the calls above async DMA. */
+void* cb_host_alloc(size_t bytes);
+void  cb_host_free(void* p);
+/* Raw device pointers of a model's result buffers, for the caller's collectives
+ * (torch.distributed / NCCL all-reduce of k-sharded LinearSrc and partial iCl). */
+enum { CB_BUF_LINEARSRC = 0, CB_BUF_DELTA = 1, CB_BUF_ICL = 2, CB_BUF_TRANSFER = 3 };
+int  cb_device_buffer(cb_ctx* ctx, cb_dmodel* dm, int which, void** ptr, size_t* bytes);
+/* sizeof() of the boundary structs as this library was compiled, for binding checks:
+ * 0 cb_params, 1 cb_model, 2 cb_modes, 3 cb_bessel, 4 cb_range, 5 cb_accuracy. */
+size_t cb_abi_sizeof(int which);
 
 #ifdef __cplusplus
 }
