@@ -171,10 +171,11 @@ def test_cl_properties_at_full_size(ctx):
 
 def test_unsupported_models_are_errors(ctx):
     hs = host_state("planck_massless_lensing", CASES["planck_massless_lensing"])
-    import copy
-    m = copy.copy(hs.model)
-    m.grhok = 1e-9  # non-flat
     import ctypes as C
+    from camb_b200._cdefs import cb_model
+    m = cb_model()
+    C.memmove(C.byref(m), C.byref(hs.model), C.sizeof(cb_model))
+    m.grhok = 1e-9  # non-flat
     dm = C.c_void_p()
     e = ctx._lib.cb_model_create(ctx._h, C.byref(m), C.byref(dm))
     assert e == 5 and b"non-flat" in ctx._lib.cb_last_error(ctx._h)
