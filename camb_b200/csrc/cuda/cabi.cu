@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -13,12 +14,9 @@
 #include "dmodel.cuh"
 
 // evolve.cu
-size_t cb_evolve_smem_per_warp(int nv, int maxl);
 void cb_mode_size(const DModel& M, double q, int transfer_only, int* nvar, int* maxl);
-int cb_evolve_warps_per_block();
-void cb_evolve_launch(const DModel*, const DModeItem*, int, int, int, unsigned int*, int*, int, size_t, cudaStream_t);
-cudaError_t cb_evolve_set_smem(size_t smem);
-int cb_evolve_max_blocks_per_sm(size_t smem);
+cudaError_t cb_evolve_launch(const DModel*, const DModeItem*, int n_items, int nv, int maxl, int lanes_per_mode, unsigned int*,
+                             int*, int n_sm, cudaStream_t, int* grid_out);
 // project.cu
 void cb_spline_k_launch(const DModel*, int, int, double* const*, cudaStream_t);
 size_t cb_los_smem(int, int);
@@ -27,6 +25,12 @@ void cb_los_launch(const DModel*, int, const DBessel&, int, int, size_t, cudaStr
 void cb_cl_launch(const DModel*, int, const DBessel&, cudaStream_t);
 // peak.cu
 double cb_fp64_peak_measure(int n_sm, cudaStream_t st, int reps);
+
+// Modes are binned by their worst-case number of equations so that every launch sizes its
+// per-mode shared-memory slab for its own class (the few low-k modes with deep photon hierarchies
+// would otherwise halve the number of resident modes of everyone else).
+#define CB_N_CLASSES 4
+static const int kClassLimit[CB_N_CLASSES] = {48, 96, 160, 1 << 30};
 
 struct cb_dmodel {
     DModel h;                      // host copy with device pointers
@@ -53,8 +57,12 @@ struct cb_ctx {
     DModel* d_models = nullptr;    size_t cap_models = 0;
     DModeItem* d_items = nullptr;  size_t cap_items = 0;
     double** d_scratch_ptrs = nullptr; size_t cap_scr = 0;
-    unsigned int* d_counter = nullptr;
+    unsigned int* d_counter = nullptr;   // one work-queue counter per size class
     int* d_error = nullptr;
+    cudaStream_t class_stream[CB_N_CLASSES] = {};
+    cudaEvent_t class_done[CB_N_CLASSES] = {}, fork = nullptr;
+    int lanes_per_mode = 0;              // 0 = automatic
+    int last_grid[CB_N_CLASSES] = {};
 };
 
 #define CK(call)                                                                                  \
@@ -109,7 +117,13 @@ int cb_create(int device, cb_ctx** out) {
     cudaEventCreate(&ctx->ev1);
     cudaEventCreate(&ctx->evt0);
     cudaEventCreate(&ctx->evt1);
-    if (cudaMalloc((void**)&ctx->d_counter, sizeof(unsigned int)) != cudaSuccess ||
+    for (int c = 0; c < CB_N_CLASSES; c++) {
+        cudaStreamCreateWithFlags(&ctx->class_stream[c], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&ctx->class_done[c], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming);
+    if (const char* e = getenv("CAMB_B200_LANES")) ctx->lanes_per_mode = atoi(e);
+    if (cudaMalloc((void**)&ctx->d_counter, sizeof(unsigned int) * CB_N_CLASSES) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_error, sizeof(int)) != cudaSuccess) { delete ctx; return CB_ERR_CUDA; }
     *out = ctx;
     return 0;
@@ -124,6 +138,11 @@ void cb_destroy(cb_ctx* ctx) {
     if (ctx->d_scratch_ptrs) cudaFree(ctx->d_scratch_ptrs);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     if (ctx->d_error) cudaFree(ctx->d_error);
+    for (int c = 0; c < CB_N_CLASSES; c++) {
+        if (ctx->class_stream[c]) cudaStreamDestroy(ctx->class_stream[c]);
+        if (ctx->class_done[c]) cudaEventDestroy(ctx->class_done[c]);
+    }
+    if (ctx->fork) cudaEventDestroy(ctx->fork);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->evt0) cudaEventDestroy(ctx->evt0);
@@ -233,8 +252,8 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
               float* const* TransferData, long long* const* stats) {
     if (!ctx) return CB_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
-    std::vector<DModeItem> items;
-    int nv = 0, maxl = 0;
+    std::vector<DModeItem> cls_items[CB_N_CLASSES];
+    int cls_nv[CB_N_CLASSES] = {}, cls_maxl[CB_N_CLASSES] = {};
     for (int m = 0; m < n_models; m++) {
         cb_dmodel* d = dm[m];
         const cb_modes& md = modes[m];
@@ -254,8 +273,9 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
                 d->cap_src = ns;
             }
             CK(cudaMemcpyAsync(d->d_q_src, md.q, sizeof(double) * n_k, cudaMemcpyHostToDevice, ctx->stream));
-            // row j = 1 is never written by the reference (allocated zero, cmbmain.f90:777-778)
-            CK(cudaMemsetAsync(d->d_src, 0, sizeof(double) * (size_t)n_k * D.n_src, ctx->stream));
+            // row tau_1 is never written by the reference (allocated zero, cmbmain.f90:777-778) and the rows
+            // after a mode's k*tau early-out are zero (:1034-1037): the kernel writes only live entries
+            CK(cudaMemsetAsync(d->d_src, 0, sizeof(double) * ns, ctx->stream));
             D.n_k = n_k; D.q_src = d->d_q_src; D.LinearSrc = d->d_src; D.ddSrc = d->d_dd;
         } else {
             D.n_k = n_k;
@@ -276,32 +296,49 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
             for (int j = 0; j < CB_MAX_NU; j++) it.nu_massive_approx_time[j] = md.nu_massive_approx_time[(size_t)i * CB_MAX_NU + j];
             int ml;
             cb_mode_size(D, it.q, it.transfer_only, &it.nvar, &ml);
-            nv = std::max(nv, it.nvar);
-            maxl = std::max(maxl, ml);
-            items.push_back(it);
+            if (ml > CBD_MAX_L_EVOLVE) { ctx->err = "Need to increase max_l_evolve"; return CB_ERR_UNSUPPORTED_PARAMS; }
+            int c = 0;
+            while (it.nvar > kClassLimit[c]) c++;
+            cls_nv[c] = std::max(cls_nv[c], it.nvar);
+            cls_maxl[c] = std::max(cls_maxl[c], ml);
+            cls_items[c].push_back(it);
         }
     }
-    const int n_items = (int)items.size();
+    int n_items = 0;
+    for (int c = 0; c < CB_N_CLASSES; c++) n_items += (int)cls_items[c].size();
     if (n_items == 0) return 0;
-    if (maxl > CBD_MAX_L_EVOLVE) { ctx->err = "Need to increase max_l_evolve"; return CB_ERR_UNSUPPORTED_PARAMS; }
-    // largest k first (cmbmain.f90:205-206: descending q with dynamic scheduling)
-    std::stable_sort(items.begin(), items.end(), [](const DModeItem& a, const DModeItem& b) { return a.q > b.q; });
+    std::vector<DModeItem> items;
+    items.reserve(n_items);
+    int cls_off[CB_N_CLASSES];
+    for (int c = 0; c < CB_N_CLASSES; c++) {
+        // largest k first (cmbmain.f90:205-206: descending q with dynamic scheduling)
+        std::stable_sort(cls_items[c].begin(), cls_items[c].end(), [](const DModeItem& a, const DModeItem& b) { return a.q > b.q; });
+        cls_off[c] = (int)items.size();
+        items.insert(items.end(), cls_items[c].begin(), cls_items[c].end());
+    }
     if (int e = push_models(ctx, n_models, dm)) return e;
     if (int e = ensure(ctx, &ctx->d_items, &ctx->cap_items, (size_t)n_items)) return e;
     CK(cudaMemcpyAsync(ctx->d_items, items.data(), sizeof(DModeItem) * n_items, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int) * CB_N_CLASSES, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_error, 0, sizeof(int), ctx->stream));
-    const int wpb = cb_evolve_warps_per_block();
-    const size_t smem = cb_evolve_smem_per_warp(nv, maxl) * wpb;
-    if (smem > 227 * 1024) { ctx->err = "evolve: shared-memory slab too large"; return CB_ERR_UNSUPPORTED_PARAMS; }
-    CK(cb_evolve_set_smem(smem));
-    int bps = cb_evolve_max_blocks_per_sm(smem);
-    if (bps < 1) bps = 1;
-    int grid = std::min((n_items + wpb - 1) / wpb, ctx->n_sm * bps);
+    int lanes = ctx->lanes_per_mode;
+    if (lanes != 8 && lanes != 16 && lanes != 32) lanes = n_items >= 16 * ctx->n_sm ? 8 : 32;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    cb_evolve_launch(ctx->d_models, ctx->d_items, n_items, nv, maxl, ctx->d_counter, ctx->d_error, grid, smem, ctx->stream);
-    ctx->launches++;
-    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->fork, ctx->stream));
+    for (int c = 0; c < CB_N_CLASSES; c++) {
+        ctx->last_grid[c] = 0;
+        const int n_c = (int)cls_items[c].size();
+        if (n_c == 0) continue;
+        // the scratch EvolutionVars of a layout switch aliases two stage vectors (evolve.cu)
+        const int nv = std::max(cls_nv[c], 32);
+        CK(cudaStreamWaitEvent(ctx->class_stream[c], ctx->fork, 0));
+        cudaError_t le = cb_evolve_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, nv, cls_maxl[c], lanes, ctx->d_counter + c,
+                                          ctx->d_error, ctx->n_sm, ctx->class_stream[c], &ctx->last_grid[c]);
+        if (le != cudaSuccess) { ctx->err = std::string("evolve launch: ") + cudaGetErrorString(le); return CB_ERR_CUDA; }
+        ctx->launches++;
+        CK(cudaEventRecord(ctx->class_done[c], ctx->class_stream[c]));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->class_done[c], 0));
+    }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     int herr = 0;
     CK(cudaMemcpyAsync(&herr, ctx->d_error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -449,6 +486,18 @@ int cb_last_timings(const cb_ctx* ctx, double ms[4]) {
 }
 
 long long cb_launch_count(const cb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int cb_set_option(cb_ctx* ctx, const char* name, double value) {
+    if (!ctx) return CB_ERR_NO_DEVICE;
+    if (!strcmp(name, "lanes_per_mode")) {
+        const int v = (int)value;
+        if (v != 0 && v != 8 && v != 16 && v != 32) { ctx->err = "lanes_per_mode must be 0 (automatic), 8, 16 or 32"; return CB_ERR_UNSUPPORTED_PARAMS; }
+        ctx->lanes_per_mode = v;
+        return 0;
+    }
+    ctx->err = std::string("unknown option ") + name;
+    return CB_ERR_UNSUPPORTED_PARAMS;
+}
 
 int cb_timer_start(cb_ctx* ctx) {
     if (!ctx) return CB_ERR_NO_DEVICE;

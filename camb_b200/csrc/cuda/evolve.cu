@@ -22,16 +22,16 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "dmodel.cuh"
 
 #define FULL 0xffffffffu
-#define WARPS_PER_BLOCK 4
 
 namespace {
 
 struct EVs {
-    double q, k, k2;
+    double q, k, k2, kinv, k2inv;
     double TightSwitchoffTime, pig, pigdot, poltruncfac;
     double MassiveNuApproxTime[CB_MAX_NU], G11[CB_MAX_NU], G30[CB_MAX_NU];
     int w_ix, r_ix, g_ix, polind, nu_pert_ix;
@@ -41,6 +41,39 @@ struct EVs {
     int MassiveNuApprox[CB_MAX_NU], nu_nonrel[CB_MAX_NU];
     int NuMethod, TransferOnly, neq, nvar;
 };
+
+// The fields of DModel that `derivs` reads on every evaluation, copied into the mode's shared-memory
+// slab when the mode is fetched (global DModel reads cost an L2 round trip each: the slabs leave
+// almost no L1).  Field names match DModel so the physics code is written once.
+struct MHot {
+    double grhob, grhoc, grhornomass, grhog, grhov, grhok, H0, tau0, tau_maxvis;
+    double tauminn, dlntau, dlntau_inv, de_w, de_wa, de_cs2, de_c_gamma_ppf, g_over_b;
+    double AccuracyBoost, TimeSwitchBoost, IntTolBoost, taurend, matter_verydom_tau, max_etak_scalar;   // schedule / switch logic
+    const double *thermo_horner, *cs2, *dotmu, *ddotmu, *dddotmu, *ddddotmu, *emmu, *demmu;
+    const double *nu_q, *nu_masses, *nu_int_kernel, *grhormass;   // into the global DModel (massive-nu models only)
+    const double *nu_tau_notmassless, *nu_tau_nonrelativistic, *tau, *transfer_times;
+    int nthermo, de_is_cc, de_model, de_nperturb, Num_Nu_massive, Nu_mass_eigenstates, nqmax, n_src;
+    int DoLateRadTruncation, AccuracyTarget, WantTransfer, transfer_high_precision, WantCls, WantLateTime, n_tau, num_transfer_redshifts;
+};
+
+__device__ inline void fill_hot(MHot& H, const DModel& M) {
+    H.grhob = M.grhob; H.grhoc = M.grhoc; H.grhornomass = M.grhornomass; H.grhog = M.grhog; H.grhov = M.grhov; H.grhok = M.grhok;
+    H.H0 = M.H0; H.tau0 = M.tau0; H.tau_maxvis = M.tau_maxvis;
+    H.tauminn = M.tauminn; H.dlntau = M.dlntau; H.dlntau_inv = M.dlntau_inv;
+    H.de_w = M.de_w; H.de_wa = M.de_wa; H.de_cs2 = M.de_cs2; H.de_c_gamma_ppf = M.de_c_gamma_ppf; H.g_over_b = M.grhog / M.grhob;
+    H.thermo_horner = M.thermo_horner; H.cs2 = M.cs2; H.dotmu = M.dotmu; H.ddotmu = M.ddotmu; H.dddotmu = M.dddotmu;
+    H.ddddotmu = M.ddddotmu; H.emmu = M.emmu; H.demmu = M.demmu;
+    H.nu_q = M.nu_q; H.nu_masses = M.nu_masses; H.nu_int_kernel = M.nu_int_kernel; H.grhormass = M.grhormass;
+    H.nthermo = M.nthermo; H.de_is_cc = M.de_is_cc; H.de_model = M.de_model; H.de_nperturb = M.de_nperturb;
+    H.Num_Nu_massive = M.Num_Nu_massive; H.Nu_mass_eigenstates = M.Nu_mass_eigenstates; H.nqmax = M.nqmax; H.n_src = M.n_src;
+    H.AccuracyBoost = M.AccuracyBoost; H.TimeSwitchBoost = M.TimeSwitchBoost; H.IntTolBoost = M.IntTolBoost; H.taurend = M.taurend;
+    H.matter_verydom_tau = M.matter_verydom_tau; H.max_etak_scalar = M.max_etak_scalar;
+    H.nu_tau_notmassless = M.nu_tau_notmassless; H.nu_tau_nonrelativistic = M.nu_tau_nonrelativistic; H.tau = M.tau;
+    H.transfer_times = M.transfer_times;
+    H.DoLateRadTruncation = M.DoLateRadTruncation; H.AccuracyTarget = M.AccuracyTarget; H.WantTransfer = M.WantTransfer;
+    H.transfer_high_precision = M.transfer_high_precision; H.WantCls = M.WantCls; H.WantLateTime = M.WantLateTime; H.n_tau = M.n_tau;
+    H.num_transfer_redshifts = M.num_transfer_redshifts;
+}
 
 __host__ __device__ inline int d_nint(double x) { return (int)llround(x); }
 __host__ __device__ inline int d_imax(int a, int b) { return a > b ? a : b; }
@@ -94,7 +127,8 @@ __device__ __forceinline__ double nu_drho(double am, double adotoa) {
 }
 
 // ---------------- thermo look-ups (results.f90:1826-1880, 3069-3108) ----------------
-__device__ __forceinline__ void thermo_values(const DModel& M, double tau, double& a, double& cs2b, double& opacity,
+template <class MT>
+__device__ __forceinline__ void thermo_values(const MT& M, double tau, double& a, double& cs2b, double& opacity,
                                               double& dopacity, bool want_dop) {
     double d = log(tau / M.tauminn) * M.dlntau_inv + 1.0;
     int i = (int)d;
@@ -117,7 +151,8 @@ __device__ __forceinline__ void thermo_values(const DModel& M, double tau, doubl
     }
 }
 
-__device__ void ionization_functions(const DModel& M, double tau, double& a, double& opac, double& dopac, double& ddopac,
+template <class MT>
+__device__ void ionization_functions(const MT& M, double tau, double& a, double& opac, double& dopac, double& ddopac,
                                      double& vis, double& dvis, double& ddvis, double& expmmu) {
     double cs2;
     thermo_values(M, tau, a, cs2, opac, dopac, true);
@@ -141,7 +176,8 @@ __device__ void ionization_functions(const DModel& M, double tau, double& a, dou
     ddvis = expmmu * (opac * opac * opac + 3 * opac * dopac + ddopac);
 }
 
-__device__ __forceinline__ void de_background(const DModel& M, double a, double& grhov_t, double& w) {
+template <class MT>
+__device__ __forceinline__ void de_background(const MT& M, double a, double& grhov_t, double& w) {
     if (a > 1e-10) {
         double g = pow(a, 1.0 - 3.0 * M.de_w - 3.0 * M.de_wa);
         if (M.de_wa != 0) g = g * exp(-3.0 * M.de_wa * (1.0 - a));
@@ -337,7 +373,8 @@ __device__ void copy_scalar_array(const DModel& M, const double* y, double* yout
 #define AY(i) ay[(i)-1]
 #define AYP(i) ayp[(i)-1]
 
-__device__ void nu_integrate_L012(const DModel& M, const EVs& E, const double* ay, double a, int nu_i, double& drhonu,
+template <class MT>
+__device__ void nu_integrate_L012(const MT& M, const EVs& E, const double* ay, double a, int nu_i, double& drhonu,
                                   double& fnu, double& dpnu, double& pinu) {
     double am = a * M.nu_masses[nu_i];
     int ind = E.nu_ix[nu_i];
@@ -366,21 +403,24 @@ __device__ void nu_integrate_L012(const DModel& M, const EVs& E, const double* a
     }
     dpnu = dpnu / 3;
 }
-
-// derivs, equations.f90:2273-2949.  `ay` (input) and `ayp` (output) are shared-memory vectors
-// of this warp.  OUT selects the source / transfer output branch (:2775-2947).
-template <bool OUT>
-__device__ __noinline__ void derivs(const DModel& M, EVs& E, const double* __restrict__ denlk, const double* __restrict__ denlk2,
-                       const double* __restrict__ polfack, double tau, const double* ay, double* ayp, int lane,
-                       double* src_out, float* tr_out, long long& nderivs) {
+// derivs, equations.f90:2273-2949.  `ay` (input) and `ayp` (output) are shared-memory vectors of
+// this mode's lane group (G lanes, `lane` = index inside the group, `gm` = the group's lane mask).
+// out_mode != 0 runs the source (1) / transfer (2) output branch (:2775-2947).
+// `th` (may be null) holds cs2b, opacity, a, dopacity evaluated ahead of time for this tau.
+template <int G>
+__device__ __forceinline__ void derivs(const MHot& M, EVs& E, const double* __restrict__ denlk, const double* __restrict__ denlk2,
+                                       const double* __restrict__ polfack, double tau, const double* ay, double* ayp, int lane,
+                                       unsigned gm, int out_mode, const double* th, double* src_out, float* tr_out) {
     const double k = E.k, k2 = E.k2;
     const bool tight = E.TightCoupling, no_nu = E.no_nu, no_phot = E.no_phot;
     double a, cs2, opacity, dopacity = 0;
-    nderivs++;
-    thermo_values(M, tau, a, cs2, opacity, dopacity, tight);
-    const double a2 = a * a;
+    if (th) { cs2 = th[0]; opacity = th[1]; a = th[2]; dopacity = th[3]; }
+    else thermo_values(M, tau, a, cs2, opacity, dopacity, tight);
+    const double a2 = a * a, ainv = 1.0 / a, a2inv = ainv * ainv, kinv = E.kinv, k2inv = E.k2inv;
     const double etak = AY(1), clxc = AY(2), clxb = AY(3), vb = AY(4);
-    const double grhob_t = M.grhob / a, grhoc_t = M.grhoc / a, grhor_t = M.grhornomass / a2, grhog_t = M.grhog / a2;
+    // one reciprocal instead of four divisions (and 1/k, 1/k^2 once per mode): differs from the reference's
+    // a/b by at most an ulp per quantity, far inside the 1e-5 parity budget
+    const double grhob_t = M.grhob * ainv, grhoc_t = M.grhoc * ainv, grhor_t = M.grhornomass * a2inv, grhog_t = M.grhog * a2inv;
     double grhov_t, w_de;
     if (M.de_is_cc) { grhov_t = M.grhov * a2; w_de = -1; }
     else de_background(M, a, grhov_t, w_de);
@@ -390,7 +430,7 @@ __device__ __noinline__ void derivs(const DModel& M, EVs& E, const double* __res
     double wnu_arr[CB_MAX_NU];
     const int n_eig = M.Num_Nu_massive > 0 ? M.Nu_mass_eigenstates : 0;
     for (int nu_i = 0; nu_i < n_eig; nu_i++) {  // MassiveNuVars, equations.f90:1358-1401
-        double grhormass_t = M.grhormass[nu_i] / (a * a), rhonu, pnu, clxnu, qnu;
+        double grhormass_t = M.grhormass[nu_i] * a2inv, rhonu, pnu, clxnu, qnu;
         double mass = M.nu_masses[nu_i];
         nu_rho_P(a * mass, rhonu, pnu);
         if (E.MassiveNuApprox[nu_i]) {
@@ -427,23 +467,23 @@ __device__ __noinline__ void derivs(const DModel& M, EVs& E, const double* __res
     const double grho = grho_matter + grhor_t + grhog_t + grhov_t;
     const double gpres_noDE = gpres_nu + (grhor_t + grhog_t) / 3;
     const double adotoa = sqrt(grho / 3);
-    const double cothxor = 1.0 / tau;
+    const double cothxor = th ? th[4] : 1.0 / tau;
     double dgrho = dgrho_matter;
     double z = 0, dz = 0, clxr, qr, pir, clxg, qg, pig = 0;
     if (no_nu) {
-        z = (0.5 * dgrho / k + etak) / adotoa;
-        dz = -adotoa * z - 0.5 * dgrho / k;
-        clxr = -4 * dz / k;
+        z = (0.5 * dgrho * kinv + etak) / adotoa;
+        dz = -adotoa * z - 0.5 * dgrho * kinv;
+        clxr = -4 * dz * kinv;
         qr = -4.0 / 3 * z;
         pir = 0;
     } else { clxr = AY(E.r_ix); qr = AY(E.r_ix + 1); pir = AY(E.r_ix + 2); }
     if (no_phot) {
         if (!no_nu) {
-            z = (0.5 * dgrho / k + etak) / adotoa;
-            dz = -adotoa * z - 0.5 * dgrho / k;
-            clxg = -4 * dz / k - 4 / k * opacity * (vb + z);
+            z = (0.5 * dgrho * kinv + etak) / adotoa;
+            dz = -adotoa * z - 0.5 * dgrho * kinv;
+            clxg = -4 * dz * kinv - 4 * kinv * opacity * (vb + z);
             qg = -4.0 / 3 * z;
-        } else { clxg = clxr - 4 / k * opacity * (vb + z); qg = qr; }
+        } else { clxg = clxr - 4 * kinv * opacity * (vb + z); qg = qr; }
     } else {
         clxg = AY(E.g_ix);
         qg = AY(E.g_ix + 1);
@@ -451,7 +491,7 @@ __device__ __noinline__ void derivs(const DModel& M, EVs& E, const double* __res
     }
     dgrho = dgrho + grhog_t * clxg + grhor_t * clxr;
     dgq = dgq + grhog_t * qg + grhor_t * qr;
-    const double photbar = grhog_t / grhob_t, pb43 = 4.0 / 3 * photbar;
+    const double photbar = M.g_over_b * ainv, pb43 = 4.0 / 3 * photbar;
     double dgrho_de = 0, dgq_de = 0, de_yp0 = 0, de_yp1 = 0;
     if (!M.de_is_cc) {
         if (M.de_model == CB_DE_PPF) {  // DarkEnergyPPF.f90:103-154
@@ -479,8 +519,8 @@ __device__ __noinline__ void derivs(const DModel& M, EVs& E, const double* __res
         dgrho = dgrho + dgrho_de;
         dgq = dgq + dgq_de;
     }
-    z = (0.5 * dgrho / k + etak) / adotoa;
-    const double sigma = (z + 1.5 * dgq / k2);
+    z = (0.5 * dgrho * kinv + etak) / adotoa;
+    const double sigma = (z + 1.5 * dgq * k2inv);
     if (!M.de_is_cc && M.de_model == CB_DE_FLUID) {  // DarkEnergyFluid.f90:115-145
         double one_plus_w = 1 + w_de, Hv3_over_k = 3 * adotoa * AY(E.w_ix + 1) / k;
         de_yp0 = -3 * adotoa * (M.de_cs2 - w_de) * (AY(E.w_ix) + one_plus_w * Hv3_over_k) - one_plus_w * k * (AY(E.w_ix + 1) + z);
@@ -532,23 +572,22 @@ __device__ __noinline__ void derivs(const DModel& M, EVs& E, const double* __res
             const double E2 = AY(pol + 2);
             polter = pig / 10 + 9.0 / 15 * E2;
             pigdot = denlk[2] * qg - denlk2[2] * AY(g + 3) - opacity * (pig - polter) + 8.0 / 15.0 * k * sigma;
-            for (int l = lane; l <= lmaxg; l += 32) {
+            // interior multipoles are one uniform formula; the l = 0, 1, 2 and truncation entries are
+            // written by lane 0 (no per-element branching inside the lane-strided loops)
+            for (int l = 3 + lane; l < lmaxg; l += G) {
                 const int ix = g + l;
-                double v;
-                if (l == 0) v = clxgdot;
-                else if (l == 1) v = qgdot;
-                else if (l == 2) v = pigdot;
-                else if (l < lmaxg) v = (denlk[l] * AY(ix - 1) - denlk2[l] * AY(ix + 1)) - opacity * AY(ix);
-                else v = k * AY(ix - 1) - (lmaxg + 1) * cothxor * AY(ix) - opacity * AY(ix);
-                AYP(ix) = v;
+                AYP(ix) = (denlk[l] * AY(ix - 1) - denlk2[l] * AY(ix + 1)) - opacity * AY(ix);
             }
-            for (int l = 2 + lane; l <= lmaxgpol; l += 32) {
+            for (int l = 3 + lane; l < lmaxgpol; l += G) {
                 const int ix = pol + l;
-                double v;
-                if (l == 2) v = -opacity * (AY(ix) - polter) - k / 3.0 * AY(ix + 1);
-                else if (l < lmaxgpol) v = -opacity * AY(ix) + (denlk[l] * AY(ix - 1) - polfack[l] * AY(ix + 1));
-                else v = -opacity * AY(ix) + k * E.poltruncfac * AY(ix - 1) - (lmaxgpol + 3) * cothxor * AY(ix);
-                AYP(ix) = v;
+                AYP(ix) = -opacity * AY(ix) + (denlk[l] * AY(ix - 1) - polfack[l] * AY(ix + 1));
+            }
+            if (lane == 0) {
+                AYP(g) = clxgdot; AYP(g + 1) = qgdot; AYP(g + 2) = pigdot;
+                AYP(g + lmaxg) = k * AY(g + lmaxg - 1) - (lmaxg + 1) * cothxor * AY(g + lmaxg) - opacity * AY(g + lmaxg);
+                AYP(pol + 2) = -opacity * (AY(pol + 2) - polter) - k / 3.0 * AY(pol + 3);
+                AYP(pol + lmaxgpol) = -opacity * AY(pol + lmaxgpol) + k * E.poltruncfac * AY(pol + lmaxgpol - 1) -
+                                      (lmaxgpol + 3) * cothxor * AY(pol + lmaxgpol);
             }
         }
     }
@@ -563,15 +602,13 @@ __device__ __noinline__ void derivs(const DModel& M, EVs& E, const double* __res
         } else {
             const int lmaxnr = E.lmaxnr;
             pirdot = denlk[2] * qr - denlk2[2] * AY(r + 3) + 8.0 / 15.0 * k * sigma;
-            for (int l = lane; l <= lmaxnr; l += 32) {
+            for (int l = 3 + lane; l < lmaxnr; l += G) {
                 const int ix = r + l;
-                double v;
-                if (l == 0) v = clxrdot;
-                else if (l == 1) v = qrdot;
-                else if (l == 2) v = pirdot;
-                else if (l < lmaxnr) v = (denlk[l] * AY(ix - 1) - denlk2[l] * AY(ix + 1));
-                else v = k * AY(ix - 1) - (lmaxnr + 1) * cothxor * AY(ix);
-                AYP(ix) = v;
+                AYP(ix) = (denlk[l] * AY(ix - 1) - denlk2[l] * AY(ix + 1));
+            }
+            if (lane == 0) {
+                AYP(r) = clxrdot; AYP(r + 1) = qrdot; AYP(r + 2) = pirdot;
+                AYP(r + lmaxnr) = k * AY(r + lmaxnr - 1) - (lmaxnr + 1) * cothxor * AY(r + lmaxnr);
             }
         }
     }
@@ -588,7 +625,7 @@ __device__ __noinline__ void derivs(const DModel& M, EVs& E, const double* __res
         } else {
             const int lt = E.lmaxnu_tau[nu_i], nq = E.nq[nu_i], base = E.nu_ix[nu_i];
             const int tot = nq * (lt + 1);
-            for (int t = lane; t < tot; t += 32) {  // momentum-major blocks of l = 0..lt
+            for (int t = lane; t < tot; t += G) {  // momentum-major blocks of l = 0..lt
                 const int iq = t / (lt + 1), l = t - iq * (lt + 1);
                 const int ind = base + t;
                 const double aq = a * M.nu_masses[nu_i] / M.nu_q[iq];
@@ -608,7 +645,7 @@ __device__ __noinline__ void derivs(const DModel& M, EVs& E, const double* __res
     }
     if (n_eig > 0 && E.has_nu_relativistic) {  // equations.f90:2759-2772
         const int p0 = E.nu_pert_ix, r0 = E.r_ix, lp = E.lmaxnu_pert;
-        for (int l = lane; l <= lp; l += 32) {
+        for (int l = lane; l <= lp; l += G) {
             const int ind = p0 + l, ind2 = r0 + l;
             double v;
             if (l == 0) v = +k * a2 * qr - k * AY(ind + 1);
@@ -617,9 +654,9 @@ __device__ __noinline__ void derivs(const DModel& M, EVs& E, const double* __res
             AYP(ind) = v;
         }
     }
-    __syncwarp();
+    __syncwarp(gm);
 
-    if (OUT) {
+    if (out_mode) {
         double E2v = 0, E3v = 0, Ed2 = 0, Ed3 = 0, octg, octgdot;
         if (!(tight || no_phot)) {
             E2v = AY(E.polind + 2); E3v = AY(E.polind + 3);
@@ -733,263 +770,50 @@ __device__ __noinline__ void derivs(const DModel& M, EVs& E, const double* __res
                     src_out[2] = (tau > M.tau_maxvis && tau0 - tau > 0.1) ? -2 * phi * (tau - M.tau_maxvis) / ((tau0 - M.tau_maxvis) * ang_dist) : 0.0;
             }
         }
-        __syncwarp();
+        __syncwarp(gm);
     }
 }
-
-__device__ __forceinline__ double warp_max(double v) {
+// ---------------- lane groups ----------------
+// A mode is owned by a group of G consecutive lanes (G = 8: four modes per warp; G = 32: one).
+template <int G>
+__device__ __forceinline__ double group_max(double v, unsigned gm) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(gm, v, o));
     return v;
 }
 
-// RungeKuttaDP45 state (RungeKuttaDP45.f90:14-73), warp-uniform registers
-struct RK {
+// Per-mode control block in shared memory: RungeKuttaDP45 state (RungeKuttaDP45.f90:14-73) and the
+// position of the mode in the CalcScalarSources / GetTransfer schedule.  Written by lane 0 of the
+// group, read by all its lanes after a group sync.
+enum { PH_FETCH = 0, PH_NEXT_GOAL, PH_PLAN, PH_STEP, PH_OUTPUT, PH_EXIT };
+enum { ST_PRE = 0, ST_MAIN, ST_101, ST_101B, ST_TONLY };
+enum { OUT_NONE = 0, OUT_SRC = 1, OUT_TR = 2 };
+
+struct Ctl {
     double max_step_size, current_step_size, estimated_error, previous_xend;
-    int xend_reached, first_derivative_valid, successive_failures;
-    long long steps, attempts, neq_evals;   // accepted steps, attempted steps, sum over derivs calls of neq
+    double tau, goal, seg_end, next_switch, tol1;
+    double t_tight, t_ktau, t_massless, t_nonrel, t_massive, t_no_nu;   // switch times of the current plan
+    double h, trial_x, css, hmin;          // the attempt in flight
+    double th[6][5];                       // thermo values (cs2b, opacity, a, dopacity, 1/tau) at the six stage times
+    long long steps, attempts, neq_evals, nderivs;
+    int xend_reached, first_derivative_valid, successive_failures, ind;
+    int phase, stage, next_stage, out_kind, j, itf, seg_switch;
+    int model, q_ix, transfer_only;
+    int s;                                 // next derivs evaluation of the attempt: 0 = k1 at (x, y), s = 1..6 -> k_{s+1}
 };
 
-// One call of RungeKuttaDP45 (RungeKuttaDP45.f90:94-408) for this warp's mode.
-__device__ void dp45(const DModel& M, EVs& E, const double* denlk, const double* denlk2, const double* polfack, double* vec,
-                     int nv, double& x, double xend, double tol, int& ind, RK& s, int lane, long long& nderivs) {
-    const int n = E.neq;
-    double* y = vec;
-    double *k1 = vec + nv, *k2 = vec + 2 * nv, *k3 = vec + 3 * nv, *k4 = vec + 4 * nv, *k5 = vec + 5 * nv, *k6 = vec + 6 * nv,
-           *k7 = vec + 7 * nv, *yt = vec + 9 * nv;
-    const double eps = 2.220446049250313e-16, tiny = 2.2250738585072014e-308;
-    if (ind == 1 || ind == 2) {
-        if (ind == 1) { s.max_step_size = 0; s.current_step_size = 0; s.estimated_error = 0; }
-        s.previous_xend = x; s.xend_reached = 0; s.first_derivative_valid = 0; s.successive_failures = 0;
-    } else if (ind == 3) {
-        if (s.xend_reached && (x != s.previous_xend || xend == s.previous_xend)) { ind = -9; return; }
-        s.xend_reached = 0;
-    } else { ind = -9; return; }
-    for (;;) {
-        if (ind != 6) {
-            if (s.first_derivative_valid) s.first_derivative_valid = 0;  // reuse_first_derivative is always on (equations.f90:223)
-            else { derivs<false>(M, E, denlk, denlk2, polfack, x, y, k1, lane, nullptr, nullptr, nderivs); s.neq_evals += n; }
-        }
-        s.attempts++;
-        s.neq_evals += 6 * n;
-        double temp = 0;
-        for (int i = lane; i < n; i += 32) temp = fmax(temp, fabs(y[i]));
-        temp = warp_max(temp);
-        const double wny = fmin(temp, 1.0);
-        const double hmin = 10.0 * fmax(tiny, eps * fmax(wny / tol, fabs(x)));
-        const double hmax = s.max_step_size != 0 ? fabs(s.max_step_size) : 20.0;
-        if (hmin > hmax) { ind = -2; return; }
-        if (ind <= 2) s.current_step_size = hmax * pow(tol, 1.0 / 5.0);
-        else if (s.successive_failures <= 1) {
-            temp = 2.0 * s.current_step_size;
-            if (tol < 54.19228098697693 * s.estimated_error)  // (2/0.9)^5
-                temp = 0.9 * pow(tol / s.estimated_error, 1.0 / 5.0) * s.current_step_size;
-            s.current_step_size = fmax(temp, 0.5 * s.current_step_size);
-        } else s.current_step_size = 0.5 * s.current_step_size;
-        s.current_step_size = fmin(s.current_step_size, hmax);
-        s.current_step_size = fmax(s.current_step_size, hmin);
-        temp = fabs(xend - x);
-        double trial_x;
-        if (s.current_step_size < temp && (temp > 1.2 * s.current_step_size || temp > hmax)) {
-            s.current_step_size = fmin(s.current_step_size, 0.5 * temp);
-            trial_x = x + copysign(s.current_step_size, xend - x);
-        } else { s.current_step_size = temp; trial_x = xend; }
-        const double h = trial_x - x;
-        for (int i = lane; i < n; i += 32) yt[i] = y[i] + h * (1.0 / 5.0) * k1[i];
-        __syncwarp();
-        derivs<false>(M, E, denlk, denlk2, polfack, x + h / 5.0, yt, k2, lane, nullptr, nullptr, nderivs);
-        for (int i = lane; i < n; i += 32) yt[i] = y[i] + h * ((3.0 / 40.0) * k1[i] + (9.0 / 40.0) * k2[i]);
-        __syncwarp();
-        derivs<false>(M, E, denlk, denlk2, polfack, x + h * (3.0 / 10.0), yt, k3, lane, nullptr, nullptr, nderivs);
-        for (int i = lane; i < n; i += 32) yt[i] = y[i] + h * ((44.0 / 45.0) * k1[i] + (-56.0 / 15.0) * k2[i] + (32.0 / 9.0) * k3[i]);
-        __syncwarp();
-        derivs<false>(M, E, denlk, denlk2, polfack, x + h * (4.0 / 5.0), yt, k4, lane, nullptr, nullptr, nderivs);
-        for (int i = lane; i < n; i += 32)
-            yt[i] = y[i] + h * ((19372.0 / 6561.0) * k1[i] + (-25360.0 / 2187.0) * k2[i] + (64448.0 / 6561.0) * k3[i] + (-212.0 / 729.0) * k4[i]);
-        __syncwarp();
-        derivs<false>(M, E, denlk, denlk2, polfack, x + h * (8.0 / 9.0), yt, k5, lane, nullptr, nullptr, nderivs);
-        for (int i = lane; i < n; i += 32)
-            yt[i] = y[i] + h * ((9017.0 / 3168.0) * k1[i] + (-355.0 / 33.0) * k2[i] + (46732.0 / 5247.0) * k3[i] + (49.0 / 176.0) * k4[i] +
-                                (-5103.0 / 18656.0) * k5[i]);
-        __syncwarp();
-        derivs<false>(M, E, denlk, denlk2, polfack, x + h, yt, k6, lane, nullptr, nullptr, nderivs);
-        for (int i = lane; i < n; i += 32)
-            yt[i] = y[i] + h * ((35.0 / 384.0) * k1[i] + (500.0 / 1113.0) * k3[i] + (125.0 / 192.0) * k4[i] + (-2187.0 / 6784.0) * k5[i] +
-                                (11.0 / 84.0) * k6[i]);
-        __syncwarp();
-        derivs<false>(M, E, denlk, denlk2, polfack, x + h, yt, k7, lane, nullptr, nullptr, nderivs);
-        temp = 0;
-        for (int i = lane; i < n; i += 32) {
-            double e = (71.0 / 57600.0) * k1[i] + (-71.0 / 16695.0) * k3[i] + (71.0 / 1920.0) * k4[i] + (-17253.0 / 339200.0) * k5[i] +
-                       (22.0 / 525.0) * k6[i] + (-1.0 / 40.0) * k7[i];
-            temp = fmax(temp, fabs(e) / fmax(1.0, fabs(y[i])));
-        }
-        temp = warp_max(temp);
-        s.estimated_error = temp * s.current_step_size;
-        ind = s.estimated_error > tol ? 6 : 5;
-        if (ind == 5) {
-            x = trial_x;
-            for (int i = lane; i < n; i += 32) { y[i] = yt[i]; k1[i] = k7[i]; }
-            __syncwarp();
-            s.steps++;
-            s.successive_failures = 0;
-            if (x == xend) {
-                ind = 3;
-                s.previous_xend = xend;
-                s.xend_reached = 1;
-                s.first_derivative_valid = 1;
-                return;
-            }
-            ind = 6;
-        } else {
-            s.successive_failures++;
-            if (s.current_step_size <= hmin) { ind = -3; return; }
-        }
-    }
-}
-
-__device__ __forceinline__ int next_nu_nq(const DModel& M, int nq) {
+template <class MT>
+__device__ __forceinline__ int next_nu_nq(const MT& M, int nq) {
     if (nq == 0) return 1;
     int q = (int)M.nu_q[nq - 1];
     return q >= 10 ? M.nqmax : nq + 1;
-}
-
-// GaugeInterface_ScalEv, equations.f90:212-234
-__device__ __forceinline__ void scal_ev(const DModel& M, EVs& E, const double* denlk, const double* denlk2, const double* polfack,
-                                        double* vec, int nv, double& tau, double tauend, double tol1, int& ind, RK& rk, int lane,
-                                        long long& nderivs) {
-    if (E.q < 2e-3 && tau <= M.taurend && M.WantCls) rk.max_step_size = 2.0;
-    else rk.max_step_size = 20.0 / M.IntTolBoost;
-    dp45(M, E, denlk, denlk2, polfack, vec, nv, tau, tauend, tol1, ind, rk, lane, nderivs);
-}
-
-// GaugeInterface_EvolveScal, equations.f90:261-460 (recursion unrolled).  E/EO are this warp's
-// shared-memory EvolutionVars; layout changes are done by lane 0 (about ten per mode).
-__device__ void evolve_scal(const DModel& M, EVs& E, EVs& EO, const double* denlk, const double* denlk2, const double* polfack,
-                            double* vec, int nv, double& tau, double tauend, double tol1, int& ind, RK& rk, int lane,
-                            long long& nderivs) {
-    double* y = vec;
-    double* yout = vec + 8 * nv;
-    const int n_eig = M.Num_Nu_massive != 0 ? M.Nu_mass_eigenstates : 0;
-    for (;;) {
-        const double noSwitch = M.tau0 + 1;
-        const double smallTime = fmin(tau, 1 / E.k) / 100;
-        const double switchBoost = M.AccuracyBoost * M.TimeSwitchBoost;
-        double t_ktau = noSwitch, t_no_nu = noSwitch, t_no_phot = noSwitch, t_massless = noSwitch, t_nonrel = noSwitch, t_massive = noSwitch;
-        if (!E.high_ktau && !E.no_nu) t_ktau = d_imax(20, E.lmaxnr - 4) / E.k;
-        for (int nu_i = 0; nu_i < n_eig; nu_i++) {
-            if (E.nq[nu_i] != M.nqmax) t_massless = fmin(t_massless, M.nu_tau_notmassless[(next_nu_nq(M, E.nq[nu_i]) - 1) + CB_MAX_NQ * nu_i]);
-            else if (!E.nu_nonrel[nu_i]) t_nonrel = fmin(M.nu_tau_nonrelativistic[nu_i], t_nonrel);
-            else if (E.NuMethod == 1 && !E.MassiveNuApprox[nu_i]) t_massive = fmin(t_massive, E.MassiveNuApproxTime[nu_i]);
-        }
-        if (M.DoLateRadTruncation) {
-            if (!E.no_nu) t_no_nu = fmax(15 / E.k * switchBoost, fmin(M.taurend, M.matter_verydom_tau));
-            if (!E.no_phot) {
-                double lb = switchBoost;
-                if (M.AccuracyTarget > 0 && M.WantTransfer && M.transfer_high_precision) lb = fmax(lb, 2.0);
-                if (!M.WantCls || E.k > 0.03 * lb) t_no_phot = fmax(15 / E.k, M.taurend) * lb;
-            }
-        }
-        const double tight_t = E.TightSwitchoffTime;
-        double next_switch = fmin(fmin(fmin(t_ktau, t_massless), fmin(tight_t, t_massive)), fmin(fmin(t_no_nu, t_no_phot), fmin(t_nonrel, noSwitch)));
-        if (!(next_switch < tauend)) break;
-        if (next_switch > tau + smallTime) {
-            scal_ev(M, E, denlk, denlk2, polfack, vec, nv, tau, next_switch, tol1, ind, rk, lane, nderivs);
-            if (ind < 0) return;
-        }
-        __syncwarp();
-        // which switch (same if-chain order as the reference, equations.f90:339-441)
-        int which;
-        if (next_switch == tight_t) which = 0;
-        else if (next_switch == t_ktau) which = 1;
-        else if (next_switch == t_massless) which = 2;
-        else if (next_switch == t_nonrel) which = 3;
-        else if (next_switch == t_massive) which = 4;
-        else if (next_switch == t_no_nu) which = 5;
-        else which = 6;
-        if (lane == 0) {
-            EO = E;
-            bool docopy = true;
-            if (which == 0) { EO.TightCoupling = 0; EO.TightSwitchoffTime = noSwitch; }
-            else if (which == 1) { EO.high_ktau = 1; for (int i = 0; i < n_eig; i++) EO.nq[i] = M.nqmax; }
-            else if (which == 2) {
-                docopy = false;
-                for (int nu_i = 0; nu_i < n_eig; nu_i++) {
-                    if (E.nq[nu_i] != M.nqmax && next_switch == M.nu_tau_notmassless[(next_nu_nq(M, E.nq[nu_i]) - 1) + CB_MAX_NQ * nu_i]) {
-                        EO.nq[nu_i] = next_nu_nq(M, E.nq[nu_i]);
-                        docopy = true;
-                        break;
-                    }
-                }
-            } else if (which == 3) {
-                docopy = false;
-                for (int nu_i = 0; nu_i < n_eig; nu_i++)
-                    if (!E.nu_nonrel[nu_i] && next_switch == M.nu_tau_nonrelativistic[nu_i]) { EO.nu_nonrel[nu_i] = 1; docopy = true; break; }
-            } else if (which == 4) {  // SwitchToMassiveNuApprox, equations.f90:1072-1111
-                docopy = false;
-                double a, cs2, opac, dop;
-                thermo_values(M, tau, a, cs2, opac, dop, false);
-                for (int nu_i = 0; nu_i < n_eig; nu_i++) {
-                    if (!E.MassiveNuApprox[nu_i] && next_switch == E.MassiveNuApproxTime[nu_i]) {
-                        EO.MassiveNuApprox[nu_i] = 1;
-                        setup_indices(M, EO);
-                        copy_scalar_array(M, y, yout, E, EO);
-                        double rhonu, pnu, clxnu, qnu, dpnu, pinu;
-                        nu_rho_P(a * M.nu_masses[nu_i], rhonu, pnu);
-                        nu_integrate_L012(M, E, y, a, nu_i, clxnu, qnu, dpnu, pinu);
-                        yout[EO.nu_ix[nu_i] - 1] = clxnu / rhonu;
-                        yout[EO.nu_ix[nu_i]] = dpnu / rhonu;
-                        yout[EO.nu_ix[nu_i] + 1] = qnu / rhonu;
-                        yout[EO.nu_ix[nu_i] + 2] = pinu / rhonu;
-                        // Nu_Intvsq, equations.f90:1328-1356
-                        double G11 = 0, G30 = 0, am = a * M.nu_masses[nu_i];
-                        int indx = E.nu_ix[nu_i];
-                        for (int iq = 1; iq <= E.nq[nu_i]; iq++) {
-                            double aq = am / M.nu_q[iq - 1], v = 1.0 / sqrt(1.0 + aq * aq);
-                            G11 = G11 + M.nu_int_kernel[iq - 1] * y[indx] * v * v;
-                            if (E.lmaxnu_tau[nu_i] > 2) G30 = G30 + M.nu_int_kernel[iq - 1] * y[indx + 2] * v * v;
-                            indx = indx + E.lmaxnu_tau[nu_i] + 1;
-                        }
-                        EO.G11[nu_i] = G11 * a * a * a / rhonu;
-                        EO.G30[nu_i] = G30 * a * a * a / rhonu;
-                        E = EO;
-                        for (int i = 0; i < E.nvar; i++) y[i] = yout[i];
-                        break;
-                    }
-                }
-            } else if (which == 5) { EO.no_nu = 1; for (int i = 0; i < n_eig; i++) EO.nq[i] = M.nqmax; }
-            else { EO.no_phot = 1; }
-            if (docopy) {
-                setup_indices(M, EO);
-                copy_scalar_array(M, y, yout, E, EO);
-                E = EO;
-                for (int i = 0; i < E.nvar; i++) y[i] = yout[i];
-                if (which == 0) {  // tight-coupling values, equations.f90:349-363
-                    double a, cs2, opacity, dopacity;
-                    thermo_values(M, tau, a, cs2, opacity, dopacity, true);
-                    const double kk = E.k, op2 = opacity * opacity;
-                    y[E.g_ix + 2 - 1] = E.pig;
-                    y[E.g_ix + 3 - 1] = (3.0 / 7.0) * y[E.g_ix + 2 - 1] * (kk / opacity) * (1.0 + dopacity / op2) +
-                                        (3.0 / 7.0) * E.pigdot * (kk / op2) * (-1.0);
-                    y[E.polind + 2 - 1] = E.pig / 4 + E.pigdot * (1.0 / opacity) * (-5.0 / 8.0 - (25.0 / 16.0) * dopacity / op2) +
-                                          E.pig * (kk / opacity) * (kk / opacity) * (-5.0 / 56.0);
-                    y[E.polind + 3 - 1] = (3.0 / 7.0) * (kk / opacity) * y[E.polind + 2 - 1] * (1.0 + dopacity / op2) +
-                                          (3.0 / 7.0) * (kk / op2) * ((E.pigdot / 4.0) * (1.0 + (5.0 / 2.0) * dopacity / op2)) * (-1.0);
-                }
-            }
-        }
-        if (which == 0 || which == 5 || which == 6) ind = 1;
-        rk.first_derivative_valid = 0;
-        __syncwarp();
-    }
-    scal_ev(M, E, denlk, denlk2, polfack, vec, nv, tau, tauend, tol1, ind, rk, lane, nderivs);
 }
 
 // initial, equations.f90:1891-2112 (adiabatic, flat); lane 0
 __device__ void initial_conditions(const DModel& M, EVs& E, double* denlk, double* denlk2, double* polfack, double* y, double tau,
                                    const DModeItem& it) {
     const double k = E.q;
-    E.k = k; E.k2 = E.q * E.q;
+    E.k = k; E.k2 = E.q * E.q; E.kinv = 1.0 / k; E.k2inv = 1.0 / E.k2;
     for (int j = 1; j <= E.MaxlNeeded; j++) {
         double denl = 1.0 / (2 * j + 1);
         denlk[j] = denl * k * j;
@@ -1040,125 +864,500 @@ __device__ __forceinline__ double get_tau_start(const DModel& M, double q) {  //
     return taustart;
 }
 
-}  // namespace
+// Shared-memory vectors of one mode (each nv doubles).  k7 reuses k2's slot (k2 is dead after
+// stage 6: the 5th-order solution and the error estimate do not use it); between steps only y and
+// k1 (FSAL) are live, so the output derivative (k3), the layout-switch scratch (k4) and the scratch
+// EvolutionVars (k5..k6) alias stage slots.
+#define NVEC 8
+struct Vecs {
+    double *y, *k1, *k2, *k3, *k4, *k5, *k6, *yt;
+    __device__ __forceinline__ Vecs(double* v, int nv)
+        : y(v), k1(v + nv), k2(v + 2 * nv), k3(v + 3 * nv), k4(v + 4 * nv), k5(v + 5 * nv), k6(v + 6 * nv), yt(v + 7 * nv) {}
+};
 
-// Persistent kernel: each warp loops over work items.  Dynamic shared memory per warp:
-// [EVs E][EVs EO][denlk, denlk2, polfack: 3*(maxl+1)][vec: 10*nv]  (nv = max nvar of the launch).
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-cb_evolve_kernel(const DModel* __restrict__ models, const DModeItem* __restrict__ items, int n_items, int nv, int maxl,
-                 unsigned int* counter, int* error_flag) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t ev_bytes = (sizeof(EVs) + 15) & ~size_t(15);
-    const size_t per_warp = 2 * ev_bytes + sizeof(double) * (3 * (size_t)(maxl + 1) + 10 * (size_t)nv);
-    unsigned char* base = smem_raw + per_warp * warp;
-    EVs& E = *reinterpret_cast<EVs*>(base);
-    EVs& EO = *reinterpret_cast<EVs*>(base + ev_bytes);
-    double* denlk = reinterpret_cast<double*>(base + 2 * ev_bytes);
-    double* denlk2 = denlk + (maxl + 1);
-    double* polfack = denlk2 + (maxl + 1);
-    double* vec = polfack + (maxl + 1);
-    double* y = vec;
-    double* yprime = vec + 8 * (size_t)nv;
+// The switch logic of GaugeInterface_EvolveScal (equations.f90:261-460): computes the next switch
+// time into C (plan) ...
+template <class MT>
+__device__ void plan_switches(const MT& M, const EVs& E, Ctl& C) {
+    const int n_eig = M.Num_Nu_massive != 0 ? M.Nu_mass_eigenstates : 0;
+    const double noSwitch = M.tau0 + 1;
+    const double switchBoost = M.AccuracyBoost * M.TimeSwitchBoost;
+    double t_ktau = noSwitch, t_no_nu = noSwitch, t_no_phot = noSwitch, t_massless = noSwitch, t_nonrel = noSwitch, t_massive = noSwitch;
+    if (!E.high_ktau && !E.no_nu) t_ktau = d_imax(20, E.lmaxnr - 4) / E.k;
+    for (int nu_i = 0; nu_i < n_eig; nu_i++) {
+        if (E.nq[nu_i] != M.nqmax) t_massless = fmin(t_massless, M.nu_tau_notmassless[(next_nu_nq(M, E.nq[nu_i]) - 1) + CB_MAX_NQ * nu_i]);
+        else if (!E.nu_nonrel[nu_i]) t_nonrel = fmin(M.nu_tau_nonrelativistic[nu_i], t_nonrel);
+        else if (E.NuMethod == 1 && !E.MassiveNuApprox[nu_i]) t_massive = fmin(t_massive, E.MassiveNuApproxTime[nu_i]);
+    }
+    if (M.DoLateRadTruncation) {
+        if (!E.no_nu) t_no_nu = fmax(15 / E.k * switchBoost, fmin(M.taurend, M.matter_verydom_tau));
+        if (!E.no_phot) {
+            double lb = switchBoost;
+            if (M.AccuracyTarget > 0 && M.WantTransfer && M.transfer_high_precision) lb = fmax(lb, 2.0);
+            if (!M.WantCls || E.k > 0.03 * lb) t_no_phot = fmax(15 / E.k, M.taurend) * lb;
+        }
+    }
+    const double tight_t = E.TightSwitchoffTime;
+    C.next_switch = fmin(fmin(fmin(t_ktau, t_massless), fmin(tight_t, t_massive)), fmin(fmin(t_no_nu, t_no_phot), fmin(t_nonrel, noSwitch)));
+    C.t_tight = tight_t; C.t_ktau = t_ktau; C.t_massless = t_massless; C.t_nonrel = t_nonrel; C.t_massive = t_massive; C.t_no_nu = t_no_nu;
+}
 
+// ... and applies the switch that fires at C.next_switch (same if-chain order as the reference,
+// equations.f90:339-441).  Lane 0 of the group; layout changes go through the scratch slots.
+__device__ void apply_switch(const DModel& M, EVs& E, Ctl& C, const Vecs& V) {
+    const int n_eig = M.Num_Nu_massive != 0 ? M.Nu_mass_eigenstates : 0;
+    const double noSwitch = M.tau0 + 1, next_switch = C.next_switch, tau = C.tau;
+    double* y = V.y;
+    double* yout = V.k4;
+    EVs& EO = *reinterpret_cast<EVs*>(V.k5);
+    int which;
+    if (next_switch == C.t_tight) which = 0;
+    else if (next_switch == C.t_ktau) which = 1;
+    else if (next_switch == C.t_massless) which = 2;
+    else if (next_switch == C.t_nonrel) which = 3;
+    else if (next_switch == C.t_massive) which = 4;
+    else if (next_switch == C.t_no_nu) which = 5;
+    else which = 6;
+    EO = E;
+    bool docopy = true;
+    if (which == 0) { EO.TightCoupling = 0; EO.TightSwitchoffTime = noSwitch; }
+    else if (which == 1) { EO.high_ktau = 1; for (int i = 0; i < n_eig; i++) EO.nq[i] = M.nqmax; }
+    else if (which == 2) {
+        docopy = false;
+        for (int nu_i = 0; nu_i < n_eig; nu_i++) {
+            if (E.nq[nu_i] != M.nqmax && next_switch == M.nu_tau_notmassless[(next_nu_nq(M, E.nq[nu_i]) - 1) + CB_MAX_NQ * nu_i]) {
+                EO.nq[nu_i] = next_nu_nq(M, E.nq[nu_i]);
+                docopy = true;
+                break;
+            }
+        }
+    } else if (which == 3) {
+        docopy = false;
+        for (int nu_i = 0; nu_i < n_eig; nu_i++)
+            if (!E.nu_nonrel[nu_i] && next_switch == M.nu_tau_nonrelativistic[nu_i]) { EO.nu_nonrel[nu_i] = 1; docopy = true; break; }
+    } else if (which == 4) {  // SwitchToMassiveNuApprox, equations.f90:1072-1111
+        docopy = false;
+        double a, cs2, opac, dop;
+        thermo_values(M, tau, a, cs2, opac, dop, false);
+        for (int nu_i = 0; nu_i < n_eig; nu_i++) {
+            if (!E.MassiveNuApprox[nu_i] && next_switch == E.MassiveNuApproxTime[nu_i]) {
+                EO.MassiveNuApprox[nu_i] = 1;
+                setup_indices(M, EO);
+                copy_scalar_array(M, y, yout, E, EO);
+                double rhonu, pnu, clxnu, qnu, dpnu, pinu;
+                nu_rho_P(a * M.nu_masses[nu_i], rhonu, pnu);
+                nu_integrate_L012(M, E, y, a, nu_i, clxnu, qnu, dpnu, pinu);
+                yout[EO.nu_ix[nu_i] - 1] = clxnu / rhonu;
+                yout[EO.nu_ix[nu_i]] = dpnu / rhonu;
+                yout[EO.nu_ix[nu_i] + 1] = qnu / rhonu;
+                yout[EO.nu_ix[nu_i] + 2] = pinu / rhonu;
+                // Nu_Intvsq, equations.f90:1328-1356
+                double G11 = 0, G30 = 0, am = a * M.nu_masses[nu_i];
+                int indx = E.nu_ix[nu_i];
+                for (int iq = 1; iq <= E.nq[nu_i]; iq++) {
+                    double aq = am / M.nu_q[iq - 1], v = 1.0 / sqrt(1.0 + aq * aq);
+                    G11 = G11 + M.nu_int_kernel[iq - 1] * y[indx] * v * v;
+                    if (E.lmaxnu_tau[nu_i] > 2) G30 = G30 + M.nu_int_kernel[iq - 1] * y[indx + 2] * v * v;
+                    indx = indx + E.lmaxnu_tau[nu_i] + 1;
+                }
+                EO.G11[nu_i] = G11 * a * a * a / rhonu;
+                EO.G30[nu_i] = G30 * a * a * a / rhonu;
+                E = EO;
+                for (int i = 0; i < E.nvar; i++) y[i] = yout[i];
+                break;
+            }
+        }
+    } else if (which == 5) { EO.no_nu = 1; for (int i = 0; i < n_eig; i++) EO.nq[i] = M.nqmax; }
+    else { EO.no_phot = 1; }
+    if (docopy) {
+        setup_indices(M, EO);
+        copy_scalar_array(M, y, yout, E, EO);
+        E = EO;
+        for (int i = 0; i < E.nvar; i++) y[i] = yout[i];
+        if (which == 0) {  // tight-coupling values, equations.f90:349-363
+            double a, cs2, opacity, dopacity;
+            thermo_values(M, tau, a, cs2, opacity, dopacity, true);
+            const double kk = E.k, op2 = opacity * opacity;
+            y[E.g_ix + 2 - 1] = E.pig;
+            y[E.g_ix + 3 - 1] = (3.0 / 7.0) * y[E.g_ix + 2 - 1] * (kk / opacity) * (1.0 + dopacity / op2) +
+                                (3.0 / 7.0) * E.pigdot * (kk / op2) * (-1.0);
+            y[E.polind + 2 - 1] = E.pig / 4 + E.pigdot * (1.0 / opacity) * (-5.0 / 8.0 - (25.0 / 16.0) * dopacity / op2) +
+                                  E.pig * (kk / opacity) * (kk / opacity) * (-5.0 / 56.0);
+            y[E.polind + 3 - 1] = (3.0 / 7.0) * (kk / opacity) * y[E.polind + 2 - 1] * (1.0 + dopacity / op2) +
+                                  (3.0 / 7.0) * (kk / op2) * ((E.pigdot / 4.0) * (1.0 + (5.0 / 2.0) * dopacity / op2)) * (-1.0);
+        }
+    }
+    if (which == 0 || which == 5 || which == 6) C.ind = 1;
+    C.first_derivative_valid = 0;
+}
+
+// Entry checks of one RungeKuttaDP45 call (RungeKuttaDP45.f90:206-228) for the segment tau -> xend.
+__device__ __forceinline__ void dp45_begin(Ctl& C, double xend) {
+    const double x = C.tau;
+    if (C.ind == 1 || C.ind == 2) {
+        if (C.ind == 1) { C.max_step_size = 0; C.current_step_size = 0; C.estimated_error = 0; }
+        C.previous_xend = x; C.xend_reached = 0; C.first_derivative_valid = 0; C.successive_failures = 0;
+    } else if (C.ind == 3) {
+        if (C.xend_reached && (x != C.previous_xend || xend == C.previous_xend)) { C.ind = -9; return; }
+        C.xend_reached = 0;
+    } else { C.ind = -9; return; }
+    C.seg_end = xend;
+}
+
+// The schedule of one mode, advanced by lane 0 of its group until the mode needs a Runge-Kutta
+// attempt (PH_STEP), an output evaluation (PH_OUTPUT) or there is no work left (PH_EXIT).
+// CalcScalarSources cmbmain.f90:998-1074 / GetTransfer :1167-1188 unrolled into a state machine;
+// rows skipped by the high-k*tau early-out stay zero (LinearSrc is cleared before the launch).
+__device__ void advance_schedule(const DModel* __restrict__ models, const DModeItem* __restrict__ items, int n_items,
+                                 unsigned int* counter, int* error_flag, EVs& E, Ctl& C, MHot& H, double* denlk, double* denlk2,
+                                 double* polfack, const Vecs& V) {
     for (;;) {
-        unsigned int item = 0;
-        if (lane == 0) item = atomicAdd(counter, 1u);
-        item = __shfl_sync(FULL, item, 0);
-        if (item >= (unsigned)n_items) break;
-        const DModeItem& it = items[item];
-        const DModel& M = models[it.model];
-        const int n_k = M.n_k, n_src = M.n_src, n_tau = M.n_tau, nz = M.num_transfer_redshifts, q_ix = it.q_ix;
-        long long nderivs = 0;
-        const double taustart = get_tau_start(M, it.q);
-        if (lane == 0) {
+        if (C.phase == PH_FETCH) {
+            const unsigned item = atomicAdd(counter, 1u);
+            if (item >= (unsigned)n_items) { C.phase = PH_EXIT; return; }
+            const DModeItem& it = items[item];
+            const DModel& M = models[it.model];
+            C.model = it.model; C.q_ix = it.q_ix; C.transfer_only = it.transfer_only;
+            fill_hot(H, M);
             E.q = it.q;
             E.TransferOnly = it.transfer_only;
             E.pig = 0; E.pigdot = 0;
             for (int i = 0; i < CB_MAX_NU; i++) { E.G11[i] = 0; E.G30[i] = 0; E.nq[i] = 0; E.nu_ix[i] = 0; E.lmaxnu_tau[i] = 0; E.nu_nonrel[i] = 0; E.MassiveNuApproxTime[i] = 0; }
             E.w_ix = E.r_ix = E.g_ix = E.polind = E.nu_pert_ix = 0; E.lmaxnu_pert = 0; E.NuMethod = 1;
             get_num_eqns(M, E);
-            initial_conditions(M, E, denlk, denlk2, polfack, y, taustart, it);
+            const double taustart = get_tau_start(M, it.q);
+            initial_conditions(M, E, denlk, denlk2, polfack, V.y, taustart, it);
+            C.max_step_size = 0; C.current_step_size = 0; C.estimated_error = 0; C.previous_xend = 0;
+            C.xend_reached = 0; C.first_derivative_valid = 0; C.successive_failures = 0;
+            C.steps = 0; C.attempts = 0; C.neq_evals = 0; C.nderivs = 0;
+            C.tau = taustart; C.ind = 1; C.itf = 1; C.j = 2;
+            double tol1 = 1.0e-4 / exp(M.AccuracyBoost * M.IntTolBoost - 1);
+            if (M.WantTransfer && M.transfer_high_precision) tol1 = tol1 / 100;
+            C.tol1 = tol1;
+            C.stage = it.transfer_only ? ST_TONLY : ST_PRE;
+            C.phase = PH_NEXT_GOAL;
         }
-        __syncwarp();
-        RK rk;
-        rk.max_step_size = 0; rk.current_step_size = 0; rk.estimated_error = 0; rk.previous_xend = 0;
-        rk.xend_reached = 0; rk.first_derivative_valid = 0; rk.successive_failures = 0; rk.steps = 0; rk.attempts = 0; rk.neq_evals = 0;
-        double tau = taustart;
-        int ind = 1, itf = 1;
-        double tol1 = 1.0e-4 / exp(M.AccuracyBoost * M.IntTolBoost - 1);
-        if (M.WantTransfer && M.transfer_high_precision) tol1 = tol1 / 100;
-        float* TD = M.TransferData;
-#define TDP(itf_) (TD + (size_t)13 * ((size_t)q_ix + (size_t)n_k * ((itf_)-1)))
-#define EVOLVE_TO(t_) evolve_scal(M, E, EO, denlk, denlk2, polfack, vec, nv, tau, (t_), tol1, ind, rk, lane, nderivs)
-#define OUTTRANSF(p_)                                                                                              \
-    do {                                                                                                           \
-        for (int i_ = lane; i_ < E.nvar; i_ += 32) yprime[i_] = 0;                                                 \
-        __syncwarp();                                                                                              \
-        derivs<true>(M, E, denlk, denlk2, polfack, tau, y, yprime, lane, nullptr, (p_), nderivs);                  \
-    } while (0)
-        bool failed = false;
-        if (it.transfer_only) {  // GetTransfer, cmbmain.f90:1167-1188
-            for (int i = 1; i <= nz; i++) {
-                EVOLVE_TO(M.transfer_times[i - 1]);
-                if (ind < 0) { failed = true; break; }
-                OUTTRANSF(TDP(i));
-            }
-        } else {  // CalcScalarSources, cmbmain.f90:998-1074
-            double* S = M.LinearSrc;
-            if (M.WantTransfer) {
-                while (itf <= nz && M.tau[1] > M.transfer_times[itf - 1]) {
-                    EVOLVE_TO(M.transfer_times[itf - 1]);
-                    if (ind < 0) { failed = true; break; }
-                    OUTTRANSF(TDP(itf));
-                    itf++;
+        const DModel& MG = models[C.model];   // the full (global) model: layout switches and statistics only
+        const MHot& M = H;
+        const int nz = M.num_transfer_redshifts, n_tau = M.n_tau;
+        if (C.phase == PH_NEXT_GOAL) {
+            bool evolve = false, finished = false;
+            C.out_kind = OUT_NONE;
+            switch (C.stage) {
+                case ST_TONLY:
+                    if (C.itf > nz) finished = true;
+                    else { C.goal = M.transfer_times[C.itf - 1]; evolve = true; C.out_kind = OUT_TR; C.next_stage = ST_TONLY; }
+                    break;
+                case ST_PRE:
+                    if (M.WantTransfer && C.itf <= nz && M.tau[1] > M.transfer_times[C.itf - 1]) {
+                        C.goal = M.transfer_times[C.itf - 1]; evolve = true; C.out_kind = OUT_TR; C.next_stage = ST_PRE;
+                    } else { C.stage = ST_MAIN; continue; }
+                    break;
+                case ST_MAIN: {
+                    if (C.j > n_tau) { finished = true; break; }
+                    const double tauend = M.tau[C.j - 1];
+                    if ((E.q * tauend > M.max_etak_scalar && tauend > M.taurend) && !M.WantLateTime &&
+                        (!M.WantTransfer || C.tau > M.transfer_times[nz - 1])) {
+                        finished = true;  // this and every later row is zero (tauend only grows)
+                    } else { C.goal = tauend; evolve = true; C.out_kind = OUT_SRC; C.next_stage = ST_101; }
+                    break;
+                }
+                case ST_101: {  // label 101, cmbmain.f90:1049-1068
+                    if (!(M.WantTransfer && C.itf <= nz)) { C.j++; C.stage = ST_MAIN; continue; }
+                    const double tt = M.transfer_times[C.itf - 1];
+                    if (C.j < n_tau && M.tau[C.j - 1] < tt && M.tau[C.j] > tt) {
+                        C.goal = tt; evolve = true; C.next_stage = ST_101B;
+                    } else { C.stage = ST_101B; continue; }
+                    break;
+                }
+                case ST_101B: {
+                    const double tt = M.transfer_times[C.itf - 1];
+                    if (fabs(C.tau - tt) < 1.e-5 || C.j == n_tau) {
+                        C.out_kind = OUT_TR;   // output without a preceding integration
+                        C.next_stage = ST_101;  // itf++ happens after the output; ST_101 then re-tests the conditions
+                    } else { C.j++; C.stage = ST_MAIN; continue; }
+                    break;
                 }
             }
-            for (int j = 2; j <= n_tau && !failed; j++) {
-                const double tauend = M.tau[j - 1];
-                if ((E.q * tauend > M.max_etak_scalar && tauend > M.taurend) && !M.WantLateTime &&
-                    (!M.WantTransfer || tau > M.transfer_times[nz - 1])) {
-                    if (lane < n_src) S[q_ix + (size_t)n_k * (lane + (size_t)n_src * (j - 1))] = 0;
+            if (finished) {
+                if (MG.stats) {
+                    long long* st = MG.stats + 4 * (size_t)C.q_ix;
+                    st[0] = C.nderivs; st[1] = C.steps; st[2] = C.neq_evals; st[3] = C.attempts;
+                }
+                C.phase = PH_FETCH;
+                continue;
+            }
+            if (!evolve) { C.phase = PH_OUTPUT; return; }
+            C.phase = PH_PLAN;
+        }
+        if (C.phase == PH_PLAN) {  // head of the GaugeInterface_EvolveScal loop
+            plan_switches(M, E, C);
+            const double smallTime = fmin(C.tau, 1 / E.k) / 100;
+            double xend;
+            if (C.next_switch < C.goal) {
+                if (!(C.next_switch > C.tau + smallTime)) { apply_switch(MG, E, C, V); continue; }
+                xend = C.next_switch; C.seg_switch = 1;
+            } else { xend = C.goal; C.seg_switch = 0; }
+            // GaugeInterface_ScalEv, equations.f90:212-234
+            if (E.q < 2e-3 && C.tau <= M.taurend && M.WantCls) C.max_step_size = 2.0;
+            else C.max_step_size = 20.0 / M.IntTolBoost;
+            dp45_begin(C, xend);   // ind == 1 resets the settings, max_step_size included (RungeKuttaDP45.f90:181-182)
+            if (C.ind < 0) { atomicExch(error_flag, CB_ERR_EVOLUTION); C.phase = PH_FETCH; continue; }
+            // first evaluation of the segment: k1 = f(x, y) unless the FSAL value is still valid
+            // (reuse_first_derivative is always on, equations.f90:223; RungeKuttaDP45.f90:213-223)
+            C.s = C.first_derivative_valid ? 1 : 0;
+            C.first_derivative_valid = 0;
+            C.phase = PH_STEP;
+            return;
+        }
+        return;
+    }
+}
+
+// Dormand-Prince 5(4) tableau in stage-vector slot order (slot j = k_j; k7 lives in k2's slot).
+// Row s = 1..6: y_trial = y + h * sum_j A[s][j] k_j feeds evaluation s+1; row 0: error weights.
+__constant__ double c_dp_a[7][6] = {
+    {71.0 / 57600.0, -1.0 / 40.0 /* k7 */, -71.0 / 16695.0, 71.0 / 1920.0, -17253.0 / 339200.0, 22.0 / 525.0},
+    {1.0 / 5.0, 0, 0, 0, 0, 0},
+    {3.0 / 40.0, 9.0 / 40.0, 0, 0, 0, 0},
+    {44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0, 0, 0, 0},
+    {19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0, 0, 0},
+    {9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0, 0},
+    {35.0 / 384.0, 0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0}};
+__constant__ double c_dp_c[7] = {0, 1.0 / 5.0, 3.0 / 10.0, 4.0 / 5.0, 8.0 / 9.0, 1.0, 1.0};
+
+// Start of one trial step (RungeKuttaDP45.f90:230-302): step-size control, evaluated redundantly by
+// every lane of the group from the shared control block; lane 0 stores the result.  Lanes 0..5 then
+// look up the thermodynamic tables at the six stage times, so the table latency is paid once per
+// step and the log/index arithmetic is not repeated by every lane at every stage.
+template <int G>
+__device__ __forceinline__ bool attempt_start(const MHot& H, const EVs& E, Ctl& C, const double* y, int lane, unsigned gm, int* error_flag) {
+    const int n = E.neq;
+    const double eps = 2.220446049250313e-16, tiny = 2.2250738585072014e-308;
+    const double x = C.tau, xend = C.seg_end, tol = C.tol1;
+    const int ind = C.ind;
+    double temp = 0;
+    for (int i = lane; i < n; i += G) temp = fmax(temp, fabs(y[i]));
+    temp = group_max<G>(temp, gm);
+    const double wny = fmin(temp, 1.0);
+    const double hmin = 10.0 * fmax(tiny, eps * fmax(wny / tol, fabs(x)));
+    const double hmax = C.max_step_size != 0 ? fabs(C.max_step_size) : 20.0;
+    double css = C.current_step_size;
+    if (hmin > hmax) {
+        __syncwarp(gm);
+        if (lane == 0) { C.ind = -2; atomicExch(error_flag, CB_ERR_EVOLUTION); C.phase = PH_FETCH; }
+        return false;
+    }
+    {   // one pow call site shared by the first-step and the error-controlled branches (warp convergence)
+        const double est = C.estimated_error;
+        const bool first = ind <= 2, shrink = tol < 54.19228098697693 * est;  // (2/0.9)^5
+        const double p = pow(first ? tol : tol / est, 1.0 / 5.0);
+        if (first) css = hmax * p;
+        else if (C.successive_failures <= 1) {
+            temp = 2.0 * css;
+            if (shrink) temp = 0.9 * p * css;
+            css = fmax(temp, 0.5 * css);
+        } else css = 0.5 * css;
+    }
+    css = fmin(css, hmax);
+    css = fmax(css, hmin);
+    temp = fabs(xend - x);
+    double trial_x;
+    if (css < temp && (temp > 1.2 * css || temp > hmax)) {
+        css = fmin(css, 0.5 * temp);
+        trial_x = x + copysign(css, xend - x);
+    } else { css = temp; trial_x = xend; }
+    const double h = trial_x - x;
+    __syncwarp(gm);   // every lane has read the control block
+    if (lane == 0) { C.css = css; C.h = h; C.trial_x = trial_x; C.hmin = hmin; }
+    if (lane < 6) {
+        const double ts = x + c_dp_c[lane + 1] * h;
+        double a, cs2, opac, dopac = 0;
+        thermo_values(H, ts, a, cs2, opac, dopac, E.TightCoupling != 0);
+        double* t = C.th[lane];
+        t[0] = cs2; t[1] = opac; t[2] = a; t[3] = dopac; t[4] = 1.0 / ts;
+    }
+    return true;
+}
+
+// End of a trial step: error estimate (RungeKuttaDP45.f90:330-347), accept/reject and what follows.
+template <int G>
+__device__ __forceinline__ void attempt_finish(const DModel& M, EVs& E, Ctl& C, const Vecs& V, int nv, int lane, unsigned gm, int* error_flag) {
+    const int n = E.neq;
+    double* y = V.y;
+    const double* v = V.y;
+    double temp = 0;
+    for (int i = lane; i < n; i += G) {
+        double e = c_dp_a[0][0] * v[nv + i];
+#pragma unroll
+        for (int j = 1; j < 6; j++) e = fma(c_dp_a[0][j], v[(j + 1) * nv + i], e);
+        temp = fmax(temp, fabs(e) / fmax(1.0, fabs(y[i])));
+    }
+    temp = group_max<G>(temp, gm);
+    const double css = C.css, est = temp * css, xend = C.seg_end, trial_x = C.trial_x;
+    const bool accept = !(est > C.tol1);
+    if (accept) {
+        const double *yt = V.yt, *k7 = V.k2;
+        double* k1 = V.k1;
+        for (int i = lane; i < n; i += G) { y[i] = yt[i]; k1[i] = k7[i]; }
+    }
+    __syncwarp(gm);
+    if (lane == 0) {
+        C.current_step_size = css;
+        C.estimated_error = est;
+        C.attempts++;
+        C.s = 1;
+        if (accept) {
+            C.tau = trial_x;
+            C.steps++;
+            C.successive_failures = 0;
+            if (trial_x == xend) {
+                C.ind = 3;
+                C.previous_xend = xend;
+                C.xend_reached = 1;
+                C.first_derivative_valid = 1;
+                if (C.seg_switch) {
+                    apply_switch(M, E, C, V);
+                    C.phase = PH_PLAN;
+                } else if (C.out_kind != OUT_NONE) {
+                    C.phase = PH_OUTPUT;
                 } else {
-                    EVOLVE_TO(tauend);
-                    if (ind < 0) { failed = true; break; }
-                    for (int i_ = lane; i_ < E.nvar; i_ += 32) yprime[i_] = 0;
-                    __syncwarp();
-                    // sources go straight to LinearSrc(q_ix, :, j): stride n_k between sources
-                    double srcs[3];
-                    derivs<true>(M, E, denlk, denlk2, polfack, tau, y, yprime, lane, srcs, nullptr, nderivs);
-                    if (lane == 0)
-                        for (int s = 0; s < n_src; s++) S[q_ix + (size_t)n_k * (s + (size_t)n_src * (j - 1))] = srcs[s];
-                    for (;;) {  // label 101
-                        if (!(M.WantTransfer && itf <= nz)) break;
-                        if (j < n_tau) {
-                            if (tauend < M.transfer_times[itf - 1] && M.tau[j] > M.transfer_times[itf - 1]) {
-                                EVOLVE_TO(M.transfer_times[itf - 1]);
-                                if (ind < 0) { failed = true; break; }
-                            }
-                        }
-                        if (fabs(tau - M.transfer_times[itf - 1]) < 1.e-5 || j == n_tau) {
-                            OUTTRANSF(TDP(itf));
-                            itf++;
-                            if (j < n_tau && itf <= nz && M.tau[j] > M.transfer_times[itf - 1]) continue;
-                        }
-                        break;
+                    C.stage = C.next_stage;
+                    C.phase = PH_NEXT_GOAL;
+                }
+            } else C.ind = 6;
+        } else {
+            C.ind = 6;
+            C.successive_failures++;
+            if (css <= C.hmin) { C.ind = -3; atomicExch(error_flag, CB_ERR_EVOLUTION); C.phase = PH_FETCH; }
+        }
+    }
+}
+
+}  // namespace
+
+#define WARPS_PER_BLOCK 2
+#ifndef EVOLVE_MIN_BLOCKS
+#define EVOLVE_MIN_BLOCKS 6   /* 64 threads x 6 blocks: <= 168 registers per thread */
+#endif
+
+// Persistent kernel.  Every group of G lanes owns one mode at a time and pulls the next
+// (cosmology, k) item from the global queue when its mode is finished.  The main loop is built
+// around ONE call site of `derivs`: each trip, every group evaluates the right-hand side once --
+// a Runge-Kutta stage, the first derivative of a segment or a source/transfer output -- so the
+// groups of a warp share the instruction stream of `derivs` whatever their position in their own
+// step / output / switch schedule; only the short stage set-up before and after it diverges.
+// Dynamic shared memory per group: [Ctl][MHot][EVs][denlk, denlk2, polfack: 3*(maxl+1)][NVEC*nv],
+// padded so that consecutive groups start 64 bytes apart modulo 128.
+template <int G>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, EVOLVE_MIN_BLOCKS)
+cb_evolve_kernel(const DModel* __restrict__ models, const DModeItem* __restrict__ items, int n_items, int nv, int maxl,
+                 unsigned long long slab_bytes, unsigned int* counter, int* error_flag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int MPW = 32 / G;
+    const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+    const int grp = wl / G, lane = wl % G;
+    const unsigned gm = G == 32 ? FULL : (((1u << G) - 1u) << (grp * G));
+    unsigned char* base = smem_raw + (size_t)slab_bytes * (warp * MPW + grp);
+    const size_t ctl_bytes = (sizeof(Ctl) + 15) & ~size_t(15), hot_bytes = (sizeof(MHot) + 15) & ~size_t(15),
+                 ev_bytes = (sizeof(EVs) + 15) & ~size_t(15);
+    Ctl& C = *reinterpret_cast<Ctl*>(base);
+    MHot& H = *reinterpret_cast<MHot*>(base + ctl_bytes);
+    EVs& E = *reinterpret_cast<EVs*>(base + ctl_bytes + hot_bytes);
+    double* denlk = reinterpret_cast<double*>(base + ctl_bytes + hot_bytes + ev_bytes);
+    double* denlk2 = denlk + (maxl + 1);
+    double* polfack = denlk2 + (maxl + 1);
+    double* vec = polfack + (maxl + 1);
+    const Vecs V(vec, nv);
+    if (lane == 0) C.phase = PH_FETCH;
+    __syncwarp(gm);
+    // t is warp-uniform: 0 = schedule / single evaluations (first derivative of a segment, source or
+    // transfer output) for the groups that need one; 1..6 = the six stage evaluations of a trial step,
+    // taken by all stepping groups of the warp together.
+    int t = 0;
+    for (;;) {
+        bool active;
+        const double* in = V.y;
+        double* out = V.k3;
+        const double* th = nullptr;
+        double tev = 0;
+        int out_mode = OUT_NONE;
+        if (t == 0) {
+            if (lane == 0 && (C.phase == PH_FETCH || C.phase == PH_NEXT_GOAL || C.phase == PH_PLAN))
+                advance_schedule(models, items, n_items, counter, error_flag, E, C, H, denlk, denlk2, polfack, V);
+            __syncwarp(gm);
+            const int phase = C.phase;
+            if (__all_sync(FULL, phase == PH_EXIT)) break;
+            active = phase == PH_OUTPUT || (phase == PH_STEP && C.s == 0);
+            if (!__any_sync(FULL, active)) { t = 1; continue; }
+            if (active) {
+                tev = C.tau;
+                if (phase == PH_STEP) out = V.k1;
+                else {  // derivs output branch + `output` (equations.f90:1739-1755, 2775-2947; outtransf :2256-2271)
+                    for (int i = lane; i < E.nvar; i += G) out[i] = 0;
+                    __syncwarp(gm);
+                    out_mode = C.out_kind;
+                }
+            }
+        } else {
+            active = C.phase == PH_STEP;
+            if (active && t == 1) {
+                active = attempt_start<G>(H, E, C, V.y, lane, gm, error_flag);
+                __syncwarp(gm);
+                if (!active && lane == 0) C.phase = PH_FETCH;   // step-size underflow: abandon the mode (error flag is set)
+            }
+            if (active) {
+                const double h = C.h;
+                const int n = E.neq;
+                double* yt = V.yt;
+                for (int i = lane; i < n; i += G) {
+                    double acc = c_dp_a[t][0] * vec[nv + i];
+                    for (int j = 1; j < t; j++) acc = fma(c_dp_a[t][j], vec[(j + 1) * nv + i], acc);
+                    yt[i] = fma(h, acc, vec[i]);
+                }
+                __syncwarp(gm);
+                in = yt;
+                out = t == 6 ? V.k2 : vec + (size_t)(t + 1) * nv;
+                tev = C.tau + c_dp_c[t] * h;
+                th = C.th[t - 1];
+            }
+        }
+        if (active) {
+            double srcs[3];
+            float* tr = nullptr;
+            if (out_mode == OUT_TR) tr = models[C.model].TransferData + (size_t)13 * ((size_t)C.q_ix + (size_t)models[C.model].n_k * (C.itf - 1));
+            derivs<G>(H, E, denlk, denlk2, polfack, tev, in, out, lane, gm, out_mode, th, out_mode == OUT_SRC ? srcs : nullptr, tr);
+            if (t == 0) {
+                if (lane == 0) {
+                    C.nderivs++;
+                    if (C.phase == PH_STEP) { C.s = 1; C.neq_evals += E.neq; }
+                    else {
+                        if (out_mode == OUT_SRC) {
+                            const DModel& M = models[C.model];
+                            double* S = M.LinearSrc;   // sources go straight to LinearSrc(q_ix, :, j): stride n_k between sources
+                            for (int i = 0; i < M.n_src; i++) S[C.q_ix + (size_t)M.n_k * (i + (size_t)M.n_src * (C.j - 1))] = srcs[i];
+                        } else C.itf++;
+                        C.stage = C.next_stage;
+                        C.phase = PH_NEXT_GOAL;
                     }
                 }
+            } else {
+                if (lane == 0) { C.nderivs++; C.neq_evals += E.neq; }
+                if (t == 6) attempt_finish<G>(models[C.model], E, C, V, nv, lane, gm, error_flag);
             }
         }
-        if (lane == 0) {
-            if (failed) atomicExch(error_flag, CB_ERR_EVOLUTION);
-            if (M.stats) { M.stats[4 * q_ix] = nderivs; M.stats[4 * q_ix + 1] = rk.steps; M.stats[4 * q_ix + 2] = rk.neq_evals; M.stats[4 * q_ix + 3] = rk.attempts; }
-        }
-        __syncwarp();
+        __syncwarp(gm);
+        if (t != 0) t = t == 6 ? 0 : t + 1;
     }
 }
 
 // ---------------- host-side helpers used by cabi.cu ----------------
-size_t cb_evolve_smem_per_warp(int nv, int maxl) {
-    const size_t ev_bytes = (sizeof(EVs) + 15) & ~size_t(15);
-    return 2 * ev_bytes + sizeof(double) * (3 * (size_t)(maxl + 1) + 10 * (size_t)nv);
+size_t cb_evolve_slab_bytes(int nv, int maxl) {
+    const size_t ctl_bytes = (sizeof(Ctl) + 15) & ~size_t(15), hot_bytes = (sizeof(MHot) + 15) & ~size_t(15),
+                 ev_bytes = (sizeof(EVs) + 15) & ~size_t(15);
+    size_t b = ctl_bytes + hot_bytes + ev_bytes + sizeof(double) * (3 * (size_t)(maxl + 1) + NVEC * (size_t)nv);
+    b = (b + 127) & ~size_t(127);
+    return b + 64;   // stride = 64 (mod 128)
 }
 
 // GetNumEqns on the host for one mode: sizes the shared-memory slab and orders the queue.
@@ -1173,19 +1372,38 @@ void cb_mode_size(const DModel& M, double q, int transfer_only, int* nvar, int* 
     *maxl = E.MaxlNeeded;
 }
 
-int cb_evolve_warps_per_block() { return WARPS_PER_BLOCK; }
-
-void cb_evolve_launch(const DModel* d_models, const DModeItem* d_items, int n_items, int nv, int maxl, unsigned int* d_counter,
-                      int* d_error, int grid, size_t smem, cudaStream_t stream) {
-    cb_evolve_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, stream>>>(d_models, d_items, n_items, nv, maxl, d_counter, d_error);
-}
-
-cudaError_t cb_evolve_set_smem(size_t smem) {
-    return cudaFuncSetAttribute(cb_evolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-}
-
-int cb_evolve_max_blocks_per_sm(size_t smem) {
+template <int G>
+static cudaError_t launch_g(const DModel* d_models, const DModeItem* d_items, int n_items, int nv, int maxl, unsigned int* d_counter,
+                            int* d_error, int n_sm, cudaStream_t stream, int* grid_out) {
+    constexpr int MPW = 32 / G;
+    const size_t slab = cb_evolve_slab_bytes(nv, maxl);
+    const size_t smem = slab * MPW * WARPS_PER_BLOCK;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(cb_evolve_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (const char* co = getenv("CAMB_B200_CARVEOUT")) {   // experiment knob: percent of the unified L1/shared array given to shared memory
+        e = cudaFuncSetAttribute(cb_evolve_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co));
+        if (e != cudaSuccess) return e;
+    }
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cb_evolve_kernel, WARPS_PER_BLOCK * 32, smem);
-    return nb;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cb_evolve_kernel<G>, WARPS_PER_BLOCK * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (const char* mb = getenv("CAMB_B200_MAXBLOCKS")) nb = nb < atoi(mb) ? nb : atoi(mb);
+    if (nb < 1) nb = 1;
+    const int per_block = MPW * WARPS_PER_BLOCK;
+    int grid = (n_items + per_block - 1) / per_block;
+    if (grid > n_sm * nb) grid = n_sm * nb;
+    if (grid_out) *grid_out = grid;
+    cb_evolve_kernel<G><<<grid, WARPS_PER_BLOCK * 32, smem, stream>>>(d_models, d_items, n_items, nv, maxl, (unsigned long long)slab,
+                                                                      d_counter, d_error);
+    return cudaGetLastError();
+}
+
+// lanes_per_mode: 8 (throughput: four modes share a warp's instruction stream) or 32 (latency:
+// one mode per warp, for launches with fewer modes than the GPU has warp slots).
+cudaError_t cb_evolve_launch(const DModel* d_models, const DModeItem* d_items, int n_items, int nv, int maxl, int lanes_per_mode,
+                             unsigned int* d_counter, int* d_error, int n_sm, cudaStream_t stream, int* grid_out) {
+    if (lanes_per_mode == 8) return launch_g<8>(d_models, d_items, n_items, nv, maxl, d_counter, d_error, n_sm, stream, grid_out);
+    if (lanes_per_mode == 16) return launch_g<16>(d_models, d_items, n_items, nv, maxl, d_counter, d_error, n_sm, stream, grid_out);
+    return launch_g<32>(d_models, d_items, n_items, nv, maxl, d_counter, d_error, n_sm, stream, grid_out);
 }

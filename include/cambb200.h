@@ -160,6 +160,10 @@ int  cb_cl(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, int tensor,
 int  cb_last_timings(const cb_ctx* ctx, double ms[4]);
 /* Number of kernels this library launched since the context was created. */
 long long cb_launch_count(const cb_ctx* ctx);
+/* Tuning knobs.  "lanes_per_mode": lanes of a warp that own one k-mode in cb_evolve: 8 (four modes
+ * share a warp's instruction stream: throughput, for batches), 16, 32 (one mode per warp: latency,
+ * for a single cosmology) or 0 = chosen from the number of modes in the call (default). */
+int  cb_set_option(cb_ctx* ctx, const char* name, double value);
 /* Device-time bracket on the library's stream (CUDA events): start, run any sequence of
  * cb_* calls, stop -> elapsed ms.  This is what bench.py times its steps with. */
 int  cb_timer_start(cb_ctx* ctx);

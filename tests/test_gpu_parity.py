@@ -54,10 +54,16 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("lanes", [32, 8, 16])
 @pytest.mark.parametrize("name", list(CASES))
-def test_cl_parity_full_chain(ctx, name):
+def test_cl_parity_full_chain(ctx, name, lanes):
+    """lanes = lanes of a warp per k-mode in the evolve kernel: every width must give the same answer."""
     hs = host_state(name, CASES[name])
-    g = run_gpu(ctx, hs)
+    ctx.set_option("lanes_per_mode", lanes)
+    try:
+        g = run_gpu(ctx, hs)
+    finally:
+        ctx.set_option("lanes_per_mode", 0)
     icl_o, aux = O.cls_from_params(hs, nthreads=8)
     errs = cl_err(g["icl"], icl_o)
     print(name, "C_l errors", errs)
