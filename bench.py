@@ -175,6 +175,8 @@ def main():
     B = args.batch
     hss = build_batch(B, seed=20261017 + 1000 * rank)       # every rank its own parameter sets
     ctx.set_bessel(hss[0])
+    for hs in hss:
+        ctx.pin_host_tables(hs)
     dms = [ctx.create_model(hs) for hs in hss]
     n_modes = sum(len(hs.source_q()) for hs in hss)
 

@@ -15,8 +15,8 @@
 
 // evolve.cu
 void cb_mode_size(const DModel& M, double q, int transfer_only, int* nvar, int* maxl);
-cudaError_t cb_evolve_launch(const DModel*, const DModeItem*, int n_items, int nv, int maxl, int lanes_per_mode, unsigned int*,
-                             int*, int n_sm, cudaStream_t, int* grid_out);
+cudaError_t cb_evolve_launch(const DModel*, const DModeItem*, int n_items, int nv, int maxl, int lanes_per_mode, int lean,
+                             unsigned int*, int*, int n_sm, cudaStream_t, int* grid_out);
 // project.cu
 void cb_spline_k_launch(const DModel*, int, int, double* const*, cudaStream_t);
 size_t cb_los_smem(int, int);
@@ -62,6 +62,9 @@ struct cb_ctx {
     cudaStream_t class_stream[CB_N_CLASSES] = {};
     cudaEvent_t class_done[CB_N_CLASSES] = {}, fork = nullptr;
     int lanes_per_mode = 0;              // 0 = automatic
+    cudaEvent_t stage_ev[4][2] = {};     // per-stage kernel brackets of the last calls (evolve, spline-k, LOS, C_l)
+    DModel* h_models = nullptr;   size_t cap_h_models = 0;   // page-locked staging
+    DModeItem* h_items = nullptr; size_t cap_h_items = 0;
     int last_grid[CB_N_CLASSES] = {};
 };
 
@@ -74,11 +77,16 @@ struct cb_ctx {
         }                                                                                         \
     } while (0)
 
+// Device memory comes from the stream-ordered pool (release threshold = never): creating and
+// destroying models every call costs no cudaMalloc/cudaFree round trips or device-wide syncs.
+static cudaError_t dev_alloc(cb_ctx* ctx, void** p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 8, ctx->stream); }
+static void dev_free(cb_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
+
 template <class T>
 static int upload(cb_ctx* ctx, const T* src, size_t n, T** dst, std::vector<void*>* owned) {
     *dst = nullptr;
     if (!src || n == 0) return 0;
-    CK(cudaMalloc((void**)dst, n * sizeof(T)));
+    CK(dev_alloc(ctx, (void**)dst, n * sizeof(T)));
     if (owned) owned->push_back(*dst);
     CK(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     return 0;
@@ -87,9 +95,9 @@ static int upload(cb_ctx* ctx, const T* src, size_t n, T** dst, std::vector<void
 template <class T>
 static int ensure(cb_ctx* ctx, T** p, size_t* cap, size_t n) {
     if (n <= *cap && *p) return 0;
-    if (*p) CK(cudaFree(*p));
+    if (*p) dev_free(ctx, *p);
     *p = nullptr;
-    CK(cudaMalloc((void**)p, n * sizeof(T)));
+    CK(dev_alloc(ctx, (void**)p, n * sizeof(T)));
     *cap = n;
     return 0;
 }
@@ -123,6 +131,14 @@ int cb_create(int device, cb_ctx** out) {
     }
     cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming);
     if (const char* e = getenv("CAMB_B200_LANES")) ctx->lanes_per_mode = atoi(e);
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
+    for (int i = 0; i < 4; i++) { cudaEventCreate(&ctx->stage_ev[i][0]); cudaEventCreate(&ctx->stage_ev[i][1]); }
     if (cudaMalloc((void**)&ctx->d_counter, sizeof(unsigned int) * CB_N_CLASSES) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_error, sizeof(int)) != cudaSuccess) { delete ctx; return CB_ERR_CUDA; }
     *out = ctx;
@@ -132,7 +148,11 @@ int cb_create(int device, cb_ctx** out) {
 void cb_destroy(cb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
     for (void* p : ctx->bess_owned) cudaFree(p);
+    for (int i = 0; i < 4; i++) { cudaEventDestroy(ctx->stage_ev[i][0]); cudaEventDestroy(ctx->stage_ev[i][1]); }
+    if (ctx->h_models) cudaFreeHost(ctx->h_models);
+    if (ctx->h_items) cudaFreeHost(ctx->h_items);
     if (ctx->d_models) cudaFree(ctx->d_models);
     if (ctx->d_items) cudaFree(ctx->d_items);
     if (ctx->d_scratch_ptrs) cudaFree(ctx->d_scratch_ptrs);
@@ -156,7 +176,7 @@ const char* cb_last_error(const cb_ctx* ctx) { return ctx ? ctx->err.c_str() : "
 int cb_set_bessel(cb_ctx* ctx, const cb_bessel* b) {
     if (!ctx) return CB_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
-    for (void* p : ctx->bess_owned) cudaFree(p);
+    for (void* p : ctx->bess_owned) dev_free(ctx, p);
     ctx->bess_owned.clear();
     DBessel& B = ctx->bess;
     B.n_l = b->n_l; B.nx = b->nx; B.n_regions = b->n_regions;
@@ -232,19 +252,25 @@ int cb_model_create(cb_ctx* ctx, const cb_model* m, cb_dmodel** out) {
 void cb_model_destroy(cb_ctx* ctx, cb_dmodel* dm) {
     if (!dm) return;
     if (ctx) cudaSetDevice(ctx->device);
-    for (void* p : dm->owned) cudaFree(p);
+    if (!ctx) { delete dm; return; }
+    for (void* p : dm->owned) dev_free(ctx, p);
     void* bufs[] = {dm->d_q_src, dm->d_src, dm->d_dd, dm->d_scratch, dm->d_delta, dm->d_icl, dm->d_q_int, dm->d_dq_int,
                     dm->d_pows, dm->d_transfer, dm->d_stats};
-    for (void* p : bufs) if (p) cudaFree(p);
+    for (void* p : bufs) dev_free(ctx, p);
     delete dm;
 }
 
 static int push_models(cb_ctx* ctx, int n_models, cb_dmodel* const* dm) {
     if (int e = ensure(ctx, &ctx->d_models, &ctx->cap_models, (size_t)n_models)) return e;
-    std::vector<DModel> hm(n_models);
-    for (int i = 0; i < n_models; i++) hm[i] = dm[i]->h;
-    CK(cudaMemcpyAsync(ctx->d_models, hm.data(), sizeof(DModel) * n_models, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));  // hm is a stack temporary
+    if ((size_t)n_models > ctx->cap_h_models) {
+        // the previous contents are not in flight: every entry point ends with a stream synchronisation
+        if (ctx->h_models) cudaFreeHost(ctx->h_models);
+        ctx->h_models = nullptr;
+        CK(cudaHostAlloc((void**)&ctx->h_models, sizeof(DModel) * n_models, cudaHostAllocDefault));
+        ctx->cap_h_models = n_models;
+    }
+    for (int i = 0; i < n_models; i++) ctx->h_models[i] = dm[i]->h;
+    CK(cudaMemcpyAsync(ctx->d_models, ctx->h_models, sizeof(DModel) * n_models, cudaMemcpyHostToDevice, ctx->stream));
     return 0;
 }
 
@@ -264,9 +290,9 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
             size_t ns = (size_t)n_k * D.n_src * D.n_tau;
             if (ns > d->cap_src) {
                 size_t c1 = 0, c2 = 0, c3 = 0;
-                if (d->d_src) { cudaFree(d->d_src); d->d_src = nullptr; }
-                if (d->d_dd) { cudaFree(d->d_dd); d->d_dd = nullptr; }
-                if (d->d_scratch) { cudaFree(d->d_scratch); d->d_scratch = nullptr; }
+                if (d->d_src) { dev_free(ctx, d->d_src); d->d_src = nullptr; }
+                if (d->d_dd) { dev_free(ctx, d->d_dd); d->d_dd = nullptr; }
+                if (d->d_scratch) { dev_free(ctx, d->d_scratch); d->d_scratch = nullptr; }
                 if (int e = ensure(ctx, &d->d_src, &c1, ns)) return e;
                 if (int e = ensure(ctx, &d->d_dd, &c2, ns)) return e;
                 if (int e = ensure(ctx, &d->d_scratch, &c3, ns)) return e;
@@ -282,7 +308,7 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
         }
         if (nz > 0) {
             size_t ntr = (size_t)13 * n_k * nz;
-            if (ntr > d->cap_tr) { if (d->d_transfer) cudaFree(d->d_transfer); d->d_transfer = nullptr; d->cap_tr = 0; }
+            if (ntr > d->cap_tr) { if (d->d_transfer) dev_free(ctx, d->d_transfer); d->d_transfer = nullptr; d->cap_tr = 0; }
             if (int e = ensure(ctx, &d->d_transfer, &d->cap_tr, ntr)) return e;
             D.TransferData = d->d_transfer;
         } else D.TransferData = nullptr;
@@ -318,12 +344,21 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
     }
     if (int e = push_models(ctx, n_models, dm)) return e;
     if (int e = ensure(ctx, &ctx->d_items, &ctx->cap_items, (size_t)n_items)) return e;
-    CK(cudaMemcpyAsync(ctx->d_items, items.data(), sizeof(DModeItem) * n_items, cudaMemcpyHostToDevice, ctx->stream));
+    if ((size_t)n_items > ctx->cap_h_items) {
+        if (ctx->h_items) cudaFreeHost(ctx->h_items);
+        ctx->h_items = nullptr;
+        CK(cudaHostAlloc((void**)&ctx->h_items, sizeof(DModeItem) * n_items, cudaHostAllocDefault));
+        ctx->cap_h_items = n_items;
+    }
+    memcpy(ctx->h_items, items.data(), sizeof(DModeItem) * n_items);
+    CK(cudaMemcpyAsync(ctx->d_items, ctx->h_items, sizeof(DModeItem) * n_items, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int) * CB_N_CLASSES, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_error, 0, sizeof(int), ctx->stream));
+    int lean = 1;   // every model massless-nu LCDM: the kernel variant without massive-nu / dark-energy code
+    for (int m = 0; m < n_models; m++) if (dm[m]->h.Num_Nu_massive != 0 || !dm[m]->h.de_is_cc) lean = 0;
     int lanes = ctx->lanes_per_mode;
     if (lanes != 8 && lanes != 16 && lanes != 32) lanes = n_items >= 16 * ctx->n_sm ? 8 : 32;
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(cudaEventRecord(ctx->stage_ev[0][0], ctx->stream));
     CK(cudaEventRecord(ctx->fork, ctx->stream));
     for (int c = 0; c < CB_N_CLASSES; c++) {
         ctx->last_grid[c] = 0;
@@ -332,14 +367,14 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
         // the scratch EvolutionVars of a layout switch aliases two stage vectors (evolve.cu)
         const int nv = std::max(cls_nv[c], 32);
         CK(cudaStreamWaitEvent(ctx->class_stream[c], ctx->fork, 0));
-        cudaError_t le = cb_evolve_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, nv, cls_maxl[c], lanes, ctx->d_counter + c,
+        cudaError_t le = cb_evolve_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, nv, cls_maxl[c], lanes, lean, ctx->d_counter + c,
                                           ctx->d_error, ctx->n_sm, ctx->class_stream[c], &ctx->last_grid[c]);
         if (le != cudaSuccess) { ctx->err = std::string("evolve launch: ") + cudaGetErrorString(le); return CB_ERR_CUDA; }
         ctx->launches++;
         CK(cudaEventRecord(ctx->class_done[c], ctx->class_stream[c]));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->class_done[c], 0));
     }
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventRecord(ctx->stage_ev[0][1], ctx->stream));
     int herr = 0;
     CK(cudaMemcpyAsync(&herr, ctx->d_error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     for (int m = 0; m < n_models; m++) {
@@ -353,9 +388,6 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
             CK(cudaMemcpyAsync(stats[m], d->d_stats, sizeof(long long) * 4 * (size_t)D.n_k, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-    ctx->ms[0] = ms;
     if (herr) { ctx->err = "RungeKuttaDP45 error: step size underflow in the device integrator"; return herr; }
     return 0;
 }
@@ -367,9 +399,9 @@ int cb_set_sources(cb_ctx* ctx, cb_dmodel* d, int n_k, const double* q, const do
     size_t ns = (size_t)n_k * D.n_src * D.n_tau;
     if (ns > d->cap_src || !d->d_src) {
         size_t c1 = 0, c2 = 0, c3 = 0;
-        if (d->d_src) { cudaFree(d->d_src); d->d_src = nullptr; }
-        if (d->d_dd) { cudaFree(d->d_dd); d->d_dd = nullptr; }
-        if (d->d_scratch) { cudaFree(d->d_scratch); d->d_scratch = nullptr; }
+        if (d->d_src) { dev_free(ctx, d->d_src); d->d_src = nullptr; }
+        if (d->d_dd) { dev_free(ctx, d->d_dd); d->d_dd = nullptr; }
+        if (d->d_scratch) { dev_free(ctx, d->d_scratch); d->d_scratch = nullptr; }
         if (int e = ensure(ctx, &d->d_src, &c1, ns)) return e;
         if (int e = ensure(ctx, &d->d_dd, &c2, ns)) return e;
         if (int e = ensure(ctx, &d->d_scratch, &c3, ns)) return e;
@@ -397,9 +429,9 @@ int cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q, 
         if (!d->d_src || D.n_k <= 0) { ctx->err = "cb_project: no sources (call cb_evolve or cb_set_sources first)"; return CB_ERR_UNSUPPORTED_PARAMS; }
         const int nq = n_q[m];
         if ((size_t)nq > d->cap_q) {
-            if (d->d_q_int) cudaFree(d->d_q_int);
-            if (d->d_dq_int) cudaFree(d->d_dq_int);
-            if (d->d_pows) cudaFree(d->d_pows);
+            dev_free(ctx, d->d_q_int);
+            dev_free(ctx, d->d_dq_int);
+            dev_free(ctx, d->d_pows);
             d->d_q_int = d->d_dq_int = d->d_pows = nullptr;
             size_t c1 = 0, c2 = 0, c3 = 0;
             if (int e = ensure(ctx, &d->d_q_int, &c1, (size_t)nq)) return e;
@@ -408,7 +440,7 @@ int cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q, 
             d->cap_q = nq;
         }
         size_t nd = (size_t)D.n_src * n_l * nq;
-        if (nd > d->cap_delta) { if (d->d_delta) cudaFree(d->d_delta); d->d_delta = nullptr; d->cap_delta = 0; }
+        if (nd > d->cap_delta) { if (d->d_delta) dev_free(ctx, d->d_delta); d->d_delta = nullptr; d->cap_delta = 0; }
         if (int e = ensure(ctx, &d->d_delta, &d->cap_delta, nd)) return e;
         CK(cudaMemcpyAsync(d->d_q_int, q_int[m], sizeof(double) * nq, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(d->d_dq_int, dq[m], sizeof(double) * nq, cudaMemcpyHostToDevice, ctx->stream));
@@ -420,32 +452,25 @@ int cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q, 
     if (int e = push_models(ctx, n_models, dm)) return e;
     if (int e = ensure(ctx, &ctx->d_scratch_ptrs, &ctx->cap_scr, (size_t)n_models)) return e;
     CK(cudaMemcpyAsync(ctx->d_scratch_ptrs, scr.data(), sizeof(double*) * n_models, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(cudaEventRecord(ctx->stage_ev[1][0], ctx->stream));
     cb_spline_k_launch(ctx->d_models, n_models, max_cols, ctx->d_scratch_ptrs, ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-    ctx->ms[1] = ms;
+    CK(cudaEventRecord(ctx->stage_ev[1][1], ctx->stream));
     const size_t smem = cb_los_smem(max_nsrc, max_ntau);
     if (smem > 227 * 1024) { ctx->err = "LOS: too many time steps for shared memory"; return CB_ERR_UNSUPPORTED_PARAMS; }
     CK(cb_los_set_smem(smem));
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(cudaEventRecord(ctx->stage_ev[2][0], ctx->stream));
     cb_los_launch(ctx->d_models, n_models, ctx->bess, max_nq, max_ntau, smem, ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventRecord(ctx->stage_ev[2][1], ctx->stream));
     for (int m = 0; m < n_models; m++) {
         const DModel& D = dm[m]->h;
         if (Delta_p_l_k && Delta_p_l_k[m])
             CK(cudaMemcpyAsync(Delta_p_l_k[m], dm[m]->d_delta, sizeof(double) * (size_t)D.n_src * n_l * D.n_q, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-    ctx->ms[2] = ms;
     return 0;
 }
 
@@ -459,29 +484,31 @@ int cb_cl(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, int tensor, const dou
         DModel& D = d->h;
         if (!d->d_delta || D.n_q <= 0) { ctx->err = "cb_cl: no transfer functions (call cb_project first)"; return CB_ERR_UNSUPPORTED_PARAMS; }
         size_t nc = (size_t)n_l * d->n_cl;
-        if (nc > d->cap_icl) { if (d->d_icl) cudaFree(d->d_icl); d->d_icl = nullptr; d->cap_icl = 0; }
+        if (nc > d->cap_icl) { if (d->d_icl) dev_free(ctx, d->d_icl); d->d_icl = nullptr; d->cap_icl = 0; }
         if (int e = ensure(ctx, &d->d_icl, &d->cap_icl, nc)) return e;
         CK(cudaMemcpyAsync(d->d_pows, pows[m], sizeof(double) * D.n_q, cudaMemcpyHostToDevice, ctx->stream));
         D.iCl = d->d_icl;
     }
     if (int e = push_models(ctx, n_models, dm)) return e;
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(cudaEventRecord(ctx->stage_ev[3][0], ctx->stream));
     cb_cl_launch(ctx->d_models, n_models, ctx->bess, ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventRecord(ctx->stage_ev[3][1], ctx->stream));
     for (int m = 0; m < n_models; m++)
         if (iCl && iCl[m]) CK(cudaMemcpyAsync(iCl[m], dm[m]->d_icl, sizeof(double) * (size_t)n_l * dm[m]->n_cl, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-    ctx->ms[3] = ms;
     return 0;
 }
 
 int cb_last_timings(const cb_ctx* ctx, double ms[4]) {
     if (!ctx) return CB_ERR_NO_DEVICE;
-    for (int i = 0; i < 4; i++) ms[i] = ctx->ms[i];
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 4; i++) {
+        float f = 0;
+        ms[i] = cudaEventElapsedTime(&f, ctx->stage_ev[i][0], ctx->stage_ev[i][1]) == cudaSuccess ? f : 0.0;
+    }
+    cudaGetLastError();   // a stage that has not run yet leaves an unrecorded event: not an error
     return 0;
 }
 
@@ -528,6 +555,14 @@ void* cb_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
     return p;
+}
+
+int cb_host_register(void* p, size_t bytes) {
+    return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? 0 : CB_ERR_CUDA;
+}
+
+void cb_host_unregister(void* p) {
+    if (p) cudaHostUnregister(p);
 }
 
 void cb_host_free(void* p) {

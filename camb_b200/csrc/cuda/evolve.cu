@@ -52,6 +52,9 @@ struct MHot {
     const double *thermo_horner, *cs2, *dotmu, *ddotmu, *dddotmu, *ddddotmu, *emmu, *demmu;
     const double *nu_q, *nu_masses, *nu_int_kernel, *grhormass;   // into the global DModel (massive-nu models only)
     const double *nu_tau_notmassless, *nu_tau_nonrelativistic, *tau, *transfer_times;
+    double* LinearSrc;
+    float* TransferData;
+    int n_k;
     int nthermo, de_is_cc, de_model, de_nperturb, Num_Nu_massive, Nu_mass_eigenstates, nqmax, n_src;
     int DoLateRadTruncation, AccuracyTarget, WantTransfer, transfer_high_precision, WantCls, WantLateTime, n_tau, num_transfer_redshifts;
 };
@@ -73,6 +76,7 @@ __device__ inline void fill_hot(MHot& H, const DModel& M) {
     H.DoLateRadTruncation = M.DoLateRadTruncation; H.AccuracyTarget = M.AccuracyTarget; H.WantTransfer = M.WantTransfer;
     H.transfer_high_precision = M.transfer_high_precision; H.WantCls = M.WantCls; H.WantLateTime = M.WantLateTime; H.n_tau = M.n_tau;
     H.num_transfer_redshifts = M.num_transfer_redshifts;
+    H.LinearSrc = M.LinearSrc; H.TransferData = M.TransferData; H.n_k = M.n_k;
 }
 
 __host__ __device__ inline int d_nint(double x) { return (int)llround(x); }
@@ -407,10 +411,14 @@ __device__ void nu_integrate_L012(const MT& M, const EVs& E, const double* ay, d
 // this mode's lane group (G lanes, `lane` = index inside the group, `gm` = the group's lane mask).
 // out_mode != 0 runs the source (1) / transfer (2) output branch (:2775-2947).
 // `th` (may be null) holds cs2b, opacity, a, dopacity evaluated ahead of time for this tau.
-template <int G>
-__device__ __forceinline__ void derivs(const MHot& M, EVs& E, const double* __restrict__ denlk, const double* __restrict__ denlk2,
+// LEAN = true compiles the massive-neutrino and dark-energy-perturbation code out (launches whose
+// models are all massless-nu LCDM): a shorter, branch-poorer instruction stream for the common case.
+template <int G, bool LEAN>
+__device__ __forceinline__ void derivs(const MHot& M_, EVs& E, const double* __restrict__ denlk, const double* __restrict__ denlk2,
                                        const double* __restrict__ polfack, double tau, const double* ay, double* ayp, int lane,
                                        unsigned gm, int out_mode, const double* th, double* src_out, float* tr_out) {
+    const MHot& M = M_;
+    const bool de_is_cc = LEAN ? true : (M.de_is_cc != 0);
     const double k = E.k, k2 = E.k2;
     const bool tight = E.TightCoupling, no_nu = E.no_nu, no_phot = E.no_phot;
     double a, cs2, opacity, dopacity = 0;
@@ -422,13 +430,13 @@ __device__ __forceinline__ void derivs(const MHot& M, EVs& E, const double* __re
     // a/b by at most an ulp per quantity, far inside the 1e-5 parity budget
     const double grhob_t = M.grhob * ainv, grhoc_t = M.grhoc * ainv, grhor_t = M.grhornomass * a2inv, grhog_t = M.grhog * a2inv;
     double grhov_t, w_de;
-    if (M.de_is_cc) { grhov_t = M.grhov * a2; w_de = -1; }
+    if (de_is_cc) { grhov_t = M.grhov * a2; w_de = -1; }
     else de_background(M, a, grhov_t, w_de);
     double dgrho_matter = grhob_t * clxb + grhoc_t * clxc;
     double dgq = grhob_t * vb;
     double gpres_nu = 0, grhonu_t = 0;
     double wnu_arr[CB_MAX_NU];
-    const int n_eig = M.Num_Nu_massive > 0 ? M.Nu_mass_eigenstates : 0;
+    const int n_eig = LEAN ? 0 : (M.Num_Nu_massive > 0 ? M.Nu_mass_eigenstates : 0);
     for (int nu_i = 0; nu_i < n_eig; nu_i++) {  // MassiveNuVars, equations.f90:1358-1401
         double grhormass_t = M.grhormass[nu_i] * a2inv, rhonu, pnu, clxnu, qnu;
         double mass = M.nu_masses[nu_i];
@@ -465,8 +473,8 @@ __device__ __forceinline__ void derivs(const MHot& M, EVs& E, const double* __re
     }
     const double grho_matter = grhonu_t + grhob_t + grhoc_t;
     const double grho = grho_matter + grhor_t + grhog_t + grhov_t;
-    const double gpres_noDE = gpres_nu + (grhor_t + grhog_t) / 3;
-    const double adotoa = sqrt(grho / 3);
+    const double gpres_noDE = gpres_nu + (grhor_t + grhog_t) * (1.0 / 3.0);
+    const double adotoa = sqrt(grho * (1.0 / 3.0));   // x * (1/3): within an ulp of the reference's x / 3
     const double cothxor = th ? th[4] : 1.0 / tau;
     double dgrho = dgrho_matter;
     double z = 0, dz = 0, clxr, qr, pir, clxg, qg, pig = 0;
@@ -493,7 +501,7 @@ __device__ __forceinline__ void derivs(const MHot& M, EVs& E, const double* __re
     dgq = dgq + grhog_t * qg + grhor_t * qr;
     const double photbar = M.g_over_b * ainv, pb43 = 4.0 / 3 * photbar;
     double dgrho_de = 0, dgq_de = 0, de_yp0 = 0, de_yp1 = 0;
-    if (!M.de_is_cc) {
+    if (!de_is_cc) {
         if (M.de_model == CB_DE_PPF) {  // DarkEnergyPPF.f90:103-154
             double adotoa_rec = 1.0 / adotoa, grhoT = grho - grhov_t;
             double vT = dgq / (grhoT + gpres_noDE), Gamma = AY(E.w_ix);
@@ -521,7 +529,7 @@ __device__ __forceinline__ void derivs(const MHot& M, EVs& E, const double* __re
     }
     z = (0.5 * dgrho * kinv + etak) / adotoa;
     const double sigma = (z + 1.5 * dgq * k2inv);
-    if (!M.de_is_cc && M.de_model == CB_DE_FLUID) {  // DarkEnergyFluid.f90:115-145
+    if (!de_is_cc && M.de_model == CB_DE_FLUID) {  // DarkEnergyFluid.f90:115-145
         double one_plus_w = 1 + w_de, Hv3_over_k = 3 * adotoa * AY(E.w_ix + 1) / k;
         de_yp0 = -3 * adotoa * (M.de_cs2 - w_de) * (AY(E.w_ix) + one_plus_w * Hv3_over_k) - one_plus_w * k * (AY(E.w_ix + 1) + z);
         if (M.de_wa != 0) de_yp0 = de_yp0 + Hv3_over_k * M.de_wa * adotoa * a;
@@ -556,7 +564,7 @@ __device__ __forceinline__ void derivs(const MHot& M, EVs& E, const double* __re
         AYP(2) = clxcdot;
         AYP(3) = clxbdot;
         AYP(4) = vbdot;
-        if (!M.de_is_cc) {
+        if (!de_is_cc) {
             AYP(E.w_ix) = de_yp0;
             if (M.de_nperturb > 1) AYP(E.w_ix + 1) = de_yp1;
         }
@@ -570,7 +578,7 @@ __device__ __forceinline__ void derivs(const MHot& M, EVs& E, const double* __re
         } else {
             const int lmaxg = E.lmaxg, pol = E.polind, lmaxgpol = E.lmaxgpol;
             const double E2 = AY(pol + 2);
-            polter = pig / 10 + 9.0 / 15 * E2;
+            polter = pig * 0.1 + 9.0 / 15 * E2;
             pigdot = denlk[2] * qg - denlk2[2] * AY(g + 3) - opacity * (pig - polter) + 8.0 / 15.0 * k * sigma;
             // interior multipoles are one uniform formula; the l = 0, 1, 2 and truncation entries are
             // written by lane 0 (no per-element branching inside the lane-strided loops)
@@ -585,7 +593,7 @@ __device__ __forceinline__ void derivs(const MHot& M, EVs& E, const double* __re
             if (lane == 0) {
                 AYP(g) = clxgdot; AYP(g + 1) = qgdot; AYP(g + 2) = pigdot;
                 AYP(g + lmaxg) = k * AY(g + lmaxg - 1) - (lmaxg + 1) * cothxor * AY(g + lmaxg) - opacity * AY(g + lmaxg);
-                AYP(pol + 2) = -opacity * (AY(pol + 2) - polter) - k / 3.0 * AY(pol + 3);
+                AYP(pol + 2) = -opacity * (AY(pol + 2) - polter) - k * (1.0 / 3.0) * AY(pol + 3);
                 AYP(pol + lmaxgpol) = -opacity * AY(pol + lmaxgpol) + k * E.poltruncfac * AY(pol + lmaxgpol - 1) -
                                       (lmaxgpol + 3) * cothxor * AY(pol + lmaxgpol);
             }
@@ -672,7 +680,7 @@ __device__ __forceinline__ void derivs(const MHot& M, EVs& E, const double* __re
             octgdot = 0;
         } else { octg = AY(E.g_ix + 3); octgdot = AYP(E.g_ix + 3); }
         (void)octg; (void)E3v;
-        if (M.de_is_cc) { dgrho_de = 0; dgq_de = 0; }
+        if (de_is_cc) { dgrho_de = 0; dgq_de = 0; }
         double dgpi = grhor_t * pir + grhog_t * pig, dgpi_diff = 0;
         double pidot_sum = grhog_t * pigdot + grhor_t * pirdot, clxnu = 0;
         if (n_eig > 0) {  // MassiveNuVarsOut, equations.f90:1113-1176
@@ -722,7 +730,7 @@ __device__ __forceinline__ void derivs(const MHot& M, EVs& E, const double* __re
         }
         const double gpres = gpres_noDE + w_de * grhov_t;
         double de_add = 0;
-        if (!M.de_is_cc && M.de_model == CB_DE_PPF) {  // DarkEnergyPPF.f90:78-101
+        if (!de_is_cc && M.de_model == CB_DE_PPF) {  // DarkEnergyPPF.f90:78-101
             double adotoa_rec = 1.0 / adotoa, k_rec = 1.0 / k;
             double hdotoh = (-3.0 * grho - 3.0 * gpres - 2.0 * M.grhok) / 6.0 * adotoa_rec;
             de_add = 3.0 * dgrho_de + dgq_de * (12.0 * k_rec * adotoa + k * adotoa_rec - 3.0 * k_rec * (adotoa + hdotoh)) +
@@ -1249,7 +1257,7 @@ __device__ __forceinline__ void attempt_finish(const DModel& M, EVs& E, Ctl& C, 
 // step / output / switch schedule; only the short stage set-up before and after it diverges.
 // Dynamic shared memory per group: [Ctl][MHot][EVs][denlk, denlk2, polfack: 3*(maxl+1)][NVEC*nv],
 // padded so that consecutive groups start 64 bytes apart modulo 128.
-template <int G>
+template <int G, bool LEAN>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, EVOLVE_MIN_BLOCKS)
 cb_evolve_kernel(const DModel* __restrict__ models, const DModeItem* __restrict__ items, int n_items, int nv, int maxl,
                  unsigned long long slab_bytes, unsigned int* counter, int* error_flag) {
@@ -1310,10 +1318,32 @@ cb_evolve_kernel(const DModel* __restrict__ models, const DModeItem* __restrict_
                 const double h = C.h;
                 const int n = E.neq;
                 double* yt = V.yt;
-                for (int i = lane; i < n; i += G) {
-                    double acc = c_dp_a[t][0] * vec[nv + i];
-                    for (int j = 1; j < t; j++) acc = fma(c_dp_a[t][j], vec[(j + 1) * nv + i], acc);
-                    yt[i] = fma(h, acc, vec[i]);
+                const double *k1 = V.k1, *k2 = V.k2, *k3 = V.k3, *k4 = V.k4, *k5 = V.k5, *k6 = V.k6, *y0 = V.y;
+                switch (t) {   // t is warp-uniform: one fully unrolled combination per stage
+                    case 1:
+                        for (int i = lane; i < n; i += G) yt[i] = fma(h, c_dp_a[1][0] * k1[i], y0[i]);
+                        break;
+                    case 2:
+                        for (int i = lane; i < n; i += G) yt[i] = fma(h, fma(c_dp_a[2][1], k2[i], c_dp_a[2][0] * k1[i]), y0[i]);
+                        break;
+                    case 3:
+                        for (int i = lane; i < n; i += G)
+                            yt[i] = fma(h, fma(c_dp_a[3][2], k3[i], fma(c_dp_a[3][1], k2[i], c_dp_a[3][0] * k1[i])), y0[i]);
+                        break;
+                    case 4:
+                        for (int i = lane; i < n; i += G)
+                            yt[i] = fma(h, fma(c_dp_a[4][3], k4[i], fma(c_dp_a[4][2], k3[i], fma(c_dp_a[4][1], k2[i], c_dp_a[4][0] * k1[i]))), y0[i]);
+                        break;
+                    case 5:
+                        for (int i = lane; i < n; i += G)
+                            yt[i] = fma(h, fma(c_dp_a[5][4], k5[i], fma(c_dp_a[5][3], k4[i], fma(c_dp_a[5][2], k3[i],
+                                        fma(c_dp_a[5][1], k2[i], c_dp_a[5][0] * k1[i])))), y0[i]);
+                        break;
+                    default:
+                        for (int i = lane; i < n; i += G)
+                            yt[i] = fma(h, fma(c_dp_a[6][5], k6[i], fma(c_dp_a[6][4], k5[i], fma(c_dp_a[6][3], k4[i],
+                                        fma(c_dp_a[6][2], k3[i], c_dp_a[6][0] * k1[i])))), y0[i]);
+                        break;
                 }
                 __syncwarp(gm);
                 in = yt;
@@ -1325,17 +1355,16 @@ cb_evolve_kernel(const DModel* __restrict__ models, const DModeItem* __restrict_
         if (active) {
             double srcs[3];
             float* tr = nullptr;
-            if (out_mode == OUT_TR) tr = models[C.model].TransferData + (size_t)13 * ((size_t)C.q_ix + (size_t)models[C.model].n_k * (C.itf - 1));
-            derivs<G>(H, E, denlk, denlk2, polfack, tev, in, out, lane, gm, out_mode, th, out_mode == OUT_SRC ? srcs : nullptr, tr);
+            if (out_mode == OUT_TR) tr = H.TransferData + (size_t)13 * ((size_t)C.q_ix + (size_t)H.n_k * (C.itf - 1));
+            derivs<G, LEAN>(H, E, denlk, denlk2, polfack, tev, in, out, lane, gm, out_mode, th, out_mode == OUT_SRC ? srcs : nullptr, tr);
             if (t == 0) {
                 if (lane == 0) {
                     C.nderivs++;
                     if (C.phase == PH_STEP) { C.s = 1; C.neq_evals += E.neq; }
                     else {
                         if (out_mode == OUT_SRC) {
-                            const DModel& M = models[C.model];
-                            double* S = M.LinearSrc;   // sources go straight to LinearSrc(q_ix, :, j): stride n_k between sources
-                            for (int i = 0; i < M.n_src; i++) S[C.q_ix + (size_t)M.n_k * (i + (size_t)M.n_src * (C.j - 1))] = srcs[i];
+                            double* S = H.LinearSrc;   // sources go straight to LinearSrc(q_ix, :, j): stride n_k between sources
+                            for (int i = 0; i < H.n_src; i++) S[C.q_ix + (size_t)H.n_k * (i + (size_t)H.n_src * (C.j - 1))] = srcs[i];
                         } else C.itf++;
                         C.stage = C.next_stage;
                         C.phase = PH_NEXT_GOAL;
@@ -1372,21 +1401,21 @@ void cb_mode_size(const DModel& M, double q, int transfer_only, int* nvar, int* 
     *maxl = E.MaxlNeeded;
 }
 
-template <int G>
+template <int G, bool LEAN>
 static cudaError_t launch_g(const DModel* d_models, const DModeItem* d_items, int n_items, int nv, int maxl, unsigned int* d_counter,
                             int* d_error, int n_sm, cudaStream_t stream, int* grid_out) {
     constexpr int MPW = 32 / G;
     const size_t slab = cb_evolve_slab_bytes(nv, maxl);
     const size_t smem = slab * MPW * WARPS_PER_BLOCK;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(cb_evolve_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(cb_evolve_kernel<G, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (const char* co = getenv("CAMB_B200_CARVEOUT")) {   // experiment knob: percent of the unified L1/shared array given to shared memory
-        e = cudaFuncSetAttribute(cb_evolve_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co));
+        e = cudaFuncSetAttribute(cb_evolve_kernel<G, LEAN>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co));
         if (e != cudaSuccess) return e;
     }
     int nb = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cb_evolve_kernel<G>, WARPS_PER_BLOCK * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cb_evolve_kernel<G, LEAN>, WARPS_PER_BLOCK * 32, smem);
     if (e != cudaSuccess) return e;
     if (const char* mb = getenv("CAMB_B200_MAXBLOCKS")) nb = nb < atoi(mb) ? nb : atoi(mb);
     if (nb < 1) nb = 1;
@@ -1394,16 +1423,19 @@ static cudaError_t launch_g(const DModel* d_models, const DModeItem* d_items, in
     int grid = (n_items + per_block - 1) / per_block;
     if (grid > n_sm * nb) grid = n_sm * nb;
     if (grid_out) *grid_out = grid;
-    cb_evolve_kernel<G><<<grid, WARPS_PER_BLOCK * 32, smem, stream>>>(d_models, d_items, n_items, nv, maxl, (unsigned long long)slab,
+    cb_evolve_kernel<G, LEAN><<<grid, WARPS_PER_BLOCK * 32, smem, stream>>>(d_models, d_items, n_items, nv, maxl, (unsigned long long)slab,
                                                                       d_counter, d_error);
     return cudaGetLastError();
 }
 
 // lanes_per_mode: 8 (throughput: four modes share a warp's instruction stream) or 32 (latency:
 // one mode per warp, for launches with fewer modes than the GPU has warp slots).
-cudaError_t cb_evolve_launch(const DModel* d_models, const DModeItem* d_items, int n_items, int nv, int maxl, int lanes_per_mode,
+cudaError_t cb_evolve_launch(const DModel* d_models, const DModeItem* d_items, int n_items, int nv, int maxl, int lanes_per_mode, int lean,
                              unsigned int* d_counter, int* d_error, int n_sm, cudaStream_t stream, int* grid_out) {
-    if (lanes_per_mode == 8) return launch_g<8>(d_models, d_items, n_items, nv, maxl, d_counter, d_error, n_sm, stream, grid_out);
-    if (lanes_per_mode == 16) return launch_g<16>(d_models, d_items, n_items, nv, maxl, d_counter, d_error, n_sm, stream, grid_out);
-    return launch_g<32>(d_models, d_items, n_items, nv, maxl, d_counter, d_error, n_sm, stream, grid_out);
+#define CB_LAUNCH(G_) (lean ? launch_g<G_, true>(d_models, d_items, n_items, nv, maxl, d_counter, d_error, n_sm, stream, grid_out) \
+                            : launch_g<G_, false>(d_models, d_items, n_items, nv, maxl, d_counter, d_error, n_sm, stream, grid_out))
+    if (lanes_per_mode == 8) return CB_LAUNCH(8);
+    if (lanes_per_mode == 16) return CB_LAUNCH(16);
+    return CB_LAUNCH(32);
+#undef CB_LAUNCH
 }

@@ -21,7 +21,8 @@ c_void_pp = C.POINTER(C.c_void_p)
 SYMBOLS = ["cb_create", "cb_destroy", "cb_last_error", "cb_device_count", "cb_set_bessel", "cb_model_create",
            "cb_model_destroy", "cb_evolve", "cb_set_sources", "cb_project", "cb_cl", "cb_last_timings",
            "cb_launch_count", "cb_abi_sizeof", "cb_timer_start", "cb_timer_stop", "cb_fp64_peak",
-           "cb_host_alloc", "cb_host_free", "cb_device_buffer", "cb_set_option"]
+           "cb_host_alloc", "cb_host_free", "cb_device_buffer", "cb_set_option", "cb_host_register",
+           "cb_host_unregister"]
 
 
 def load_gpu_lib():
@@ -55,6 +56,8 @@ def load_gpu_lib():
         lib.cb_host_alloc.argtypes = [C.c_size_t]
         lib.cb_host_free.argtypes = [C.c_void_p]
         lib.cb_device_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_void_pp, C.POINTER(C.c_size_t)]
+        lib.cb_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        lib.cb_host_unregister.argtypes = [C.c_void_p]
         lib.cb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         lib.cb_abi_sizeof.restype = C.c_size_t
         lib.cb_abi_sizeof.argtypes = [C.c_int]
@@ -171,6 +174,17 @@ class GpuContext:
         o_p = (c_double_p * n)(*[_dp(a) for a in out])
         self._check(self._lib.cb_cl(self._h, n, dm_arr, 0, p_p, o_p))
         return [o.T.copy() for o in out]
+
+    def pin_host_tables(self, hs):
+        """Page-lock the host's boundary tables in place (what a Fortran host would do with its
+        allocatables) so cb_model_create's host->device copies are asynchronous DMA."""
+        m = hs.model
+        n = m.nthermo
+        for ptr, cnt in [(m.thermo_horner, 16 * n), (m.cs2, n), (m.dotmu, n), (m.ddotmu, n), (m.dddotmu, n), (m.ddddotmu, n),
+                         (m.emmu, n), (m.demmu, n), (m.tau, m.n_tau), (m.dtau, m.n_tau)]:
+            addr = C.cast(ptr, C.c_void_p).value
+            if addr:
+                self._lib.cb_host_register(addr, 8 * cnt)   # best effort: an unpinned table is still copied correctly
 
     def set_option(self, name, value):
         self._check(self._lib.cb_set_option(self._h, name.encode(), float(value)))

@@ -175,6 +175,8 @@ int  cb_fp64_peak(cb_ctx* ctx, double* tflops);
  * cudaHostRegister on its allocatables): makes the H2D/D2H copies of the calls above async DMA. */
 void* cb_host_alloc(size_t bytes);
 void  cb_host_free(void* p);
+int   cb_host_register(void* p, size_t bytes);     /* page-lock an existing host array in place */
+void  cb_host_unregister(void* p);
 /* Raw device pointers of a model's result buffers, for the caller's collectives
  * (torch.distributed / NCCL all-reduce of k-sharded LinearSrc and partial iCl). */
 enum { CB_BUF_LINEARSRC = 0, CB_BUF_DELTA = 1, CB_BUF_ICL = 2, CB_BUF_TRANSFER = 3 };

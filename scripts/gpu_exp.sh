@@ -1,8 +1,8 @@
 #!/bin/bash
 OUT=gpurun_out; mkdir -p $OUT
-timeout 900 python -m pytest tests -m gpu -x -q -s > $OUT/exp_pytest.log 2>&1; tail -4 $OUT/exp_pytest.log; grep -E "C_l errors|identical" $OUT/exp_pytest.log | head -30
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/exp_pytest.log 2>&1; tail -2 $OUT/exp_pytest.log
 run() { name=$1; shift
-  env "$@" timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/exp_bench_$name.json 2> $OUT/exp_bench_$name.err
+  env "$@" > $OUT/exp_bench_$name.json 2> $OUT/exp_bench_$name.err
   python - <<PY
 import json
 try:
@@ -10,6 +10,5 @@ try:
 except Exception as e: print("$name failed", e); print(open("$OUT/exp_bench_$name.err").read()[-1500:])
 PY
 }
-run L8 CAMB_B200_LANES=8
-run L16 CAMB_B200_LANES=16
-run L32 CAMB_B200_LANES=32
+run b64 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --batch 64
+run b128 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --batch 128
