@@ -121,7 +121,8 @@ class cb_model(C.Structure):
 
 class cb_modes(C.Structure):
     _fields_ = [("n_k", C.c_int), ("q", c_double_p), ("tight_switchoff", c_double_p),
-                ("nu_massive_approx_time", c_double_p), ("transfer_only", C.c_int)]
+                ("nu_massive_approx_time", c_double_p), ("transfer_only", C.c_int),
+                ("n_active", C.c_int), ("active", c_int_p)]
 
 
 class cb_bessel(C.Structure):

@@ -314,7 +314,16 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
         } else D.TransferData = nullptr;
         if (int e = ensure(ctx, &d->d_stats, &d->cap_stats, (size_t)4 * n_k)) return e;
         D.stats = d->d_stats;
-        for (int i = 0; i < n_k; i++) {
+        // k-sharding (cb_modes.active): this call evolves a subset; rows of the other modes stay zero
+        const bool subset = md.n_active > 0 && md.active;
+        const int n_act = subset ? md.n_active : n_k;
+        if (subset) {
+            CK(cudaMemsetAsync(d->d_stats, 0, sizeof(long long) * 4 * (size_t)n_k, ctx->stream));
+            if (nz > 0) CK(cudaMemsetAsync(d->d_transfer, 0, sizeof(float) * (size_t)13 * n_k * nz, ctx->stream));
+        }
+        for (int a = 0; a < n_act; a++) {
+            const int i = subset ? md.active[a] : a;
+            if (i < 0 || i >= n_k) { ctx->err = "cb_evolve: cb_modes.active index out of range"; return CB_ERR_UNSUPPORTED_PARAMS; }
             DModeItem it;
             memset(&it, 0, sizeof(it));
             it.model = m; it.q_ix = i; it.transfer_only = md.transfer_only; it.q = md.q[i];

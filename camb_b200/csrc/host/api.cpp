@@ -104,6 +104,7 @@ int cbh_get_modes(cbh_state* s, cb_modes* out, int transfer_only) {
         out->tight_switchoff = s->tight_T.data(); out->nu_massive_approx_time = s->nuapp_T.data();
     }
     out->transfer_only = transfer_only;
+    out->n_active = 0; out->active = nullptr;
     return 0;
 }
 

@@ -104,12 +104,19 @@ class GpuContext:
         self._lib.cb_model_destroy(self._h, dm)
 
     # ---- the three loops, batched over cosmologies ----
-    def evolve(self, hss, dms, transfer_only=False, want_sources=True, want_stats=True):
+    def evolve(self, hss, dms, transfer_only=False, want_sources=True, want_stats=True, active=None):
+        """`active` (k-sharding): per cosmology an int array of the 0-based mode indices this call evolves;
+        outputs keep their full shape with zero rows for the other modes."""
         n = len(hss)
         dm_arr = (C.c_void_p * n)(*dms)
         md_arr = (cb_modes * n)()
         mds = [hs.modes(transfer_only) for hs in hss]
+        act = [None] * n
         for i, md in enumerate(mds):
+            if active is not None and active[i] is not None:
+                act[i] = np.ascontiguousarray(active[i], dtype=np.int32)
+                md.n_active = len(act[i])
+                md.active = act[i].ctypes.data_as(c_int_p)
             md_arr[i] = md
         src, tr, st = [], [], []
         src_p = (c_double_p * n)()
@@ -144,18 +151,20 @@ class GpuContext:
         src = np.ascontiguousarray(src)
         self._check(self._lib.cb_set_sources(self._h, dm, len(q_src), _dp(q_src), _dp(src)))
 
-    def project(self, hss, dms, want_delta=True):
+    def project(self, hss, dms, want_delta=True, q_slices=None):
+        """`q_slices` (q-sharding of loop B): per cosmology a (lo, hi) slice of the integration grid."""
         n = len(hss)
         dm_arr = (C.c_void_p * n)(*dms)
-        nq = (C.c_int * n)(*[len(hs.q_int) for hs in hss])
-        qs = [np.ascontiguousarray(hs.q_int) for hs in hss]
-        dqs = [np.ascontiguousarray(hs.dq_int) for hs in hss]
+        sl = [slice(None)] * n if q_slices is None else [slice(lo, hi) for lo, hi in q_slices]
+        qs = [np.ascontiguousarray(hs.q_int[s]) for hs, s in zip(hss, sl)]
+        dqs = [np.ascontiguousarray(hs.dq_int[s]) for hs, s in zip(hss, sl)]
+        nq = (C.c_int * n)(*[len(q) for q in qs])
         q_p = (c_double_p * n)(*[_dp(a) for a in qs])
         dq_p = (c_double_p * n)(*[_dp(a) for a in dqs])
         out, out_p = [], (c_double_p * n)()
         for i, hs in enumerate(hss):
             if want_delta:
-                a = np.zeros((len(hs.q_int), self.n_l, hs.model.n_src))
+                a = np.zeros((len(qs[i]), self.n_l, hs.model.n_src))
                 out.append(a)
                 out_p[i] = _dp(a)
             else:

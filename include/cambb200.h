@@ -100,6 +100,11 @@ typedef struct cb_modes {
     const double* tight_switchoff; /* [n_k] EV%TightSwitchoffTime from `initial` */
     const double* nu_massive_approx_time; /* [n_k*CB_MAX_NU] EV%MassiveNuApproxTime */
     int    transfer_only;          /* 1: loop A' (GetTransfer), no sources */
+    /* k-sharding across GPUs: evolve only the modes q[active[0..n_active-1]] (0-based).  The
+     * outputs keep their full (n_k, ...) shape; rows of the other modes are zero, so a sum over ranks is the
+     * gather along k.  n_active = 0 / active = NULL: all modes (the reference's call). */
+    int    n_active;
+    const int* active;
 } cb_modes;
 
 /* Spherical-Bessel spline table + x grid (bessels.f90:20-41,168-182). */

@@ -1351,8 +1351,14 @@ int oracle_evolve(const cb_model* M, const cb_modes* modes, double* LinearSrc, f
         for (size_t i = 0; i < tot; i++) LinearSrc[i] = 0;
     }
     if (nthreads < 1) nthreads = 1;
+    /* k-sharding: only the listed modes (cb_modes.active); the other rows stay zero */
+    const int subset = modes->n_active > 0 && modes->active;
+    const int n_act = subset ? modes->n_active : n_k;
+    if (subset && TransferData && M->num_transfer_redshifts > 0)
+        memset(TransferData, 0, sizeof(float) * (size_t)Transfer_max * n_k * M->num_transfer_redshifts);
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
-    for (int qq = n_k - 1; qq >= 0; qq--) {
+    for (int aa = n_act - 1; aa >= 0; aa--) {
+        const int qq = subset ? modes->active[aa] : aa;
         int e = evolve_one_mode(M, modes, qq, LinearSrc, TransferData, stats);
         if (e) {
 #pragma omp critical

@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""k-sharded single cosmology over N GPUs (torchrun): checks the NCCL path of camb_b200.sharded against the
+one-GPU chain on the same box and prints the latency of one C_l set at N GPUs.
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/gpu_kshard.py"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+from camb_b200.gpu import GpuContext
+from camb_b200.host import HostState
+from camb_b200.sharded import GpuBackend, ShardedBoltzmann
+from camb_b200.workloads import planck2018_params
+
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ctx = GpuContext(local)
+hs = HostState(planck2018_params(lmax=2500, lensing=True, massless=True))
+ctx.set_bessel(hs)
+sb = ShardedBoltzmann(GpuBackend(ctx), rank, world)
+icl = sb.cls(hs)
+# the plain chain on this rank's own GPU
+dm = ctx.create_model(hs)
+ctx.evolve([hs], [dm], want_sources=False, want_stats=False)
+ctx.project([hs], [dm], want_delta=False)
+ref = ctx.cl([hs], [dm])[0]
+err = float(np.max(np.abs(icl - ref) / np.abs(ref).max(axis=0)))
+ts = []
+for it in range(5):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sb.cls(hs)
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ts.append(float(t.item()))
+t1 = []
+for it in range(3):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ctx.evolve([hs], [dm], want_sources=False, want_stats=False)
+    ctx.project([hs], [dm], want_delta=False)
+    ctx.cl([hs], [dm])
+    t1.append(time.perf_counter() - t0)
+ctx.destroy_model(dm)
+if rank == 0:
+    print(json.dumps({"kshard_n_gpus": world, "max_rel_diff_vs_one_gpu": err, "ms_per_cl_set_sharded": 1e3 * min(ts),
+                      "ms_per_cl_set_one_gpu": 1e3 * min(t1), "n_k": int(len(hs.source_q())), "n_q": int(len(hs.q_int))}))
+    assert err < 1e-11, err
+ctx.close()
+if world > 1:
+    dist.destroy_process_group()

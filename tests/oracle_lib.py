@@ -34,11 +34,14 @@ def _dp(a):
     return a.ctypes.data_as(c_double_p)
 
 
-def evolve(hs, transfer_only=False, nthreads=1, modes=None):
+def evolve(hs, transfer_only=False, nthreads=1, modes=None, active=None):
     """Returns LinearSrc with shape (n_tau, n_src, n_k) (C order == Fortran (k, src, tau)),
     TransferData (n_z, n_k, 13) float32, stats (n_k, 2) int64."""
     lib = load()
     md = modes if modes is not None else hs.modes(transfer_only)
+    if active is not None:   # k-sharding: only these modes, the other rows stay zero
+        active = np.ascontiguousarray(active, dtype=np.int32)
+        md.n_active, md.active = len(active), active.ctypes.data_as(C.POINTER(C.c_int))
     m = hs.model
     src = np.zeros((m.n_tau, m.n_src, md.n_k))
     nz = max(1, m.num_transfer_redshifts)
@@ -60,26 +63,29 @@ def spline_k(q_src, src):
     return dd
 
 
-def project(hs, q_src, src, dd, nthreads=1):
-    """Delta_p_l_k with shape (n_q, n_l, n_src) (C order == Fortran (src, l, q))."""
+def project(hs, q_src, src, dd, nthreads=1, q_slice=None):
+    """Delta_p_l_k with shape (n_q, n_l, n_src) (C order == Fortran (src, l, q)); `q_slice` = (lo, hi)
+    restricts loop B to a slice of the integration grid (q-sharding)."""
     lib = load()
     b = hs.bessel()
     q_src = np.ascontiguousarray(q_src)
-    qi = np.ascontiguousarray(hs.q_int)
+    qi = np.ascontiguousarray(hs.q_int if q_slice is None else hs.q_int[q_slice[0]:q_slice[1]])
     out = np.zeros((len(qi), b.n_l, hs.model.n_src))
     lib.oracle_project(C.byref(hs.model), C.byref(b), len(q_src), _dp(q_src), _dp(src), _dp(dd), len(qi), _dp(qi),
                        _dp(out), nthreads)
     return out
 
 
-def cl(hs, delta, pows=None):
-    """iCl with shape (n_l, n_cl)."""
+def cl(hs, delta, pows=None, q_slice=None):
+    """iCl with shape (n_l, n_cl); with `q_slice` the partial sum over that slice of the integration grid."""
     lib = load()
     b = hs.bessel()
-    qi = np.ascontiguousarray(hs.q_int)
-    dq = np.ascontiguousarray(hs.dq_int)
+    sl = slice(None) if q_slice is None else slice(q_slice[0], q_slice[1])
+    qi = np.ascontiguousarray(hs.q_int[sl])
+    dq = np.ascontiguousarray(hs.dq_int[sl])
     if pows is None:
         pows = hs.scalar_power()
+    pows = np.ascontiguousarray(pows[sl]) if len(pows) != len(qi) else np.ascontiguousarray(pows)
     n_cl = 6 if hs.model.n_src > 2 else 3
     out = np.zeros((n_cl, b.n_l))
     lib.oracle_cl(C.byref(hs.model), C.byref(b), len(qi), _dp(qi), _dp(dq), _dp(pows), _dp(delta), _dp(out))

@@ -185,3 +185,37 @@ def test_unsupported_models_are_errors(ctx):
     dm = C.c_void_p()
     e = ctx._lib.cb_model_create(ctx._h, C.byref(m), C.byref(dm))
     assert e == 5 and b"non-flat" in ctx._lib.cb_last_error(ctx._h)
+
+
+def test_kshard_subsets_and_q_slices_compose(ctx):
+    """SURVEY.md 8(e) on one device: two 'ranks' run one after the other.  Evolving the two halves of the
+    mode list (cb_modes.active) and adding the zero-filled outputs reproduces the full LinearSrc bit for bit;
+    partial iCl over two q slices add up to the full iCl; and ShardedBoltzmann with world=1 is the plain chain."""
+    from camb_b200.sharded import GpuBackend, ShardedBoltzmann, partition_modes, partition_q
+    hs = host_state("kshard", lambda: planck2018_params(lmax=800, lensing=True, massless=False, want_transfer=True))
+    ctx.set_bessel(hs)
+    dm = ctx.create_model(hs)
+    try:
+        src_full, tr_full, _ = ctx.evolve([hs], [dm])
+        ctx.project([hs], [dm], want_delta=False)
+        icl_full = ctx.cl([hs], [dm])[0]
+        parts = partition_modes(hs.source_q(), 2)
+        acc, acc_tr, nd = 0, 0, 0
+        for idx in parts:
+            s, t, st = ctx.evolve([hs], [dm], active=[idx])
+            assert np.all(st[0][np.setdiff1d(np.arange(len(hs.source_q())), idx)] == 0)
+            nd += int(st[0][:, 0].sum())
+            acc = acc + s[0]
+            acc_tr = acc_tr + t[0]
+        assert np.array_equal(acc, src_full[0]) and np.array_equal(acc_tr, tr_full[0])
+        ctx.set_sources(dm, hs.source_q(), acc)
+        pw = hs.scalar_power()
+        tot = 0
+        for lo, hi in partition_q(hs.q_int, hs.ls, hs.model.tau0, 2):
+            ctx.project([hs], [dm], want_delta=False, q_slices=[(lo, hi)])
+            tot = tot + ctx.cl([hs], [dm], [pw[lo:hi]])[0]
+        assert np.allclose(tot, icl_full, rtol=1e-12, atol=0)
+    finally:
+        ctx.destroy_model(dm)
+    one = ShardedBoltzmann(GpuBackend(ctx), 0, 1).cls(hs)
+    assert np.array_equal(one, icl_full)
