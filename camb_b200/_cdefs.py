@@ -116,6 +116,7 @@ class cb_model(C.Structure):
         ("max_etak_scalar", C.c_double), ("max_etak_tensor", C.c_double), ("qmin", C.c_double), ("qmax", C.c_double),
         ("WantLateTime", C.c_int),
         ("n_src", C.c_int),
+        ("adot", c_double_p), ("dadot", c_double_p),
     ]
 
 

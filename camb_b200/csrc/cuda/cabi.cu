@@ -17,6 +17,10 @@
 void cb_mode_size(const DModel& M, double q, int transfer_only, int* nvar, int* maxl);
 cudaError_t cb_evolve_launch(const DModel*, const DModeItem*, int n_items, int nv, int maxl, int lanes_per_mode, int lean,
                              unsigned int*, int*, int n_sm, cudaStream_t, int* grid_out);
+// evolve_tensor.cu
+void cb_tensor_mode_size(const DModel& M, int* nvart, int* maxl);
+cudaError_t cb_evolve_tensor_launch(const DModel*, const DModeItem*, int n_items, int nv, int maxl, unsigned int*, int*, int n_sm,
+                                    cudaStream_t, int* grid_out);
 // project.cu
 void cb_spline_k_launch(const DModel*, int, int, double* const*, cudaStream_t);
 size_t cb_los_smem(int, int);
@@ -29,8 +33,10 @@ double cb_fp64_peak_measure(int n_sm, cudaStream_t st, int reps);
 // Modes are binned by their worst-case number of equations so that every launch sizes its
 // per-mode shared-memory slab for its own class (the few low-k modes with deep photon hierarchies
 // would otherwise halve the number of resident modes of everyone else).
-#define CB_N_CLASSES 4
-static const int kClassLimit[CB_N_CLASSES] = {48, 96, 160, 1 << 30};
+// The last class holds tensor modes (their own kernel, evolve_tensor.cu).
+#define CB_N_CLASSES 5
+#define CB_TENSOR_CLASS 4
+static const int kClassLimit[CB_N_CLASSES] = {48, 96, 160, 1 << 30, 1 << 30};
 
 struct cb_dmodel {
     DModel h;                      // host copy with device pointers
@@ -202,7 +208,10 @@ int cb_model_create(cb_ctx* ctx, const cb_model* m, cb_dmodel** out) {
     if (m->Scalar_initial_condition != 1) { ctx->err = "only adiabatic initial conditions are supported"; return CB_ERR_UNSUPPORTED_PARAMS; }
     if (m->n_tau_regions > 8) { ctx->err = "too many time-step regions"; return CB_ERR_UNSUPPORTED_PARAMS; }
     if (m->n_src > 3) { ctx->err = "source windows / custom sources are not supported"; return CB_ERR_UNSUPPORTED_PARAMS; }
-    if (!m->WantScalars) { ctx->err = "tensor/vector modes are not supported yet"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    const bool is_tensor = !m->WantScalars && m->WantTensors;
+    if (m->WantScalars && m->WantTensors) { ctx->err = "cmbmain cannot generate tensors and scalars in one pass (cmbmain.f90:142)"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    if (!m->WantScalars && !is_tensor) { ctx->err = "vector modes are not supported"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    if (is_tensor && (m->n_src != 3 || !m->adot || !m->dadot)) { ctx->err = "tensor models need n_src = 3 and the adot/dadot tables"; return CB_ERR_UNSUPPORTED_PARAMS; }
     cb_dmodel* dm = new cb_dmodel();
     DModel& D = dm->h;
     memset(&D, 0, sizeof(D));
@@ -233,7 +242,8 @@ int cb_model_create(cb_ctx* ctx, const cb_model* m, cb_dmodel** out) {
     D.num_transfer_redshifts = m->WantTransfer ? m->num_transfer_redshifts : 0;
     D.max_etak_scalar = m->max_etak_scalar; D.max_etak_tensor = m->max_etak_tensor;
     D.WantLateTime = m->WantLateTime; D.n_src = m->n_src;
-    dm->n_cl = m->n_src > 2 ? 6 : 3;
+    D.is_tensor = is_tensor ? 1 : 0;
+    dm->n_cl = is_tensor ? 4 : (m->n_src > 2 ? 6 : 3);
     int e = 0;
     double* p;
     size_t nt = (size_t)m->nthermo;
@@ -243,6 +253,7 @@ int cb_model_create(cb_ctx* ctx, const cb_model* m, cb_dmodel** out) {
     UP(ddddotmu, m->ddddotmu, nt); UP(emmu, m->emmu, nt); UP(demmu, m->demmu, nt);
     UP(tau, m->tau, (size_t)m->n_tau); UP(dtau, m->dtau, (size_t)m->n_tau);
     if (D.num_transfer_redshifts > 0) UP(transfer_times, m->transfer_times, (size_t)D.num_transfer_redshifts);
+    if (is_tensor) { UP(adot, m->adot, nt); UP(dadot, m->dadot, nt); }
 #undef UP
     CK(cudaStreamSynchronize(ctx->stream));
     *out = dm;
@@ -330,10 +341,12 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
             it.tight_switchoff = md.tight_switchoff[i];
             for (int j = 0; j < CB_MAX_NU; j++) it.nu_massive_approx_time[j] = md.nu_massive_approx_time[(size_t)i * CB_MAX_NU + j];
             int ml;
-            cb_mode_size(D, it.q, it.transfer_only, &it.nvar, &ml);
+            if (D.is_tensor) cb_tensor_mode_size(D, &it.nvar, &ml);
+            else cb_mode_size(D, it.q, it.transfer_only, &it.nvar, &ml);
             if (ml > CBD_MAX_L_EVOLVE) { ctx->err = "Need to increase max_l_evolve"; return CB_ERR_UNSUPPORTED_PARAMS; }
             int c = 0;
-            while (it.nvar > kClassLimit[c]) c++;
+            if (D.is_tensor) c = CB_TENSOR_CLASS;
+            else while (it.nvar > kClassLimit[c]) c++;
             cls_nv[c] = std::max(cls_nv[c], it.nvar);
             cls_maxl[c] = std::max(cls_maxl[c], ml);
             cls_items[c].push_back(it);
@@ -376,8 +389,11 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
         // the scratch EvolutionVars of a layout switch aliases two stage vectors (evolve.cu)
         const int nv = std::max(cls_nv[c], 32);
         CK(cudaStreamWaitEvent(ctx->class_stream[c], ctx->fork, 0));
-        cudaError_t le = cb_evolve_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, nv, cls_maxl[c], lanes, lean, ctx->d_counter + c,
-                                          ctx->d_error, ctx->n_sm, ctx->class_stream[c], &ctx->last_grid[c]);
+        cudaError_t le = c == CB_TENSOR_CLASS
+                             ? cb_evolve_tensor_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, cls_nv[c], cls_maxl[c], ctx->d_counter + c,
+                                                       ctx->d_error, ctx->n_sm, ctx->class_stream[c], &ctx->last_grid[c])
+                             : cb_evolve_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, nv, cls_maxl[c], lanes, lean, ctx->d_counter + c,
+                                                ctx->d_error, ctx->n_sm, ctx->class_stream[c], &ctx->last_grid[c]);
         if (le != cudaSuccess) { ctx->err = std::string("evolve launch: ") + cudaGetErrorString(le); return CB_ERR_CUDA; }
         ctx->launches++;
         CK(cudaEventRecord(ctx->class_done[c], ctx->class_stream[c]));
@@ -486,11 +502,11 @@ int cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q, 
 int cb_cl(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, int tensor, const double* const* pows, double* const* iCl) {
     if (!ctx) return CB_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
-    if (tensor) { ctx->err = "tensor C_l are not supported yet"; return CB_ERR_UNSUPPORTED_PARAMS; }
     const int n_l = ctx->bess.n_l;
     for (int m = 0; m < n_models; m++) {
         cb_dmodel* d = dm[m];
         DModel& D = d->h;
+        if ((tensor != 0) != (D.is_tensor != 0)) { ctx->err = "cb_cl: `tensor` does not match the model (CalcScalCls vs CalcTensCls)"; return CB_ERR_UNSUPPORTED_PARAMS; }
         if (!d->d_delta || D.n_q <= 0) { ctx->err = "cb_cl: no transfer functions (call cb_project first)"; return CB_ERR_UNSUPPORTED_PARAMS; }
         size_t nc = (size_t)n_l * d->n_cl;
         if (nc > d->cap_icl) { if (d->d_icl) dev_free(ctx, d->d_icl); d->d_icl = nullptr; d->cap_icl = 0; }

@@ -34,6 +34,9 @@ struct DModel {
     const double* ddddotmu;
     const double* emmu;
     const double* demmu;
+    const double* adot;           // tensor models only: Thermo_expansion_values
+    const double* dadot;
+    int is_tensor;                // WantTensors && !WantScalars: derivst / outputt / CalcTensCls
     // time steps
     int n_tau;
     const double* tau;

@@ -105,8 +105,9 @@ cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
     if (tid < M.n_tau_regions) s_tau_regions[tid] = M.tau_regions[tid];
     __syncthreads();
     // ---- InterpolateSources, cmbmain.f90:1351-1480 ----
-    const bool ignore_etak = M.WantLateTime != 0;
-    const double max_etak = ignore_etak ? 0.0 : M.max_etak_scalar;
+    const bool tensors = M.is_tensor != 0;   // cmbmain.f90:1391-1403
+    const bool ignore_etak = !tensors && M.WantLateTime != 0;
+    const double max_etak = ignore_etak ? 0.0 : (tensors ? M.max_etak_tensor : M.max_etak_scalar);
     const double* qs = M.q_src;
     int klo;
     if (q <= qs[0]) klo = 1;
@@ -180,7 +181,7 @@ cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
             bool DoInt = true;
             if (nsrc > 2) {
                 const double qmax_int = (l > 850 ? l : 850) * 3 * BessIntBoost / tau0 * 1.2;
-                DoInt = q < qmax_int;
+                DoInt = tensors || q < qmax_int;   // DoInt = .not. CP%WantScalars .or. IV%q < qmax_int
             }
             if (DoInt) {
                 for (int n = n1 + lane; n <= n2; n += 32) {
@@ -196,7 +197,7 @@ cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
                 s0 = warp_sum(s0); s1 = warp_sum(s1);
                 if (nsrc > 2) s2 = warp_sum(s2);
             }
-            if (nsrc > 2) {  // UseLimber, cmbmain.f90:1619-1636, 1821-1832
+            if (nsrc > 2 && !tensors) {  // UseLimber, cmbmain.f90:1619-1636, 1821-1832 (scalars only)
                 const bool limber = l > 400 * pow(M.AccuracyBoost * M.LimberBoost, 0.5);
                 if (!DoInt || limber) {
                     double xf = tau0 - (l + 0.5) / q;
@@ -221,7 +222,8 @@ cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
 __global__ void __launch_bounds__(256) cb_cl_kernel(const DModel* __restrict__ models, DBessel B) {
     const DModel& M = models[blockIdx.y];
     const int j = blockIdx.x, n_l = B.n_l, nsrc = M.n_src, n_q = M.n_q;
-    const int ncl = nsrc > 2 ? 6 : 3;
+    const bool tensors = M.is_tensor != 0;
+    const int ncl = tensors ? 4 : (nsrc > 2 ? 6 : 3);
     double c[6] = {0, 0, 0, 0, 0, 0};
     for (int iq = threadIdx.x; iq < n_q; iq += blockDim.x) {
         const double dlnk = M.dq_int[iq] / M.q_int[iq], ap = M.pows[iq];
@@ -229,6 +231,12 @@ __global__ void __launch_bounds__(256) cb_cl_kernel(const DModel* __restrict__ m
         const double d0 = D[0], d1 = D[1];
         c[0] += ap * (d0 * d0) * dlnk;
         c[1] += ap * (d1 * d1) * dlnk;
+        if (tensors) {   // CalcTensCls, cmbmain.f90:3424-3476: T, E, B autos and the TE cross
+            const double d2 = D[2];
+            c[2] += ap * (d2 * d2) * dlnk;
+            c[3] += ap * d0 * d1 * dlnk;
+            continue;
+        }
         c[2] += ap * d0 * d1 * dlnk;
         if (nsrc > 2) {
             const double d2 = D[2];
@@ -256,6 +264,15 @@ __global__ void __launch_bounds__(256) cb_cl_kernel(const DModel* __restrict__ m
         const double ctnorm = (ell * ell - 1) * (ell + 2) * ell;
         const double dbletmp = (ell * (ell + 1)) / twopi * fourpi;
         double* out = M.iCl;
+        if (tensors) {
+            double dt = (ell * (ell + 1)) / twopi * 3.1415926535897932384626433832795 / 4;
+            out[j + n_l * 0] = s[0] * dt * ctnorm;
+            if (B.l[j] == 1) dt = 0;
+            out[j + n_l * 1] = s[1] * dt;
+            out[j + n_l * 2] = s[2] * dt;
+            out[j + n_l * 3] = s[3] * dt * sqrt(ctnorm);
+            return;
+        }
         out[j + n_l * 0] = s[0] * dbletmp;
         out[j + n_l * 1] = s[1] * dbletmp * ctnorm;
         out[j + n_l * 2] = s[2] * dbletmp * sqrt(ctnorm);

@@ -219,11 +219,15 @@ void HostState::PerModeLookups(const std::vector<double>& q, std::vector<double>
     size_t n = q.size();
     tight.assign(n, 0.0);
     nuapprox.assign(n * CB_MAX_NU, tau0 + 1);
+    const bool tensors = CP.WantTensors && !CP.WantScalars;
     for (size_t i = 0; i < n; i++) {
         double k = q[i], ep;
-        if (k > epsw) ep = k > epsw * 5 ? ep0 * 5 / CP.Accuracy.AccuracyBoost * 0.65 : ep0;
-        else ep = ep0;
-        ep *= 2;  // second_order_tightcoupling
+        if (tensors) ep = k > 0.06 * epsw ? ep0 : 0.2 * ep0;  // initialt, equations.f90:2147-2154
+        else {
+            if (k > epsw) ep = k > epsw * 5 ? ep0 * 5 / CP.Accuracy.AccuracyBoost * 0.65 : ep0;
+            else ep = ep0;
+            ep *= 2;  // second_order_tightcoupling
+        }
         tight[i] = std::fmin(th.tight_tau, th.opacity_to_time(k / ep));
         for (int nu_i = 0; nu_i < CP.Nu_mass_eigenstates; nu_i++) {
             double m = nu_masses[nu_i];
@@ -402,6 +406,7 @@ void HostState::fill_model(cb_model& m) const {
     m.transfer_times = transfer_times.data();
     m.max_etak_scalar = max_etak_scalar; m.max_etak_tensor = max_etak_tensor; m.qmin = qmin; m.qmax = qmax;
     m.WantLateTime = WantLateTime; m.n_src = n_src;
+    m.adot = th.adot.data(); m.dadot = th.dadot.data();
 }
 
 }  // namespace cbh

@@ -175,13 +175,16 @@ class GpuContext:
     def cl(self, hss, dms, pows=None):
         n = len(hss)
         dm_arr = (C.c_void_p * n)(*dms)
+        tens = [bool(hs.model.WantTensors and not hs.model.WantScalars) for hs in hss]
+        if any(tens) != all(tens):
+            raise CAMBError("cl: a call is either CalcScalCls or CalcTensCls, not a mixture", 5)
         if pows is None:
-            pows = [hs.scalar_power() for hs in hss]
+            pows = [hs.tensor_power() if t else hs.scalar_power() for hs, t in zip(hss, tens)]
         pows = [np.ascontiguousarray(p) for p in pows]
         p_p = (c_double_p * n)(*[_dp(a) for a in pows])
-        out = [np.zeros((6 if hs.model.n_src > 2 else 3, self.n_l)) for hs in hss]
+        out = [np.zeros((4 if t else (6 if hs.model.n_src > 2 else 3), self.n_l)) for hs, t in zip(hss, tens)]
         o_p = (c_double_p * n)(*[_dp(a) for a in out])
-        self._check(self._lib.cb_cl(self._h, n, dm_arr, 0, p_p, o_p))
+        self._check(self._lib.cb_cl(self._h, n, dm_arr, 1 if all(tens) and n else 0, p_p, o_p))
         return [o.T.copy() for o in out]
 
     def pin_host_tables(self, hs):

@@ -112,3 +112,17 @@ def synthetic_lcdm_batch(n, seed=20261017, lmax=2500, lensing=True, massless=Tru
             p.w, p.wa = w0, wa
         out.append(p)
     return out
+
+
+def tensor_params(r=0.1, nt=0.0, lmax_tensor=600, k_eta_max_tensor=1200.0, massless=True, accuracy_boost=1.0):
+    """The tensor pass of CAMB_GetResults (camb.f90:85-104: WantScalars=F, WantTransfer=F) on the
+    planck_2018.ini cosmology: tensor T/E/B sources, C_l^{TT,EE,BB,TE} to Max_l_tensor."""
+    p = planck2018_params(lmax=2500, lensing=False, massless=massless, accuracy_boost=accuracy_boost)
+    p.WantScalars = 0
+    p.WantTensors = 1
+    p.WantTransfer = 0
+    p.r = float(r)
+    p.nt = float(nt)
+    p.Max_l_tensor = int(lmax_tensor)
+    p.Max_eta_k_tensor = float(k_eta_max_tensor)
+    return p

@@ -89,6 +89,9 @@ typedef struct cb_model {
     double max_etak_scalar, max_etak_tensor, qmin, qmax;
     int    WantLateTime;           /* cmbmain.f90:139 */
     int    n_src;                  /* ThisSources%SourceNum, cmbmain.f90:755-773 */
+    /* ---- tensor modes only (WantTensors && !WantScalars): Thermo_expansion_values, results.f90:1882-1906 ---- */
+    const double* adot;            /* [nthermo] da/dtau on the thermo grid */
+    const double* dadot;           /* [nthermo] its unit-grid derivative (unit_grid_pade_derivative) */
 } cb_model;
 
 /* Per-call mode list for loop A / A'.  The two per-k host look-ups that the
@@ -97,7 +100,7 @@ typedef struct cb_model {
 typedef struct cb_modes {
     int    n_k;                    /* number of modes */
     const double* q;               /* [n_k] */
-    const double* tight_switchoff; /* [n_k] EV%TightSwitchoffTime from `initial` */
+    const double* tight_switchoff; /* [n_k] EV%TightSwitchoffTime from `initial` (tensors: `initialt`, equations.f90:2147-2154) */
     const double* nu_massive_approx_time; /* [n_k*CB_MAX_NU] EV%MassiveNuApproxTime */
     int    transfer_only;          /* 1: loop A' (GetTransfer), no sources */
     /* k-sharding across GPUs: evolve only the modes q[active[0..n_active-1]] (0-based).  The

@@ -25,6 +25,9 @@
  *   Thermo_values / IonizationFunctionsAtTime  fortran/results.f90:1826-1880, 3069-3108
  *   ThermalNuBackground rho_P / drho           fortran/massive_neutrinos.f90:180-214, 336-360
  *   dark energy fluid / PPF   fortran/DarkEnergyFluid.f90:96-145, DarkEnergyPPF.f90:78-154
+ *   tensors: SetupTensorArrayIndices/CopyTensorVariableArray :793-858, initialt :2114-2193,
+ *            derivst :3115-3286, outputt :1757-1836, GaugeInterface_EvolveTens :462-490,
+ *            CalcTensorSources cmbmain.f90:1076-1103
  */
 #include <math.h>
 #include <stdlib.h>
@@ -53,6 +56,12 @@ typedef struct EVars {
     double* OutputSources;   /* n_src values or NULL */
     float* OutputTransfer;   /* 13 values or NULL */
     long long nderivs;
+    /* the right-hand side RungeKuttaDP45 integrates: derivs (scalars) or derivst (tensors) */
+    void (*fcn)(struct EVars*, int, double, const double*, double*);
+    /* ---- tensors (equations.f90:793-858, 1031-1048) ---- */
+    int lmaxt, lmaxpolt, lmaxnrt, lmaxnut, MaxlNeededt, E_ix, B_ix, TensTightCoupling, nvart, TensEqsToPropagate;
+    int EvolveTensorMassiveNu[MAXNU];
+    double denlkt[4][MAX_L_EVOLVE + 1];
 } EVars;
 
 static int f_nint(double x) { return (int)lround(x); }
@@ -923,7 +932,7 @@ static void RungeKuttaDP45(EVars* EV, int n, double* x, double* y, double xend, 
     for (;;) {
         if (*ind != 6) {
             if (s->reuse_first_derivative && s->first_derivative_valid) s->first_derivative_valid = 0;
-            else { derivs(EV, n, *x, y, W(1)); s->function_evaluations++; }
+            else { EV->fcn(EV, n, *x, y, W(1)); s->function_evaluations++; }
         }
         temp = 0;
         for (k = 0; k < n; k++) { double ab = fabs(y[k]); if (ab > temp) temp = ab; }
@@ -949,23 +958,23 @@ static void RungeKuttaDP45(EVars* EV, int n, double* x, double* y, double xend, 
         double h = trial_x - *x;
         double *k1 = W(1), *k2 = W(2), *k3 = W(3), *k4 = W(4), *k5 = W(5), *k6 = W(6), *k7 = W(7), *yt = W(9);
         for (k = 0; k < n; k++) yt[k] = y[k] + h * (1.0 / 5.0) * k1[k];
-        derivs(EV, n, *x + h / 5.0, yt, k2);
+        EV->fcn(EV, n, *x + h / 5.0, yt, k2);
         for (k = 0; k < n; k++) yt[k] = y[k] + h * ((3.0 / 40.0) * k1[k] + (9.0 / 40.0) * k2[k]);
-        derivs(EV, n, *x + h * (3.0 / 10.0), yt, k3);
+        EV->fcn(EV, n, *x + h * (3.0 / 10.0), yt, k3);
         for (k = 0; k < n; k++) yt[k] = y[k] + h * ((44.0 / 45.0) * k1[k] + (-56.0 / 15.0) * k2[k] + (32.0 / 9.0) * k3[k]);
-        derivs(EV, n, *x + h * (4.0 / 5.0), yt, k4);
+        EV->fcn(EV, n, *x + h * (4.0 / 5.0), yt, k4);
         for (k = 0; k < n; k++)
             yt[k] = y[k] + h * ((19372.0 / 6561.0) * k1[k] + (-25360.0 / 2187.0) * k2[k] + (64448.0 / 6561.0) * k3[k] +
                                 (-212.0 / 729.0) * k4[k]);
-        derivs(EV, n, *x + h * (8.0 / 9.0), yt, k5);
+        EV->fcn(EV, n, *x + h * (8.0 / 9.0), yt, k5);
         for (k = 0; k < n; k++)
             yt[k] = y[k] + h * ((9017.0 / 3168.0) * k1[k] + (-355.0 / 33.0) * k2[k] + (46732.0 / 5247.0) * k3[k] +
                                 (49.0 / 176.0) * k4[k] + (-5103.0 / 18656.0) * k5[k]);
-        derivs(EV, n, *x + h, yt, k6);
+        EV->fcn(EV, n, *x + h, yt, k6);
         for (k = 0; k < n; k++)
             yt[k] = y[k] + h * ((35.0 / 384.0) * k1[k] + (500.0 / 1113.0) * k3[k] + (125.0 / 192.0) * k4[k] +
                                 (-2187.0 / 6784.0) * k5[k] + (11.0 / 84.0) * k6[k]);
-        derivs(EV, n, *x + h, yt, k7);
+        EV->fcn(EV, n, *x + h, yt, k7);
         s->function_evaluations += 6;
         temp = 0;
         for (k = 0; k < n; k++) {
@@ -1274,6 +1283,7 @@ static int evolve_one_mode(const cb_model* M, const cb_modes* modes, int q_ix, d
     EV.q = modes->q[q_ix];
     EV.q2 = EV.q * EV.q;
     EV.TransferOnly = modes->transfer_only;
+    EV.fcn = derivs;
     double taustart = get_tau_start(M, EV.q);
     get_num_eqns(&EV);
     int nvar = EV.nvar, n_k = modes->n_k, n_src = M->n_src, n_tau = M->n_tau, nz = M->num_transfer_redshifts;
@@ -1341,6 +1351,363 @@ done:
     return err;
 }
 
+/* =====================================================================================
+ * Tensor modes: SetupTensorArrayIndices / CopyTensorVariableArray equations.f90:793-858,
+ * GetNumEqns tensor block :1029-1050, initialt :2114-2193, derivst :3115-3286,
+ * outputt :1757-1836, GaugeInterface_EvolveTens :462-490, CalcTensorSources
+ * cmbmain.f90:1076-1103, Thermo_expansion_values results.f90:1882-1906, dtauda
+ * equations.f90:5-24 (+ grho_no_de results.f90:1393-1410).  Flat only (Kft = aux = 1).
+ * ===================================================================================== */
+static void thermo_expansion_values(const cb_model* M, double tau, double* a, double* adot, double* opacity) {
+    int i;
+    double d;
+    thermo_index(M, tau, &i, &d);
+    if (i >= M->nthermo) {
+        *opacity = M->dotmu[M->nthermo - 1];
+        *a = 1;
+        *adot = M->adot[M->nthermo - 1];
+    } else {
+        const double* h = M->thermo_horner + 16 * (size_t)(i - 1);
+        const double *A = M->adot, *D = M->dadot;
+        int j = i - 1;
+        *a = (h[8] + d * (h[9] + d * (h[10] + d * h[11]))) * tau;
+        *opacity = h[4] + d * (h[5] + d * (h[6] + d * h[7]));
+        *adot = (A[j] + d * (D[j] + d * (3 * (A[j + 1] - A[j]) - 2 * D[j] - D[j + 1] + d * (D[j] + D[j + 1] + 2 * (A[j] - A[j + 1])))));
+    }
+}
+
+static double dtauda(const cb_model* M, double a) {
+    double grhov_t, w;
+    de_background(M, a, &grhov_t, &w);
+    double grhoa2 = M->grhok * a * a + (M->grhoc + M->grhob) * a + M->grhog + M->grhornomass;
+    if (M->Num_Nu_massive != 0)
+        for (int nu_i = 0; nu_i < M->Nu_mass_eigenstates; nu_i++) {
+            double rhonu, pnu;
+            nu_rho_P(a * M->nu_masses[nu_i], &rhonu, &pnu);
+            grhoa2 = grhoa2 + rhonu * M->grhormass[nu_i];
+        }
+    grhoa2 = grhoa2 + grhov_t * a * a;
+    return sqrt(3 / grhoa2);
+}
+
+static void setup_tensor_indices(EVars* EV, int* maxeq_out) {
+    const cb_model* M = EV->M;
+    int neq = 2, maxeq;
+    EV->g_ix = neq - 1;
+    if (!EV->TensTightCoupling) {
+        EV->E_ix = EV->g_ix + (EV->lmaxt - 1);
+        EV->B_ix = EV->E_ix + (EV->lmaxpolt - 1);
+        neq = neq + (EV->lmaxt - 1) + (EV->lmaxpolt - 1) * 2;
+    }
+    maxeq = 2 + (EV->lmaxt - 1) + (EV->lmaxpolt - 1) * 2;
+    EV->r_ix = neq - 1;
+    neq = neq + EV->lmaxnrt - 1; /* DoTensorNeutrinos = .true. */
+    maxeq = maxeq + EV->lmaxnrt - 1;
+    if (M->Num_Nu_massive != 0) {
+        for (int nu_i = 0; nu_i < M->Nu_mass_eigenstates; nu_i++) {
+            EV->EvolveTensorMassiveNu[nu_i] = M->nu_tau_nonrelativistic[nu_i] < 0.8 * M->tau_maxvis * M->AccuracyBoost;
+            if (EV->EvolveTensorMassiveNu[nu_i]) {
+                EV->nu_ix[nu_i] = neq - 1;
+                neq = neq + M->nqmax * (EV->lmaxnut - 1);
+                maxeq = maxeq + M->nqmax * (EV->lmaxnut - 1);
+            }
+        }
+    }
+    EV->TensEqsToPropagate = neq;
+    if (maxeq_out) *maxeq_out = maxeq;
+}
+
+#define Y(i) y[(i)-1]
+#define YO(i) yout[(i)-1]
+static void copy_tensor_array(const double* y, double* yout, const EVars* EV, const EVars* EVo) {
+    const cb_model* M = EV->M;
+    int l, lmaxt, lmaxpolt, nu_i, i;
+    for (i = 0; i < EVo->nvart; i++) yout[i] = 0;
+    YO(1) = Y(1); YO(2) = Y(2);
+    if (!EVo->TensTightCoupling && !EV->TensTightCoupling) {
+        lmaxt = imin(EVo->lmaxt, EV->lmaxt);
+        for (l = 2; l <= lmaxt; l++) YO(EVo->g_ix + l) = Y(EV->g_ix + l);
+        lmaxpolt = imin(EV->lmaxpolt, EVo->lmaxpolt);
+        for (l = 2; l <= lmaxpolt; l++) { YO(EVo->E_ix + l) = Y(EV->E_ix + l); YO(EVo->B_ix + l) = Y(EV->B_ix + l); }
+    }
+    lmaxt = imin(EV->lmaxnrt, EVo->lmaxnrt);
+    for (l = 2; l <= lmaxt; l++) YO(EVo->r_ix + l) = Y(EV->r_ix + l);
+    for (nu_i = 0; nu_i < M->Nu_mass_eigenstates; nu_i++) {
+        if (EV->EvolveTensorMassiveNu[nu_i]) {
+            lmaxt = imin(EV->lmaxnut, EVo->lmaxnut);
+            for (i = 1; i <= M->nqmax; i++) {
+                int ind = EV->nu_ix[nu_i] + (i - 1) * (EV->lmaxnut - 1), ind2 = EVo->nu_ix[nu_i] + (i - 1) * (EVo->lmaxnut - 1);
+                for (l = 2; l <= lmaxt; l++) YO(ind2 + l) = Y(ind + l);
+            }
+        }
+    }
+}
+#undef Y
+#undef YO
+
+static void get_num_eqns_tensor(EVars* EV) { /* equations.f90:870-892 (nq), 1029-1050 */
+    const cb_model* M = EV->M;
+    double lab = M->lAccuracyBoost;
+    for (int nu_i = 0; nu_i < M->Nu_mass_eigenstates; nu_i++) EV->nq[nu_i] = M->nqmax; /* WantTensors */
+    EV->TensTightCoupling = 1;
+    EV->lmaxt = imax(3, f_nint(8 * lab));
+    EV->lmaxpolt = imax(3, f_nint(4 * lab));
+    EV->lmaxnrt = f_nint(6 * lab);
+    EV->lmaxnut = EV->lmaxnrt;
+    EV->MaxlNeededt = imax(imax(EV->lmaxpolt, EV->lmaxt), imax(EV->lmaxnrt, EV->lmaxnut));
+    setup_tensor_indices(EV, &EV->nvart);
+}
+
+/* Nu_pi, equations.f90:1306-1326.  The stride lmaxnut+1 is the reference's (the tensor blocks
+ * written by derivst are lmaxnut-1 long); restated as it is.  For nqmax > 3 the reference's last
+ * reads fall past y(nvart) (out of bounds there); they are taken as zero here and on the GPU. */
+static double Nu_pi(const EVars* EV, const double* y, double a, int nu_i) {
+    const cb_model* M = EV->M;
+    double pinu = 0, am = a * M->nu_masses[nu_i];
+    int ind = EV->nu_ix[nu_i] + 2;
+    for (int iq = 1; iq <= EV->nq[nu_i]; iq++) {
+        double aq = am / M->nu_q[iq - 1];
+        double v = 1.0 / sqrt(1.0 + aq * aq);
+        pinu = pinu + M->nu_int_kernel[iq - 1] * (ind <= EV->nvart ? y[ind - 1] : 0.0) * v;
+        ind = ind + EV->lmaxnut + 1;
+    }
+    return pinu;
+}
+
+#define AY(i) ayt[(i)-1]
+#define AYP(i) aytprime[(i)-1]
+#define DK(c, l) EV->denlkt[(c)-1][l]
+static void derivst(EVars* EV, int n, double tau, const double* ayt, double* aytprime) {
+    const cb_model* M = EV->M;
+    double k = EV->k_buf, a, adot, opacity;
+    int l, i, ind, nu_i;
+    (void)n;
+    EV->nderivs++;
+    thermo_expansion_values(M, tau, &a, &adot, &opacity);
+    double Hchi = AY(1), shear = AY(2);
+    double a2 = a * a, adotoa = adot / a, cothxor = 1.0 / tau, pig, polter;
+    if (!EV->TensTightCoupling) {
+        const int Ei = EV->E_ix, Bi = EV->B_ix;
+#define E_(l) AY(Ei + (l))
+#define B_(l) AY(Bi + (l))
+#define EP_(l) AYP(Ei + (l))
+#define BP_(l) AYP(Bi + (l))
+        ind = EV->g_ix + 2;
+        pig = AY(ind);
+        polter = 0.1 * pig + 9.0 / 15.0 * E_(2);
+        if (EV->lmaxt > 2) {
+            AYP(ind) = -DK(2, 2) * AY(ind + 1) + k * 8.0 / 15.0 * shear - opacity * (pig - polter);
+            for (l = 3; l <= EV->lmaxt - 1; l++) {
+                ind = ind + 1;
+                AYP(ind) = DK(1, l) * AY(ind - 1) - DK(2, l) * AY(ind + 1) - opacity * AY(ind);
+            }
+            ind = ind + 1;
+            AYP(ind) = k * EV->lmaxt / (EV->lmaxt - 2.0) * AY(ind - 1) - (EV->lmaxt + 3.0) * cothxor * AY(ind) - opacity * AY(ind);
+            EP_(2) = -opacity * (E_(2) - polter) + DK(4, 2) * B_(2) - DK(3, 2) * E_(3);
+            for (l = 3; l <= EV->lmaxpolt - 1; l++)
+                EP_(l) = (DK(1, l) * E_(l - 1) - DK(3, l) * E_(l + 1) + DK(4, l) * B_(l)) - opacity * E_(l);
+            l = EV->lmaxpolt;
+            EP_(l) = (DK(1, l) * E_(l - 1) + DK(4, l) * B_(l)) - opacity * E_(l);
+            BP_(2) = -DK(3, 2) * B_(3) - DK(4, 2) * E_(2) - opacity * B_(2);
+            for (l = 3; l <= EV->lmaxpolt - 1; l++)
+                BP_(l) = (DK(1, l) * B_(l - 1) - DK(3, l) * B_(l + 1) - DK(4, l) * E_(l)) - opacity * B_(l);
+            l = EV->lmaxpolt;
+            BP_(l) = (DK(1, l) * B_(l - 1) - DK(4, l) * E_(l)) - opacity * B_(l);
+        } else {
+            AYP(ind) = k * 8.0 / 15.0 * shear - opacity * (pig - polter);
+            EP_(2) = -opacity * (E_(2) - polter) + DK(4, 2) * B_(2);
+            BP_(2) = -DK(4, 2) * E_(2) - opacity * B_(2);
+        }
+#undef E_
+#undef B_
+#undef EP_
+#undef BP_
+    } else pig = 32.0 / 45.0 * k / opacity * shear;
+    double grhor_t = M->grhornomass / a2, grhog_t = M->grhog / a2;
+    double rhopi = grhog_t * pig;
+    {   /* DoTensorNeutrinos */
+        const int r = EV->r_ix;
+        double pir = AY(r + 2), pirdt;
+        rhopi = rhopi + grhor_t * pir;
+        if (EV->lmaxnrt > 2) {
+            pirdt = -DK(2, 2) * AY(r + 3) + 8.0 / 15.0 * k * shear;
+            AYP(r + 2) = pirdt;
+            for (l = 3; l <= EV->lmaxnrt - 1; l++) AYP(r + l) = DK(1, l) * AY(r + l - 1) - DK(2, l) * AY(r + l + 1);
+            AYP(r + EV->lmaxnrt) = k * EV->lmaxnrt / (EV->lmaxnrt - 2.0) * AY(r + EV->lmaxnrt - 1) -
+                                   (EV->lmaxnrt + 3.0) * cothxor * AY(r + EV->lmaxnrt);
+        } else {
+            pirdt = 8.0 / 15.0 * k * shear;
+            AYP(r + 2) = pirdt;
+        }
+        if (M->Num_Nu_massive > 0) {
+            for (nu_i = 0; nu_i < M->Nu_mass_eigenstates; nu_i++) {
+                if (!EV->EvolveTensorMassiveNu[nu_i]) {
+                    rhopi = rhopi + M->grhormass[nu_i] / a2 * pir;
+                } else {
+                    ind = EV->nu_ix[nu_i] + 2;
+                    double pinu = Nu_pi(EV, ayt, a, nu_i);
+                    rhopi = rhopi + M->grhormass[nu_i] / a2 * pinu;
+                    for (i = 1; i <= M->nqmax; i++) {
+                        double q = M->nu_q[i - 1];
+                        double aq = a * M->nu_masses[nu_i] / q;
+                        double v = 1.0 / sqrt(1.0 + aq * aq);
+                        if (EV->lmaxnut > 2) {
+                            AYP(ind) = -v * DK(2, 2) * AY(ind + 1) + 8.0 / 15.0 * k * shear;
+                            for (l = 3; l <= EV->lmaxnut - 1; l++) {
+                                ind = ind + 1;
+                                AYP(ind) = v * (DK(1, l) * AY(ind - 1) - DK(2, l) * AY(ind + 1));
+                            }
+                            ind = ind + 1;
+                            AYP(ind) = k * v * EV->lmaxnut / (EV->lmaxnut - 2.0) * AY(ind - 1) - (EV->lmaxnut + 3) * cothxor * AY(ind);
+                        } else AYP(ind) = 8.0 / 15.0 * k * shear;
+                        ind = ind + 1;
+                    }
+                }
+            }
+        }
+    }
+    AYP(2) = -2 * adotoa * shear + k * Hchi - rhopi / k;
+    AYP(1) = -k * shear;
+}
+
+/* outputt, equations.f90:1757-1836 (flat: curvature_radius = 1, rofChi(x) = x, cosfunc = 1) */
+static void outputt(EVars* EV, const double* yt, double tau, double* dt, double* dte, double* dtb, double* ytprime) {
+    const cb_model* M = EV->M;
+    const double* ayt = yt;
+    double* aytprime = ytprime;
+    for (int i = 0; i < EV->nvart; i++) ytprime[i] = 0;
+    derivst(EV, EV->nvart, tau, yt, ytprime);
+    double k2 = EV->k2_buf, k = EV->k_buf, aux = 1.0, shear = AY(2);
+    double x = (M->tau0 - tau) / 1.0;
+    double a, opacity, dopacity, ddopacity, visibility, dvisibility, ddvisibility, exptau;
+    ionization_functions(M, tau, &a, &opacity, &dopacity, &ddopacity, &visibility, &dvisibility, &ddvisibility, &exptau);
+    double pig, pigdot, octg, E2, Ep2, Ep3, Bp2;
+    if (!EV->TensTightCoupling) {
+        pig = AY(EV->g_ix + 2);
+        pigdot = AYP(EV->g_ix + 2);
+        E2 = AY(EV->E_ix + 2);
+        Ep2 = AYP(EV->E_ix + 2); Ep3 = AYP(EV->E_ix + 3);
+        Bp2 = AYP(EV->B_ix + 2);
+        octg = AYP(EV->g_ix + 3);
+    } else {
+        double adotoa = 1 / (a * dtauda(M, a));
+        pigdot = 32.0 / 45.0 * k / opacity * (2.0 * adotoa * shear + AYP(2));
+        pig = 32.0 / 45.0 * k / opacity * shear;
+        E2 = pig / 4.0;
+        Ep2 = pigdot / 4; Ep3 = 0; Bp2 = 0;
+        octg = 0;
+    }
+    double sinhxr = x * 1.0;
+    if (EV->q * sinhxr > 1.e-8) {
+        double prefac = sqrt(EV->q2 * 1.0 * 1.0 - 0);
+        double cothxor = 1.0 / sinhxr;
+        double polter = 0.1 * pig + 9.0 / 15.0 * E2;
+        double polterdot = 9.0 / 15.0 * Ep2 + 0.1 * pigdot;
+        double polterddot = 9.0 / 15.0 * (-dopacity * (E2 - polter) - opacity * (Ep2 - polterdot) +
+                                          k * (2.0 / 3.0 * Bp2 * aux - 5.0 / 27.0 * Ep3 * 1.0)) +
+                            0.1 * (k * (-octg * 1.0 / 3.0 + 8.0 / 15.0 * AYP(2)) - dopacity * (pig - polter) - opacity * (pigdot - polterdot));
+        *dt = (shear * exptau + (15.0 / 8.0) * polter * visibility / k) * 1.0 / (sinhxr * sinhxr) / prefac;
+        *dte = 1.0 * 15.0 / 8.0 / k / prefac *
+               ((ddvisibility * polter + 2.0 * dvisibility * polterdot + visibility * polterddot) +
+                4.0 * cothxor * (dvisibility * polter + visibility * polterdot) - visibility * polter * (k2 - 6 * cothxor * cothxor));
+        *dtb = 15.0 / 4.0 * EV->q * 1.0 / k / prefac * (visibility * (2.0 * cothxor * polter + polterdot) + dvisibility * polter);
+    } else { *dt = 0; *dte = 0; *dtb = 0; }
+}
+#undef AY
+#undef AYP
+
+/* initialt, equations.f90:2114-2193 (TightSwitchoffTime hoisted to the host like the scalar one) */
+static void initialt(EVars* EV, double* yt, double tau, double tight_switchoff) {
+    const cb_model* M = EV->M;
+    EV->k2_buf = EV->q2;
+    EV->k_buf = EV->q;
+    double k = EV->k_buf, k2 = EV->k2_buf;
+    for (int l = 1; l <= EV->MaxlNeededt; l++) {
+        double denl = 1.0 / (2 * l + 1);
+        EV->denlkt[0][l] = k * denl * l;
+        double tensfac = (double)((l + 3) * (l - 1)) / (l + 1);
+        EV->denlkt[1][l] = k * denl * tensfac * 1.0;
+        EV->denlkt[2][l] = k * denl * (tensfac * tensfac) / (l + 1) * 1.0;
+        EV->denlkt[3][l] = k * 4.0 / (l * (l + 1)) * 1.0;
+    }
+    EV->TightSwitchoffTime = tight_switchoff;
+    double rhomass = 0;
+    for (int i = 0; i < M->Nu_mass_eigenstates; i++) rhomass += M->grhormass[i];
+    double bigR = (rhomass + M->grhornomass) / (rhomass + M->grhornomass + M->grhog);
+    double x = k * tau, tens0 = 1;
+    for (int i = 0; i < EV->nvart; i++) yt[i] = 0;
+    yt[0] = tens0;
+    double elec = -tens0 * (1 + 2 * 0.0 / k2) * (2 * bigR + 10) / (4 * bigR + 15);
+    yt[1] = -5.0 / 2 / (bigR + 5) * x * elec;
+    double pir = -2.0 / 3.0 / (bigR + 5) * (x * x) * elec;
+    double aj3r = -2.0 / 21.0 / (bigR + 5) * (x * x * x) * elec;
+    yt[EV->r_ix + 2 - 1] = pir;
+    yt[EV->r_ix + 3 - 1] = aj3r;
+}
+
+/* GaugeInterface_EvolveTens, equations.f90:462-490 */
+static int EvolveTens(EVars* EV, double* tau, double* y, double tauend, double tol1, int* ind, RKSettings* rk, double* w, double* yout) {
+    const cb_model* M = EV->M;
+    rk->reuse_first_derivative = 1;
+    if (EV->TensTightCoupling && tauend > EV->TightSwitchoffTime) {
+        if (EV->TightSwitchoffTime > *tau) {
+            RungeKuttaDP45(EV, EV->TensEqsToPropagate, tau, y, EV->TightSwitchoffTime, tol1, ind, rk, EV->nvart, w);
+            if (*ind < 0) return CB_ERR_EVOLUTION;
+        }
+        EVars EVo = *EV;
+        EVo.TensTightCoupling = 0;
+        setup_tensor_indices(&EVo, NULL);
+        copy_tensor_array(y, yout, EV, &EVo);
+        *EV = EVo;
+        memcpy(y, yout, sizeof(double) * EV->nvart);
+        double a, cs2, opacity;
+        thermo_values(M, *tau, &a, &cs2, &opacity, NULL);
+        y[EV->g_ix + 2 - 1] = 32.0 / 45.0 * EV->k_buf / opacity * y[1];
+        y[EV->E_ix + 2 - 1] = y[EV->g_ix + 2 - 1] / 4;
+        rk->first_derivative_valid = 0;
+    }
+    RungeKuttaDP45(EV, EV->TensEqsToPropagate, tau, y, tauend, tol1, ind, rk, EV->nvart, w);
+    if (*ind < 0) return CB_ERR_EVOLUTION;
+    return 0;
+}
+
+/* DoSourcek + CalcTensorSources, cmbmain.f90:731-753, 1076-1103 */
+static int evolve_one_mode_tensor(const cb_model* M, const cb_modes* modes, int q_ix, double* LinearSrc, long long* stats) {
+    EVars EV;
+    memset(&EV, 0, sizeof(EV));
+    EV.M = M;
+    EV.q = modes->q[q_ix];
+    EV.q2 = EV.q * EV.q;
+    EV.fcn = derivst;
+    double taustart = get_tau_start(M, EV.q);
+    get_num_eqns_tensor(&EV);
+    int nvart = EV.nvart, n_k = modes->n_k, n_tau = M->n_tau, err = 0;
+    double* w = (double*)calloc((size_t)nvart * 9, sizeof(double));
+    double* y = (double*)calloc(nvart, sizeof(double));
+    double* yout = (double*)calloc(nvart, sizeof(double));
+    double* yprime = (double*)calloc(nvart, sizeof(double));
+    RKSettings rk;
+    memset(&rk, 0, sizeof(rk));
+    initialt(&EV, y, taustart, modes->tight_switchoff[q_ix]);
+    double tau = taustart;
+    int ind = 1;
+    double tol = 1.0e-4 / exp(M->AccuracyBoost * M->IntTolBoost - 1);
+    for (int j = 2; j <= n_tau; j++) {
+        double tauend = M->tau[j - 1];
+        double* S = LinearSrc + q_ix + (size_t)n_k * 3 * (j - 1);
+        if (EV.q * tauend > M->max_etak_tensor) {
+            S[0] = 0; S[n_k] = 0; S[2 * (size_t)n_k] = 0;
+        } else {
+            err = EvolveTens(&EV, &tau, y, tauend, tol, &ind, &rk, w, yout);
+            if (err) break;
+            outputt(&EV, y, tau, &S[0], &S[n_k], &S[2 * (size_t)n_k], yprime);
+        }
+    }
+    if (stats) { stats[2 * q_ix] = EV.nderivs; stats[2 * q_ix + 1] = rk.successful_steps; }
+    free(w); free(y); free(yout); free(yprime);
+    return err;
+}
+
 int oracle_evolve(const cb_model* M, const cb_modes* modes, double* LinearSrc, float* TransferData, long long* stats,
                   int nthreads) {
     nu_consts_init();
@@ -1359,7 +1726,8 @@ int oracle_evolve(const cb_model* M, const cb_modes* modes, double* LinearSrc, f
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
     for (int aa = n_act - 1; aa >= 0; aa--) {
         const int qq = subset ? modes->active[aa] : aa;
-        int e = evolve_one_mode(M, modes, qq, LinearSrc, TransferData, stats);
+        int e = (!M->WantScalars && M->WantTensors) ? evolve_one_mode_tensor(M, modes, qq, LinearSrc, stats)
+                                                      : evolve_one_mode(M, modes, qq, LinearSrc, TransferData, stats);
         if (e) {
 #pragma omp critical
             err = e;

@@ -86,8 +86,10 @@ static void project_one_q(const cb_model* M, const cb_bessel* B, int n_k, const 
     /* ---- InterpolateSources ---- */
     for (i = 0; i < ntime * nsrc; i++) Source_q[i] = 0; /* Source_q(ntime, nsrc), time fastest */
     int step = 2, klo, khi;
-    int ignore_etak = M->WantLateTime ? 1 : 0;
-    double max_etak = ignore_etak ? 0.0 : M->max_etak_scalar;
+    /* cmbmain.f90:1391-1403: scalars ignore the cut with late-time sources; tensors use max_etak_tensor */
+    const int tensors = !M->WantScalars && M->WantTensors;
+    int ignore_etak = (!tensors && M->WantLateTime) ? 1 : 0;
+    double max_etak = ignore_etak ? 0.0 : (tensors ? M->max_etak_tensor : M->max_etak_scalar);
     if (q <= q_src[0]) klo = 1;
     else if (q >= q_src[n_k - 1]) klo = n_k - 1;
     else {
@@ -157,7 +159,7 @@ static void project_one_q(const cb_model* M, const cb_bessel* B, int n_k, const 
             }
         } else {
             double qmax_int = (l > 850 ? l : 850) * 3 * BessIntBoost / tau0 * 1.2;
-            int DoInt = q < qmax_int;
+            int DoInt = tensors || q < qmax_int; /* DoInt = .not. CP%WantScalars .or. IV%q < qmax_int */
             if (DoInt) {
                 for (n = n1; n <= n2; n++) {
                     double a2 = left_weight[n - 1];
@@ -169,7 +171,7 @@ static void project_one_q(const cb_model* M, const cb_bessel* B, int n_k, const 
                     sums[2] = sums[2] + Source_q[(n - 1) + 2 * ntime] * J_l;
                 }
             }
-            if (!DoInt || use_limber(M, l)) {
+            if (!DoInt || (use_limber(M, l) && !tensors)) { /* .not. DoInt .or. UseLimber(l) .and. CP%WantScalars */
                 double xf = tau0 - (l + 0.5) / q;
                 if (xf < M->tau_highest && xf > M->tau_lowest) {
                     n = ranges_index_of(M->tau_regions, M->n_tau_regions, M->n_tau, M->tau_highest, xf);
@@ -201,8 +203,34 @@ int oracle_project(const cb_model* M, const cb_bessel* B, int n_k, const double*
     return 0;
 }
 
+/* CalcTensCls, cmbmain.f90:3424-3476 (flat): iCl_tensor (n_l, CT_Temp:CT_Cross) = T, E, B, TE */
+static int oracle_cl_tensor(const cb_bessel* B, int n_q, const double* q_int, const double* dq, const double* pows,
+                            const double* Delta, double* iCl) {
+    const int n_l = B->n_l;
+    const double OutputDenominator = 2 * const_pi;
+    for (int j = 0; j < n_l; j++) {
+        double c[4] = {0, 0, 0, 0};
+        double ell = (double)B->l[j];
+        for (int iq = 0; iq < n_q; iq++) {
+            double measure = dq[iq] / q_int[iq], apowert = pows[iq];
+            const double* D = Delta + (size_t)3 * (j + (size_t)n_l * iq);
+            for (int t = 0; t < 3; t++) c[t] = c[t] + apowert * (D[t] * D[t]) * measure;
+            c[3] = c[3] + apowert * D[0] * D[1] * measure;
+        }
+        double ctnorm = (ell * ell - 1) * ((ell + 2) * ell);
+        double dbletmp = (ell * (ell + 1)) / OutputDenominator * const_pi / 4;
+        iCl[j + n_l * 0] = c[0] * dbletmp * ctnorm;
+        if (B->l[j] == 1) dbletmp = 0;
+        iCl[j + n_l * 1] = c[1] * dbletmp;
+        iCl[j + n_l * 2] = c[2] * dbletmp;
+        iCl[j + n_l * 3] = c[3] * dbletmp * sqrt(ctnorm);
+    }
+    return 0;
+}
+
 int oracle_cl(const cb_model* M, const cb_bessel* B, int n_q, const double* q_int, const double* dq, const double* pows,
               const double* Delta, double* iCl) {
+    if (!M->WantScalars && M->WantTensors) return oracle_cl_tensor(B, n_q, q_int, dq, pows, Delta, iCl);
     int nsrc = M->n_src, n_l = B->n_l, n_cl = nsrc > 2 ? 6 : 3;
     const double fourpi = 4 * const_pi, OutputDenominator = 2 * const_pi;
     for (int j = 0; j < n_l; j++) {

@@ -83,10 +83,11 @@ def cl(hs, delta, pows=None, q_slice=None):
     sl = slice(None) if q_slice is None else slice(q_slice[0], q_slice[1])
     qi = np.ascontiguousarray(hs.q_int[sl])
     dq = np.ascontiguousarray(hs.dq_int[sl])
+    tensors = bool(hs.model.WantTensors and not hs.model.WantScalars)
     if pows is None:
-        pows = hs.scalar_power()
+        pows = hs.tensor_power() if tensors else hs.scalar_power()
     pows = np.ascontiguousarray(pows[sl]) if len(pows) != len(qi) else np.ascontiguousarray(pows)
-    n_cl = 6 if hs.model.n_src > 2 else 3
+    n_cl = 4 if tensors else (6 if hs.model.n_src > 2 else 3)
     out = np.zeros((n_cl, b.n_l))
     lib.oracle_cl(C.byref(hs.model), C.byref(b), len(qi), _dp(qi), _dp(dq), _dp(pows), _dp(delta), _dp(out))
     return out.T.copy()

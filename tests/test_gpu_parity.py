@@ -7,7 +7,7 @@ import pytest
 
 import oracle_lib as O
 from camb_b200.host import CAMBError, HostState
-from camb_b200.workloads import params_ini_config1, planck2018_params, synthetic_lcdm_batch
+from camb_b200.workloads import params_ini_config1, planck2018_params, synthetic_lcdm_batch, tensor_params
 from conftest import host_state
 
 pytestmark = pytest.mark.gpu
@@ -73,6 +73,49 @@ def test_cl_parity_full_chain(ctx, name, lanes):
     print(name, "modes with identical derivs-evaluation count: %.3f" % same)
     assert same > 0.9
     assert abs(g["stats"][:, 0].sum() / aux["stats"][:, 0].sum() - 1) < 1e-3
+
+
+def _heavy_nu_tensor():
+    p = tensor_params(massless=False)
+    p.omnuh2 = 0.0215   # ~2 eV: non-relativistic before 0.8 tau_maxvis, so derivst evolves the massive-nu moments
+    return p
+
+
+TENSOR_CASES = {"tensor_massless": lambda: tensor_params(massless=True),
+                "tensor_light_nu": lambda: tensor_params(massless=False),
+                "tensor_heavy_nu": _heavy_nu_tensor}
+
+
+@pytest.mark.parametrize("name", list(TENSOR_CASES))
+def test_tensor_cl_parity(ctx, name):
+    """Tensor pass (CalcTensorSources -> DoFlatIntegration -> CalcTensCls): C_l^{TT,EE,BB} relative,
+    TE relative to sqrt(TT EE); sources per mode; identical derivst counts."""
+    hs = host_state(name, TENSOR_CASES[name])
+    if name == "tensor_heavy_nu":
+        assert hs.model.nu_tau_nonrelativistic[0] < 0.8 * hs.model.tau_maxvis
+    g = run_gpu(ctx, hs)
+    icl_o, aux = O.cls_from_params(hs, nthreads=8)
+    assert g["icl"].shape == icl_o.shape == (len(hs.ls), 4)
+    errs = []
+    for c in range(3):
+        errs.append(float(np.max(np.abs(g["icl"][:, c] - icl_o[:, c]) / np.abs(icl_o[:, c]))))
+    errs.append(float(np.max(np.abs(g["icl"][:, 3] - icl_o[:, 3]) / np.sqrt(icl_o[:, 0] * icl_o[:, 1]))))
+    print(name, "tensor C_l errors", errs)
+    assert max(errs) < CL_RTOL, errs
+    for s in range(3):
+        scale = np.abs(aux["src"][:, s, :]).max(axis=0, keepdims=True)
+        assert (np.abs(g["src"][:, s, :] - aux["src"][:, s, :]) / scale).max() < 2e-6
+    assert (g["stats"][:, 0] == aux["stats"][:, 0]).mean() > 0.9
+    # a scalar C_l call on a tensor model is an error, not a silent reinterpretation
+    ctx.set_bessel(hs)
+    dm = ctx.create_model(hs)
+    try:
+        import ctypes as C
+        from camb_b200._cdefs import c_double_p
+        e = ctx._lib.cb_cl(ctx._h, 1, (C.c_void_p * 1)(dm), 0, (c_double_p * 1)(), (c_double_p * 1)())
+        assert e == 5
+    finally:
+        ctx.destroy_model(dm)
 
 
 def test_sources_parity(ctx):
