@@ -66,6 +66,7 @@ class cb_params(C.Structure):
         ("use_cl_spline_template", C.c_int), ("min_l_logl_sampling", C.c_int),
         ("Alens", C.c_double),
         ("Accuracy", cb_accuracy),
+        ("InitialConditionVector", C.c_double * 5),
     ]
 
 
@@ -117,6 +118,7 @@ class cb_model(C.Structure):
         ("WantLateTime", C.c_int),
         ("n_src", C.c_int),
         ("adot", c_double_p), ("dadot", c_double_p),
+        ("InitialConditionVector", C.c_double * 5),
     ]
 
 

@@ -27,6 +27,7 @@ size_t cb_los_smem(int, int);
 cudaError_t cb_los_set_smem(size_t);
 void cb_los_launch(const DModel*, int, const DBessel&, int, int, size_t, cudaStream_t);
 void cb_cl_launch(const DModel*, int, const DBessel&, cudaStream_t);
+void cb_cl_array_launch(const DModel*, int, const DBessel&, double* const*, cudaStream_t);
 // peak.cu
 double cb_fp64_peak_measure(int n_sm, cudaStream_t st, int reps);
 
@@ -43,7 +44,8 @@ struct cb_dmodel {
     std::vector<void*> owned;      // table allocations freed with the model
     // per-call buffers (grown on demand)
     double *d_q_src = nullptr, *d_src = nullptr, *d_dd = nullptr, *d_scratch = nullptr, *d_delta = nullptr, *d_icl = nullptr;
-    double *d_q_int = nullptr, *d_dq_int = nullptr, *d_pows = nullptr;
+    double *d_q_int = nullptr, *d_dq_int = nullptr, *d_pows = nullptr, *d_icl_array = nullptr;
+    size_t cap_icl_array = 0;
     float* d_transfer = nullptr;
     long long* d_stats = nullptr;
     size_t cap_src = 0, cap_k = 0, cap_q = 0, cap_delta = 0, cap_tr = 0, cap_icl = 0, cap_stats = 0;
@@ -205,7 +207,8 @@ int cb_model_create(cb_ctx* ctx, const cb_model* m, cb_dmodel** out) {
     CK(cudaSetDevice(ctx->device));
     // things the device path does not implement are errors, never a fallback
     if (m->grhok != 0) { ctx->err = "non-flat models are not supported by the GPU path"; return CB_ERR_UNSUPPORTED_PARAMS; }
-    if (m->Scalar_initial_condition != 1) { ctx->err = "only adiabatic initial conditions are supported"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    if (m->Scalar_initial_condition < 0 || m->Scalar_initial_condition > 5) { ctx->err = "Invalid initial condition for scalar modes"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    if (m->Scalar_initial_condition != 1 && m->omch2 == 0) { ctx->err = "Isocurvature initial conditions assume non-zero dark matter"; return CB_ERR_UNSUPPORTED_PARAMS; }
     if (m->n_tau_regions > 8) { ctx->err = "too many time-step regions"; return CB_ERR_UNSUPPORTED_PARAMS; }
     if (m->n_src > 3) { ctx->err = "source windows / custom sources are not supported"; return CB_ERR_UNSUPPORTED_PARAMS; }
     const bool is_tensor = !m->WantScalars && m->WantTensors;
@@ -243,6 +246,8 @@ int cb_model_create(cb_ctx* ctx, const cb_model* m, cb_dmodel** out) {
     D.max_etak_scalar = m->max_etak_scalar; D.max_etak_tensor = m->max_etak_tensor;
     D.WantLateTime = m->WantLateTime; D.n_src = m->n_src;
     D.is_tensor = is_tensor ? 1 : 0;
+    D.Scalar_initial_condition = m->Scalar_initial_condition; D.omch2 = m->omch2; D.ombh2 = m->ombh2;
+    for (int i = 0; i < 5; i++) D.InitialConditionVector[i] = m->InitialConditionVector[i];
     dm->n_cl = is_tensor ? 4 : (m->n_src > 2 ? 6 : 3);
     int e = 0;
     double* p;
@@ -266,7 +271,7 @@ void cb_model_destroy(cb_ctx* ctx, cb_dmodel* dm) {
     if (!ctx) { delete dm; return; }
     for (void* p : dm->owned) dev_free(ctx, p);
     void* bufs[] = {dm->d_q_src, dm->d_src, dm->d_dd, dm->d_scratch, dm->d_delta, dm->d_icl, dm->d_q_int, dm->d_dq_int,
-                    dm->d_pows, dm->d_transfer, dm->d_stats};
+                    dm->d_pows, dm->d_transfer, dm->d_stats, dm->d_icl_array};
     for (void* p : bufs) dev_free(ctx, p);
     delete dm;
 }
@@ -522,6 +527,35 @@ int cb_cl(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, int tensor, const dou
     CK(cudaEventRecord(ctx->stage_ev[3][1], ctx->stream));
     for (int m = 0; m < n_models; m++)
         if (iCl && iCl[m]) CK(cudaMemcpyAsync(iCl[m], dm[m]->d_icl, sizeof(double) * (size_t)n_l * dm[m]->n_cl, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int cb_cl_array(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const double* const* pows, double* const* iCl_Array) {
+    if (!ctx) return CB_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    const int n_l = ctx->bess.n_l;
+    std::vector<double*> outs(n_models);
+    for (int m = 0; m < n_models; m++) {
+        cb_dmodel* d = dm[m];
+        DModel& D = d->h;
+        if (D.is_tensor || D.n_src != 3) { ctx->err = "cb_cl_array: scalar models with n_src = 3 only (Want_cl_2D_Array needs NumSources > 2)"; return CB_ERR_UNSUPPORTED_PARAMS; }
+        if (!d->d_delta || D.n_q <= 0) { ctx->err = "cb_cl_array: no transfer functions (call cb_project first)"; return CB_ERR_UNSUPPORTED_PARAMS; }
+        const size_t nc = (size_t)n_l * D.n_src * D.n_src;
+        if (nc > d->cap_icl_array) { if (d->d_icl_array) dev_free(ctx, d->d_icl_array); d->d_icl_array = nullptr; d->cap_icl_array = 0; }
+        if (int e = ensure(ctx, &d->d_icl_array, &d->cap_icl_array, nc)) return e;
+        if (pows && pows[m]) CK(cudaMemcpyAsync(d->d_pows, pows[m], sizeof(double) * D.n_q, cudaMemcpyHostToDevice, ctx->stream));
+        outs[m] = d->d_icl_array;
+    }
+    if (int e = push_models(ctx, n_models, dm)) return e;
+    if (int e = ensure(ctx, &ctx->d_scratch_ptrs, &ctx->cap_scr, (size_t)n_models)) return e;
+    CK(cudaMemcpyAsync(ctx->d_scratch_ptrs, outs.data(), sizeof(double*) * n_models, cudaMemcpyHostToDevice, ctx->stream));
+    cb_cl_array_launch(ctx->d_models, n_models, ctx->bess, ctx->d_scratch_ptrs, ctx->stream);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    for (int m = 0; m < n_models; m++)
+        if (iCl_Array && iCl_Array[m])
+            CK(cudaMemcpyAsync(iCl_Array[m], dm[m]->d_icl_array, sizeof(double) * (size_t)n_l * dm[m]->h.n_src * dm[m]->h.n_src, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

@@ -37,6 +37,9 @@ struct DModel {
     const double* adot;           // tensor models only: Thermo_expansion_values
     const double* dadot;
     int is_tensor;                // WantTensors && !WantScalars: derivst / outputt / CalcTensCls
+    // `initial` (equations.f90:1891-2112): mode 1..5, or 0 = initial_vector with the weights below
+    int Scalar_initial_condition;
+    double omch2, ombh2, InitialConditionVector[5];
     // time steps
     int n_tau;
     const double* tau;

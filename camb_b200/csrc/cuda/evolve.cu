@@ -711,7 +711,7 @@ __device__ __forceinline__ int next_nu_nq(const MT& M, int nq) {
     return q >= 10 ? M.nqmax : nq + 1;
 }
 
-// initial, equations.f90:1891-2112 (adiabatic, flat); lane 0
+// initial, equations.f90:1891-2112 (adiabatic and the four isocurvature modes, initial_vector; flat); lane 0
 __device__ void initial_conditions(const DModel& M, EVs& E, double* denlk, double* denlk2, double* polfack, double* y, double tau,
                                    const DModeItem& it) {
     const double k = E.q;
@@ -731,14 +731,60 @@ __device__ void initial_conditions(const DModel& M, EVs& E, double* denlk, doubl
     const double om = (M.grhob + M.grhoc) / sqrt(3 * (M.grhog + grhonu));
     const double omtau = om * tau, Rv = grhonu / (grhonu + M.grhog), Rp15 = 4 * Rv + 15;
     const double chi = 1;
-    double i_clxg = -chi * 1.0 / 3 * x2 * (1 - omtau / 5);
-    double i_clxr = i_clxg, i_clxb = 0.75 * i_clxg, i_clxc = i_clxb, i_qg = i_clxg * x / 9.0;
-    double i_qr = -chi * 1.0 * (4 * Rv + 23) / Rp15 * x3 / 27, i_vb = 0.75 * i_qg;
-    double i_pir = chi * 4.0 / 3 * x2 / Rp15 * (1 + omtau / 4 * (4 * Rv - 5) / (2 * Rv + 15));
-    double i_aj3r = chi * 4 / 21.0 / Rp15 * x3;
-    double i_eta = -chi * 2 * 1.0 * (1 - x2 / 12 * (-10.0 / Rp15 + 1.0));
-    i_clxg = -i_clxg; i_clxr = -i_clxr; i_clxb = -i_clxb; i_clxc = -i_clxc; i_qg = -i_qg; i_qr = -i_qr; i_vb = -i_vb;
-    i_pir = -i_pir; i_aj3r = -i_aj3r; i_eta = -i_eta;
+    // initv(mode, variable), equations.f90:1895-1905 and :1977-2050
+    enum { I_CLXG, I_CLXR, I_CLXC, I_CLXB, I_QG, I_QR, I_VB, I_PIR, I_ETA, I_AJ3R, I_N };
+    double initvec[I_N];
+    const int ic = M.Scalar_initial_condition;
+    for (int mode = 1; mode <= 5; mode++) {
+        double w;   // weight of this mode in initvec
+        if (ic == 0) w = M.InitialConditionVector[mode - 1];
+        else w = mode == ic ? (ic == 1 ? -1.0 : 1.0) : 0.0;   // pure adiabatic starts from chi = -1 (:2049)
+        if (mode == 1) for (int j = 0; j < I_N; j++) initvec[j] = 0;
+        if (w == 0.0) continue;
+        double v[I_N];
+        for (int j = 0; j < I_N; j++) v[j] = 0;
+        const double Rg = 1 - Rv, Rc = M.omch2 / (M.omch2 + M.ombh2), Rb = 1 - Rc;
+        if (mode == 1) {
+            v[I_CLXG] = -chi * 1.0 / 3 * x2 * (1 - omtau / 5);
+            v[I_CLXR] = v[I_CLXG]; v[I_CLXB] = 0.75 * v[I_CLXG]; v[I_CLXC] = v[I_CLXB]; v[I_QG] = v[I_CLXG] * x / 9.0;
+            v[I_QR] = -chi * 1.0 * (4 * Rv + 23) / Rp15 * x3 / 27; v[I_VB] = 0.75 * v[I_QG];
+            v[I_PIR] = chi * 4.0 / 3 * x2 / Rp15 * (1 + omtau / 4 * (4 * Rv - 5) / (2 * Rv + 15));
+            v[I_AJ3R] = chi * 4 / 21.0 / Rp15 * x3;
+            v[I_ETA] = -chi * 2 * 1.0 * (1 - x2 / 12 * (-10.0 / Rp15 + 1.0));
+        } else if (mode == 2 || mode == 3) {   // CDM / baryon isocurvature
+            v[I_CLXG] = Rc * omtau * (-2.0 / 3 + omtau / 4);
+            v[I_CLXR] = v[I_CLXG]; v[I_CLXB] = v[I_CLXG] * 0.75; v[I_CLXC] = 1 + v[I_CLXB];
+            v[I_QG] = -Rc / 9 * omtau * x; v[I_QR] = v[I_QG]; v[I_VB] = 0.75 * v[I_QG];
+            v[I_PIR] = -Rc * omtau * x2 / 3 / (2 * Rv + 15.0);
+            v[I_ETA] = Rc * omtau * (1.0 / 3 - omtau / 8) * 1.0;
+            if (mode == 3) {
+                for (int j = 0; j < I_N; j++) v[j] = v[j] * (Rb / Rc);
+                v[I_CLXC] = v[I_CLXB];
+                v[I_CLXB] = v[I_CLXB] + 1;
+            }
+        } else if (mode == 4) {   // neutrino isocurvature density
+            v[I_CLXG] = Rv / Rg * (-1 + x2 / 6); v[I_CLXR] = 1 - x2 / 6;
+            v[I_CLXC] = -omtau * x2 / 80 * Rv * Rb / Rg; v[I_CLXB] = Rv / Rg / 8 * x2;
+            const double iqg = -Rv / Rg * (x / 3 - Rb / 4 / Rg * omtau * x);
+            v[I_QG] = iqg; v[I_QR] = x / 3; v[I_VB] = 0.75 * iqg; v[I_PIR] = x2 / Rp15;
+            v[I_ETA] = 1.0 * Rv / Rp15 / 3 * x2;
+        } else {   // neutrino isocurvature velocity
+            v[I_CLXG] = Rv / Rg * x - 3 * x * omtau / 16 * Rv * Rb * (2 + Rg) / (Rg * Rg);
+            v[I_CLXR] = -x - 3 * x * omtau * Rv * Rb / 16 / Rg;
+            v[I_CLXC] = -9 * omtau * x / 64 * Rv * Rb / Rg;
+            v[I_CLXB] = 3 * Rv / 4 / Rg * x - 9 * omtau * x / 64 * Rv * Rb * (2 + Rg) / (Rg * Rg);
+            const double iqg = Rv / Rg * (-1 + 3 * Rb / 4 / Rg * omtau + x2 / 6 + 3 * (omtau * omtau) / 16 * Rb / (Rg * Rg) * (Rg - 3 * Rb));
+            v[I_QG] = iqg; v[I_QR] = 1 - x2 / 6 * (1 + 4 * 1.0 / (4 * Rv + 5)); v[I_VB] = 0.75 * iqg;
+            v[I_PIR] = 2 * x / (4 * Rv + 5) + omtau * x * 6 * Rv / Rp15 / (4 * Rv + 5);
+            v[I_ETA] = 2 * 1.0 * x * Rv / (4 * Rv + 5) + omtau * x * 3 * 1.0 * Rv / 32 * (Rb / Rg - 80 / Rp15 / (4 * Rv + 5));
+            v[I_AJ3R] = 3.0 / 7 * x2 / (4 * Rv + 5);
+        }
+        if (ic == 0) { for (int j = 0; j < I_N; j++) initvec[j] = initvec[j] + v[j] * w; }
+        else { for (int j = 0; j < I_N; j++) initvec[j] = w < 0 ? -v[j] : v[j]; }
+    }
+    const double i_clxg = initvec[I_CLXG], i_clxr = initvec[I_CLXR], i_clxc = initvec[I_CLXC], i_clxb = initvec[I_CLXB];
+    const double i_qg = initvec[I_QG], i_qr = initvec[I_QR], i_vb = initvec[I_VB], i_pir = initvec[I_PIR], i_eta = initvec[I_ETA];
+    const double i_aj3r = initvec[I_AJ3R];
     y[0] = -i_eta * k / 2; y[1] = i_clxc; y[2] = i_clxb; y[3] = i_vb;
     y[E.g_ix - 1] = i_clxg; y[E.g_ix] = i_qg;
     y[E.r_ix - 1] = i_clxr; y[E.r_ix] = i_qr; y[E.r_ix + 1] = i_pir;

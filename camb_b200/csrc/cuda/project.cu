@@ -284,7 +284,47 @@ __global__ void __launch_bounds__(256) cb_cl_kernel(const DModel* __restrict__ m
     }
 }
 
+// iCl_Array (cmbmain.f90:3224-3281, 3303-3326): grid = (n_l, n_models), one CTA per l; every pair (w_ix <= w_ix2)
+// is a fixed-order block reduction over q.  out[m] = (n_l, n, n) column-major.
+__global__ void __launch_bounds__(256) cb_cl_array_kernel(const DModel* __restrict__ models, DBessel B, double* const* __restrict__ out) {
+    const DModel& M = models[blockIdx.y];
+    const int j = blockIdx.x, n_l = B.n_l, n = M.n_src, n_q = M.n_q;
+    __shared__ double red[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double ell = (double)B.l[j];
+    const double ctnorm = (ell * ell - 1) * (ell + 2) * ell;
+    const double dbletmp = (ell * (ell + 1)) / (2 * 3.1415926535897932384626433832795) * (4 * 3.1415926535897932384626433832795);
+    double* O = out[blockIdx.y];
+    for (int w1 = 0; w1 < n; w1++)
+        for (int w2 = w1; w2 < n; w2++) {
+            double c = 0;
+            for (int iq = threadIdx.x; iq < n_q; iq += blockDim.x) {
+                const double dlnk = M.dq_int[iq] / M.q_int[iq], ap = M.pows[iq];
+                const double* D = M.Delta + (size_t)n * (j + (size_t)n_l * iq);
+                c += D[w1] * D[w2] * ap * dlnk;
+            }
+            c = warp_sum(c);
+            __syncthreads();
+            if (lane == 0) red[warp] = c;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double v = 0;
+                for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += red[w];
+                const double f1 = w1 == 1 ? sqrt(ctnorm) : (w1 == 2 ? sqrt(ell * (ell + 1) * M.Alens) : 1.0);
+                const double f2 = w2 == 1 ? sqrt(ctnorm) : (w2 == 2 ? sqrt(ell * (ell + 1) * M.Alens) : 1.0);
+                v = v * f1 * f2 * dbletmp;
+                O[j + (size_t)n_l * (w1 + (size_t)n * w2)] = v;
+                O[j + (size_t)n_l * (w2 + (size_t)n * w1)] = v;
+            }
+        }
+}
+
 // ---------------- launch wrappers (called from cabi.cu) ----------------
+void cb_cl_array_launch(const DModel* d_models, int n_models, const DBessel& B, double* const* d_out, cudaStream_t st) {
+    dim3 grid(B.n_l, n_models);
+    cb_cl_array_kernel<<<grid, 256, 0, st>>>(d_models, B, d_out);
+}
+
 void cb_spline_k_launch(const DModel* d_models, int n_models, int max_cols, double* const* d_scratch, cudaStream_t st) {
     dim3 grid((max_cols + 127) / 128, n_models);
     cb_spline_k_kernel<<<grid, 128, 0, st>>>(d_models, n_models, d_scratch);

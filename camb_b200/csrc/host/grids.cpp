@@ -407,6 +407,7 @@ void HostState::fill_model(cb_model& m) const {
     m.max_etak_scalar = max_etak_scalar; m.max_etak_tensor = max_etak_tensor; m.qmin = qmin; m.qmax = qmax;
     m.WantLateTime = WantLateTime; m.n_src = n_src;
     m.adot = th.adot.data(); m.dadot = th.dadot.data();
+    for (int i = 0; i < 5; i++) m.InitialConditionVector[i] = CP.InitialConditionVector[i];
 }
 
 }  // namespace cbh

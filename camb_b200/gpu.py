@@ -22,7 +22,7 @@ SYMBOLS = ["cb_create", "cb_destroy", "cb_last_error", "cb_device_count", "cb_se
            "cb_model_destroy", "cb_evolve", "cb_set_sources", "cb_project", "cb_cl", "cb_last_timings",
            "cb_launch_count", "cb_abi_sizeof", "cb_timer_start", "cb_timer_stop", "cb_fp64_peak",
            "cb_host_alloc", "cb_host_free", "cb_device_buffer", "cb_set_option", "cb_host_register",
-           "cb_host_unregister"]
+           "cb_host_unregister", "cb_cl_array"]
 
 
 def load_gpu_lib():
@@ -46,6 +46,7 @@ def load_gpu_lib():
         lib.cb_project.argtypes = [C.c_void_p, C.c_int, c_void_pp, c_int_p, C.POINTER(c_double_p),
                                    C.POINTER(c_double_p), C.POINTER(c_double_p)]
         lib.cb_cl.argtypes = [C.c_void_p, C.c_int, c_void_pp, C.c_int, C.POINTER(c_double_p), C.POINTER(c_double_p)]
+        lib.cb_cl_array.argtypes = [C.c_void_p, C.c_int, c_void_pp, C.POINTER(c_double_p), C.POINTER(c_double_p)]
         lib.cb_last_timings.argtypes = [C.c_void_p, C.c_double * 4]
         lib.cb_launch_count.restype = C.c_longlong
         lib.cb_launch_count.argtypes = [C.c_void_p]
@@ -186,6 +187,19 @@ class GpuContext:
         o_p = (c_double_p * n)(*[_dp(a) for a in out])
         self._check(self._lib.cb_cl(self._h, n, dm_arr, 1 if all(tens) and n else 0, p_p, o_p))
         return [o.T.copy() for o in out]
+
+    def cl_array(self, hss, dms, pows=None):
+        """iCl_Array of CalcScalCls (Cl_Scalar_Array in the reference's Python API): (n_src, n_src, n_l) per cosmology."""
+        n = len(hss)
+        dm_arr = (C.c_void_p * n)(*dms)
+        if pows is None:
+            pows = [hs.scalar_power() for hs in hss]
+        pows = [np.ascontiguousarray(p) for p in pows]
+        p_p = (c_double_p * n)(*[_dp(a) for a in pows])
+        out = [np.zeros((hs.model.n_src, hs.model.n_src, self.n_l)) for hs in hss]
+        o_p = (c_double_p * n)(*[_dp(a) for a in out])
+        self._check(self._lib.cb_cl_array(self._h, n, dm_arr, p_p, o_p))
+        return out
 
     def pin_host_tables(self, hs):
         """Page-lock the host's boundary tables in place (what a Fortran host would do with its

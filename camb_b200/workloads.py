@@ -126,3 +126,19 @@ def tensor_params(r=0.1, nt=0.0, lmax_tensor=600, k_eta_max_tensor=1200.0, massl
     p.Max_l_tensor = int(lmax_tensor)
     p.Max_eta_k_tensor = float(k_eta_max_tensor)
     return p
+
+
+def isocurvature_params(mode=2, vector=None, lmax=800, lensing=False, massless=True):
+    """`initial_condition` of the ini driver (camb.f90:734-742): 2 CDM-, 3 baryon-, 4 neutrino-density-,
+    5 neutrino-velocity-isocurvature, or 0 = `initial_vector` with five weights.  The driver switches the C_l
+    spline template off for anything but adiabatic modes (camb.f90:740)."""
+    p = planck2018_params(lmax=lmax, lensing=lensing, massless=massless)
+    if vector is not None:
+        p.Scalar_initial_condition = 0
+        for i, w in enumerate(vector):
+            p.InitialConditionVector[i] = float(w)
+    else:
+        p.Scalar_initial_condition = int(mode)
+    if p.Scalar_initial_condition != 1:
+        p.use_cl_spline_template = 0
+    return p

@@ -92,6 +92,8 @@ typedef struct cb_model {
     /* ---- tensor modes only (WantTensors && !WantScalars): Thermo_expansion_values, results.f90:1882-1906 ---- */
     const double* adot;            /* [nthermo] da/dtau on the thermo grid */
     const double* dadot;           /* [nthermo] its unit-grid derivative (unit_grid_pade_derivative) */
+    /* ---- `initial` with Scalar_initial_condition == initial_vector (0), equations.f90:2042-2047 ---- */
+    double InitialConditionVector[5];
 } cb_model;
 
 /* Per-call mode list for loop A / A'.  The two per-k host look-ups that the
@@ -162,6 +164,12 @@ int  cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q,
  *   iCl[i] double (n_l, n_cl) column-major, n_cl = 3 (n_src==2) or 6; tensor: 4. */
 int  cb_cl(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, int tensor,
            const double* const* pows, double* const* iCl);
+
+/* Loop C, full source covariance: iCl_Array(n_l, n, n) of CalcScalCls (cmbmain.f90:3224-3281, 3303-3326), the
+ * array the reference fills whenever n_src > 2 (Want_cl_2D_Array, model.f90:119) and hands back as
+ * Cl_Scalar_Array (cmbmain.f90:3538-3549).  n = n_src; column-major (l fastest), symmetric; uses the pows of the
+ * last cb_cl call when pows[i] is NULL.  Scalar models with n_src == 3 (no source windows). */
+int  cb_cl_array(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const double* const* pows, double* const* iCl_Array);
 
 /* Kernel timing of the last call of each stage, ms, measured with CUDA events on
  * the launching stream: [0] evolve, [1] spline-k, [2] LOS, [3] C_l. */

@@ -84,6 +84,9 @@ typedef struct cb_params {
     int use_cl_spline_template, min_l_logl_sampling;
     double Alens;
     cb_accuracy Accuracy;
+    /* weights of the adiabatic, CDM-, baryon-, neutrino-density- and neutrino-velocity-isocurvature modes; read only
+     * when Scalar_initial_condition == 0 (initial_vector, equations.f90:62-64, model.f90:166-168) */
+    double InitialConditionVector[5];
 } cb_params;
 
 /* Fill *p with the reference's defaults (model.f90 type defaults + the

@@ -26,6 +26,10 @@ int oracle_project(const cb_model* M, const cb_bessel* B, int n_k, const double*
 int oracle_cl(const cb_model* M, const cb_bessel* B, int n_q, const double* q_int, const double* dq, const double* pows,
               const double* Delta_p_l_k, double* iCl);
 
+/* loop C, full source covariance iCl_Array (n_l, n_src, n_src) column-major. */
+int oracle_cl_array(const cb_model* M, const cb_bessel* B, int n_q, const double* q_int, const double* dq, const double* pows,
+                    const double* Delta_p_l_k, double* iCl_Array);
+
 #ifdef __cplusplus
 }
 #endif

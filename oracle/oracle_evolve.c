@@ -1178,7 +1178,7 @@ static int EvolveScal(EVars* EV, double* tau, double* y, double tauend, double t
     return ScalEv(EV, y, tau, tauend, tol1, ind, rk, w);
 }
 
-/* initial, equations.f90:1891-2112 (adiabatic, flat; TightSwitchoffTime / MassiveNuApproxTime hoisted) */
+/* initial, equations.f90:1891-2112 (all five modes + initial_vector, flat; TightSwitchoffTime / MassiveNuApproxTime hoisted) */
 static void initial(EVars* EV, double* y, double tau, double tight_switchoff, const double* nu_massive_approx_time) {
     const cb_model* M = EV->M;
     int j, nu_i, i, ind;
@@ -1205,22 +1205,73 @@ static void initial(EVars* EV, double* y, double tau, double tight_switchoff, co
     double om = (M->grhob + M->grhoc) / sqrt(3 * (M->grhog + grhonu));
     double omtau = om * tau;
     double Rv = grhonu / (grhonu + M->grhog);
+    double Rg = 1 - Rv, Rc = M->omch2 / (M->omch2 + M->ombh2), Rb = 1 - Rc;
     double Rp15 = 4 * Rv + 15;
     double a = tau * M->adotrad * (1 + omtau / 4);
     double chi = 1;
-    double i_clxg = -chi * 1.0 / 3 * x2 * (1 - omtau / 5);
-    double i_clxr = i_clxg;
-    double i_clxb = 0.75 * i_clxg;
-    double i_clxc = i_clxb;
-    double i_qg = i_clxg * x / 9.0;
-    double i_qr = -chi * 1.0 * (4 * Rv + 23) / Rp15 * x3 / 27;
-    double i_vb = 0.75 * i_qg;
-    double i_pir = chi * 4.0 / 3 * x2 / Rp15 * (1 + omtau / 4 * (4 * Rv - 5) / (2 * Rv + 15));
-    double i_aj3r = chi * 4 / 21.0 / Rp15 * x3;
-    double i_eta = -chi * 2 * 1.0 * (1 - x2 / 12 * (-10.0 / Rp15 + 1.0));
-    /* adiabatic: initvec = -initv */
-    i_clxg = -i_clxg; i_clxr = -i_clxr; i_clxb = -i_clxb; i_clxc = -i_clxc; i_qg = -i_qg; i_qr = -i_qr; i_vb = -i_vb;
-    i_pir = -i_pir; i_aj3r = -i_aj3r; i_eta = -i_eta;
+    /* initv(mode, variable), equations.f90:1895-1905: variables clxg clxr clxc clxb qg qr vb pir eta aj3r */
+    enum { I_CLXG, I_CLXR, I_CLXC, I_CLXB, I_QG, I_QR, I_VB, I_PIR, I_ETA, I_AJ3R, I_N };
+    double initv[5][I_N], initvec[I_N];
+    memset(initv, 0, sizeof(initv));
+    initv[0][I_CLXG] = -chi * 1.0 / 3 * x2 * (1 - omtau / 5);
+    initv[0][I_CLXR] = initv[0][I_CLXG];
+    initv[0][I_CLXB] = 0.75 * initv[0][I_CLXG];
+    initv[0][I_CLXC] = initv[0][I_CLXB];
+    initv[0][I_QG] = initv[0][I_CLXG] * x / 9.0;
+    initv[0][I_QR] = -chi * 1.0 * (4 * Rv + 23) / Rp15 * x3 / 27;
+    initv[0][I_VB] = 0.75 * initv[0][I_QG];
+    initv[0][I_PIR] = chi * 4.0 / 3 * x2 / Rp15 * (1 + omtau / 4 * (4 * Rv - 5) / (2 * Rv + 15));
+    initv[0][I_AJ3R] = chi * 4 / 21.0 / Rp15 * x3;
+    initv[0][I_ETA] = -chi * 2 * 1.0 * (1 - x2 / 12 * (-10.0 / Rp15 + 1.0));
+    if (M->Scalar_initial_condition != 1) { /* equations.f90:1992-2040 */
+        double iqg;
+        initv[1][I_CLXG] = Rc * omtau * (-2.0 / 3 + omtau / 4);
+        initv[1][I_CLXR] = initv[1][I_CLXG];
+        initv[1][I_CLXB] = initv[1][I_CLXG] * 0.75;
+        initv[1][I_CLXC] = 1 + initv[1][I_CLXB];
+        initv[1][I_QG] = -Rc / 9 * omtau * x;
+        initv[1][I_QR] = initv[1][I_QG];
+        initv[1][I_VB] = 0.75 * initv[1][I_QG];
+        initv[1][I_PIR] = -Rc * omtau * x2 / 3 / (2 * Rv + 15.0);
+        initv[1][I_ETA] = Rc * omtau * (1.0 / 3 - omtau / 8) * 1.0;
+        initv[1][I_AJ3R] = 0;
+        for (j = 0; j < I_N; j++) initv[2][j] = initv[1][j] * (Rb / Rc);
+        initv[2][I_CLXC] = initv[2][I_CLXB];
+        initv[2][I_CLXB] = initv[2][I_CLXB] + 1;
+        initv[3][I_CLXG] = Rv / Rg * (-1 + x2 / 6);
+        initv[3][I_CLXR] = 1 - x2 / 6;
+        initv[3][I_CLXC] = -omtau * x2 / 80 * Rv * Rb / Rg;
+        initv[3][I_CLXB] = Rv / Rg / 8 * x2;
+        iqg = -Rv / Rg * (x / 3 - Rb / 4 / Rg * omtau * x);
+        initv[3][I_QG] = iqg;
+        initv[3][I_QR] = x / 3;
+        initv[3][I_VB] = 0.75 * iqg;
+        initv[3][I_PIR] = x2 / Rp15;
+        initv[3][I_ETA] = 1.0 * Rv / Rp15 / 3 * x2;
+        initv[4][I_CLXG] = Rv / Rg * x - 3 * x * omtau / 16 * Rv * Rb * (2 + Rg) / (Rg * Rg);
+        initv[4][I_CLXR] = -x - 3 * x * omtau * Rv * Rb / 16 / Rg;
+        initv[4][I_CLXC] = -9 * omtau * x / 64 * Rv * Rb / Rg;
+        initv[4][I_CLXB] = 3 * Rv / 4 / Rg * x - 9 * omtau * x / 64 * Rv * Rb * (2 + Rg) / (Rg * Rg);
+        iqg = Rv / Rg * (-1 + 3 * Rb / 4 / Rg * omtau + x2 / 6 + 3 * (omtau * omtau) / 16 * Rb / (Rg * Rg) * (Rg - 3 * Rb));
+        initv[4][I_QG] = iqg;
+        initv[4][I_QR] = 1 - x2 / 6 * (1 + 4 * 1.0 / (4 * Rv + 5));
+        initv[4][I_VB] = 0.75 * iqg;
+        initv[4][I_PIR] = 2 * x / (4 * Rv + 5) + omtau * x * 6 * Rv / Rp15 / (4 * Rv + 5);
+        initv[4][I_ETA] = 2 * 1.0 * x * Rv / (4 * Rv + 5) + omtau * x * 3 * 1.0 * Rv / 32 * (Rb / Rg - 80 / Rp15 / (4 * Rv + 5));
+        initv[4][I_AJ3R] = 3.0 / 7 * x2 / (4 * Rv + 5);
+    }
+    if (M->Scalar_initial_condition == 0) { /* initial_vector */
+        for (j = 0; j < I_N; j++) initvec[j] = 0;
+        for (i = 0; i < 5; i++)
+            for (j = 0; j < I_N; j++) initvec[j] = initvec[j] + initv[i][j] * M->InitialConditionVector[i];
+    } else {
+        for (j = 0; j < I_N; j++) initvec[j] = initv[M->Scalar_initial_condition - 1][j];
+        if (M->Scalar_initial_condition == 1)
+            for (j = 0; j < I_N; j++) initvec[j] = -initvec[j];
+    }
+    double i_clxg = initvec[I_CLXG], i_clxr = initvec[I_CLXR], i_clxc = initvec[I_CLXC], i_clxb = initvec[I_CLXB];
+    double i_qg = initvec[I_QG], i_qr = initvec[I_QR], i_vb = initvec[I_VB], i_pir = initvec[I_PIR], i_eta = initvec[I_ETA];
+    double i_aj3r = initvec[I_AJ3R];
     y[0] = -i_eta * k / 2;
     y[1] = i_clxc;
     y[2] = i_clxb;

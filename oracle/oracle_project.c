@@ -262,3 +262,34 @@ int oracle_cl(const cb_model* M, const cb_bessel* B, int n_q, const double* q_in
     (void)n_cl;
     return 0;
 }
+
+/* iCl_Array of CalcScalCls, cmbmain.f90:3224-3281 (accumulation) and :3303-3326 (normalisation): full covariance of the
+ * n_src = 3 sources (T, E, lensing potential), no source windows.  out (n_l, n, n) column-major. */
+int oracle_cl_array(const cb_model* M, const cb_bessel* B, int n_q, const double* q_int, const double* dq, const double* pows,
+                    const double* Delta, double* out) {
+    int n = M->n_src, n_l = B->n_l;
+    const double OutputDenominator = 2 * const_pi, fourpi = 4 * const_pi;
+    for (int j = 0; j < n_l; j++) {
+        double ell = (double)B->l[j], acc[16][16];
+        for (int a = 0; a < n; a++) for (int b = 0; b < n; b++) acc[a][b] = 0;
+        for (int iq = 0; iq < n_q; iq++) {
+            double dlnk = dq[iq] / q_int[iq], apowers = pows[iq];
+            const double* D = Delta + (size_t)n * (j + (size_t)n_l * iq);
+            for (int w1 = 0; w1 < n; w1++)
+                for (int w2 = w1; w2 < n; w2++) acc[w1][w2] = acc[w1][w2] + D[w1] * D[w2] * apowers * dlnk;
+        }
+        double ctnorm = (ell * ell - 1) * (ell + 2) * ell;
+        double dbletmp = (ell * (ell + 1)) / OutputDenominator * fourpi;
+        double fac[16];
+        for (int a = 0; a < n; a++) fac[a] = 1;
+        fac[1] = sqrt(ctnorm);
+        if (n > 2) fac[2] = sqrt(ell * (ell + 1) * M->Alens);
+        for (int w1 = 0; w1 < n; w1++)
+            for (int w2 = w1; w2 < n; w2++) {
+                double v = acc[w1][w2] * fac[w1] * fac[w2] * dbletmp;
+                out[j + (size_t)n_l * (w1 + (size_t)n * w2)] = v;
+                out[j + (size_t)n_l * (w2 + (size_t)n * w1)] = v;
+            }
+    }
+    return 0;
+}

@@ -26,6 +26,7 @@ def load():
                                        c_double_p, C.c_int, c_double_p, c_double_p, C.c_int]
         lib.oracle_cl.argtypes = [C.POINTER(cb_model), C.POINTER(cb_bessel), C.c_int, c_double_p, c_double_p,
                                   c_double_p, c_double_p, c_double_p]
+        lib.oracle_cl_array.argtypes = lib.oracle_cl.argtypes
         _lib = lib
     return _lib
 
@@ -91,6 +92,18 @@ def cl(hs, delta, pows=None, q_slice=None):
     out = np.zeros((n_cl, b.n_l))
     lib.oracle_cl(C.byref(hs.model), C.byref(b), len(qi), _dp(qi), _dp(dq), _dp(pows), _dp(delta), _dp(out))
     return out.T.copy()
+
+
+def cl_array(hs, delta, pows=None):
+    """iCl_Array with shape (n_src, n_src, n_l) (C order == Fortran (l, n, n))."""
+    lib = load()
+    b = hs.bessel()
+    qi, dq = np.ascontiguousarray(hs.q_int), np.ascontiguousarray(hs.dq_int)
+    pows = np.ascontiguousarray(hs.scalar_power() if pows is None else pows)
+    n = hs.model.n_src
+    out = np.zeros((n, n, b.n_l))
+    lib.oracle_cl_array(C.byref(hs.model), C.byref(b), len(qi), _dp(qi), _dp(dq), _dp(pows), _dp(delta), _dp(out))
+    return out
 
 
 def cls_from_params(hs, nthreads=1):

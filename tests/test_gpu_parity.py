@@ -7,7 +7,8 @@ import pytest
 
 import oracle_lib as O
 from camb_b200.host import CAMBError, HostState
-from camb_b200.workloads import params_ini_config1, planck2018_params, synthetic_lcdm_batch, tensor_params
+from camb_b200.workloads import (isocurvature_params, params_ini_config1, planck2018_params, synthetic_lcdm_batch,
+                                 tensor_params)
 from conftest import host_state
 
 pytestmark = pytest.mark.gpu
@@ -118,6 +119,24 @@ def test_tensor_cl_parity(ctx, name):
         ctx.destroy_model(dm)
 
 
+ISO_CASES = {"iso_cdm": lambda: isocurvature_params(2), "iso_baryon": lambda: isocurvature_params(3),
+             "iso_nu_density": lambda: isocurvature_params(4, massless=False),
+             "iso_nu_velocity": lambda: isocurvature_params(5),
+             "iso_vector": lambda: isocurvature_params(vector=[1.0, 0.3, -0.2, 0.1, 0.05], lensing=True)}
+
+
+@pytest.mark.parametrize("name", list(ISO_CASES))
+def test_isocurvature_cl_parity(ctx, name):
+    """`initial` for the isocurvature modes and initial_vector (equations.f90:1992-2050)."""
+    hs = host_state(name, ISO_CASES[name])
+    g = run_gpu(ctx, hs)
+    icl_o, aux = O.cls_from_params(hs, nthreads=8)
+    errs = cl_err(g["icl"], icl_o)
+    print(name, "C_l errors", errs)
+    assert max(errs) < CL_RTOL, errs
+    assert (g["stats"][:, 0] == aux["stats"][:, 0]).mean() > 0.9
+
+
 def test_sources_parity(ctx):
     hs = host_state("planck_massless_lensing", CASES["planck_massless_lensing"])
     g = run_gpu(ctx, hs)
@@ -152,6 +171,28 @@ def test_los_and_cl_stage_parity_on_identical_sources(ctx):
         assert (np.abs(delta[:, :, s] - delta_o[:, :, s]) / peak).max() < 1e-10
     assert (delta_o == 0).sum() == (delta == 0).sum()  # same l > llmax / window cuts
     assert max(cl_err(icl, icl_o)) < 1e-11
+
+
+def test_cl_array_parity(ctx):
+    """iCl_Array (CalcScalCls cmbmain.f90:3224-3281, 3303-3326) against the oracle, and its built-in identities:
+    the (T,E) block reproduces iCl_scalar's TT / EE / TE columns."""
+    hs = host_state("planck_massless_lensing", CASES["planck_massless_lensing"])
+    ctx.set_bessel(hs)
+    dm = ctx.create_model(hs)
+    try:
+        ctx.evolve([hs], [dm], want_sources=False, want_stats=False)
+        delta = ctx.project([hs], [dm])[0]
+        icl = ctx.cl([hs], [dm])[0]
+        arr = ctx.cl_array([hs], [dm])[0]
+    finally:
+        ctx.destroy_model(dm)
+    arr_o = O.cl_array(hs, delta)
+    assert arr.shape == arr_o.shape == (3, 3, len(hs.ls))
+    scale = np.sqrt(np.abs(np.einsum("iil,jjl->ijl", arr_o, arr_o)))
+    assert (np.abs(arr - arr_o) / scale).max() < 1e-12
+    assert np.array_equal(arr, arr.transpose(1, 0, 2))
+    assert np.allclose(arr[0, 0], icl[:, 0], rtol=1e-13) and np.allclose(arr[1, 1], icl[:, 1], rtol=1e-13)
+    assert np.allclose(arr[0, 1], icl[:, 2], rtol=1e-12, atol=1e-30)
 
 
 def test_transfer_outputs_parity(ctx):

@@ -110,3 +110,23 @@ def test_oracle_cl_is_quadratic_in_delta_and_linear_in_power():
     c1 = O.cl(hs, delta, pw)
     assert np.allclose(O.cl(hs, 2 * delta, pw), 4 * c1, rtol=1e-13)
     assert np.allclose(O.cl(hs, delta, 3 * pw), 3 * c1, rtol=1e-13)
+
+
+def test_cl_array_identities():
+    """iCl_Array (cmbmain.f90:3224-3326) against iCl_scalar on the same transfer functions: the T/E block is
+    TT, EE, TE; the lensing row differs from C_Phi, C_PhiTemp only by the documented l factors
+    (fac(3) = sqrt(l(l+1) Alens) and l(l+1)/2pi*4pi versus 4pi l^4, 4pi l^3)."""
+    import oracle_lib as O
+    from camb_b200.workloads import planck2018_params
+    from conftest import host_state
+    hs = host_state("arr_small", lambda: planck2018_params(lmax=400, lensing=True, massless=True))
+    icl, aux = O.cls_from_params(hs, nthreads=8)
+    arr = O.cl_array(hs, aux["delta"])
+    ell = hs.ls.astype(float)
+    assert np.allclose(arr[0, 0], icl[:, 0], rtol=1e-13)
+    assert np.allclose(arr[1, 1], icl[:, 1], rtol=1e-13)
+    assert np.allclose(arr[0, 1], icl[:, 2], rtol=1e-12, atol=1e-30)
+    pp = icl[:, 3] / (4 * np.pi * ell ** 4)           # sum Delta_phi^2 P dlnk
+    assert np.allclose(arr[2, 2], pp * ell * (ell + 1) * (ell * (ell + 1)) / (2 * np.pi) * 4 * np.pi, rtol=1e-12)
+    pt = icl[:, 4] / (4 * np.pi * ell ** 3)
+    assert np.allclose(arr[0, 2], pt * np.sqrt(ell * (ell + 1)) * (ell * (ell + 1)) / (2 * np.pi) * 4 * np.pi, rtol=1e-12, atol=1e-30)
