@@ -26,6 +26,28 @@ class cb_accuracy(C.Structure):
     ]
 
 
+CB_MAX_WINDOWS = 8
+
+
+class cb_source_window(C.Structure):
+    _fields_ = [("source_type", C.c_int), ("redshift", C.c_double), ("sigma", C.c_double), ("bias", C.c_double),
+                ("dlog10Ndm", C.c_double)]
+
+
+class cb_source_terms(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("limber_windows", "limber_phi_lmin", "counts_density", "counts_redshift",
+                                       "counts_lensing", "counts_velocity", "counts_radial", "counts_timedelay",
+                                       "counts_ISW", "counts_potential", "counts_evolve")]
+
+
+class cb_window(C.Structure):
+    _fields_ = [("kind", C.c_int), ("mag_index", C.c_int), ("Fq", C.c_double), ("dlog10Ndm", C.c_double),
+                ("bias", C.c_double), ("tau_start", C.c_double), ("tau_end", C.c_double), ("chi0", C.c_double),
+                ("sigma_tau", C.c_double)] + [(n, C.POINTER(C.c_double)) for n in (
+                    "wing", "wing2", "dwing2", "ddwing2", "wingtau", "dwingtau", "winV", "winF", "win_lens",
+                    "comoving_density_ev")]
+
+
 class cb_params(C.Structure):
     _fields_ = [
         ("WantCls", C.c_int), ("WantTransfer", C.c_int), ("WantScalars", C.c_int), ("WantTensors", C.c_int),
@@ -67,6 +89,9 @@ class cb_params(C.Structure):
         ("Alens", C.c_double),
         ("Accuracy", cb_accuracy),
         ("InitialConditionVector", C.c_double * 5),
+        ("num_redshiftwindows", C.c_int),
+        ("SourceWindows", cb_source_window * CB_MAX_WINDOWS),
+        ("SourceTerms", cb_source_terms),
     ]
 
 
@@ -119,6 +144,13 @@ class cb_model(C.Structure):
         ("n_src", C.c_int),
         ("adot", c_double_p), ("dadot", c_double_p),
         ("InitialConditionVector", C.c_double * 5),
+        ("num_redshiftwindows", C.c_int), ("num_extra_redshiftwindows", C.c_int),
+        ("windows", C.POINTER(cb_window)),
+        ("SourceTerms", cb_source_terms),
+        ("tau_start_redshiftwindows", C.c_double),
+        ("Want_CMB_lensing", C.c_int),
+        ("max_bessels_l_index", C.c_int),
+        ("Limber_l_min", C.c_int * (3 + CB_MAX_WINDOWS)),
     ]
 
 
@@ -130,4 +162,4 @@ class cb_modes(C.Structure):
 
 class cb_bessel(C.Structure):
     _fields_ = [("n_l", C.c_int), ("l", c_int_p), ("nx", C.c_int), ("x", c_double_p),
-                ("n_regions", C.c_int), ("regions", cb_range_p), ("horner", c_double_p)]
+                ("n_regions", C.c_int), ("regions", cb_range_p), ("horner", c_double_p), ("n_l_all", C.c_int)]

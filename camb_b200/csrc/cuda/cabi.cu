@@ -28,6 +28,8 @@ cudaError_t cb_los_set_smem(size_t);
 void cb_los_launch(const DModel*, int, const DBessel&, int, int, size_t, cudaStream_t);
 void cb_cl_launch(const DModel*, int, const DBessel&, cudaStream_t);
 void cb_cl_array_launch(const DModel*, int, const DBessel&, double* const*, cudaStream_t);
+void cb_limber_launch(const DModel*, int, const DBessel&, int, double* const*, cudaStream_t);
+void cb_cl_windows_launch(const DModel*, int, const DBessel&, double* const*, double* const*, double* const*, cudaStream_t);
 // peak.cu
 double cb_fp64_peak_measure(int n_sm, cudaStream_t st, int reps);
 
@@ -46,6 +48,8 @@ struct cb_dmodel {
     double *d_q_src = nullptr, *d_src = nullptr, *d_dd = nullptr, *d_scratch = nullptr, *d_delta = nullptr, *d_icl = nullptr;
     double *d_q_int = nullptr, *d_dq_int = nullptr, *d_pows = nullptr, *d_icl_array = nullptr;
     size_t cap_icl_array = 0;
+    double *d_limb = nullptr, *d_lpow = nullptr, *d_icl_w = nullptr;   // source windows: Limber sources, Limber P(k), iCl (n_l_all, 6)
+    size_t cap_limb = 0, cap_lpow = 0, cap_icl_w = 0;
     float* d_transfer = nullptr;
     long long* d_stats = nullptr;
     size_t cap_src = 0, cap_k = 0, cap_q = 0, cap_delta = 0, cap_tr = 0, cap_icl = 0, cap_stats = 0;
@@ -188,11 +192,12 @@ int cb_set_bessel(cb_ctx* ctx, const cb_bessel* b) {
     ctx->bess_owned.clear();
     DBessel& B = ctx->bess;
     B.n_l = b->n_l; B.nx = b->nx; B.n_regions = b->n_regions;
+    B.n_l_all = b->n_l_all > 0 ? b->n_l_all : b->n_l;
     if (b->n_regions > 8) { ctx->err = "too many Bessel x regions"; return CB_ERR_UNSUPPORTED_PARAMS; }
     for (int i = 0; i < b->n_regions; i++) B.regions[i] = b->regions[i];
     B.xmax = b->x[b->nx - 1];
     int* dl; double *dx, *dh;
-    if (int e = upload(ctx, b->l, (size_t)b->n_l, &dl, &ctx->bess_owned)) return e;
+    if (int e = upload(ctx, b->l, (size_t)B.n_l_all, &dl, &ctx->bess_owned)) return e;
     if (int e = upload(ctx, b->x, (size_t)b->nx, &dx, &ctx->bess_owned)) return e;
     if (int e = upload(ctx, b->horner, (size_t)4 * (b->nx - 1) * b->n_l, &dh, &ctx->bess_owned)) return e;
     B.l = dl; B.x = dx; B.horner = dh;
@@ -210,7 +215,11 @@ int cb_model_create(cb_ctx* ctx, const cb_model* m, cb_dmodel** out) {
     if (m->Scalar_initial_condition < 0 || m->Scalar_initial_condition > 5) { ctx->err = "Invalid initial condition for scalar modes"; return CB_ERR_UNSUPPORTED_PARAMS; }
     if (m->Scalar_initial_condition != 1 && m->omch2 == 0) { ctx->err = "Isocurvature initial conditions assume non-zero dark matter"; return CB_ERR_UNSUPPORTED_PARAMS; }
     if (m->n_tau_regions > 8) { ctx->err = "too many time-step regions"; return CB_ERR_UNSUPPORTED_PARAMS; }
-    if (m->n_src > 3) { ctx->err = "source windows / custom sources are not supported"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    const int nwin = m->WantScalars ? m->num_redshiftwindows : 0;
+    if (nwin < 0 || nwin > CB_MAX_WINDOWS || (nwin > 0 && !m->windows)) { ctx->err = "bad source-window count"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    if (m->WantScalars && m->n_src > 3 && m->n_src != 3 + nwin + m->num_extra_redshiftwindows) { ctx->err = "custom sources are not supported"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    for (int i = 0; i < nwin; i++)
+        if (m->windows[i].kind != CB_WINDOW_COUNTS && m->windows[i].kind != CB_WINDOW_LENSING) { ctx->err = "21cm source windows are not supported"; return CB_ERR_UNSUPPORTED_PARAMS; }
     const bool is_tensor = !m->WantScalars && m->WantTensors;
     if (m->WantScalars && m->WantTensors) { ctx->err = "cmbmain cannot generate tensors and scalars in one pass (cmbmain.f90:142)"; return CB_ERR_UNSUPPORTED_PARAMS; }
     if (!m->WantScalars && !is_tensor) { ctx->err = "vector modes are not supported"; return CB_ERR_UNSUPPORTED_PARAMS; }
@@ -260,6 +269,20 @@ int cb_model_create(cb_ctx* ctx, const cb_model* m, cb_dmodel** out) {
     if (D.num_transfer_redshifts > 0) UP(transfer_times, m->transfer_times, (size_t)D.num_transfer_redshifts);
     if (is_tensor) { UP(adot, m->adot, nt); UP(dadot, m->dadot, nt); }
 #undef UP
+    D.num_redshiftwindows = nwin; D.num_extra_redshiftwindows = nwin > 0 ? m->num_extra_redshiftwindows : 0;
+    D.SourceTerms = m->SourceTerms; D.tau_start_redshiftwindows = m->tau_start_redshiftwindows; D.qmax = m->qmax;
+    D.Want_CMB_lensing = m->Want_CMB_lensing; D.max_bessels_l_index = m->max_bessels_l_index;
+    for (int i = 0; i < 3 + CB_MAX_WINDOWS; i++) D.Limber_l_min[i] = nwin > 0 || m->SourceTerms.limber_windows ? m->Limber_l_min[i] : 0;
+    for (int i = 0; i < nwin; i++) {
+        cb_window w = m->windows[i];
+        const double** fields[] = {&w.wing, &w.wing2, &w.dwing2, &w.ddwing2, &w.wingtau, &w.dwingtau, &w.winV, &w.winF, &w.win_lens, &w.comoving_density_ev};
+        for (const double** f : fields) {
+            double* dp;
+            if ((e = upload(ctx, *f, (size_t)m->n_tau, &dp, &dm->owned))) { cb_model_destroy(ctx, dm); return e; }
+            *f = dp;
+        }
+        D.windows[i] = w;
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     *out = dm;
     return 0;
@@ -271,7 +294,7 @@ void cb_model_destroy(cb_ctx* ctx, cb_dmodel* dm) {
     if (!ctx) { delete dm; return; }
     for (void* p : dm->owned) dev_free(ctx, p);
     void* bufs[] = {dm->d_q_src, dm->d_src, dm->d_dd, dm->d_scratch, dm->d_delta, dm->d_icl, dm->d_q_int, dm->d_dq_int,
-                    dm->d_pows, dm->d_transfer, dm->d_stats, dm->d_icl_array};
+                    dm->d_pows, dm->d_transfer, dm->d_stats, dm->d_icl_array, dm->d_limb, dm->d_lpow, dm->d_icl_w};
     for (void* p : bufs) dev_free(ctx, p);
     delete dm;
 }
@@ -382,7 +405,7 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
     CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int) * CB_N_CLASSES, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_error, 0, sizeof(int), ctx->stream));
     int lean = 1;   // every model massless-nu LCDM: the kernel variant without massive-nu / dark-energy code
-    for (int m = 0; m < n_models; m++) if (dm[m]->h.Num_Nu_massive != 0 || !dm[m]->h.de_is_cc) lean = 0;
+    for (int m = 0; m < n_models; m++) if (dm[m]->h.Num_Nu_massive != 0 || !dm[m]->h.de_is_cc || dm[m]->h.num_redshiftwindows > 0) lean = 0;
     int lanes = ctx->lanes_per_mode;
     if (lanes != 8 && lanes != 16 && lanes != 32) lanes = n_items >= 16 * ctx->n_sm ? 8 : 32;
     CK(cudaEventRecord(ctx->stage_ev[0][0], ctx->stream));
@@ -511,6 +534,7 @@ int cb_cl(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, int tensor, const dou
     for (int m = 0; m < n_models; m++) {
         cb_dmodel* d = dm[m];
         DModel& D = d->h;
+        if (D.num_redshiftwindows > 0) { ctx->err = "cb_cl: models with source windows go through cb_cl_windows"; return CB_ERR_UNSUPPORTED_PARAMS; }
         if ((tensor != 0) != (D.is_tensor != 0)) { ctx->err = "cb_cl: `tensor` does not match the model (CalcScalCls vs CalcTensCls)"; return CB_ERR_UNSUPPORTED_PARAMS; }
         if (!d->d_delta || D.n_q <= 0) { ctx->err = "cb_cl: no transfer functions (call cb_project first)"; return CB_ERR_UNSUPPORTED_PARAMS; }
         size_t nc = (size_t)n_l * d->n_cl;
@@ -556,6 +580,51 @@ int cb_cl_array(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const double* c
     for (int m = 0; m < n_models; m++)
         if (iCl_Array && iCl_Array[m])
             CK(cudaMemcpyAsync(iCl_Array[m], dm[m]->d_icl_array, sizeof(double) * (size_t)n_l * dm[m]->h.n_src * dm[m]->h.n_src, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int cb_cl_windows(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const double* const* pows, const double* const* limber_pows,
+                  double* const* iCl, double* const* iCl_Array) {
+    if (!ctx) return CB_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    const int n_l = ctx->bess.n_l_all;
+    std::vector<double*> limb(n_models), lpow(n_models), outs(2 * (size_t)n_models);
+    int max_nw = 0;
+    for (int m = 0; m < n_models; m++) {
+        cb_dmodel* d = dm[m];
+        DModel& D = d->h;
+        if (D.is_tensor || D.n_src < 3) { ctx->err = "cb_cl_windows: scalar models with n_src >= 3 only"; return CB_ERR_UNSUPPORTED_PARAMS; }
+        if (!d->d_delta || D.n_q <= 0 || !d->d_dd) { ctx->err = "cb_cl_windows: no transfer functions (call cb_project first)"; return CB_ERR_UNSUPPORTED_PARAMS; }
+        const int nw = D.num_redshiftwindows, n = 3 + nw;
+        max_nw = std::max(max_nw, nw);
+        if (int e = ensure(ctx, &d->d_limb, &d->cap_limb, (size_t)(1 + nw) * n_l * D.n_tau)) return e;
+        if (int e = ensure(ctx, &d->d_lpow, &d->cap_lpow, (size_t)n_l * D.n_tau)) return e;
+        if (int e = ensure(ctx, &d->d_icl_w, &d->cap_icl_w, (size_t)n_l * 6)) return e;
+        const size_t nc = (size_t)n_l * n * n;
+        if (nc > d->cap_icl_array) { if (d->d_icl_array) dev_free(ctx, d->d_icl_array); d->d_icl_array = nullptr; d->cap_icl_array = 0; }
+        if (int e = ensure(ctx, &d->d_icl_array, &d->cap_icl_array, nc)) return e;
+        if (pows && pows[m]) CK(cudaMemcpyAsync(d->d_pows, pows[m], sizeof(double) * D.n_q, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d->d_lpow, limber_pows[m], sizeof(double) * (size_t)n_l * D.n_tau, cudaMemcpyHostToDevice, ctx->stream));
+        limb[m] = d->d_limb; lpow[m] = d->d_lpow; outs[2 * m] = d->d_icl_w; outs[2 * m + 1] = d->d_icl_array;
+    }
+    if (int e = push_models(ctx, n_models, dm)) return e;
+    if (int e = ensure(ctx, &ctx->d_scratch_ptrs, &ctx->cap_scr, 4 * (size_t)n_models)) return e;
+    double** dp = ctx->d_scratch_ptrs;
+    CK(cudaMemcpyAsync(dp, limb.data(), sizeof(double*) * n_models, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dp + n_models, lpow.data(), sizeof(double*) * n_models, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dp + 2 * n_models, outs.data(), sizeof(double*) * 2 * n_models, cudaMemcpyHostToDevice, ctx->stream));
+    cb_limber_launch(ctx->d_models, n_models, ctx->bess, max_nw, dp, ctx->stream);
+    CK(cudaGetLastError());
+    cb_cl_windows_launch(ctx->d_models, n_models, ctx->bess, dp, dp + n_models, dp + 2 * n_models, ctx->stream);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+    for (int m = 0; m < n_models; m++) {
+        const int n = 3 + dm[m]->h.num_redshiftwindows;
+        if (iCl && iCl[m]) CK(cudaMemcpyAsync(iCl[m], dm[m]->d_icl_w, sizeof(double) * (size_t)n_l * 6, cudaMemcpyDeviceToHost, ctx->stream));
+        if (iCl_Array && iCl_Array[m])
+            CK(cudaMemcpyAsync(iCl_Array[m], dm[m]->d_icl_array, sizeof(double) * (size_t)n_l * n * n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

@@ -58,6 +58,12 @@ struct DModel {
     // cmbmain scalars
     double max_etak_scalar, max_etak_tensor;
     int WantLateTime, n_src;
+    // source windows (device pointers inside each cb_window), cmbmain/equations window code
+    int num_redshiftwindows, num_extra_redshiftwindows, Want_CMB_lensing, max_bessels_l_index;
+    cb_window windows[CB_MAX_WINDOWS];
+    cb_source_terms SourceTerms;
+    double tau_start_redshiftwindows, qmax;
+    int Limber_l_min[3 + CB_MAX_WINDOWS];
     // ---- per-call buffers owned by the cb_dmodel (device) ----
     int n_k;                 // source modes of the last cb_evolve
     const double* q_src;     // [n_k]
@@ -85,7 +91,7 @@ struct DModeItem {
 };
 
 struct DBessel {
-    int n_l, nx, n_regions;
+    int n_l, n_l_all, nx, n_regions;   // n_l: l samples with Bessel tables; n_l_all: all sampled l (Limber-only above n_l)
     const int* l;
     const double* x;
     const double* horner;  // (4, nx-1, n_l)

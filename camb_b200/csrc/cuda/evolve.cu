@@ -28,6 +28,13 @@
 #include "thermo.cuh"
 
 #define FULL 0xffffffffu
+// Cold per-mode / per-segment control code (mode fetch, layout switches, schedule): kept out of line so the hot
+// stage loop around `derivs` stays small in the instruction cache and does not carry their registers.
+#ifdef CB_COLD_NOINLINE
+#define CB_COLD __noinline__
+#else
+#define CB_COLD
+#endif
 
 namespace {
 
@@ -56,6 +63,10 @@ struct MHot {
     double* LinearSrc;
     float* TransferData;
     int n_k;
+    const cb_window* windows;   // source windows (device copies inside the global DModel); null without windows
+    cb_source_terms terms;
+    double tau_start_redshiftwindows;
+    int nwin;
     int nthermo, de_is_cc, de_model, de_nperturb, Num_Nu_massive, Nu_mass_eigenstates, nqmax, n_src;
     int DoLateRadTruncation, AccuracyTarget, WantTransfer, transfer_high_precision, WantCls, WantLateTime, n_tau, num_transfer_redshifts;
 };
@@ -78,6 +89,8 @@ __device__ inline void fill_hot(MHot& H, const DModel& M) {
     H.transfer_high_precision = M.transfer_high_precision; H.WantCls = M.WantCls; H.WantLateTime = M.WantLateTime; H.n_tau = M.n_tau;
     H.num_transfer_redshifts = M.num_transfer_redshifts;
     H.LinearSrc = M.LinearSrc; H.TransferData = M.TransferData; H.n_k = M.n_k;
+    H.nwin = M.num_redshiftwindows; H.windows = M.num_redshiftwindows > 0 ? M.windows : nullptr; H.terms = M.SourceTerms;
+    H.tau_start_redshiftwindows = M.tau_start_redshiftwindows;
 }
 
 __host__ __device__ inline int d_nint(double x) { return (int)llround(x); }
@@ -92,7 +105,7 @@ __host__ __device__ inline double nu_l_accuracy_boost(const DModel& M, double nu
 }
 
 // SetupScalarArrayIndices, equations.f90:585-701.  Returns maxeq.
-__host__ __device__ int setup_indices(const DModel& M, EVs& E) {
+CB_COLD __host__ __device__ int setup_indices(const DModel& M, EVs& E) {
     int neq = 4, maxeq = 4;
     if (!E.no_phot) {
         E.g_ix = 5;
@@ -138,7 +151,7 @@ __host__ __device__ int setup_indices(const DModel& M, EVs& E) {
 }
 
 // GetNumEqns, equations.f90:860-1070 (scalars, flat)
-__host__ __device__ void get_num_eqns(const DModel& M, EVs& E) {
+CB_COLD __host__ __device__ void get_num_eqns(const DModel& M, EVs& E) {
     double lab = M.lAccuracyBoost, max_nu_mass = 0;
     int min_lmaxnr = d_imax(3, d_nint(3 * lab));
     if (M.Num_Nu_massive == 0) E.lmaxnu = 0;
@@ -216,7 +229,7 @@ __host__ __device__ void get_num_eqns(const DModel& M, EVs& E) {
 }
 
 // CopyScalarVariableArray, equations.f90:703-791.  Executed by lane 0 (rare: ~10 per mode).
-__device__ void copy_scalar_array(const DModel& M, const double* y, double* yout, const EVs& E, const EVs& O) {
+CB_COLD __device__ void copy_scalar_array(const DModel& M, const double* y, double* yout, const EVs& E, const EVs& O) {
 #define Y(i) y[(i)-1]
 #define YO(i) yout[(i)-1]
     int lmax, l;
@@ -310,7 +323,8 @@ __device__ void nu_integrate_L012(const MT& M, const EVs& E, const double* ay, d
 template <int G, bool LEAN>
 __device__ __forceinline__ void derivs(const MHot& M_, EVs& E, const double* __restrict__ denlk, const double* __restrict__ denlk2,
                                        const double* __restrict__ polfack, double tau, const double* ay, double* ayp, int lane,
-                                       unsigned gm, int out_mode, const double* th, double* src_out, float* tr_out) {
+                                       unsigned gm, int out_mode, const double* th, double* src_out, float* tr_out, int q_ix = 0,
+                                       int jstep = 0) {
     const MHot& M = M_;
     const bool de_is_cc = LEAN ? true : (M.de_is_cc != 0);
     const double k = E.k, k2 = E.k2;
@@ -671,6 +685,44 @@ __device__ __forceinline__ void derivs(const MHot& M_, EVs& E, const double* __r
                 if (M.n_src > 2)
                     src_out[2] = (tau > M.tau_maxvis && tau0 - tau > 0.1) ? -2 * phi * (tau - M.tau_maxvis) / ((tau0 - M.tau_maxvis) * ang_dist) : 0.0;
             }
+            // output_window_sources, equations.f90:1474-1737 (lensing and number-count windows).  Written straight to
+            // LinearSrc(q_ix, 4.., jstep) by lane 0; models with windows never run the LEAN variant.
+            if (!LEAN && M.nwin > 0 && lane == 0) {
+                const int nw = M.nwin, jj = jstep - 1;
+                double* S = M.LinearSrc + q_ix + (size_t)M.n_k * ((size_t)M.n_src * jj);
+                for (int s_ix = 3; s_ix < M.n_src; s_ix++) S[(size_t)M.n_k * s_ix] = 0;
+                if (tau > M.tau_start_redshiftwindows) {
+                    const cb_source_terms& T = M.terms;
+                    for (int w_ix = 1; w_ix <= nw; w_ix++) {
+                        const cb_window& w = M.windows[w_ix - 1];
+                        if (w.kind == CB_WINDOW_LENSING) {
+                            S[(size_t)M.n_k * (3 + w_ix - 1)] = -2 * phi * __ldg(&w.win_lens[jj]);
+                        } else if (w.kind == CB_WINDOW_COUNTS) {
+                            const double wing = __ldg(&w.wing[jj]), wing2 = __ldg(&w.wing2[jj]), dwing2 = __ldg(&w.dwing2[jj]),
+                                         ddwing2 = __ldg(&w.ddwing2[jj]), wingtau = __ldg(&w.wingtau[jj]), dwingtau = __ldg(&w.dwingtau[jj]);
+                            double c_density = 0, c_redshift = 0, c_radial = 0, c_timedelay = 0, c_ISW = 0, c_potential = 0, c_velocity = 0;
+                            if (T.counts_density) c_density = wing * (clxc * w.bias + (__ldg(&w.comoving_density_ev[jj]) - 3 * adotoa) * sigma / k);
+                            if (T.counts_redshift)
+                                c_redshift = ((4.0 * (adotoa * adotoa) + gpres + grho / 3.0) / k * wing2 + (-4.0 * dwing2 * adotoa + ddwing2) / k) * sigma +
+                                             (-etak / adotoa * k / 3.0 - dgrho / adotoa / 6.0 +
+                                              (etak / adotoa * k / 3.0 + dgrho / adotoa / 6.0 + (dgq / 2.0 - 2.0 * etak * adotoa) / k) / 1.0) * wing2 +
+                                             2.0 * dwing2 * etak / k / 1.0;
+                            if (tau0 - tau > 0.1 && T.counts_radial) {
+                                const double chi = tau0 - tau;
+                                c_radial = (1 - 2.5 * w.dlog10Ndm) * ((-4.0 * wing2 / chi * adotoa - 2.0 * (-dwing2 * chi - wing2) / (chi * chi)) / k * sigma +
+                                                                       2.0 * wing2 * etak / chi / k / 1.0);
+                            }
+                            if (T.counts_timedelay) c_timedelay = 2 * (1 - 2.5 * w.dlog10Ndm) * __ldg(&w.winV[jj]) * 2 * phi;
+                            if (T.counts_ISW) c_ISW = __ldg(&w.winF[jj]) * 2 * phidot;
+                            if (T.counts_potential) c_potential = (phidot / adotoa + phi + (5 * w.dlog10Ndm - 2) * phi) * wing + phi * wingtau;
+                            if (T.counts_velocity) c_velocity = (-2.0 * wingtau * adotoa + dwingtau) / k * sigma + wingtau * etak / k / 1.0 - c_radial;
+                            double v = c_radial + c_density + c_redshift + c_timedelay + c_potential + c_ISW + c_velocity;
+                            S[(size_t)M.n_k * (3 + w_ix - 1)] = v / w.Fq;
+                            if (T.counts_lensing) S[(size_t)M.n_k * (3 + w.mag_index + nw - 1)] = phi * __ldg(&w.win_lens[jj]) * (2 - 5 * w.dlog10Ndm);
+                        }
+                    }
+                }
+            }
         }
         __syncwarp(gm);
     }
@@ -712,7 +764,7 @@ __device__ __forceinline__ int next_nu_nq(const MT& M, int nq) {
 }
 
 // initial, equations.f90:1891-2112 (adiabatic and the four isocurvature modes, initial_vector; flat); lane 0
-__device__ void initial_conditions(const DModel& M, EVs& E, double* denlk, double* denlk2, double* polfack, double* y, double tau,
+CB_COLD __device__ void initial_conditions(const DModel& M, EVs& E, double* denlk, double* denlk2, double* polfack, double* y, double tau,
                                    const DModeItem& it) {
     const double k = E.q;
     E.k = k; E.k2 = E.q * E.q; E.kinv = 1.0 / k; E.k2inv = 1.0 / E.k2;
@@ -826,7 +878,7 @@ struct Vecs {
 // The switch logic of GaugeInterface_EvolveScal (equations.f90:261-460): computes the next switch
 // time into C (plan) ...
 template <class MT>
-__device__ void plan_switches(const MT& M, const EVs& E, Ctl& C) {
+CB_COLD __device__ void plan_switches(const MT& M, const EVs& E, Ctl& C) {
     const int n_eig = M.Num_Nu_massive != 0 ? M.Nu_mass_eigenstates : 0;
     const double noSwitch = M.tau0 + 1;
     const double switchBoost = M.AccuracyBoost * M.TimeSwitchBoost;
@@ -852,7 +904,7 @@ __device__ void plan_switches(const MT& M, const EVs& E, Ctl& C) {
 
 // ... and applies the switch that fires at C.next_switch (same if-chain order as the reference,
 // equations.f90:339-441).  Lane 0 of the group; layout changes go through the scratch slots.
-__device__ void apply_switch(const DModel& M, EVs& E, Ctl& C, const Vecs& V) {
+CB_COLD __device__ void apply_switch(const DModel& M, EVs& E, Ctl& C, const Vecs& V) {
     const int n_eig = M.Num_Nu_massive != 0 ? M.Nu_mass_eigenstates : 0;
     const double noSwitch = M.tau0 + 1, next_switch = C.next_switch, tau = C.tau;
     double* y = V.y;
@@ -956,7 +1008,7 @@ __device__ __forceinline__ void dp45_begin(Ctl& C, double xend) {
 // attempt (PH_STEP), an output evaluation (PH_OUTPUT) or there is no work left (PH_EXIT).
 // CalcScalarSources cmbmain.f90:998-1074 / GetTransfer :1167-1188 unrolled into a state machine;
 // rows skipped by the high-k*tau early-out stay zero (LinearSrc is cleared before the launch).
-__device__ void advance_schedule(const DModel* __restrict__ models, const DModeItem* __restrict__ items, int n_items,
+CB_COLD __device__ void advance_schedule(const DModel* __restrict__ models, const DModeItem* __restrict__ items, int n_items,
                                  unsigned int* counter, int* error_flag, EVs& E, Ctl& C, MHot& H, double* denlk, double* denlk2,
                                  double* polfack, const Vecs& V) {
     for (;;) {
@@ -1296,7 +1348,7 @@ cb_evolve_kernel(const DModel* __restrict__ models, const DModeItem* __restrict_
             double srcs[3];
             float* tr = nullptr;
             if (out_mode == OUT_TR) tr = H.TransferData + (size_t)13 * ((size_t)C.q_ix + (size_t)H.n_k * (C.itf - 1));
-            derivs<G, LEAN>(H, E, denlk, denlk2, polfack, tev, in, out, lane, gm, out_mode, th, out_mode == OUT_SRC ? srcs : nullptr, tr);
+            derivs<G, LEAN>(H, E, denlk, denlk2, polfack, tev, in, out, lane, gm, out_mode, th, out_mode == OUT_SRC ? srcs : nullptr, tr, LEAN ? 0 : C.q_ix, LEAN ? 0 : C.j);
             if (t == 0) {
                 if (lane == 0) {
                     C.nderivs++;
@@ -1304,7 +1356,8 @@ cb_evolve_kernel(const DModel* __restrict__ models, const DModeItem* __restrict_
                     else {
                         if (out_mode == OUT_SRC) {
                             double* S = H.LinearSrc;   // sources go straight to LinearSrc(q_ix, :, j): stride n_k between sources
-                            for (int i = 0; i < H.n_src; i++) S[C.q_ix + (size_t)H.n_k * (i + (size_t)H.n_src * (C.j - 1))] = srcs[i];
+                            const int n3 = H.n_src < 3 ? H.n_src : 3;   // window sources (4..n_src) were written inside derivs
+                            for (int i = 0; i < n3; i++) S[C.q_ix + (size_t)H.n_k * (i + (size_t)H.n_src * (C.j - 1))] = srcs[i];
                         } else C.itf++;
                         C.stage = C.next_stage;
                         C.phase = PH_NEXT_GOAL;

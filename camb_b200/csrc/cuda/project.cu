@@ -161,16 +161,36 @@ cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
     else llmax = (int)llround(q * (tau0 + 6.0 * 3.1415926535897932384626433832795 / q));
     const double BessIntBoost = M.AccuracyBoost * M.BessIntBoost;
     double* Dout = M.Delta + (size_t)nsrc * n_l * iq;
+    // source-window tails, cmbmain.f90:1658-1676
+    const int nwin_src = tensors ? 0 : M.num_redshiftwindows;
+    bool has_narrow_source_window = false;
+    double source_window_tail_lmax = 0;
+    int nwin_ix = ntime + 1;
+    if (nwin_src > 0) {
+        source_window_tail_lmax = 20;
+        for (int w = 0; w < nwin_src; w++) {
+            const cb_window& win = M.windows[w];
+            if (win.kind != CB_WINDOW_LENSING && win.chi0 > 0 && win.sigma_tau > 0) {
+                source_window_tail_lmax = fmax(source_window_tail_lmax, fmin(160.0, fmax(20.0, 4.0 * win.chi0 / win.sigma_tau)));
+                if (win.sigma_tau < 0.02 * win.chi0) has_narrow_source_window = true;
+            }
+        }
+        nwin_ix = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, M.tau_start_redshiftwindows);
+    }
     for (int j = 1 + warp; j <= n_l; j += nwarp) {
         const int l = B.l[j - 1];
         double s0 = 0, s1 = 0, s2 = 0;
         bool active = l <= llmax;
         double tmin = 0, tmax = 0;
+        double BessIntBoostL = BessIntBoost;
+        if (has_narrow_source_window) BessIntBoostL = fmax(BessIntBoostL, 20.0 / l);
         if (active) {
             const double xlim = fmax(0.0, l - 4.2 * pow((double)l, 1.0 / 3.0));
-            const double xlmax1 = 80 * l * BessIntBoost;
+            double xlmax1 = 80 * l * BessIntBoostL;
+            if (source_window_tail_lmax > 0) xlmax1 = xlmax1 * fmax(1.0, fmin(8.0, source_window_tail_lmax / l));
             tmin = fmax(TimePoints[1], tau0 - xlmax1 / q);
             tmax = tau0 - xlim / q;
+            if (!M.Want_CMB && !M.Want_CMB_lensing) tmin = fmax(tmin, M.tau_start_redshiftwindows);
             if (tmax < TimePoints[1]) active = false;
         }
         if (active) {
@@ -180,7 +200,7 @@ cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
             if (n2 > SourceSteps) n2 = SourceSteps;
             bool DoInt = true;
             if (nsrc > 2) {
-                const double qmax_int = (l > 850 ? l : 850) * 3 * BessIntBoost / tau0 * 1.2;
+                const double qmax_int = (l > 850 ? l : 850) * 3 * BessIntBoostL / tau0 * 1.2;
                 DoInt = tensors || q < qmax_int;   // DoInt = .not. CP%WantScalars .or. IV%q < qmax_int
             }
             if (DoInt) {
@@ -215,6 +235,192 @@ cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
             o[0] = s0; o[1] = s1;
             if (nsrc > 2) o[2] = s2;
         }
+        if (nsrc > 3) {   // window sources, cmbmain.f90:1763-1787 (n >= nwin) and :1834-1857 (CMB needs no integral, windows do)
+            int na = 0, nb = -1;
+            if (active) {
+                const int n1 = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, tmin);
+                int n2 = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, tmax);
+                if (n2 > SourceSteps) n2 = SourceSteps;
+                const double qmax_int = (l > 850 ? l : 850) * 3 * BessIntBoostL / tau0 * 1.2;
+                if (q < qmax_int) { na = n1 > nwin_ix ? n1 : nwin_ix; nb = n2; }
+                else {
+                    bool any = M.num_extra_redshiftwindows > 0;   // Limber_l_min of the extra sources is never set
+                    for (int s = 3; s < 3 + nwin_src; s++) any = any || M.Limber_l_min[s] == 0 || M.Limber_l_min[s] > j;
+                    if (any) { na = nwin_ix; nb = n2; }
+                }
+            }
+            const double* H = B.horner + (size_t)4 * (B.nx - 1) * (j - 1);
+            for (int s = 3; s < nsrc; s++) {
+                double acc = 0;
+                const double* Sq = Source_q + (size_t)s * max_n_tau;
+                for (int n = na + lane; n <= nb; n += 32) {
+                    const double a2 = left_weight[n - 1];
+                    const double2* h = reinterpret_cast<const double2*>(H + 4 * (size_t)(bes_index[n - 1] - 1));
+                    const double2 h0 = __ldg(h), h1 = __ldg(h + 1);
+                    double J_l = h0.x + a2 * (h0.y + a2 * (h1.x + a2 * h1.y));
+                    J_l = J_l * dtau_s[n - 1];
+                    acc = acc + Sq[n - 1] * J_l;
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) Dout[(size_t)nsrc * (j - 1) + s] = acc;
+            }
+        }
+    }
+}
+
+// GetLimberTransfers, cmbmain.f90:472-536: LimbSrc[(i, ell, n)] = sqrt(chi dtau) S_{3+i}(k = (l+1/2)/chi, tau_n), n fastest.
+// grid = (n_l_all, 1 + nw, n_models); threads over n.  limb[m] = (n_tau, n_l_all, 1 + nw), zero outside the Limber range.
+__global__ void cb_limber_kernel(const DModel* __restrict__ models, DBessel B, double* const* __restrict__ limb) {
+    const DModel& M = models[blockIdx.z];
+    const int ell = blockIdx.x + 1, i = blockIdx.y, nw = M.num_redshiftwindows, n_l = B.n_l_all, ntime = M.n_tau, nsrc = M.n_src, n_k = M.n_k;
+    if (i > nw) return;
+    double* out = limb[blockIdx.z] + ((size_t)i * n_l + (ell - 1)) * ntime;
+    const int s_ix = 3 + i, lmin = M.Limber_l_min[s_ix - 1];
+    int n1 = 1, n2 = 0, s_ix_lens = 0;
+    if (lmin != 0 && ell >= lmin) {
+        if (i == 0) { n1 = ranges_index_of(M.tau_regions, M.n_tau_regions, ntime, M.tau_highest, M.tau_maxvis); n2 = ntime - 1; }
+        else {
+            const cb_window& W = M.windows[i - 1];
+            n1 = ranges_index_of(M.tau_regions, M.n_tau_regions, ntime, M.tau_highest, W.tau_start);
+            if (W.kind == CB_WINDOW_LENSING || (W.kind == CB_WINDOW_COUNTS && M.SourceTerms.counts_lensing)) n2 = ntime - 1;
+            else n2 = min(ntime - 1, ranges_index_of(M.tau_regions, M.n_tau_regions, ntime, M.tau_highest, W.tau_end));
+            if (W.kind == CB_WINDOW_COUNTS && M.SourceTerms.counts_lensing) s_ix_lens = 3 + W.mag_index + nw;
+        }
+    }
+    const double reall = (double)B.l[ell - 1];
+    const double* qs = M.q_src;
+    for (int n = 1 + threadIdx.x; n <= ntime; n += blockDim.x) {
+        double v = 0;
+        if (n >= n1 && n <= n2) {
+            const double chi = M.tau0 - M.tau[n - 1], k = (reall + 0.5) / chi;
+            if (k <= M.qmax) {
+                int klo;
+                if (k <= qs[0]) klo = 1;
+                else if (k >= qs[n_k - 1]) klo = n_k - 1;
+                else {
+                    int lo = 1, hi = n_k;
+                    while (hi - lo > 1) { const int mid = (lo + hi) / 2; if (k >= qs[mid - 1]) lo = mid; else hi = mid; }
+                    klo = lo;
+                }
+                const int khi = klo + 1;
+                const double ho = qs[khi - 1] - qs[klo - 1], a0 = (qs[khi - 1] - k) / ho, b0 = (k - qs[klo - 1]) / ho, ho2o6 = ho * ho / 6;
+                const double a03 = (a0 * a0 * a0 - a0), b03 = (b0 * b0 * b0 - b0), w = sqrt(chi * M.dtau[n - 1]);
+                size_t off = (size_t)n_k * ((s_ix - 1) + (size_t)nsrc * (n - 1));
+                v = w * (a0 * M.LinearSrc[off + klo - 1] + b0 * M.LinearSrc[off + khi - 1] + (a03 * M.ddSrc[off + klo - 1] + b03 * M.ddSrc[off + khi - 1]) * ho2o6);
+                if (s_ix_lens > 0) {
+                    off = (size_t)n_k * ((s_ix_lens - 1) + (size_t)nsrc * (n - 1));
+                    v = v + reall * (reall + 1) * w *
+                                (a0 * M.LinearSrc[off + klo - 1] + b0 * M.LinearSrc[off + khi - 1] + (a03 * M.ddSrc[off + klo - 1] + b03 * M.ddSrc[off + khi - 1]) * ho2o6);
+                }
+            }
+        }
+        out[n - 1] = v;
+    }
+}
+
+// ClTransferToCl with source windows: CalcLimberScalCls (cmbmain.f90:358-417) + CalcScalCls (:3179-3343).
+// grid = (n_l_all, n_models), one CTA per l.  outs[2m] = iCl (n_l_all, 6), outs[2m+1] = iCl_Array (n_l_all, n, n), n = 3 + nw.
+// limb[m] as written by cb_limber_kernel; lpow[m] = P_R((l+1/2)/(tau0 - tau_n)) (n_tau, n_l_all).
+__global__ void __launch_bounds__(256) cb_cl_windows_kernel(const DModel* __restrict__ models, DBessel B, double* const* __restrict__ limb,
+                                                            double* const* __restrict__ lpow, double* const* __restrict__ outs) {
+    const DModel& M = models[blockIdx.y];
+    const int j = blockIdx.x + 1, n_lb = B.n_l, n_l = B.n_l_all, nw = M.num_redshiftwindows, n = 3 + nw, nsrc = M.n_src, n_q = M.n_q, ntime = M.n_tau;
+    const double* L = limb[blockIdx.y];
+    const double* P = lpow[blockIdx.y] + (size_t)(j - 1) * ntime;
+    double* iCl = outs[2 * blockIdx.y];
+    double* Arr = outs[2 * blockIdx.y + 1];
+    __shared__ double red[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto block_sum = [&](double c) {   // fixed-order: deterministic
+        c = warp_sum(c);
+        __syncthreads();
+        if (lane == 0) red[warp] = c;
+        __syncthreads();
+        double v = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += red[w];
+        return v;
+    };
+    const double ell = (double)B.l[j - 1], pi = 3.1415926535897932384626433832795, fourpi = 4 * pi;
+    const double ctnorm = (ell * ell - 1) * (ell + 2) * ell, dbletmp = (ell * (ell + 1)) / (2 * pi) * fourpi;
+    const cb_source_terms& T = M.SourceTerms;
+    auto fac_of = [&](int w) { return w == 1 ? sqrt(ctnorm) : (w == 2 ? sqrt(ell * (ell + 1) * M.Alens) : 1.0); };
+    auto delta_of = [&](const double* D, int w_ix) {   // w_ix 1-based source index
+        double d = D[w_ix - 1];
+        if (w_ix > 3) {
+            const cb_window& win = M.windows[w_ix - 4];
+            if (win.kind == CB_WINDOW_LENSING) d = d / 2 * ell * (ell + 1);
+            if (win.kind == CB_WINDOW_COUNTS && T.counts_lensing) d = d + ell * (ell + 1) * D[3 + win.mag_index + nw - 1];
+        }
+        return d;
+    };
+    double cphi_limber = 0;
+    for (int w_ix = 1; w_ix <= n; w_ix++)
+        for (int w_ix2 = w_ix; w_ix2 <= n; w_ix2++) {
+            double val = 0;
+            const int la = M.Limber_l_min[w_ix - 1], lb = M.Limber_l_min[w_ix2 - 1];
+            const bool both_limber = w_ix >= 3 && w_ix2 >= 3 && la != 0 && lb != 0 && j >= la && j >= lb;
+            const int winmin = T.limber_phi_lmin > 0 ? 0 : 1;
+            if (both_limber && w_ix - 3 >= winmin) {   // CalcLimberScalCls
+                const int i1 = w_ix - 3, i2 = w_ix2 - 3;
+                int n1a, n2a, n1b, n2b;
+                {   // n1, n2 of both sources (same rules as cb_limber_kernel)
+                    auto range = [&](int i, int& n1, int& n2) {
+                        if (i == 0) { n1 = ranges_index_of(M.tau_regions, M.n_tau_regions, ntime, M.tau_highest, M.tau_maxvis); n2 = ntime - 1; }
+                        else {
+                            const cb_window& W = M.windows[i - 1];
+                            n1 = ranges_index_of(M.tau_regions, M.n_tau_regions, ntime, M.tau_highest, W.tau_start);
+                            if (W.kind == CB_WINDOW_LENSING || (W.kind == CB_WINDOW_COUNTS && T.counts_lensing)) n2 = ntime - 1;
+                            else n2 = min(ntime - 1, ranges_index_of(M.tau_regions, M.n_tau_regions, ntime, M.tau_highest, W.tau_end));
+                        }
+                    };
+                    range(i1, n1a, n2a); range(i2, n1b, n2b);
+                }
+                const int na = max(n1a, n1b), nb = min(n2a, n2b);
+                const double* S1 = L + ((size_t)i1 * n_l + (j - 1)) * ntime;
+                const double* S2 = L + ((size_t)i2 * n_l + (j - 1)) * ntime;
+                double c = 0;
+                for (int t = na + threadIdx.x; t <= nb; t += blockDim.x) c += S1[t - 1] * S2[t - 1] * P[t - 1];
+                c = block_sum(c);
+                double fac = (2 * pi * pi) / fourpi / ((ell + 0.5) * (ell + 0.5) * (ell + 0.5));
+                if (i2 >= 1 && M.windows[i2 - 1].kind == CB_WINDOW_LENSING) fac = fac / 2 * ell * (ell + 1);
+                if (i1 >= 1 && M.windows[i1 - 1].kind == CB_WINDOW_LENSING) fac = fac / 2 * ell * (ell + 1);
+                val = c * fac;
+                if (i1 == 0 && i2 == 0) cphi_limber = val;
+            }
+            if (j <= n_lb && !both_limber) {   // CalcScalCls accumulation over q
+                double c = 0;
+                for (int iq = threadIdx.x; iq < n_q; iq += blockDim.x) {
+                    const double dlnk = M.dq_int[iq] / M.q_int[iq], ap = M.pows[iq];
+                    const double* D = M.Delta + (size_t)nsrc * ((j - 1) + (size_t)n_lb * iq);
+                    c += delta_of(D, w_ix) * delta_of(D, w_ix2) * ap * dlnk;
+                }
+                val = val + block_sum(c);
+            }
+            if (threadIdx.x == 0) {
+                const double v = val * fac_of(w_ix - 1) * fac_of(w_ix2 - 1) * dbletmp;
+                Arr[(j - 1) + (size_t)n_l * ((w_ix - 1) + (size_t)n * (w_ix2 - 1))] = v;
+                Arr[(j - 1) + (size_t)n_l * ((w_ix2 - 1) + (size_t)n * (w_ix - 1))] = v;
+            }
+        }
+    // iCl_scalar
+    double c[6] = {0, 0, 0, 0, 0, 0};
+    const bool phi_q = T.limber_phi_lmin == 0 || M.Limber_l_min[2] == 0 || j < M.Limber_l_min[2];
+    if (j <= n_lb)
+        for (int iq = threadIdx.x; iq < n_q; iq += blockDim.x) {
+            const double dlnk = M.dq_int[iq] / M.q_int[iq], ap = M.pows[iq];
+            const double* D = M.Delta + (size_t)nsrc * ((j - 1) + (size_t)n_lb * iq);
+            c[0] += ap * (D[0] * D[0]) * dlnk; c[1] += ap * (D[1] * D[1]) * dlnk; c[2] += ap * D[0] * D[1] * dlnk;
+            if (phi_q) { c[3] += ap * (D[2] * D[2]) * dlnk; c[4] += ap * D[2] * D[0] * dlnk; c[5] += ap * D[2] * D[1] * dlnk; }
+        }
+    for (int t = 0; t < 6; t++) c[t] = block_sum(c[t]);
+    if (threadIdx.x == 0) {
+        double* o = iCl + (j - 1);
+        o[0] = c[0] * dbletmp;
+        o[(size_t)n_l * 1] = c[1] * dbletmp * ctnorm;
+        o[(size_t)n_l * 2] = c[2] * dbletmp * sqrt(ctnorm);
+        o[(size_t)n_l * 3] = M.Alens * (cphi_limber + c[3]) * fourpi * (ell * ell * ell * ell);
+        o[(size_t)n_l * 4] = sqrt(M.Alens) * c[4] * fourpi * (ell * ell * ell);
+        o[(size_t)n_l * 5] = sqrt(M.Alens) * c[5] * fourpi * (ell * ell * ell) * sqrt(ctnorm);
     }
 }
 
@@ -320,6 +526,17 @@ __global__ void __launch_bounds__(256) cb_cl_array_kernel(const DModel* __restri
 }
 
 // ---------------- launch wrappers (called from cabi.cu) ----------------
+void cb_limber_launch(const DModel* d_models, int n_models, const DBessel& B, int max_nw, double* const* d_limb, cudaStream_t st) {
+    dim3 grid(B.n_l_all, 1 + max_nw, n_models);
+    cb_limber_kernel<<<grid, 256, 0, st>>>(d_models, B, d_limb);
+}
+
+void cb_cl_windows_launch(const DModel* d_models, int n_models, const DBessel& B, double* const* d_limb, double* const* d_lpow,
+                          double* const* d_outs, cudaStream_t st) {
+    dim3 grid(B.n_l_all, n_models);
+    cb_cl_windows_kernel<<<grid, 256, 0, st>>>(d_models, B, d_limb, d_lpow, d_outs);
+}
+
 void cb_cl_array_launch(const DModel* d_models, int n_models, const DBessel& B, double* const* d_out, cudaStream_t st) {
     dim3 grid(B.n_l, n_models);
     cb_cl_array_kernel<<<grid, 256, 0, st>>>(d_models, B, d_out);

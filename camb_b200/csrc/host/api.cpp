@@ -36,6 +36,11 @@ void cb_params_set_defaults(cb_params* p) {
     p->rosenbrock_handoff_xH = 0.976; p->rosenbrock_tol = 3e-4;
     p->Scalar_initial_condition = 1; p->DoLateRadTruncation = 1; p->MassiveNuMethod = 3;
     p->AccuracyTarget = 1; p->use_cl_spline_template = 1; p->min_l_logl_sampling = 5000; p->Alens = 1;
+    // SourceTermParams defaults, SourceWindows.f90:46-67
+    p->SourceTerms.limber_windows = 1; p->SourceTerms.limber_phi_lmin = 100;
+    p->SourceTerms.counts_density = 1; p->SourceTerms.counts_redshift = 1; p->SourceTerms.counts_lensing = 0;
+    p->SourceTerms.counts_velocity = 1; p->SourceTerms.counts_radial = 0; p->SourceTerms.counts_timedelay = 1;
+    p->SourceTerms.counts_ISW = 1; p->SourceTerms.counts_potential = 1; p->SourceTerms.counts_evolve = 0;
     cb_accuracy& a = p->Accuracy;
     a.AccuracyBoost = a.lSampleBoost = a.lAccuracyBoost = 1;
     a.AccuratePolarization = 1; a.AccurateBB = 0; a.AccurateReionization = 1;
@@ -67,7 +72,19 @@ cbh_state* cbh_create(const cb_params* pin, int* err, char* errmsg, int errmsg_l
             if (S.CP.WantCls) {
                 S.SetkValuesForSources();
                 S.lSamplesInit(S.CP.Min_l, S.maximum_l);
+                S.LimberSetup();
                 S.SetkValuesForInt();
+                S.windows_c.clear();
+                for (const RedWin& W : S.Redshift_W) {
+                    cb_window w;
+                    std::memset(&w, 0, sizeof(w));
+                    w.kind = W.kind; w.mag_index = W.mag_index; w.Fq = W.Fq; w.dlog10Ndm = W.dlog10Ndm; w.bias = W.bias;
+                    w.tau_start = W.tau_start; w.tau_end = W.tau_end; w.chi0 = W.chi0; w.sigma_tau = W.sigma_tau;
+                    w.wing = W.wing.data(); w.wing2 = W.wing2.data(); w.dwing2 = W.dwing2.data(); w.ddwing2 = W.ddwing2.data();
+                    w.wingtau = W.wingtau.data(); w.dwingtau = W.dwingtau.data(); w.winV = W.winV.data(); w.winF = W.winF.data();
+                    w.win_lens = W.win_lens.data(); w.comoving_density_ev = W.comoving_density_ev.data();
+                    S.windows_c.push_back(w);
+                }
             }
             if (S.CP.WantTransfer) S.InitTransfer();
             if (S.CP.WantCls) S.PerModeLookups(S.Evolve_q.points, st->tight_A, st->nuapp_A);
@@ -111,9 +128,9 @@ int cbh_get_modes(cbh_state* s, cb_modes* out, int transfer_only) {
 int cbh_get_bessel(cbh_state* s, cb_bessel* out) {
     HostState& S = s->S;
     try {
-        if (!s->have_bessel) { S.GenerateBessels(S.maximum_qeta); s->have_bessel = true; }
+        if (!s->have_bessel) { S.GenerateBessels(S.max_bessels_etak); s->have_bessel = true; }
     } catch (const std::exception& ex) { S.error_msg = ex.what(); return CB_ERR_UNSUPPORTED_PARAMS; }
-    out->n_l = (int)S.ls.size(); out->l = S.ls.data();
+    out->n_l = S.max_bessels_l_index; out->l = S.ls.data(); out->n_l_all = (int)S.ls.size();
     out->nx = S.BessRanges.npoints; out->x = S.BessRanges.points.data();
     out->n_regions = (int)S.bess_regions_c.size(); out->regions = S.bess_regions_c.data();
     out->horner = S.bessel_horner.data();
@@ -129,6 +146,11 @@ int cbh_get_ls(cbh_state* s, int* n_l, const int** l) { *n_l = (int)s->S.ls.size
 int cbh_get_pows(cbh_state* s, int tensor, double* pows) {
     const HostState& S = s->S;
     for (int i = 0; i < S.q_int.npoints; i++) pows[i] = tensor ? S.TensorPower(S.q_int.points[i]) : S.ScalarPower(S.q_int.points[i]);
+    return 0;
+}
+
+int cbh_scalar_power_at(cbh_state* s, int n, const double* k, double* out) {
+    for (int i = 0; i < n; i++) out[i] = s->S.ScalarPower(k[i]);
     return 0;
 }
 

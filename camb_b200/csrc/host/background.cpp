@@ -210,6 +210,28 @@ double HostState::TensorPower(double k) const {  // InitialPower.f90:147-173 (fl
     return CP.At * k_dep;
 }
 
+double RedWin::count_obs_window_z(double z, double& winamp) const {
+    const double root2pi = 2.506628274;
+    double dz = z - w_redshift;
+    winamp = std::exp(-(dz / w_sigma) * (dz / w_sigma) / 2);
+    return winamp / w_sigma / root2pi;
+}
+double RedWin::Window_f_a(double a, double& winamp) const { return count_obs_window_z(1 / a - 1, winamp) / (a * a); }
+
+double HostState::WindowKmaxForL(const RedWin& W, int ell) const {
+    double res;
+    if (W.kind == CB_WINDOW_LENSING) res = CP.Accuracy.AccuracyBoost * 18 * ell / W.chi0;
+    else res = CP.Accuracy.AccuracyBoost * std::fmax(0.05, 2.5 * ell / W.chimin);
+    return res * CP.Accuracy.KmaxBoost;
+}
+
+int HostState::Win_Limber_ell(const RedWin& W, int lmax) const {
+    if (!CP.SourceTerms.limber_windows) return lmax;
+    double LimBoost = CP.Accuracy.AccuracyBoost * CP.Accuracy.SourceLimberBoost;
+    if (W.kind == CB_WINDOW_LENSING) return std::max(CP.SourceTerms.limber_phi_lmin, f_nint(50 * LimBoost));
+    return std::max(CP.SourceTerms.limber_phi_lmin, f_nint(LimBoost * 6 * W.chi0 / W.sigma_tau));
+}
+
 int HostState::SetParams(const cb_params& P) {  // results.f90:332-627 (flat, no source windows)
     using namespace K;
     CP = P;
@@ -308,6 +330,35 @@ int HostState::SetParams(const cb_params& P) {  // results.f90:332-627 (flat, no
     DMt0 = tau0;
     scale = 1.0;
     if (ReionInit()) return error;
+    // source windows, results.f90:543-585
+    num_redshiftwindows = CP.WantScalars ? CP.num_redshiftwindows : 0;
+    if (CP.num_redshiftwindows == 0) CP.SourceTerms.limber_windows = 0;
+    num_extra_redshiftwindows = 0;
+    Redshift_W.clear();
+    if (CP.WantScalars && CP.WantCls && num_redshiftwindows > 0) {
+        if (num_redshiftwindows > CB_MAX_WINDOWS) { fail(CB_ERR_UNSUPPORTED_PARAMS, "too many source windows"); return error; }
+        Redshift_W.resize(num_redshiftwindows);
+        for (int i = 0; i < num_redshiftwindows; i++) {
+            RedWin& W = Redshift_W[i];
+            const cb_source_window& sw = CP.SourceWindows[i];
+            if (sw.source_type != CB_WINDOW_COUNTS && sw.source_type != CB_WINDOW_LENSING) {
+                fail(CB_ERR_UNSUPPORTED_PARAMS, "only counts and lensing source windows are supported (21cm is out of scope)");
+                return error;
+            }
+            W.kind = sw.source_type; W.w_redshift = sw.redshift; W.w_sigma = sw.sigma; W.bias = sw.bias; W.dlog10Ndm = sw.dlog10Ndm;
+            // TGaussianSourceWindow_GetScales, SourceWindows.f90:213-226
+            double sigma_z = sw.sigma, zpeak = sw.redshift, zpeakstart = sw.redshift + sigma_z * 3, zpeakend = std::fmax(0.0, sw.redshift - sigma_z * 3);
+            W.Redshift = zpeak;
+            W.tau = TimeOfz(zpeak, 1e-4);
+            W.sigma_tau = sigma_z * dtauda(1 / (1 + zpeak)) / ((1 + zpeak) * (1 + zpeak));
+            W.tau_peakstart = TimeOfz(zpeakstart, 1e-4);
+            W.tau_peakend = TimeOfz(std::fmax(0.0, zpeakend), 1e-4);
+            W.chi0 = tau0 - W.tau;
+            W.chimin = std::fmin(W.chi0, tau0 - TimeOfz(std::fmax(0.05, zpeakend), 1e-4));
+            CP.Max_eta_k = std::fmax(CP.Max_eta_k, tau0 * WindowKmaxForL(W, CP.Max_l));
+            if (W.kind == CB_WINDOW_COUNTS && CP.SourceTerms.counts_lensing) { num_extra_redshiftwindows++; W.mag_index = num_extra_redshiftwindows; }
+        }
+    }
     // non-linear lensing raises kmax (results.f90:589-593)
     if ((CP.NonLinear == 2 || CP.NonLinear == 3) && CP.Max_eta_k / tau0 > CP.transfer_kmax) CP.transfer_kmax = CP.Max_eta_k / tau0;
     // transfer redshifts: only the user's PK redshifts (the NL-lensing redshift grid

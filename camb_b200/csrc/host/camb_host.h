@@ -61,6 +61,20 @@ struct Thermo {  // results.f90 TThermoData
     void values(double tau, double& a, double& cs2b, double& opacity) const;
 };
 
+struct RedWin {  // SourceWindows.f90:72-84 TRedWin + its TGaussianSourceWindow (:22-30) + CalWins temporaries
+    int kind = CB_WINDOW_COUNTS;
+    double w_redshift = 0, w_sigma = 0, bias = 1, dlog10Ndm = 0;
+    double Redshift = 0, tau = 0, tau_start = 0, tau_end = 0, tau_peakstart = 0, tau_peakend = 0, sigma_tau = 0, chi0 = 0, chimin = 0;
+    int mag_index = 0;
+    std::vector<double> winF, wing, wing2, wingtau, dwing, dwing2, dwingtau, ddwing, ddwing2, ddwingtau, winV, dwinV, ddwinV, win_lens,
+        comoving_density_ev;
+    double Fq = 0;
+    bool has_lensing_window = false;
+    std::vector<double> awin_lens, dawin_lens;
+    double count_obs_window_z(double z, double& winamp) const;   // SourceWindows.f90:156-171
+    double Window_f_a(double a, double& winamp) const;           // :173-190 (counts / lensing)
+};
+
 struct Derived {
     double age, zstar, rstar, thetastar, DAstar, zdrag, rdrag, kD, thetaD, zEQ, keq, thetaEQ, theta_rs_EQ;
 };
@@ -111,6 +125,20 @@ struct HostState {
     std::vector<cb_range> tau_regions_c, bess_regions_c;
     Derived derived{};
     bool has_derived = false;
+    // source windows (results.f90:543-585, 1982-2193, 2689-2779, 2781-3066; cmbmain.f90:420-470)
+    int num_redshiftwindows = 0, num_extra_redshiftwindows = 0;
+    std::vector<RedWin> Redshift_W;
+    double tau_start_redshiftwindows = 0, tau_end_redshiftwindows = 0;
+    std::vector<double> redshift_time, dredshift_time, step_redshift;
+    std::vector<cb_window> windows_c;
+    int Limber_l_min[3 + CB_MAX_WINDOWS] = {0};
+    int max_bessels_l_index = 0;
+    double max_bessels_etak = 0;
+    double WindowKmaxForL(const RedWin& W, int ell) const;   // results.f90:1472-1488
+    int Win_Limber_ell(const RedWin& W, int lmax) const;      // results.f90:3156-3175
+    void DoWindowSpline(int j2, double tau);                  // results.f90:3014-3066
+    void SetTimeStepWindows();                                // results.f90:2781-2984
+    void LimberSetup();                                       // index part of GetLimberTransfers, cmbmain.f90:420-470
 
     // --- background ---
     double grho_no_de(double a) const;

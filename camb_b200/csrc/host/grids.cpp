@@ -112,7 +112,6 @@ void HostState::InitTransfer() {  // cmbmain.f90:564-704 (flat)
 
 void HostState::SetkValuesForInt() {  // cmbmain.f90:1267-1349 (flat, no bispectrum, no windows)
     const cb_accuracy& A = CP.Accuracy;
-    double max_bessels_etak = maximum_qeta;
     double qmax_int = std::fmin(qmax, max_bessels_etak / tau0);
     double IntSampleBoost = A.AccuracyBoost * A.IntkAccuracyBoost;
     q_int.init();
@@ -126,6 +125,7 @@ void HostState::SetkValuesForInt() {  // cmbmain.f90:1267-1349 (flat, no bispect
     double dk = 3.0 / DMt0 / IntSampleBoost / 1.6;
     double k_max_log = lognum * dk0, k_max_0 = no * dk0;
     double dk2 = 0.04 / IntSampleBoost;
+    if (num_redshiftwindows > 0) dk2 = dk;
     q_int.add_delta(qmin, k_max_log, dlnk1, true);
     q_int.add_delta(k_max_log, std::fmin(qmax_int, k_max_0), dk0);
     if (qmax_int > k_max_0) {
@@ -134,6 +134,41 @@ void HostState::SetkValuesForInt() {  // cmbmain.f90:1267-1349 (flat, no bispect
         if (qmax_int > max_k_dk) q_int.add_delta(max_k_dk, qmax_int, dk2);
     }
     q_int.get_array(true, true);  // Init_ClTransfer: GetArray(.true.)
+}
+
+// TimeSourcesToCl :262-270 + the index part of GetLimberTransfers, cmbmain.f90:420-470: which l samples switch to Limber
+// per source, the last l index that needs Bessel integration, and the k*eta range the Bessel table must cover.
+void HostState::LimberSetup() {
+    const int nl = (int)ls.size();
+    for (int& v : Limber_l_min) v = 0;
+    max_bessels_l_index = nl;
+    max_bessels_etak = maximum_qeta;
+    if (!CP.WantScalars) return;
+    if (!CP.SourceTerms.limber_windows || (num_redshiftwindows == 0 && CP.SourceTerms.limber_phi_lmin == 0)) return;
+    if (ls[nl - 1] > 5000) {
+        int idx = nl;   // lSamples_indexOf(5000), results.f90:1490-1503
+        for (int i = 2; i <= nl; i++) if (5000 < ls[i - 1]) { idx = i - 1; break; }
+        max_bessels_l_index = idx;
+    } else max_bessels_l_index = nl;
+    if (CP.Want_CMB) max_bessels_etak = std::min(ls[nl - 1], 3000) * 2.5 * CP.Accuracy.AccuracyBoost;
+    else max_bessels_etak = 5000;
+    for (int i = 0; i <= num_redshiftwindows; i++) {
+        const int s_ix = 3 + i;
+        int ell_limb = i == 0 ? CP.SourceTerms.limber_phi_lmin : Win_Limber_ell(Redshift_W[i - 1], ls[nl - 1]);
+        int ell_needed = ls[nl - 1];
+        for (int ell = 1; ell <= nl; ell++) {
+            if (ls[ell - 1] >= ell_limb) {
+                Limber_l_min[s_ix - 1] = ell;
+                ell_needed = ls[ell - 1];
+                max_bessels_l_index = std::max(max_bessels_l_index, Limber_l_min[s_ix - 1] - 1);
+                break;
+            }
+        }
+        if (i == 0) {
+            if (CP.Want_CMB_lensing) max_bessels_etak = std::fmax(max_bessels_etak, std::fmin(CP.Max_eta_k, ell_needed * 25.0 * CP.Accuracy.AccuracyBoost));
+        } else max_bessels_etak = std::fmax(max_bessels_etak, WindowKmaxForL(Redshift_W[i - 1], ell_needed) * tau0);
+        if (Limber_l_min[s_ix - 1] == 0) max_bessels_l_index = nl;
+    }
 }
 
 void HostState::lSamplesInit(int lmin, int max_l) {  // results.f90:1505-1704
@@ -303,8 +338,8 @@ void HostState::GenerateBessels(double max_etak) {  // bessels.f90:64-113, 140-2
     BessRanges.add_delta(25.0, 150.0, 0.5 / file_acc);
     BessRanges.add_delta(150.0, requested_xmax, 0.7 / file_acc);
     BessRanges.get_array(false);
-    int nx = BessRanges.npoints, nl = (int)ls.size();
-    int lmax = ls.empty() ? 0 : ls.back();
+    int nx = BessRanges.npoints, nl = max_bessels_l_index > 0 ? max_bessels_l_index : (int)ls.size();
+    int lmax = ls.empty() ? 0 : ls[nl - 1];
     // table of exact j_l at the knots for the sampled l: vals[j][i]
     std::vector<std::vector<double>> vals(nl, std::vector<double>(nx, 0.0));
     std::vector<double> dend(nl, 0.0);
@@ -408,6 +443,13 @@ void HostState::fill_model(cb_model& m) const {
     m.WantLateTime = WantLateTime; m.n_src = n_src;
     m.adot = th.adot.data(); m.dadot = th.dadot.data();
     for (int i = 0; i < 5; i++) m.InitialConditionVector[i] = CP.InitialConditionVector[i];
+    m.num_redshiftwindows = num_redshiftwindows; m.num_extra_redshiftwindows = num_extra_redshiftwindows;
+    m.windows = windows_c.empty() ? nullptr : windows_c.data();
+    m.SourceTerms = CP.SourceTerms;
+    m.tau_start_redshiftwindows = tau_start_redshiftwindows;
+    m.Want_CMB_lensing = CP.Want_CMB_lensing;
+    m.max_bessels_l_index = max_bessels_l_index;
+    for (int i = 0; i < 3 + CB_MAX_WINDOWS; i++) m.Limber_l_min[i] = Limber_l_min[i];
 }
 
 }  // namespace cbh

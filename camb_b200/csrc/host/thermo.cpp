@@ -534,7 +534,7 @@ static double binary_search(const fn1& func, double goal, double x1, double x2, 
     return (try_t * (goal - last_bot) + try_b * (last_top - goal)) / (last_top - last_bot);
 }
 
-int HostState::ThermoInit(double taumin) {  // results.f90:1924-2656 (no source windows)
+int HostState::ThermoInit(double taumin) {  // results.f90:1924-2656 (counts / lensing source windows; no 21cm)
     using namespace K;
     Thermo& T = th;
     const cb_accuracy& A = CP.Accuracy;
@@ -542,6 +542,13 @@ int HostState::ThermoInit(double taumin) {  // results.f90:1924-2656 (no source 
     int nthermo = f_nint(20000 * std::log(1.4e4 / taumin) / std::log(1.4e4 / 2e-4) * background_boost);
     T.tauminn = 0.95 * taumin;
     T.dlntau = std::log(tau0 / T.tauminn) / (nthermo - 1);
+    for (const RedWin& win : Redshift_W) {  // steps small enough for the source windows, results.f90:1982-1993
+        if (win.sigma_tau / 5 / background_boost < win.tau * (std::exp(T.dlntau) - 1)) {
+            T.dlntau = std::log(win.sigma_tau / 5 / background_boost / win.tau + 1);
+            nthermo = f_nint(std::log(tau0 / T.tauminn) / T.dlntau) + 1;
+            T.dlntau = std::log(tau0 / T.tauminn) / (nthermo - 1);
+        }
+    }
     T.nthermo = nthermo;
     double sum_grhormass = 0;
     for (int i = 0; i < CP.Nu_mass_eigenstates; i++) sum_grhormass += grhormass[i];
@@ -600,10 +607,53 @@ int HostState::ThermoInit(double taumin) {  // results.f90:1924-2656 (no source 
     T.ScaleFactor[0] = a0;
     T.ScaleFactor[nthermo - 1] = 1;
     T.adot[0] = 1 / dtauda(a0);
+    const int nwin = num_redshiftwindows;
+    std::vector<double> awin_lens1(nwin, 0.0), awin_lens2(nwin, 0.0);
+    if (nwin > 0) {
+        redshift_time.assign(nthermo, 0.0);
+        redshift_time[0] = 1.0 / a0 - 1.0;
+        for (RedWin& W : Redshift_W) {
+            W.tau_start = 0; W.tau_end = tau0;
+            if (W.kind == CB_WINDOW_LENSING || (W.kind == CB_WINDOW_COUNTS && CP.SourceTerms.counts_lensing)) W.awin_lens.assign(nthermo, 0.0);
+        }
+    }
+    double tau01 = T.tauminn;
     for (int i = 1; i < nthermo; i++) {
-        double a = T.ScaleFactor[i];
-        T.adot[i] = 1 / dtauda(a);
+        double a = T.ScaleFactor[i], tau = taus[i], dtau = tau - tau01;
+        double adot = 1 / dtauda(a);
+        T.adot[i] = adot;
         if (T.matter_verydom_tau == 0 && a > a_verydom) T.matter_verydom_tau = taus[i];
+        if (nwin > 0) {  // results.f90:2133-2178
+            redshift_time[i] = 1.0 / a - 1.0;
+            for (int w = 0; w < nwin; w++) {
+                RedWin& W = Redshift_W[w];
+                const bool lens = W.kind == CB_WINDOW_LENSING || (W.kind == CB_WINDOW_COUNTS && CP.SourceTerms.counts_lensing);
+                if (a > 1e-4) {
+                    double winamp, window = W.Window_f_a(a, winamp);
+                    if (lens) {
+                        if (tau0 - tau > 2) {
+                            double dwing_lens = adot * window * dtau;
+                            awin_lens1[w] = awin_lens1[w] + dwing_lens;
+                            awin_lens2[w] = awin_lens2[w] + dwing_lens / (tau0 - tau);
+                            W.awin_lens[i] = awin_lens1[w] / (tau0 - tau) - awin_lens2[w];
+                        } else W.awin_lens[i] = 0;
+                    }
+                    if (W.tau_start == 0 && winamp > 1e-8) W.tau_start = tau01;
+                    else if (W.tau_start != 0 && W.tau_end == tau0 && winamp < 1e-8) W.tau_end = std::fmin(tau0, tau + dtau);
+                } else if (lens) W.awin_lens[i] = 0;
+            }
+        }
+        tau01 = tau;
+    }
+    for (int w = 0; w < nwin; w++) {  // results.f90:2180-2196
+        RedWin& W = Redshift_W[w];
+        W.has_lensing_window = false;
+        if (W.kind == CB_WINDOW_LENSING || (W.kind == CB_WINDOW_COUNTS && CP.SourceTerms.counts_lensing)) {
+            if (awin_lens1[w] != 0) {
+                W.has_lensing_window = true;
+                for (double& v : W.awin_lens) v = v / awin_lens1[w];
+            }
+        }
     }
     rec.xe_Tm(a0, T.xe[0], T.tb[0]);
     double barssc = barssc0 * (1.0 - 0.75 * CP.Yhe + (1.0 - CP.Yhe) * T.xe[0]);
@@ -710,6 +760,10 @@ int HostState::ThermoInit(double taumin) {  // results.f90:1924-2656 (no source 
             sf1 = sf2; dSF1 = dSF2;
         }
     }
+    if (nwin > 0) {  // results.f90:2465-2475
+        pade_derivative(redshift_time, dredshift_time, nthermo, g);
+        for (RedWin& W : Redshift_W) if (W.has_lensing_window) pade_derivative(W.awin_lens, W.dawin_lens, nthermo, g);
+    }
     SetTimeSteps();
     pade_derivative(T.cs2, dcs2, nthermo, g);
     pade_derivative(T.emmu, T.demmu, nthermo, g);
@@ -730,6 +784,10 @@ int HostState::ThermoInit(double taumin) {  // results.f90:1924-2656 (no source 
     double rs = 0;
     if (T.z_drag > 0) rs = sound_horizon(T.z_drag);
     if (T.z_drag > 0 && DMt0 > 0) scale = 0.010392206684501 / (rs / DMt0);
+    if (nwin > 0) {  // results.f90:2502-2509
+        for (int j2 = 1; j2 <= TimeSteps.npoints; j2++) DoWindowSpline(j2, TimeSteps.points[j2 - 1]);
+        SetTimeStepWindows();
+    }
     if (CP.WantDerivedParameters) {  // results.f90:2511-2536
         Derived& D = derived;
         D.age = romberg([this](double a) { return dtauda(a) * a; }, 0.0, 1.0, 1e-4 / std::exp(A.AccuracyBoost - 1)) * Mpc / c / Gyr;
@@ -755,7 +813,7 @@ int HostState::ThermoInit(double taumin) {  // results.f90:1924-2656 (no source 
     return 0;
 }
 
-void HostState::SetTimeSteps() {  // results.f90:2658-2779 (no windows)
+void HostState::SetTimeSteps() {  // results.f90:2658-2779
     double TimeSampleBoost = CP.Accuracy.AccuracyBoost * CP.Accuracy.TimeStepBoost;
     TimeSteps.init();
     TimeSteps.add_delta(taurst, taurend, dtaurec);
@@ -763,11 +821,163 @@ void HostState::SetTimeSteps() {  // results.f90:2658-2779 (no windows)
     if (CP.WantTensors) dtau0 = std::fmax(taurst / 40, tau0 / 2000.0 / TimeSampleBoost);
     else dtau0 = tau0 / 500.0 / TimeSampleBoost;
     TimeSteps.add_delta(taurend, tau0, dtau0);
+    tau_start_redshiftwindows = tau0;
+    tau_end_redshiftwindows = 0;
+    if (CP.WantScalars) {  // results.f90:2691-2734
+        for (RedWin& win : Redshift_W) {
+            win.tau_start = std::fmax(win.tau_start, taurst);
+            int nwindow;
+            double win_end;
+            if (win.kind != CB_WINDOW_LENSING) {
+                tau_end_redshiftwindows = std::fmax(win.tau_end, tau_end_redshiftwindows);
+                nwindow = f_nint(150 * TimeSampleBoost);
+                win_end = win.tau_end;
+            } else {
+                nwindow = f_nint(TimeSampleBoost * win.chi0 / 100);
+                win_end = tau0;
+            }
+            int L_limb = Win_Limber_ell(win, CP.Max_l);
+            double keff = WindowKmaxForL(win, L_limb);
+            nwindow = std::max(nwindow, f_nint(TimeSampleBoost * (win_end - win.tau_start) * keff / 3));
+            if (win.kind != CB_WINDOW_LENSING && win.sigma_tau < (win_end - win.tau_start) / nwindow * 8)
+                nwindow = f_nint(TimeSampleBoost * (win_end - win.tau_start) / win.sigma_tau * 8);
+            double delta = (win_end - win.tau_start) / nwindow;
+            win.tau_start = win.tau_start - delta * 3;
+            win_end = std::fmin(tau0, win_end + delta * 2);
+            tau_start_redshiftwindows = std::fmin(win.tau_start, tau_start_redshiftwindows);
+            TimeSteps.add(win.tau_start, win_end, nwindow);
+            if (win.kind != CB_WINDOW_LENSING && win.tau_peakend - win.tau_peakstart < f_nint(60 * TimeSampleBoost) * delta)
+                TimeSteps.add(win.tau_peakstart, win.tau_peakend, f_nint(60 * TimeSampleBoost));
+        }
+    }
     if (reion_on) {
         int nri0 = (int)(reion_n_steps * TimeSampleBoost);
         TimeSteps.add(reion_tau_start, reion_tau_complete, nri0);
     }
+    if (!CP.Want_CMB && CP.WantCls) {
+        if (num_redshiftwindows == 0) { fail(CB_ERR_UNSUPPORTED_PARAMS, "Want_CMB=false and WantCls=true, but no redshift windows either"); return; }
+        TimeSteps.add_delta(tau_start_redshiftwindows, tau0, dtau0);
+    }
     TimeSteps.get_array(true, true);
+    const int nstep = TimeSteps.npoints;
+    if (num_redshiftwindows > 0) {
+        step_redshift.assign(nstep, 0.0);
+        for (RedWin& w : Redshift_W) {
+            for (std::vector<double>* v : {&w.winF, &w.wing, &w.dwing, &w.ddwing, &w.winV, &w.dwinV, &w.ddwinV, &w.win_lens, &w.wing2, &w.dwing2,
+                                           &w.ddwing2, &w.wingtau, &w.dwingtau, &w.ddwingtau, &w.comoving_density_ev})
+                v->assign(nstep, 0.0);
+        }
+    }
+}
+
+// DoWindowSpline, results.f90:3014-3066 (no 21cm: rhos_fac / drhos_fac are not needed)
+void HostState::DoWindowSpline(int j2, double tau) {
+    const Thermo& T = th;
+    double dd = std::log(tau / T.tauminn) * (1.0 / T.dlntau) + 1.0;
+    int i = (int)dd;
+    double d = dd - i;
+    auto herm = [&](const std::vector<double>& f, const std::vector<double>& df) {
+        int j = i - 1;
+        return f[j] + d * (df[j] + d * (3.0 * (f[j + 1] - f[j]) - 2.0 * df[j] - df[j + 1] + d * (df[j] + df[j + 1] + 2.0 * (f[j] - f[j + 1]))));
+    };
+    if (i < T.nthermo) {
+        step_redshift[j2 - 1] = herm(redshift_time, dredshift_time);
+        for (RedWin& w : Redshift_W) w.win_lens[j2 - 1] = w.has_lensing_window ? herm(w.awin_lens, w.dawin_lens) : 0.0;
+    } else {
+        step_redshift[j2 - 1] = 0;
+        for (RedWin& w : Redshift_W) w.win_lens[j2 - 1] = 0;
+    }
+}
+
+namespace {
+// forutils/Interpolation.f90:966-1020
+void cs_second_derivs(const double* x, const double* y, int n, double* d2) { spline(x, y, n, SPLINE_DANGLE, SPLINE_DANGLE, d2); }
+void cs_derivs_from_d2(const double* x, const double* y, const double* d2, double* dy, int n) {
+    for (int i = 0; i < n - 1; i++) {
+        double dx = x[i + 1] - x[i];
+        dy[i] = (y[i + 1] - y[i]) / dx - dx * (2 * d2[i] + d2[i + 1]) / 6;
+    }
+    double dx = x[n - 1] - x[n - 2];
+    dy[n - 1] = (y[n - 1] - y[n - 2]) / dx + dx * (d2[n - 2] + 2 * d2[n - 1]) / 6;
+}
+void cs_derivatives(const double* x, const double* y, int n, double* d2, double* dy) {
+    cs_second_derivs(x, y, n, d2);
+    cs_derivs_from_d2(x, y, d2, dy, n);
+}
+void cs_integral_array(const double* x, const double* y, const double* d2, double* yint, int n) {
+    yint[0] = 0;
+    for (int i = 1; i < n; i++) {
+        double dx = x[i] - x[i - 1];
+        yint[i] = yint[i - 1] + dx * ((y[i] + y[i - 1]) / 2 - dx * dx / 24 * (d2[i] + d2[i - 1]));
+    }
+}
+}  // namespace
+
+// SetTimeStepWindows, results.f90:2781-2984 (counts and lensing windows)
+void HostState::SetTimeStepWindows() {
+    const int np = TimeSteps.npoints;
+    const int jstart = TimeSteps.index_of(tau_start_redshiftwindows);   // 1-based
+    const int ninterp = np - jstart + 1, o = jstart - 1;                 // o: 0-based offset of jstart
+    const int nw = num_redshiftwindows;
+    std::vector<double> tmp(np, 0.0), tmp2(np, 0.0), hubble_tmp(np, 0.0);
+    std::vector<std::vector<double>> int_tmp(nw, std::vector<double>(np, 0.0)), back_count_tmp(nw, std::vector<double>(np, 0.0));
+    for (RedWin& W : Redshift_W) W.Fq = 0;
+    for (int j = jstart; j <= np; j++) {
+        double tau = TimeSteps.points[j - 1], z = step_redshift[j - 1];
+        double a = 1.0 / (1.0 + z), adot = 1.0 / dtauda(a);
+        hubble_tmp[j - 1] = adot / a;
+        for (int i = 0; i < nw; i++) {
+            RedWin& W = Redshift_W[i];
+            if (tau < W.tau_start) continue;
+            double winamp, window = W.Window_f_a(a, winamp);
+            if (W.kind == CB_WINDOW_COUNTS) {
+                W.wing[j - 1] = adot * window;
+                W.wing2[j - 1] = W.wing[j - 1] / (adot / a);
+                W.winV[j - 1] = 0;
+                int_tmp[i][j - 1] = tau < tau0 - 0.1 ? W.wing[j - 1] / (tau0 - tau) : 0.0;
+                if (CP.SourceTerms.counts_evolve) {
+                    double wa2;
+                    back_count_tmp[i][j - 1] = W.count_obs_window_z(1 / a - 1, wa2) / a;   // counts_background_z
+                    W.comoving_density_ev[j - 1] = tau < tau0 - 0.1 ? back_count_tmp[i][j - 1] * (adot / a) / ((tau0 - tau) * (tau0 - tau)) : 0.0;
+                }
+            }
+        }
+    }
+    const double* x = &TimeSteps.points[o];
+    for (int i = 0; i < nw; i++) {
+        RedWin& W = Redshift_W[i];
+        cs_second_derivs(x, &int_tmp[i][o], ninterp, tmp.data());
+        cs_integral_array(x, &int_tmp[i][o], tmp.data(), &tmp2[o], ninterp);
+        for (int j = o; j < np; j++) W.winV[j] = W.winV[j] + tmp2[j];
+        cs_derivatives(x, &W.winV[o], ninterp, &W.ddwinV[o], &W.dwinV[o]);
+        cs_derivatives(x, &W.wing[o], ninterp, &W.ddwing[o], &W.dwing[o]);
+        cs_derivatives(x, &W.wing2[o], ninterp, &W.ddwing2[o], &W.dwing2[o]);
+        cs_integral_array(x, &W.wing[o], &W.ddwing[o], &W.winF[o], ninterp);
+        W.Fq = W.winF[np - 1];
+        if (W.kind == CB_WINDOW_COUNTS) {
+            if (CP.SourceTerms.counts_evolve) {
+                cs_derivatives(x, &back_count_tmp[i][o], ninterp, tmp.data(), &tmp2[o]);
+                for (int ix = o; ix < np; ix++) {
+                    if (W.wing[ix] == 0.0) W.wingtau[ix] = 0;
+                    else W.wingtau[ix] = -tmp2[ix] * W.wing[ix] / (back_count_tmp[i][ix] * hubble_tmp[ix]) + 10 * W.dlog10Ndm * W.wing[ix];
+                }
+                cs_derivatives(x, &W.comoving_density_ev[o], ninterp, tmp.data(), &tmp2[o]);
+                for (int ix = o; ix < np; ix++) {
+                    if (W.wing[ix] == 0.0) W.comoving_density_ev[ix] = 0;
+                    else if (W.comoving_density_ev[ix] != 0.0)
+                        W.comoving_density_ev[ix] = tmp2[ix] / W.comoving_density_ev[ix] - 5 * W.dlog10Ndm * (hubble_tmp[ix] + int_tmp[i][ix] / W.wing[ix]);
+                }
+            } else {
+                for (double& v : W.comoving_density_ev) v = 0;
+                cs_derivatives(x, &hubble_tmp[o], ninterp, tmp.data(), &tmp2[o]);
+                for (int ix = o; ix < np; ix++)
+                    W.wingtau[ix] = 2 * (1 - 2.5 * W.dlog10Ndm) * int_tmp[i][ix] / hubble_tmp[ix] + 5 * W.dlog10Ndm * W.wing[ix] +
+                                    tmp2[ix] / (hubble_tmp[ix] * hubble_tmp[ix]) * W.wing[ix];
+            }
+            cs_derivatives(x, &W.wingtau[o], ninterp, &W.ddwingtau[o], &W.dwingtau[o]);
+            cs_integral_array(x, &W.wingtau[o], &W.ddwingtau[o], &W.winF[o], ninterp);
+        }
+    }
 }
 
 // ====================== GaugeInterface_Init, equations.f90:534-583 ======================
@@ -809,7 +1019,7 @@ int HostState::InitVars() {
         if (CP.WantTensors && !CP.WantScalars) { maximum_l = CP.Max_l_tensor; maximum_qeta = CP.Max_eta_k_tensor; }
         else { maximum_l = CP.Max_l; maximum_qeta = CP.Max_eta_k; }
     }
-    WantLateTime = CP.DoLensing != 0;
+    WantLateTime = CP.DoLensing != 0 || num_redshiftwindows > 0;   // cmbmain.f90:139
     double initAccuracyBoost = A.AccuracyBoost * A.TimeStepBoost;
     qmax = maximum_qeta / tau0;
     qmin = 0.1 / tau0 / initAccuracyBoost;
@@ -834,7 +1044,7 @@ int HostState::InitVars() {
             transfer_times.push_back(acc);
         }
     }
-    n_src = CP.WantScalars ? (WantLateTime ? 3 : 2) : 3;
+    n_src = CP.WantScalars ? (WantLateTime ? 3 + num_redshiftwindows + num_extra_redshiftwindows : 2) : 3;   // GetSourceMem, cmbmain.f90:755-773
     return 0;
 }
 

@@ -22,13 +22,14 @@ SYMBOLS = ["cb_create", "cb_destroy", "cb_last_error", "cb_device_count", "cb_se
            "cb_model_destroy", "cb_evolve", "cb_set_sources", "cb_project", "cb_cl", "cb_last_timings",
            "cb_launch_count", "cb_abi_sizeof", "cb_timer_start", "cb_timer_stop", "cb_fp64_peak",
            "cb_host_alloc", "cb_host_free", "cb_device_buffer", "cb_set_option", "cb_host_register",
-           "cb_host_unregister", "cb_cl_array"]
+           "cb_host_unregister", "cb_cl_array", "cb_cl_windows"]
 
 
 def load_gpu_lib():
     global _lib
     if _lib is None:
-        path = os.path.join(_HERE, "libcambb200.so")
+        # CAMB_B200_LIB: an alternative build of the same library (kernel tuning experiments)
+        path = os.environ.get("CAMB_B200_LIB") or os.path.join(_HERE, "libcambb200.so")
         if not os.path.exists(path):
             raise ImportError(f"{path} not built: run `make cuda` (or __graft_entry__.build()). "
                               "camb_b200 has no CPU fallback.")
@@ -47,6 +48,8 @@ def load_gpu_lib():
                                    C.POINTER(c_double_p), C.POINTER(c_double_p)]
         lib.cb_cl.argtypes = [C.c_void_p, C.c_int, c_void_pp, C.c_int, C.POINTER(c_double_p), C.POINTER(c_double_p)]
         lib.cb_cl_array.argtypes = [C.c_void_p, C.c_int, c_void_pp, C.POINTER(c_double_p), C.POINTER(c_double_p)]
+        lib.cb_cl_windows.argtypes = [C.c_void_p, C.c_int, c_void_pp, C.POINTER(c_double_p), C.POINTER(c_double_p),
+                                      C.POINTER(c_double_p), C.POINTER(c_double_p)]
         lib.cb_last_timings.argtypes = [C.c_void_p, C.c_double * 4]
         lib.cb_launch_count.restype = C.c_longlong
         lib.cb_launch_count.argtypes = [C.c_void_p]
@@ -200,6 +203,21 @@ class GpuContext:
         o_p = (c_double_p * n)(*[_dp(a) for a in out])
         self._check(self._lib.cb_cl_array(self._h, n, dm_arr, p_p, o_p))
         return out
+
+    def cl_windows(self, hss, dms, pows=None):
+        """Scalar models with source windows: (iCl (n_l_all, 6), iCl_Array (n, n, n_l_all)) per cosmology, Limber included."""
+        n = len(hss)
+        dm_arr = (C.c_void_p * n)(*dms)
+        pows = [np.ascontiguousarray(hs.scalar_power() if pows is None else pows[i]) for i, hs in enumerate(hss)]
+        lps = [np.ascontiguousarray(hs.limber_power()) for hs in hss]
+        p_p = (c_double_p * n)(*[_dp(a) for a in pows])
+        lp_p = (c_double_p * n)(*[_dp(a) for a in lps])
+        icl = [np.zeros((6, len(hs.ls))) for hs in hss]
+        arr = [np.zeros((3 + hs.model.num_redshiftwindows, 3 + hs.model.num_redshiftwindows, len(hs.ls))) for hs in hss]
+        i_p = (c_double_p * n)(*[_dp(a) for a in icl])
+        a_p = (c_double_p * n)(*[_dp(a) for a in arr])
+        self._check(self._lib.cb_cl_windows(self._h, n, dm_arr, p_p, lp_p, i_p, a_p))
+        return [o.T.copy() for o in icl], arr
 
     def pin_host_tables(self, hs):
         """Page-lock the host's boundary tables in place (what a Fortran host would do with its

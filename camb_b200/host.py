@@ -42,6 +42,7 @@ def load_host_lib():
         lib.cbh_get_qint.argtypes = [C.c_void_p, c_int_p, C.POINTER(c_double_p), C.POINTER(c_double_p)]
         lib.cbh_get_ls.argtypes = [C.c_void_p, c_int_p, C.POINTER(c_int_p)]
         lib.cbh_get_pows.argtypes = [C.c_void_p, C.c_int, c_double_p]
+        lib.cbh_scalar_power_at.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p]
         lib.cbh_get_derived.argtypes = [C.c_void_p, C.c_double * 13]
         lib.cbh_get_background.argtypes = [C.c_void_p, C.c_double * 16]
         lib.cbh_interp_cl.argtypes = [C.c_void_p, c_double_p, c_double_p]
@@ -126,6 +127,19 @@ class HostState:
         out = np.zeros(len(self.q_int))
         self._lib.cbh_get_pows(self._h, 0, _dp(out))
         return out
+
+    def scalar_power_at(self, k):
+        k = np.ascontiguousarray(k, dtype=np.float64)
+        out = np.zeros(k.shape)
+        self._lib.cbh_scalar_power_at(self._h, k.size, _dp(k), _dp(out))
+        return out
+
+    def limber_power(self):
+        """P_R(k = (l + 1/2)/(tau0 - tau_n)) on the (l sample, time step) grid of GetLimberTransfers
+        (cmbmain.f90:499-501), shape (n_l_all, n_tau); zero where tau_n = tau0."""
+        chi = self.model.tau0 - self.tau
+        k = np.where(chi[None, :] > 0, (self.ls[:, None] + 0.5) / np.where(chi > 0, chi, 1.0)[None, :], 1.0)
+        return np.where(chi[None, :] > 0, self.scalar_power_at(k), 0.0)
 
     def tensor_power(self):
         out = np.zeros(len(self.q_int))

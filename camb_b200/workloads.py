@@ -142,3 +142,40 @@ def isocurvature_params(mode=2, vector=None, lmax=800, lensing=False, massless=T
     if p.Scalar_initial_condition != 1:
         p.use_cl_spline_template = 0
     return p
+
+
+def _set_windows(p, windows):
+    p.num_redshiftwindows = len(windows)
+    for i, (kind, z, sigma, bias, dlog10Ndm) in enumerate(windows):
+        w = p.SourceWindows[i]
+        w.source_type = {"counts": 2, "lensing": 3}[kind]
+        w.redshift, w.sigma, w.bias, w.dlog10Ndm = float(z), float(sigma), float(bias), float(dlog10Ndm)
+
+
+def params_counts_config4(lmax=800, counts_lensing=True, limber=True):
+    """inifiles/params_counts.ini (BASELINE.json configs[3]): params.ini cosmology, lmax 800, lensing, two Gaussian
+    number-count windows (z=0.3 sigma=0.06 b=1.5 s=0.42; z=1 sigma=0.3 b=2) with every counts term on,
+    DoRedshiftLensing (magnification extra sources), limber_windows with limber_phiphi = 100.  The ini's
+    do_nonlinear=3 needs halofit on the host; the linear sources are what the path computes."""
+    p = params_ini_config1()
+    p.DoLensing = 1
+    p.Max_l = int(lmax)
+    p.Max_eta_k = 2.5 * lmax
+    _set_windows(p, [("counts", 0.3, 0.06, 1.5, 0.42), ("counts", 1.0, 0.3, 2.0, 0.0)])
+    st = p.SourceTerms
+    st.limber_windows = 1 if limber else 0
+    st.limber_phi_lmin = 100
+    st.counts_density = st.counts_redshift = st.counts_radial = st.counts_timedelay = 1
+    st.counts_ISW = st.counts_velocity = st.counts_potential = 1
+    st.counts_evolve = 0
+    st.counts_lensing = 1 if counts_lensing else 0
+    return p
+
+
+def lensing_window_params(z=1089.0, sigma=30.0, lmax=400, limber=False):
+    """camb/tests/camb_test.py:1220-1226: a broad lensing window at recombination reproduces the CMB lensing potential
+    (W1xW1 = PP l(l+1)/4, PxW1 = PP sqrt(l(l+1))/2 to 1e-3)."""
+    p = planck2018_params(lmax=lmax, lensing=True, massless=True)
+    _set_windows(p, [("lensing", z, sigma, 1.0, 0.0)])
+    p.SourceTerms.limber_windows = 1 if limber else 0
+    return p

@@ -36,6 +36,15 @@ typedef struct cb_range {
     double low, high, delta;
 } cb_range;
 
+/* One source window on the time grid: TRedWin (SourceWindows.f90:72-84) as SetTimeStepWindows / DoWindowSpline
+ * leave it (results.f90:2781-2984, 3014-3066).  Arrays are [n_tau]. */
+typedef struct cb_window {
+    int kind, mag_index;           /* window_counts = 2, window_lensing = 3; index of the magnification extra source */
+    double Fq, dlog10Ndm, bias;    /* Window%GetBias(k, a) of a Gaussian window is the constant bias */
+    double tau_start, tau_end, chi0, sigma_tau;
+    const double *wing, *wing2, *dwing2, *ddwing2, *wingtau, *dwingtau, *winV, *winF, *win_lens, *comoving_density_ev;
+} cb_window;
+
 /* Read-only boundary data of one cosmology: everything the hot path reads from
  * CAMBdata/CAMBParams/TThermoData (SURVEY.md section 8(b) "Inputs to marshal").
  * Built by the Fortran host in the real integration; by camb_b200/csrc/host here. */
@@ -94,6 +103,15 @@ typedef struct cb_model {
     const double* dadot;           /* [nthermo] its unit-grid derivative (unit_grid_pade_derivative) */
     /* ---- `initial` with Scalar_initial_condition == initial_vector (0), equations.f90:2042-2047 ---- */
     double InitialConditionVector[5];
+    /* ---- source windows (scalars, config 4): State%Redshift_W, CP%SourceTerms, ThermoData%tau_start_redshiftwindows,
+     *      and the Limber switch GetLimberTransfers sets up (cmbmain.f90:420-470) ---- */
+    int    num_redshiftwindows, num_extra_redshiftwindows;
+    const cb_window* windows;      /* [num_redshiftwindows] */
+    cb_source_terms SourceTerms;
+    double tau_start_redshiftwindows;
+    int    Want_CMB_lensing;
+    int    max_bessels_l_index;    /* l samples above this index are Limber-only; 0 = all of them are integrated */
+    int    Limber_l_min[3 + CB_MAX_WINDOWS];   /* 1-based by source (slots 0..1 unused, slot 2 = phi); 0 = never Limber */
 } cb_model;
 
 /* Per-call mode list for loop A / A'.  The two per-k host look-ups that the
@@ -115,12 +133,15 @@ typedef struct cb_modes {
 /* Spherical-Bessel spline table + x grid (bessels.f90:20-41,168-182). */
 typedef struct cb_bessel {
     int    n_l;
-    const int* l;                  /* ls%l [n_l] */
+    const int* l;                  /* ls%l [n_l_all] */
     int    nx;                     /* BessRanges%npoints */
     const double* x;               /* BessRanges%points [nx] */
     int    n_regions;
     const cb_range* regions;
     const double* horner;          /* bessel_horner(4, nx-1, n_l) column-major */
+    /* l[] holds all n_l_all sampled multipoles; only the first n_l (= max_bessels_l_index, cmbmain.f90:262-270) have
+     * Bessel tables, the rest are Limber-only (source windows).  n_l_all = 0 means n_l. */
+    int    n_l_all;
 } cb_bessel;
 
 typedef struct cb_ctx cb_ctx;      /* one per device/process: streams, device buffers */
@@ -170,6 +191,13 @@ int  cb_cl(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, int tensor,
  * Cl_Scalar_Array (cmbmain.f90:3538-3549).  n = n_src; column-major (l fastest), symmetric; uses the pows of the
  * last cb_cl call when pows[i] is NULL.  Scalar models with n_src == 3 (no source windows). */
 int  cb_cl_array(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const double* const* pows, double* const* iCl_Array);
+
+/* Loop C for scalar models with source windows (config 4): GetLimberTransfers (cmbmain.f90:472-536, on the device-resident
+ * spline of the sources) + CalcLimberScalCls (:358-417) + CalcScalCls (:3179-3343).
+ *   limber_pows[i] double (n_tau, n_l_all): P_R(k = (l + 1/2)/(tau0 - tau_n)), the host's InitPower on the Limber grid
+ *   iCl[i]         double (n_l_all, 6); iCl_Array[i] double (n_l_all, n, n), n = 3 + num_redshiftwindows; either may be NULL. */
+int  cb_cl_windows(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const double* const* pows, const double* const* limber_pows,
+                   double* const* iCl, double* const* iCl_Array);
 
 /* Kernel timing of the last call of each stage, ms, measured with CUDA events on
  * the launching stream: [0] evolve, [1] spline-k, [2] LOS, [3] C_l. */

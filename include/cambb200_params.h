@@ -45,6 +45,20 @@ typedef struct cb_accuracy {
     double SourceLimberBoost, KmaxBoost, neutrino_q_boost;
 } cb_accuracy;
 
+/* Source windows (SourceWindows.f90:8-30 TGaussianSourceWindow) and the terms that enter them
+ * (SourceTermParams, SourceWindows.f90:46-67). */
+#define CB_MAX_WINDOWS 8
+enum { CB_WINDOW_21CM = 1, CB_WINDOW_COUNTS = 2, CB_WINDOW_LENSING = 3 };
+typedef struct cb_source_window {
+    int source_type;               /* CB_WINDOW_COUNTS or CB_WINDOW_LENSING (21cm is out of scope) */
+    double redshift, sigma, bias, dlog10Ndm;
+} cb_source_window;
+typedef struct cb_source_terms {
+    int limber_windows, limber_phi_lmin;
+    int counts_density, counts_redshift, counts_lensing, counts_velocity, counts_radial, counts_timedelay,
+        counts_ISW, counts_potential, counts_evolve;
+} cb_source_terms;
+
 typedef struct cb_params {
     /* what to compute (model.f90:110-127) */
     int WantCls, WantTransfer, WantScalars, WantTensors, WantVectors;
@@ -87,6 +101,10 @@ typedef struct cb_params {
     /* weights of the adiabatic, CDM-, baryon-, neutrino-density- and neutrino-velocity-isocurvature modes; read only
      * when Scalar_initial_condition == 0 (initial_vector, equations.f90:62-64, model.f90:166-168) */
     double InitialConditionVector[5];
+    /* source windows (config 4: inifiles/params_counts.ini) */
+    int num_redshiftwindows;
+    cb_source_window SourceWindows[CB_MAX_WINDOWS];
+    cb_source_terms SourceTerms;
 } cb_params;
 
 /* Fill *p with the reference's defaults (model.f90 type defaults + the

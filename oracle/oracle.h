@@ -30,6 +30,15 @@ int oracle_cl(const cb_model* M, const cb_bessel* B, int n_q, const double* q_in
 int oracle_cl_array(const cb_model* M, const cb_bessel* B, int n_q, const double* q_int, const double* dq, const double* pows,
                     const double* Delta_p_l_k, double* iCl_Array);
 
+/* Source windows: GetLimberTransfers (cmbmain.f90:472-536) and CalcLimberScalCls + CalcScalCls (:358-417, 3179-3343).
+ * LimbSrc (n_tau, n_l_all, 1 + nw) n fastest; n1n2 (2, 1 + nw); limber_pows (n_tau, n_l_all);
+ * iCl (n_l_all, 6); iCl_Array (n_l_all, 3 + nw, 3 + nw). */
+int oracle_limber(const cb_model* M, const cb_bessel* B, int n_k, const double* q_src, const double* ScaledSrc, const double* ddScaledSrc,
+                  double* LimbSrc, int* n1n2);
+int oracle_cl_windows(const cb_model* M, const cb_bessel* B, int n_q, const double* q_int, const double* dq, const double* pows,
+                      const double* Delta_p_l_k, const double* LimbSrc, const int* n1n2, const double* limber_pows, double* iCl,
+                      double* iCl_Array);
+
 #ifdef __cplusplus
 }
 #endif

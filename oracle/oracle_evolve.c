@@ -54,6 +54,7 @@ typedef struct EVars {
     double pig, pigdot, poltruncfac;
     double denlk[MAX_L_EVOLVE + 1], denlk2[MAX_L_EVOLVE + 1], polfack[MAX_L_EVOLVE + 1];
     double* OutputSources;   /* n_src values or NULL */
+    int OutputStep;          /* 1-based index of the output time in TimeSteps (window tables) */
     float* OutputTransfer;   /* 13 values or NULL */
     long long nderivs;
     /* the right-hand side RungeKuttaDP45 integrates: derivs (scalars) or derivst (tensors) */
@@ -893,6 +894,45 @@ static void derivs(EVars* EV, int n, double tau, const double* ay, double* aypri
                 if (tau > M->tau_maxvis && tau0 - tau > 0.1)
                     S[2] = -2 * phi * (tau - M->tau_maxvis) / ((tau0 - M->tau_maxvis) * ang_dist);
             }
+            /* output_window_sources, equations.f90:1474-1737 (lensing and number-count windows) */
+            if (M->num_redshiftwindows > 0 && tau > M->tau_start_redshiftwindows) {
+                const int jj = EV->OutputStep - 1, nw = M->num_redshiftwindows;
+                const cb_source_terms* T = &M->SourceTerms;
+                for (int w_ix = 1; w_ix <= nw; w_ix++) {
+                    const cb_window* w = &M->windows[w_ix - 1];
+                    if (w->kind == CB_WINDOW_LENSING) {
+                        S[3 + w_ix - 1] = -2 * phi * w->win_lens[jj];
+                    } else if (w->kind == CB_WINDOW_COUNTS) {
+                        double counts_density_source = 0, counts_redshift_source = 0, counts_radial_source = 0, counts_timedelay_source = 0,
+                               counts_ISW_source = 0, counts_potential_source = 0, counts_velocity_source = 0;
+                        if (T->counts_density)
+                            counts_density_source = w->wing[jj] * (clxc * w->bias + (w->comoving_density_ev[jj] - 3 * adotoa) * sigma / k);
+                        if (T->counts_redshift)
+                            counts_redshift_source =
+                                ((4.0 * (adotoa * adotoa) + gpres + grho / 3.0) / k * w->wing2[jj] + (-4.0 * w->dwing2[jj] * adotoa + w->ddwing2[jj]) / k) * sigma +
+                                (-etak / adotoa * k / 3.0 - dgrho / adotoa / 6.0 +
+                                 (etak / adotoa * k / 3.0 + dgrho / adotoa / 6.0 + (dgq / 2.0 - 2.0 * etak * adotoa) / k) / 1.0) * w->wing2[jj] +
+                                2.0 * w->dwing2[jj] * etak / k / 1.0;
+                        if (tau0 - tau > 0.1 && T->counts_radial) {
+                            double chi = tau0 - tau;
+                            counts_radial_source = (1 - 2.5 * w->dlog10Ndm) *
+                                                   ((-4.0 * w->wing2[jj] / chi * adotoa - 2.0 * (-w->dwing2[jj] * chi - w->wing2[jj]) / (chi * chi)) / k * sigma +
+                                                    2.0 * w->wing2[jj] * etak / chi / k / 1.0);
+                        }
+                        if (T->counts_timedelay) counts_timedelay_source = 2 * (1 - 2.5 * w->dlog10Ndm) * w->winV[jj] * 2 * phi;
+                        if (T->counts_ISW) counts_ISW_source = w->winF[jj] * 2 * phidot;
+                        if (T->counts_potential)
+                            counts_potential_source = (phidot / adotoa + phi + (5 * w->dlog10Ndm - 2) * phi) * w->wing[jj] + phi * w->wingtau[jj];
+                        if (T->counts_velocity)
+                            counts_velocity_source = (-2.0 * w->wingtau[jj] * adotoa + w->dwingtau[jj]) / k * sigma + w->wingtau[jj] * etak / k / 1.0 -
+                                                     counts_radial_source;
+                        S[3 + w_ix - 1] = counts_radial_source + counts_density_source + counts_redshift_source + counts_timedelay_source +
+                                          counts_potential_source + counts_ISW_source + counts_velocity_source;
+                        S[3 + w_ix - 1] = S[3 + w_ix - 1] / w->Fq;
+                        if (T->counts_lensing) S[3 + w->mag_index + nw - 1] = phi * w->win_lens[jj] * (2 - 5 * w->dlog10Ndm);
+                    }
+                }
+            }
         }
     }
 }
@@ -1298,9 +1338,10 @@ static void initial(EVars* EV, double* y, double tau, double tight_switchoff, co
     }
 }
 
-static void output(EVars* EV, double* y, double tau, double* sources, double* yprime) {
+static void output(EVars* EV, double* y, int j, double tau, double* sources, double* yprime) {
     for (int i = 0; i < EV->nvar; i++) yprime[i] = 0;
     EV->OutputSources = sources;
+    EV->OutputStep = j;
     derivs(EV, EV->ScalEqsToPropagate, tau, y, yprime);
     EV->OutputSources = NULL;
 }
@@ -1342,7 +1383,7 @@ static int evolve_one_mode(const cb_model* M, const cb_modes* modes, int q_ix, d
     double* y = (double*)calloc(nvar, sizeof(double));
     double* yout = (double*)calloc(nvar, sizeof(double));
     double* yprime = (double*)calloc(nvar, sizeof(double));
-    double sources[16];
+    double sources[3 + 2 * CB_MAX_WINDOWS];
     RKSettings rk;
     memset(&rk, 0, sizeof(rk));
     initial(&EV, y, taustart, modes->tight_switchoff[q_ix], modes->nu_massive_approx_time + (size_t)q_ix * CB_MAX_NU);
@@ -1374,7 +1415,7 @@ static int evolve_one_mode(const cb_model* M, const cb_modes* modes, int q_ix, d
         } else {
             err = EvolveScal(&EV, &tau, y, tauend, tol1, &ind, &rk, w, yout);
             if (err) goto done;
-            output(&EV, y, tau, sources, yprime);
+            output(&EV, y, j, tau, sources, yprime);
             for (s = 0; s < n_src; s++) LinearSrc[q_ix + (size_t)n_k * (s + (size_t)n_src * (j - 1))] = sources[s];
             for (;;) { /* label 101 */
                 if (!(M->WantTransfer && itf <= nz)) break;

@@ -123,6 +123,20 @@ static void project_one_q(const cb_model* M, const cb_bessel* B, int n_k, const 
     else llmax = (int)lround(q * (tau0 + 6.0 * const_pi / q)); /* nu*rofChi(tau0/r + 6pi/nu), r = 1 */
     /* ---- DoFlatIntegration ---- */
     double BessIntBoost = M->AccuracyBoost * M->BessIntBoost;
+    /* source-window tails, cmbmain.f90:1658-1676 */
+    int has_narrow_source_window = 0;
+    double source_window_tail_lmax = 0;
+    const int nwin_src = tensors ? 0 : M->num_redshiftwindows;
+    if (nwin_src > 0) {
+        source_window_tail_lmax = 20;
+        for (int w = 0; w < nwin_src; w++) {
+            const cb_window* win = &M->windows[w];
+            if (win->kind != CB_WINDOW_LENSING && win->chi0 > 0 && win->sigma_tau > 0) {
+                source_window_tail_lmax = fmax(source_window_tail_lmax, fmin(160.0, fmax(20.0, 4.0 * win->chi0 / win->sigma_tau)));
+                if (win->sigma_tau < 0.02 * win->chi0) has_narrow_source_window = 1;
+            }
+        }
+    }
     for (j = 1; j <= SourceSteps; j++) left_weight[j - 1] = fabs(q * (tau0 - TimePoints[j - 1]));
     for (j = 1; j <= SourceSteps; j++)
         bes_index[j - 1] = ranges_index_of_ordered(B->regions, B->n_regions, B->nx, B->x[B->nx - 1], left_weight[j - 1]);
@@ -132,16 +146,22 @@ static void project_one_q(const cb_model* M, const cb_bessel* B, int n_k, const 
         double x_hi = B->x[bes_ix], dx = x_hi - B->x[bes_ix - 1];
         left_weight[j - 1] = (x_hi - left_weight[j - 1]) / dx;
     }
-    double sums[16];
+    double sums[3 + 2 * CB_MAX_WINDOWS];
+    const int nwin_ix = nwin_src > 0 ? ranges_index_of(M->tau_regions, M->n_tau_regions, M->n_tau, M->tau_highest, M->tau_start_redshiftwindows)
+                                     : M->n_tau + 1;
     for (j = 1; j <= n_l; j++) {
         int l = B->l[j - 1];
         if (l > llmax) return;
+        double BessIntBoostL = BessIntBoost;
+        if (has_narrow_source_window) BessIntBoostL = fmax(BessIntBoostL, 20.0 / l);
         double xlim = fmax(0.0, l - 4.2 * pow((double)l, 1.0 / 3.0));
-        double xlmax1 = 80 * l * BessIntBoost;
+        double xlmax1 = 80 * l * BessIntBoostL;
+        if (source_window_tail_lmax > 0) xlmax1 = xlmax1 * fmax(1.0, fmin(8.0, source_window_tail_lmax / l));
         double tmin = tau0 - xlmax1 / q;
         tmin = fmax(TimePoints[1], tmin);
         double tmax = tau0 - xlim / q;
         tmin = fmax(TimePoints[1], tmin);
+        if (!M->Want_CMB && !M->Want_CMB_lensing) tmin = fmax(tmin, M->tau_start_redshiftwindows);
         if (tmax < TimePoints[1]) break;
         for (s = 0; s < nsrc; s++) sums[s] = 0;
         const double* H = B->horner + (size_t)4 * (B->nx - 1) * (j - 1);
@@ -158,7 +178,7 @@ static void project_one_q(const cb_model* M, const cb_bessel* B, int n_k, const 
                 sums[1] = sums[1] + Source_q[(n - 1) + ntime] * J_l;
             }
         } else {
-            double qmax_int = (l > 850 ? l : 850) * 3 * BessIntBoost / tau0 * 1.2;
+            double qmax_int = (l > 850 ? l : 850) * 3 * BessIntBoostL / tau0 * 1.2;
             int DoInt = tensors || q < qmax_int; /* DoInt = .not. CP%WantScalars .or. IV%q < qmax_int */
             if (DoInt) {
                 for (n = n1; n <= n2; n++) {
@@ -169,6 +189,8 @@ static void project_one_q(const cb_model* M, const cb_bessel* B, int n_k, const 
                     sums[0] = sums[0] + Source_q[(n - 1)] * J_l;
                     sums[1] = sums[1] + Source_q[(n - 1) + ntime] * J_l;
                     sums[2] = sums[2] + Source_q[(n - 1) + 2 * ntime] * J_l;
+                    if (n >= nwin_ix) /* cmbmain.f90:1763-1787 */
+                        for (s = 3; s < nsrc; s++) sums[s] = sums[s] + Source_q[(n - 1) + s * ntime] * J_l;
                 }
             }
             if (!DoInt || (use_limber(M, l) && !tensors)) { /* .not. DoInt .or. UseLimber(l) .and. CP%WantScalars */
@@ -179,6 +201,21 @@ static void project_one_q(const cb_model* M, const cb_bessel* B, int n_k, const 
                     sums[2] = (Source_q[(n - 1) + 2 * ntime] * (1 - xf) + xf * Source_q[n + 2 * ntime]) *
                               sqrt(const_pi / 2 / (l + 0.5)) / q;
                 } else sums[2] = 0;
+            }
+            if (!DoInt && nsrc > 3) { /* cmbmain.f90:1834-1857: the CMB does not need the integral but other sources do */
+                int any = 0;
+                for (s = 3; s < 3 + nwin_src + M->num_extra_redshiftwindows; s++)   /* Limber_l_min of the extra sources is never set */
+                    if (s >= 3 + nwin_src || M->Limber_l_min[s] == 0 || M->Limber_l_min[s] > j) any = 1;
+                if (any) {
+                    int na = ranges_index_of(M->tau_regions, M->n_tau_regions, M->n_tau, M->tau_highest, M->tau_start_redshiftwindows);
+                    for (n = na; n <= n2; n++) {
+                        double a2 = left_weight[n - 1];
+                        const double* h = H + 4 * (bes_index[n - 1] - 1);
+                        double J_l = h[0] + a2 * (h[1] + a2 * (h[2] + a2 * h[3]));
+                        J_l = J_l * M->dtau[n - 1];
+                        for (s = 3; s < nsrc; s++) sums[s] = sums[s] + Source_q[(n - 1) + s * ntime] * J_l;
+                    }
+                }
             }
         }
         for (s = 0; s < nsrc; s++) Delta[s + nsrc * (j - 1)] += sums[s];
@@ -291,5 +328,171 @@ int oracle_cl_array(const cb_model* M, const cb_bessel* B, int n_q, const double
                 out[j + (size_t)n_l * (w2 + (size_t)n * w1)] = v;
             }
     }
+    return 0;
+}
+
+/* ---- Limber for the lensing potential and the source windows ----
+ * GetLimberTransfers, cmbmain.f90:472-536: LimbSrc[(i, ell, n)] = sqrt(chi dtau) * S_{3+i}(k = (l+1/2)/chi, tau_n) for
+ * i = 0 (phi) .. num_redshiftwindows, ell >= Limber_l_min(3+i), n in [n1(i), n2(i)]; zero elsewhere.
+ * Layout: n fastest, then ell (n_l_all), then i.  n1n2: (2, 1+nw). */
+int oracle_limber(const cb_model* M, const cb_bessel* B, int n_k, const double* q_src, const double* Src, const double* dd,
+                  double* LimbSrc, int* n1n2) {
+    const int nw = M->num_redshiftwindows, n_l = B->n_l_all > 0 ? B->n_l_all : B->n_l, ntime = M->n_tau, nsrc = M->n_src;
+    memset(LimbSrc, 0, sizeof(double) * (size_t)(1 + nw) * n_l * ntime);
+    for (int i = 0; i <= nw; i++) {
+        const int s_ix = 3 + i;
+        n1n2[2 * i] = 1; n1n2[2 * i + 1] = 0;
+        if (M->Limber_l_min[s_ix - 1] == 0) continue;
+        int n1, n2, s_ix_lens = 0;
+        if (i == 0) {
+            n1 = ranges_index_of(M->tau_regions, M->n_tau_regions, ntime, M->tau_highest, M->tau_maxvis);
+            n2 = ntime - 1;
+        } else {
+            const cb_window* W = &M->windows[i - 1];
+            n1 = ranges_index_of(M->tau_regions, M->n_tau_regions, ntime, M->tau_highest, W->tau_start);
+            if (W->kind == CB_WINDOW_LENSING || (W->kind == CB_WINDOW_COUNTS && M->SourceTerms.counts_lensing)) n2 = ntime - 1;
+            else {
+                n2 = ranges_index_of(M->tau_regions, M->n_tau_regions, ntime, M->tau_highest, W->tau_end);
+                if (n2 > ntime - 1) n2 = ntime - 1;
+            }
+            if (W->kind == CB_WINDOW_COUNTS && M->SourceTerms.counts_lensing) s_ix_lens = 3 + W->mag_index + nw;
+        }
+        n1n2[2 * i] = n1; n1n2[2 * i + 1] = n2;
+        for (int ell = M->Limber_l_min[s_ix - 1]; ell <= n_l; ell++) {
+            double reall = (double)B->l[ell - 1];
+            double* out = LimbSrc + ((size_t)i * n_l + (ell - 1)) * ntime;
+            for (int n = n1; n <= n2; n++) {
+                double chi = (M->tau0 - M->tau[n - 1]);
+                double k = (reall + 0.5) / chi;
+                if (k <= M->qmax) {
+                    int klo;   /* Evolve_q%IndexOf(k) */
+                    if (k <= q_src[0]) klo = 1;
+                    else if (k >= q_src[n_k - 1]) klo = n_k - 1;
+                    else {
+                        int lo = 1, hi = n_k;
+                        while (hi - lo > 1) { int mid = (lo + hi) / 2; if (k >= q_src[mid - 1]) lo = mid; else hi = mid; }
+                        klo = lo;
+                    }
+                    int khi = klo + 1;
+                    double ho = q_src[khi - 1] - q_src[klo - 1];
+                    double a0 = (q_src[khi - 1] - k) / ho, b0 = (k - q_src[klo - 1]) / ho, ho2o6 = ho * ho / 6;
+                    double a03 = (a0 * a0 * a0 - a0), b03 = (b0 * b0 * b0 - b0);
+                    size_t off = (size_t)n_k * ((s_ix - 1) + (size_t)nsrc * (n - 1));
+                    double v = sqrt(chi * M->dtau[n - 1]) *
+                               (a0 * Src[off + klo - 1] + b0 * Src[off + khi - 1] + (a03 * dd[off + klo - 1] + b03 * dd[off + khi - 1]) * ho2o6);
+                    if (s_ix_lens > 0) {
+                        size_t o2 = (size_t)n_k * ((s_ix_lens - 1) + (size_t)nsrc * (n - 1));
+                        v = v + reall * (reall + 1) * sqrt(chi * M->dtau[n - 1]) *
+                                    (a0 * Src[o2 + klo - 1] + b0 * Src[o2 + khi - 1] + (a03 * dd[o2 + klo - 1] + b03 * dd[o2 + khi - 1]) * ho2o6);
+                    }
+                    out[n - 1] = v;
+                } else out[n - 1] = 0;
+            }
+        }
+    }
+    return 0;
+}
+
+/* ClTransferToCl for scalars with source windows: CalcLimberScalCls (cmbmain.f90:358-417) followed by CalcScalCls
+ * (:3179-3343).  iCl (n_l_all, 6), iCl_Array (n_l_all, n, n) with n = 3 + num_redshiftwindows, both column-major.
+ * limber_pows[(ell, n)] = P_R(k = (l + 1/2)/(tau0 - tau_n)), n fastest (host-evaluated InitPower). */
+int oracle_cl_windows(const cb_model* M, const cb_bessel* B, int n_q, const double* q_int, const double* dq, const double* pows,
+                      const double* Delta, const double* LimbSrc, const int* n1n2, const double* limber_pows, double* iCl,
+                      double* iCl_Array) {
+    const int nw = M->num_redshiftwindows, nsrc = M->n_src, n = 3 + nw, n_lb = B->n_l, n_l = B->n_l_all > 0 ? B->n_l_all : B->n_l;
+    const int ntime = M->n_tau;
+    const double fourpi = 4 * const_pi, OutputDenominator = 2 * const_pi;
+    const cb_source_terms* T = &M->SourceTerms;
+#define ARR(j, a, b) iCl_Array[(j) + (size_t)n_l * ((a) + (size_t)n * (b))]
+    memset(iCl, 0, sizeof(double) * (size_t)n_l * 6);
+    memset(iCl_Array, 0, sizeof(double) * (size_t)n_l * n * n);
+    /* CalcLimberScalCls */
+    const int winmin = T->limber_phi_lmin > 0 ? 0 : 1;
+    for (int i = winmin; i <= nw; i++) {
+        int s_ix = 3 + i;
+        if (M->Limber_l_min[s_ix - 1] == 0) continue;
+        for (int j = i; j <= nw; j++) {
+            int s_ix2 = 3 + j;
+            if (M->Limber_l_min[s_ix2 - 1] == 0) continue;
+            int l0 = M->Limber_l_min[s_ix - 1] > M->Limber_l_min[s_ix2 - 1] ? M->Limber_l_min[s_ix - 1] : M->Limber_l_min[s_ix2 - 1];
+            for (int ell = l0; ell <= n_l; ell++) {
+                const double* S1 = LimbSrc + ((size_t)i * n_l + (ell - 1)) * ntime;
+                const double* S2 = LimbSrc + ((size_t)j * n_l + (ell - 1)) * ntime;
+                const double* P = limber_pows + (size_t)(ell - 1) * ntime;
+                int na = n1n2[2 * i] > n1n2[2 * j] ? n1n2[2 * i] : n1n2[2 * j];
+                int nb = n1n2[2 * i + 1] < n1n2[2 * j + 1] ? n1n2[2 * i + 1] : n1n2[2 * j + 1];
+                double Cl = 0;
+                for (int t = na; t <= nb; t++) Cl = Cl + S1[t - 1] * S2[t - 1] * P[t - 1];
+                double reall = (double)B->l[ell - 1];
+                double fac = (2 * const_pi * const_pi) / fourpi / ((reall + 0.5) * (reall + 0.5) * (reall + 0.5));
+                if (j >= 1 && M->windows[j - 1].kind == CB_WINDOW_LENSING) fac = fac / 2 * reall * (reall + 1);
+                if (i >= 1 && M->windows[i - 1].kind == CB_WINDOW_LENSING) fac = fac / 2 * reall * (reall + 1);
+                Cl = Cl * fac;
+                if (j == 0 && i == 0) iCl[(ell - 1) + (size_t)n_l * 3] = Cl;
+                ARR(ell - 1, s_ix - 1, s_ix2 - 1) = Cl;
+                if (i != j) ARR(ell - 1, s_ix2 - 1, s_ix - 1) = Cl;
+            }
+        }
+    }
+    /* CalcScalCls */
+    for (int j = 1; j <= n_l; j++) {
+        double ell = (double)B->l[j - 1];
+        double c[6] = {0, 0, 0, 0, 0, 0};
+        if (j <= n_lb) {
+            for (int iq = 0; iq < n_q; iq++) {
+                double dlnk = dq[iq] / q_int[iq], apowers = pows[iq];
+                const double* D = Delta + (size_t)nsrc * ((j - 1) + (size_t)n_lb * iq);
+                c[0] = c[0] + apowers * (D[0] * D[0]) * dlnk;
+                c[1] = c[1] + apowers * (D[1] * D[1]) * dlnk;
+                c[2] = c[2] + apowers * D[0] * D[1] * dlnk;
+                for (int w_ix = 1; w_ix <= 3 + nw; w_ix++) {
+                    double Delta1 = D[w_ix - 1];
+                    if (w_ix > 3) {
+                        const cb_window* win = &M->windows[w_ix - 4];
+                        if (win->kind == CB_WINDOW_LENSING) Delta1 = Delta1 / 2 * ell * (ell + 1);
+                        if (win->kind == CB_WINDOW_COUNTS && T->counts_lensing) Delta1 = Delta1 + ell * (ell + 1) * D[3 + win->mag_index + nw - 1];
+                    }
+                    for (int w_ix2 = w_ix; w_ix2 <= 3 + nw; w_ix2++) {
+                        if (w_ix2 >= 3 && w_ix >= 3) {
+                            if (M->Limber_l_min[w_ix2 - 1] != 0 && j >= M->Limber_l_min[w_ix2 - 1] && M->Limber_l_min[w_ix - 1] != 0 &&
+                                j >= M->Limber_l_min[w_ix - 1])
+                                continue;
+                        }
+                        double Delta2 = D[w_ix2 - 1];
+                        if (w_ix2 > 3) {
+                            const cb_window* win = &M->windows[w_ix2 - 4];
+                            if (win->kind == CB_WINDOW_LENSING) Delta2 = Delta2 / 2 * ell * (ell + 1);
+                            if (win->kind == CB_WINDOW_COUNTS && T->counts_lensing) Delta2 = Delta2 + ell * (ell + 1) * D[3 + win->mag_index + nw - 1];
+                        }
+                        ARR(j - 1, w_ix - 1, w_ix2 - 1) = ARR(j - 1, w_ix - 1, w_ix2 - 1) + Delta1 * Delta2 * apowers * dlnk;
+                    }
+                }
+                if (T->limber_phi_lmin == 0 || M->Limber_l_min[2] == 0 || j < M->Limber_l_min[2]) {
+                    c[3] = c[3] + apowers * (D[2] * D[2]) * dlnk;
+                    c[4] = c[4] + apowers * D[2] * D[0] * dlnk;
+                    c[5] = c[5] + apowers * D[2] * D[1] * dlnk;
+                }
+            }
+        }
+        double ctnorm = (ell * ell - 1) * (ell + 2) * ell;
+        double dbletmp = (ell * (ell + 1)) / OutputDenominator * fourpi;
+        double fac[3 + CB_MAX_WINDOWS];
+        for (int a = 0; a < n; a++) fac[a] = 1;
+        fac[1] = sqrt(ctnorm);
+        fac[2] = sqrt(ell * (ell + 1) * M->Alens);
+        for (int w1 = 0; w1 < n; w1++)
+            for (int w2 = w1; w2 < n; w2++) {
+                ARR(j - 1, w1, w2) = ARR(j - 1, w1, w2) * fac[w1] * fac[w2] * dbletmp;
+                ARR(j - 1, w2, w1) = ARR(j - 1, w1, w2);
+            }
+        double* o = iCl + (j - 1);
+        o[0] = c[0] * dbletmp;
+        o[(size_t)n_l * 1] = c[1] * dbletmp * ctnorm;
+        o[(size_t)n_l * 2] = c[2] * dbletmp * sqrt(ctnorm);
+        o[(size_t)n_l * 3] = M->Alens * (o[(size_t)n_l * 3] + c[3]) * fourpi * (ell * ell * ell * ell);
+        o[(size_t)n_l * 4] = sqrt(M->Alens) * c[4] * fourpi * (ell * ell * ell);
+        o[(size_t)n_l * 5] = sqrt(M->Alens) * c[5] * fourpi * (ell * ell * ell) * sqrt(ctnorm);
+    }
+#undef ARR
     return 0;
 }

@@ -27,6 +27,10 @@ def load():
         lib.oracle_cl.argtypes = [C.POINTER(cb_model), C.POINTER(cb_bessel), C.c_int, c_double_p, c_double_p,
                                   c_double_p, c_double_p, c_double_p]
         lib.oracle_cl_array.argtypes = lib.oracle_cl.argtypes
+        lib.oracle_limber.argtypes = [C.POINTER(cb_model), C.POINTER(cb_bessel), C.c_int, c_double_p, c_double_p, c_double_p,
+                                      c_double_p, C.POINTER(C.c_int)]
+        lib.oracle_cl_windows.argtypes = [C.POINTER(cb_model), C.POINTER(cb_bessel), C.c_int, c_double_p, c_double_p, c_double_p,
+                                          c_double_p, c_double_p, C.POINTER(C.c_int), c_double_p, c_double_p, c_double_p]
         _lib = lib
     return _lib
 
@@ -104,6 +108,45 @@ def cl_array(hs, delta, pows=None):
     out = np.zeros((n, n, b.n_l))
     lib.oracle_cl_array(C.byref(hs.model), C.byref(b), len(qi), _dp(qi), _dp(dq), _dp(pows), _dp(delta), _dp(out))
     return out
+
+
+def limber(hs, q_src, src, dd):
+    """LimbSrc (1 + nw, n_l_all, n_tau) and n1n2 (1 + nw, 2) of GetLimberTransfers."""
+    lib = load()
+    b = hs.bessel()
+    nw, n_l = hs.model.num_redshiftwindows, len(hs.ls)
+    out = np.zeros((1 + nw, n_l, hs.model.n_tau))
+    n1n2 = np.zeros((1 + nw, 2), dtype=np.int32)
+    q_src = np.ascontiguousarray(q_src)
+    lib.oracle_limber(C.byref(hs.model), C.byref(b), len(q_src), _dp(q_src), _dp(src), _dp(dd), _dp(out),
+                      n1n2.ctypes.data_as(C.POINTER(C.c_int)))
+    return out, n1n2
+
+
+def cl_windows(hs, delta, limb_src, n1n2, pows=None):
+    """(iCl (n_l_all, 6), iCl_Array (n, n, n_l_all)) with source windows and Limber."""
+    lib = load()
+    b = hs.bessel()
+    qi, dq = np.ascontiguousarray(hs.q_int), np.ascontiguousarray(hs.dq_int)
+    pows = np.ascontiguousarray(hs.scalar_power() if pows is None else pows)
+    lp = np.ascontiguousarray(hs.limber_power())
+    n, n_l = 3 + hs.model.num_redshiftwindows, len(hs.ls)
+    icl = np.zeros((6, n_l))
+    arr = np.zeros((n, n, n_l))
+    n1n2 = np.ascontiguousarray(n1n2, dtype=np.int32)
+    lib.oracle_cl_windows(C.byref(hs.model), C.byref(b), len(qi), _dp(qi), _dp(dq), _dp(pows), _dp(delta), _dp(limb_src),
+                          n1n2.ctypes.data_as(C.POINTER(C.c_int)), _dp(lp), _dp(icl), _dp(arr))
+    return icl.T.copy(), arr
+
+
+def cls_windows_from_params(hs, nthreads=1):
+    src, tr, stats = evolve(hs, nthreads=nthreads)
+    q_src = hs.source_q()
+    dd = spline_k(q_src, src)
+    delta = project(hs, q_src, src, dd, nthreads=nthreads)
+    limb_src, n1n2 = limber(hs, q_src, src, dd)
+    icl, arr = cl_windows(hs, delta, limb_src, n1n2)
+    return icl, arr, dict(src=src, dd=dd, delta=delta, stats=stats, limb_src=limb_src, n1n2=n1n2)
 
 
 def cls_from_params(hs, nthreads=1):

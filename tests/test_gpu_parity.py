@@ -7,7 +7,7 @@ import pytest
 
 import oracle_lib as O
 from camb_b200.host import CAMBError, HostState
-from camb_b200.workloads import (isocurvature_params, params_ini_config1, planck2018_params, synthetic_lcdm_batch,
+from camb_b200.workloads import (isocurvature_params, lensing_window_params, params_counts_config4, params_ini_config1, planck2018_params, synthetic_lcdm_batch,
                                  tensor_params)
 from conftest import host_state
 
@@ -53,6 +53,30 @@ CASES = {
     "planck_massive_lensing": lambda: planck2018_params(lmax=2500, lensing=True, massless=False),
     "w0wa_ppf_massive": lambda: synthetic_lcdm_batch(1, seed=11, lmax=1200, extended=True)[0],
 }
+
+
+def _config3():
+    """BASELINE.json configs[2] as SURVEY.md 8(d) reads it: planck_2018.ini + AccuracyBoost 2, lmax 5000,
+    one massive neutrino, matter transfer to kmax = 10 (high precision off: the stand-in has no halofit)."""
+    p = planck2018_params(lmax=5000, lensing=True, massless=False, k_eta_max=12500, accuracy_boost=2.0, want_transfer=True)
+    p.transfer_kmax = 10.0
+    return p
+
+
+def test_config3_high_accuracy_parity(ctx):
+    hs = host_state("config3", _config3)
+    ctx.set_option("lanes_per_mode", 8)
+    try:
+        g = run_gpu(ctx, hs)
+    finally:
+        ctx.set_option("lanes_per_mode", 0)
+    icl_o, aux = O.cls_from_params(hs, nthreads=8)
+    errs = cl_err(g["icl"], icl_o)
+    print("config3 C_l errors", errs, "n_l", len(hs.ls), "n_k", len(hs.source_q()), "n_q", len(hs.q_int))
+    assert hs.ls[-1] == 5000 and max(errs) < CL_RTOL, errs
+    tr, tr_o = g["transfer"], aux["transfer"]
+    for c in range(13):
+        assert np.abs(tr[:, :, c] - tr_o[:, :, c]).max() <= 2e-5 * np.abs(tr_o[:, :, c]).max(), c
 
 
 @pytest.mark.parametrize("lanes", [32, 8, 16])
@@ -135,6 +159,48 @@ def test_isocurvature_cl_parity(ctx, name):
     print(name, "C_l errors", errs)
     assert max(errs) < CL_RTOL, errs
     assert (g["stats"][:, 0] == aux["stats"][:, 0]).mean() > 0.9
+
+
+WINDOW_CASES = {"counts_config4": params_counts_config4,
+                "counts_no_magnification_no_limber": lambda: params_counts_config4(lmax=400, counts_lensing=False, limber=False),
+                "lensing_window": lambda: lensing_window_params(limber=True)}
+
+
+@pytest.mark.parametrize("name", list(WINDOW_CASES))
+def test_source_windows_parity(ctx, name):
+    """BASELINE.json configs[3] (params_counts.ini): output_window_sources, the window variant of DoFlatIntegration,
+    GetLimberTransfers + CalcLimberScalCls and the window terms of CalcScalCls, against the oracle."""
+    hs = host_state(name, WINDOW_CASES[name])
+    ctx.set_bessel(hs)
+    dm = ctx.create_model(hs)
+    try:
+        src, _, st = ctx.evolve([hs], [dm])
+        delta = ctx.project([hs], [dm])[0]
+        icl, arr = ctx.cl_windows([hs], [dm])
+        icl, arr = icl[0], arr[0]
+    finally:
+        ctx.destroy_model(dm)
+    icl_o, arr_o, aux = O.cls_windows_from_params(hs, nthreads=8)
+    n = 3 + hs.model.num_redshiftwindows
+    assert arr.shape == arr_o.shape == (n, n, len(hs.ls)) and hs.n_src == n + hs.model.num_extra_redshiftwindows
+    for s in range(hs.n_src):   # every source, window and magnification sources included
+        scale = np.abs(aux["src"][:, s, :]).max(axis=0, keepdims=True)
+        scale[scale == 0] = 1
+        assert (np.abs(src[0][:, s, :] - aux["src"][:, s, :]) / scale).max() < 2e-6, s
+        peak = np.abs(aux["delta"][:, :, s]).max(axis=0, keepdims=True)
+        peak[peak == 0] = 1
+        assert (np.abs(delta[:, :, s] - aux["delta"][:, :, s]) / peak).max() < 1e-5, s
+    diag = np.sqrt(np.abs(np.einsum("iil,jjl->ijl", arr_o, arr_o)))
+    diag[diag == 0] = 1
+    err = (np.abs(arr - arr_o) / diag).max()
+    print(name, "iCl_Array error", err, "iCl errors", cl_err(icl, icl_o))
+    assert err < CL_RTOL and max(cl_err(icl, icl_o)) < CL_RTOL
+    assert (st[0][:, 0] == aux["stats"][:, 0]).mean() > 0.9
+    if name == "lensing_window":   # camb/tests/camb_test.py:1220-1226, rtol 1e-3 there
+        ell = hs.ls.astype(float)
+        sel = ell >= 4
+        assert np.allclose(arr[3, 3][sel], arr[2, 2][sel] / 4 * (ell * (ell + 1))[sel], rtol=1e-3)
+        assert np.allclose(arr[2, 3][sel], arr[2, 2][sel] / 2 * np.sqrt(ell * (ell + 1))[sel], rtol=1e-3)
 
 
 def test_sources_parity(ctx):
