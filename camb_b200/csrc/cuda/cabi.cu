@@ -26,6 +26,7 @@ void cb_spline_k_launch(const DModel*, int, int, double* const*, cudaStream_t);
 size_t cb_los_smem(int, int);
 cudaError_t cb_los_set_smem(size_t);
 void cb_los_launch(const DModel*, int, const DBessel&, int, int, size_t, cudaStream_t);
+cudaError_t cb_los_win_launch(const DModel*, int, const DBessel&, int, int, cudaStream_t);
 void cb_cl_launch(const DModel*, int, const DBessel&, cudaStream_t);
 void cb_cl_array_launch(const DModel*, int, const DBessel&, double* const*, cudaStream_t);
 void cb_limber_launch(const DModel*, int, const DBessel&, int, double* const*, cudaStream_t);
@@ -510,11 +511,20 @@ int cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q, 
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->stage_ev[1][1], ctx->stream));
+    bool any_windows = false;
+    for (int m = 0; m < n_models; m++) any_windows = any_windows || dm[m]->h.num_redshiftwindows > 0;
     const size_t smem = cb_los_smem(max_nsrc, max_ntau);
-    if (smem > 227 * 1024) { ctx->err = "LOS: too many time steps for shared memory"; return CB_ERR_UNSUPPORTED_PARAMS; }
-    CK(cb_los_set_smem(smem));
     CK(cudaEventRecord(ctx->stage_ev[2][0], ctx->stream));
-    cb_los_launch(ctx->d_models, n_models, ctx->bess, max_nq, max_ntau, smem, ctx->stream);
+    if (any_windows || smem > 227 * 1024) {
+        // source windows (or a time grid too long to stage the sources): the general kernel
+        for (int m = 0; m < n_models; m++)
+            if (dm[m]->h.is_tensor) { ctx->err = "LOS: tensor models cannot share a call with source-window models"; return CB_ERR_UNSUPPORTED_PARAMS; }
+        cudaError_t le = cb_los_win_launch(ctx->d_models, n_models, ctx->bess, max_nq, max_ntau, ctx->stream);
+        if (le != cudaSuccess) { ctx->err = std::string("LOS (windows): ") + cudaGetErrorString(le); return le == cudaErrorInvalidValue ? CB_ERR_UNSUPPORTED_PARAMS : CB_ERR_CUDA; }
+    } else {
+        CK(cb_los_set_smem(smem));
+        cb_los_launch(ctx->d_models, n_models, ctx->bess, max_nq, max_ntau, smem, ctx->stream);
+    }
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->stage_ev[2][1], ctx->stream));

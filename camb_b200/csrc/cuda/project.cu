@@ -161,36 +161,16 @@ cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
     else llmax = (int)llround(q * (tau0 + 6.0 * 3.1415926535897932384626433832795 / q));
     const double BessIntBoost = M.AccuracyBoost * M.BessIntBoost;
     double* Dout = M.Delta + (size_t)nsrc * n_l * iq;
-    // source-window tails, cmbmain.f90:1658-1676
-    const int nwin_src = tensors ? 0 : M.num_redshiftwindows;
-    bool has_narrow_source_window = false;
-    double source_window_tail_lmax = 0;
-    int nwin_ix = ntime + 1;
-    if (nwin_src > 0) {
-        source_window_tail_lmax = 20;
-        for (int w = 0; w < nwin_src; w++) {
-            const cb_window& win = M.windows[w];
-            if (win.kind != CB_WINDOW_LENSING && win.chi0 > 0 && win.sigma_tau > 0) {
-                source_window_tail_lmax = fmax(source_window_tail_lmax, fmin(160.0, fmax(20.0, 4.0 * win.chi0 / win.sigma_tau)));
-                if (win.sigma_tau < 0.02 * win.chi0) has_narrow_source_window = true;
-            }
-        }
-        nwin_ix = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, M.tau_start_redshiftwindows);
-    }
     for (int j = 1 + warp; j <= n_l; j += nwarp) {
         const int l = B.l[j - 1];
         double s0 = 0, s1 = 0, s2 = 0;
         bool active = l <= llmax;
         double tmin = 0, tmax = 0;
-        double BessIntBoostL = BessIntBoost;
-        if (has_narrow_source_window) BessIntBoostL = fmax(BessIntBoostL, 20.0 / l);
         if (active) {
             const double xlim = fmax(0.0, l - 4.2 * pow((double)l, 1.0 / 3.0));
-            double xlmax1 = 80 * l * BessIntBoostL;
-            if (source_window_tail_lmax > 0) xlmax1 = xlmax1 * fmax(1.0, fmin(8.0, source_window_tail_lmax / l));
+            const double xlmax1 = 80 * l * BessIntBoost;
             tmin = fmax(TimePoints[1], tau0 - xlmax1 / q);
             tmax = tau0 - xlim / q;
-            if (!M.Want_CMB && !M.Want_CMB_lensing) tmin = fmax(tmin, M.tau_start_redshiftwindows);
             if (tmax < TimePoints[1]) active = false;
         }
         if (active) {
@@ -200,7 +180,7 @@ cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
             if (n2 > SourceSteps) n2 = SourceSteps;
             bool DoInt = true;
             if (nsrc > 2) {
-                const double qmax_int = (l > 850 ? l : 850) * 3 * BessIntBoostL / tau0 * 1.2;
+                const double qmax_int = (l > 850 ? l : 850) * 3 * BessIntBoost / tau0 * 1.2;
                 DoInt = tensors || q < qmax_int;   // DoInt = .not. CP%WantScalars .or. IV%q < qmax_int
             }
             if (DoInt) {
@@ -235,35 +215,153 @@ cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
             o[0] = s0; o[1] = s1;
             if (nsrc > 2) o[2] = s2;
         }
-        if (nsrc > 3) {   // window sources, cmbmain.f90:1763-1787 (n >= nwin) and :1834-1857 (CMB needs no integral, windows do)
-            int na = 0, nb = -1;
-            if (active) {
-                const int n1 = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, tmin);
-                int n2 = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, tmax);
-                if (n2 > SourceSteps) n2 = SourceSteps;
-                const double qmax_int = (l > 850 ? l : 850) * 3 * BessIntBoostL / tau0 * 1.2;
-                if (q < qmax_int) { na = n1 > nwin_ix ? n1 : nwin_ix; nb = n2; }
-                else {
-                    bool any = M.num_extra_redshiftwindows > 0;   // Limber_l_min of the extra sources is never set
-                    for (int s = 3; s < 3 + nwin_src; s++) any = any || M.Limber_l_min[s] == 0 || M.Limber_l_min[s] > j;
-                    if (any) { na = nwin_ix; nb = n2; }
+    }
+}
+
+// Scalar models with source windows (config 4): the same loop B for any number of sources.  Window runs have far more time
+// steps (up to ~1e4 without the Limber switch) and sources than fit shared memory, so only the per-q Bessel index and weight
+// are staged; Source_q(n, s) is evaluated from the k-spline where it is used.  Not the benchmark path: clarity over speed.
+// grid = (max n_q, n_models); dynamic smem: left_weight[max_n_tau] doubles + bes_index[max_n_tau] ints.
+__global__ void __launch_bounds__(LOS_THREADS)
+cb_los_win_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
+    const DModel& M = models[blockIdx.y];
+    const int iq = blockIdx.x;
+    if (iq >= M.n_q) return;
+    extern __shared__ __align__(16) double sm[];
+    const int ntime = M.n_tau, nsrc = M.n_src, n_k = M.n_k, n_l = B.n_l;
+    double* left_weight = sm;
+    int* bes_index = reinterpret_cast<int*>(left_weight + max_n_tau);
+    __shared__ int s_firstfail;
+    __shared__ cb_range s_tau_regions[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = LOS_THREADS / 32;
+    const double q = M.q_int[iq], tau0 = M.tau0;
+    const double* TimePoints = M.tau;
+    if (tid == 0) s_firstfail = ntime + 1;
+    if (tid < M.n_tau_regions) s_tau_regions[tid] = M.tau_regions[tid];
+    __syncthreads();
+    // ---- InterpolateSources, cmbmain.f90:1351-1480 (scalars with late-time sources ignore the k*tau cut) ----
+    const bool ignore_etak = M.WantLateTime != 0;
+    const double max_etak = ignore_etak ? 0.0 : M.max_etak_scalar;
+    const double* qs = M.q_src;
+    int klo;
+    if (q <= qs[0]) klo = 1;
+    else if (q >= qs[n_k - 1]) klo = n_k - 1;
+    else {
+        int lo = 1, hi = n_k;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) / 2;
+            if (q >= qs[mid - 1]) lo = mid; else hi = mid;
+        }
+        klo = lo;
+    }
+    const int khi = klo + 1;
+    const double ho = qs[khi - 1] - qs[klo - 1];
+    const double a0 = (qs[khi - 1] - q) / ho, b0 = (q - qs[klo - 1]) / ho, ho2o6 = ho * ho / 6.0;
+    const double a03 = a0 * a0 * a0 - a0, b03 = b0 * b0 * b0 - b0;
+    for (int i = 2 + tid; i <= ntime; i += LOS_THREADS) {
+        const double tau = TimePoints[i - 1];
+        const bool pass = (ignore_etak || q * tau < max_etak) && (q * (tau0 - tau) > 1.e-8);
+        if (!pass) atomicMin(&s_firstfail, i);
+    }
+    __syncthreads();
+    const int firstfail = s_firstfail, SourceSteps = max(2, firstfail - 1);
+    auto source_q = [&](int n, int s) {   // IV%Source_q(n, s+1): zero for n = 1 and after the first failing step
+        if (n < 2 || n >= firstfail) return 0.0;
+        const size_t off = (size_t)n_k * (s + (size_t)nsrc * (n - 1));
+        const double* S = M.LinearSrc + off;
+        const double* D = M.ddSrc + off;
+        return a0 * __ldg(&S[klo - 1]) + b0 * __ldg(&S[khi - 1]) + (a03 * __ldg(&D[klo - 1]) + b03 * __ldg(&D[khi - 1])) * ho2o6;
+    };
+    for (int i = 1 + tid; i <= SourceSteps; i += LOS_THREADS) {   // DoFlatIntegration preamble, cmbmain.f90:1680-1692
+        const double xf = fabs(q * (tau0 - TimePoints[i - 1]));
+        int bes_ix = ranges_index_of_ordered(B.regions, B.n_regions, B.nx, B.xmax, xf);
+        if (bes_ix >= B.nx) bes_ix = B.nx - 1;
+        const double x_hi = B.x[bes_ix], dx = x_hi - B.x[bes_ix - 1];
+        left_weight[i - 1] = (x_hi - xf) / dx;
+        bes_index[i - 1] = bes_ix;
+    }
+    __syncthreads();
+    int llmax = (int)llround(q * tau0);   // DoSourceIntegration (flat), cmbmain.f90:1516-1521
+    if (llmax < 15) llmax = 17;
+    else llmax = (int)llround(q * (tau0 + 6.0 * 3.1415926535897932384626433832795 / q));
+    const double BessIntBoost = M.AccuracyBoost * M.BessIntBoost;
+    double* Dout = M.Delta + (size_t)nsrc * n_l * iq;
+    // source-window tails, cmbmain.f90:1658-1676
+    const int nwin_src = M.num_redshiftwindows;
+    bool has_narrow_source_window = false;
+    double source_window_tail_lmax = 0;
+    int nwin_ix = ntime + 1;
+    if (nwin_src > 0) {
+        source_window_tail_lmax = 20;
+        for (int w = 0; w < nwin_src; w++) {
+            const cb_window& win = M.windows[w];
+            if (win.kind != CB_WINDOW_LENSING && win.chi0 > 0 && win.sigma_tau > 0) {
+                source_window_tail_lmax = fmax(source_window_tail_lmax, fmin(160.0, fmax(20.0, 4.0 * win.chi0 / win.sigma_tau)));
+                if (win.sigma_tau < 0.02 * win.chi0) has_narrow_source_window = true;
+            }
+        }
+        nwin_ix = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, M.tau_start_redshiftwindows);
+    }
+    for (int j = 1 + warp; j <= n_l; j += nwarp) {
+        const int l = B.l[j - 1];
+        double* o = Dout + (size_t)nsrc * (j - 1);
+        bool active = l <= llmax;
+        double tmin = 0, tmax = 0;
+        double BessIntBoostL = BessIntBoost;
+        if (has_narrow_source_window) BessIntBoostL = fmax(BessIntBoostL, 20.0 / l);
+        if (active) {
+            const double xlim = fmax(0.0, l - 4.2 * pow((double)l, 1.0 / 3.0));
+            double xlmax1 = 80 * l * BessIntBoostL;
+            if (source_window_tail_lmax > 0) xlmax1 = xlmax1 * fmax(1.0, fmin(8.0, source_window_tail_lmax / l));
+            tmin = fmax(TimePoints[1], tau0 - xlmax1 / q);
+            tmax = tau0 - xlim / q;
+            if (!M.Want_CMB && !M.Want_CMB_lensing) tmin = fmax(tmin, M.tau_start_redshiftwindows);
+            if (tmax < TimePoints[1]) active = false;
+        }
+        if (!active) {
+            if (lane == 0) for (int s = 0; s < nsrc; s++) o[s] = 0;
+            continue;
+        }
+        const double* H = B.horner + (size_t)4 * (B.nx - 1) * (j - 1);
+        const int n1 = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, tmin);
+        int n2 = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, tmax);
+        if (n2 > SourceSteps) n2 = SourceSteps;
+        const double qmax_int = (l > 850 ? l : 850) * 3 * BessIntBoostL / tau0 * 1.2;
+        const bool DoInt = nsrc == 2 || q < qmax_int;
+        // time range of every source: T, E, phi over [n1, n2] when DoInt; windows from nwin on; when the CMB needs no
+        // integral the windows still do unless all of them are in their Limber range (:1834-1857)
+        int wa = 0, wb = -1;
+        if (DoInt) { wa = n1 > nwin_ix ? n1 : nwin_ix; wb = n2; }
+        else if (nsrc > 3) {
+            bool any = M.num_extra_redshiftwindows > 0;   // Limber_l_min of the extra sources is never set
+            for (int s = 3; s < 3 + nwin_src; s++) any = any || M.Limber_l_min[s] == 0 || M.Limber_l_min[s] > j;
+            if (any) { wa = nwin_ix; wb = n2; }
+        }
+        for (int s = 0; s < nsrc; s++) {
+            const int na = s < 3 ? (DoInt ? n1 : 0) : wa, nb = s < 3 ? (DoInt ? n2 : -1) : wb;
+            double acc = 0;
+            for (int n = na + lane; n <= nb; n += 32) {
+                const double a2 = left_weight[n - 1];
+                const double2* h = reinterpret_cast<const double2*>(H + 4 * (size_t)(bes_index[n - 1] - 1));
+                const double2 h0 = __ldg(h), h1 = __ldg(h + 1);
+                double J_l = h0.x + a2 * (h0.y + a2 * (h1.x + a2 * h1.y));
+                J_l = J_l * __ldg(&M.dtau[n - 1]);
+                acc = acc + source_q(n, s) * J_l;
+            }
+            acc = warp_sum(acc);
+            if (s == 2) {   // UseLimber, cmbmain.f90:1619-1636, 1821-1832
+                const bool limber = M.SourceTerms.limber_windows ? l >= M.SourceTerms.limber_phi_lmin
+                                                                 : l > 400 * pow(M.AccuracyBoost * M.LimberBoost, 0.5);
+                if (!DoInt || limber) {
+                    double xf = tau0 - (l + 0.5) / q;
+                    if (xf < M.tau_highest && xf > M.tau_lowest) {
+                        const int n = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, xf);
+                        xf = (xf - TimePoints[n - 1]) / (TimePoints[n] - TimePoints[n - 1]);
+                        acc = (source_q(n, 2) * (1 - xf) + xf * source_q(n + 1, 2)) * sqrt(3.1415926535897932384626433832795 / 2 / (l + 0.5)) / q;
+                    } else acc = 0;
                 }
             }
-            const double* H = B.horner + (size_t)4 * (B.nx - 1) * (j - 1);
-            for (int s = 3; s < nsrc; s++) {
-                double acc = 0;
-                const double* Sq = Source_q + (size_t)s * max_n_tau;
-                for (int n = na + lane; n <= nb; n += 32) {
-                    const double a2 = left_weight[n - 1];
-                    const double2* h = reinterpret_cast<const double2*>(H + 4 * (size_t)(bes_index[n - 1] - 1));
-                    const double2 h0 = __ldg(h), h1 = __ldg(h + 1);
-                    double J_l = h0.x + a2 * (h0.y + a2 * (h1.x + a2 * h1.y));
-                    J_l = J_l * dtau_s[n - 1];
-                    acc = acc + Sq[n - 1] * J_l;
-                }
-                acc = warp_sum(acc);
-                if (lane == 0) Dout[(size_t)nsrc * (j - 1) + s] = acc;
-            }
+            if (lane == 0) o[s] = acc;
         }
     }
 }
@@ -558,6 +656,18 @@ cudaError_t cb_los_set_smem(size_t smem) {
 void cb_los_launch(const DModel* d_models, int n_models, const DBessel& B, int max_n_q, int max_n_tau, size_t smem, cudaStream_t st) {
     dim3 grid(max_n_q, n_models);
     cb_los_kernel<<<grid, LOS_THREADS, smem, st>>>(d_models, B, max_n_tau);
+}
+
+size_t cb_los_win_smem(int max_n_tau) { return (sizeof(double) + sizeof(int)) * (size_t)max_n_tau + 16; }
+
+cudaError_t cb_los_win_launch(const DModel* d_models, int n_models, const DBessel& B, int max_n_q, int max_n_tau, cudaStream_t st) {
+    const size_t smem = cb_los_win_smem(max_n_tau);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(cb_los_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid(max_n_q, n_models);
+    cb_los_win_kernel<<<grid, LOS_THREADS, smem, st>>>(d_models, B, max_n_tau);
+    return cudaGetLastError();
 }
 
 void cb_cl_launch(const DModel* d_models, int n_models, const DBessel& B, cudaStream_t st) {

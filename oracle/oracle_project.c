@@ -75,7 +75,10 @@ static int ranges_index_of_ordered(const cb_range* R, int count, int npoints, do
     return -1;
 }
 
-static int use_limber(const cb_model* M, int l) { return l > 400 * pow(M->AccuracyBoost * M->LimberBoost, 0.5); }
+static int use_limber(const cb_model* M, int l) { /* cmbmain.f90:1619-1636 */
+    if (M->SourceTerms.limber_windows) return l >= M->SourceTerms.limber_phi_lmin;
+    return l > 400 * pow(M->AccuracyBoost * M->LimberBoost, 0.5);
+}
 
 static void project_one_q(const cb_model* M, const cb_bessel* B, int n_k, const double* q_src, const double* Src,
                           const double* dd, double q, double* Delta /* (n_src, n_l) for this q */, double* Source_q,
