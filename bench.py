@@ -141,6 +141,33 @@ def run_reference(args, rank, world):
     }))
 
 
+def los_gather_evals(hs):
+    """Number of (q, l, tau) terms loop B evaluates for one cosmology: N_eval = sum_q sum_{l <= llmax(q)} (n2 - n1 + 1)
+    with the limits of DoFlatIntegration (cmbmain.f90:1702-1724).  Each term gathers one 32-byte Bessel record, so
+    32 * N_eval is the L1/L2 sector traffic that actually bounds the kernel (SURVEY.md 8(d) 'gather bytes')."""
+    m = hs.model
+    tau, tau0, ls = np.asarray(hs.tau), m.tau0, np.asarray(hs.ls, dtype=np.float64)
+    boost = m.AccuracyBoost * m.BessIntBoost
+    total = 0
+    for q in np.asarray(hs.q_int):
+        llmax = int(round(q * tau0))
+        llmax = 17 if llmax < 15 else int(round(q * tau0 + 6 * np.pi))
+        l = ls[ls <= llmax]
+        if not len(l):
+            continue
+        tmin = np.maximum(tau[1], tau0 - 80 * l * boost / q)
+        tmax = tau0 - np.maximum(0.0, l - 4.2 * l ** (1 / 3.0)) / q
+        ok = tmax >= tau[1]
+        n1 = np.searchsorted(tau, tmin[ok], side="right")
+        n2 = np.searchsorted(tau, tmax[ok], side="right")
+        if m.n_src > 2:   # the phi column's DoInt cut removes whole (q, l) pairs at high q
+            qmax_int = np.maximum(850.0, l[ok]) * 3 * boost / tau0 * 1.2
+            keep = q < qmax_int
+            n1, n2 = n1[keep], n2[keep]
+        total += int(np.clip(n2 - n1 + 1, 0, None).sum())
+    return total
+
+
 def model_h2d_bytes(hs):
     m = hs.model
     return 8 * (m.nthermo * (16 + 7) + 2 * m.n_tau) + 8 * max(0, m.num_transfer_redshifts)
@@ -260,6 +287,12 @@ def main():
         b = hss[0].bessel()
         los_bytes = 32.0 * (b.nx - 1) * b.n_l + sum(
             8.0 * (2 * len(hs.source_q()) * hs.n_src * hs.n_tau + hs.n_src * len(hs.ls) * len(hs.q_int)) for hs in hss)
+        gather_bytes = 32.0 * sum(los_gather_evals(hs) for hs in hss)
+        traffic = {}
+        try:   # DRAM bytes per launch of the two kernels from the committed `ncu --set full` capture of this command
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -272,13 +305,17 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "kernel": "cb_evolve_kernel", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": ach / fp64_peak if fp64_peak else None, "traffic": None,
+                         "frac": ach / fp64_peak if fp64_peak else None, "traffic": traffic.get("cb_evolve_kernel_dram_bytes_per_launch"),
                          "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "ms_per_launch": ev_ms, "share_of_step": t_ev / (t_ev + t_los + t_spl + t_cl),
                          "derivs_evals_per_launch": evals, "algorithmic_flops_per_launch": ode_flops},
             "roofline_los": {"bound": "hbm", "kernel": "cb_los_kernel", "achieved": los_bytes / (los_ms * 1e-3) / 1e9,
                              "peak": hbm_peak, "unit": "GB/s", "frac": los_bytes / (los_ms * 1e-3) / 1e9 / hbm_peak,
-                             "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",
+                             "traffic": traffic.get("cb_los_kernel_dram_bytes_per_launch"),
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",
+                             "gather_bytes_per_launch": gather_bytes, "l2_gather_gbs": gather_bytes / (los_ms * 1e-3) / 1e9,
+                             "note": "working set is L2-resident: the kernel is bound by the 32-byte Bessel-record gathers through L1/L2 "
+                                     "(l2_gather_gbs), not by HBM",
                              "ms_per_launch": los_ms, "share_of_step": t_los / (t_ev + t_los + t_spl + t_cl)},
             "stage_ms_per_step": {"evolve": ev_ms, "spline_k": t_spl / args.steps, "los": los_ms, "cl": t_cl / args.steps},
         }
