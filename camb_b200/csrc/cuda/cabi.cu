@@ -34,13 +34,15 @@ void cb_cl_windows_launch(const DModel*, int, const DBessel&, double* const*, do
 // peak.cu
 double cb_fp64_peak_measure(int n_sm, cudaStream_t st, int reps);
 
-// Modes are binned by their worst-case number of equations so that every launch sizes its
-// per-mode shared-memory slab for its own class (the few low-k modes with deep photon hierarchies
-// would otherwise halve the number of resident modes of everyone else).
+// Modes are binned by the size of their shared-memory slab (worst-case number of equations AND deepest multipole:
+// the low-k modes carry a 32..64-deep photon hierarchy that would otherwise inflate everyone's coefficient
+// tables), so that every launch sizes its per-mode slab for its own class.  The limits are the slab sizes at
+// which 6, 5, 4 and 3 blocks of eight modes fit one SM's 227 KB (1 KB per block is reserved by the system).
 // The last class holds tensor modes (their own kernel, evolve_tensor.cu).
-#define CB_N_CLASSES 5
-#define CB_TENSOR_CLASS 4
-static const int kClassLimit[CB_N_CLASSES] = {48, 96, 160, 1 << 30, 1 << 30};
+#define CB_N_CLASSES 6
+#define CB_TENSOR_CLASS 5
+static const size_t kClassSlabLimit[CB_N_CLASSES - 1] = {4714, 5683, 7136, 9557, ~size_t(0)};
+size_t cb_evolve_slab_bytes(int nv, int maxl);   // evolve.cu
 
 struct cb_dmodel {
     DModel h;                      // host copy with device pointers
@@ -318,7 +320,7 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
               float* const* TransferData, long long* const* stats) {
     if (!ctx) return CB_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
-    std::vector<DModeItem> cls_items[CB_N_CLASSES];
+    std::vector<DModeItem> cls_items[CB_N_CLASSES], all_items;
     int cls_nv[CB_N_CLASSES] = {}, cls_maxl[CB_N_CLASSES] = {};
     for (int m = 0; m < n_models; m++) {
         cb_dmodel* d = dm[m];
@@ -373,13 +375,27 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
             if (D.is_tensor) cb_tensor_mode_size(D, &it.nvar, &ml);
             else cb_mode_size(D, it.q, it.transfer_only, &it.nvar, &ml);
             if (ml > CBD_MAX_L_EVOLVE) { ctx->err = "Need to increase max_l_evolve"; return CB_ERR_UNSUPPORTED_PARAMS; }
-            int c = 0;
-            if (D.is_tensor) c = CB_TENSOR_CLASS;
-            else while (it.nvar > kClassLimit[c]) c++;
-            cls_nv[c] = std::max(cls_nv[c], it.nvar);
-            cls_maxl[c] = std::max(cls_maxl[c], ml);
-            cls_items[c].push_back(it);
+            it.transfer_only |= ml << 8;   // deepest multipole rides along until the binning pass below
+            all_items.push_back(it);
         }
+    }
+    // Binning pass, most expensive modes first (largest k: cmbmain.f90:205-206 runs them first too): a mode joins the first
+    // class whose slab, grown to hold it, stays inside that class's limit -- so the high-k bulk (45-ish equations, 14
+    // multipoles) keeps the smallest slab and the few deep low-k hierarchies land in the larger classes.
+    std::stable_sort(all_items.begin(), all_items.end(), [](const DModeItem& a, const DModeItem& b) { return a.q > b.q; });
+    for (DModeItem& it : all_items) {
+        const int ml = it.transfer_only >> 8;
+        it.transfer_only &= 0xff;
+        int c = 0;
+        if (dm[it.model]->h.is_tensor) c = CB_TENSOR_CLASS;
+        else
+            for (;; c++) {
+                const size_t grown = cb_evolve_slab_bytes(std::max(std::max(cls_nv[c], it.nvar), 32), std::max(cls_maxl[c], ml));
+                if (grown <= kClassSlabLimit[c]) break;
+            }
+        cls_nv[c] = std::max(cls_nv[c], it.nvar);
+        cls_maxl[c] = std::max(cls_maxl[c], ml);
+        cls_items[c].push_back(it);
     }
     int n_items = 0;
     for (int c = 0; c < CB_N_CLASSES; c++) n_items += (int)cls_items[c].size();
@@ -515,7 +531,7 @@ int cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q, 
     for (int m = 0; m < n_models; m++) any_windows = any_windows || dm[m]->h.num_redshiftwindows > 0;
     const size_t smem = cb_los_smem(max_nsrc, max_ntau);
     CK(cudaEventRecord(ctx->stage_ev[2][0], ctx->stream));
-    if (any_windows || smem > 227 * 1024) {
+    if (any_windows || smem > 227 * 1024 || n_l > 192 /* LOS_MAX_L */) {
         // source windows (or a time grid too long to stage the sources): the general kernel
         for (int m = 0; m < n_models; m++)
             if (dm[m]->h.is_tensor) { ctx->err = "LOS: tensor models cannot share a call with source-window models"; return CB_ERR_UNSUPPORTED_PARAMS; }

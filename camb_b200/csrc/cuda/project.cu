@@ -21,6 +21,10 @@
 
 #define FULL 0xffffffffu
 #define LOS_THREADS 256
+#define LOS_MAX_L 192   /* l samples with per-l constants in shared memory (more: the general kernel) */
+#ifndef LOS_MIN_BLOCKS
+#define LOS_MIN_BLOCKS 5
+#endif
 
 namespace {
 
@@ -47,6 +51,12 @@ __device__ __forceinline__ int ranges_index_of_ordered(const cb_range* R, int co
         }
     }
     return -1;
+}
+
+// One 32-byte Horner record of bessel_horner(:, ix, l) with a single 256-bit read-only load (LDG.E.256 on sm_100a; PTX
+// ld.global.nc.v4.f64): half the L1 requests of two 128-bit loads -- the records are 32-byte aligned by construction.
+__device__ __forceinline__ void ld_horner(const double* rec, double& c0, double& c1, double& c2, double& c3) {
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(c0), "=d"(c1), "=d"(c2), "=d"(c3) : "l"(rec));
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -85,7 +95,7 @@ __global__ void cb_spline_k_kernel(const DModel* __restrict__ models, int n_mode
 }
 
 // grid = (max n_q, n_models); dynamic smem: Source_q[n_src*n_tau] + left_weight[n_tau] + dtau[n_tau] + bes_index[n_tau]
-__global__ void __launch_bounds__(LOS_THREADS)
+__global__ void __launch_bounds__(LOS_THREADS, LOS_MIN_BLOCKS)
 cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
     const DModel& M = models[blockIdx.y];
     const int iq = blockIdx.x;
@@ -98,11 +108,25 @@ cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
     int* bes_index = reinterpret_cast<int*>(dtau_s + max_n_tau);
     __shared__ int s_firstfail;
     __shared__ cb_range s_tau_regions[8];
+    // per-l constants of DoFlatIntegration (x limits, the phi column's DoInt and Limber switches): evaluated once per CTA
+    // instead of once per (warp, l) -- pow() and sqrt() leave the l loop
+    __shared__ double s_xlim[LOS_MAX_L], s_xlmax1[LOS_MAX_L], s_qmax_int[LOS_MAX_L], s_limfac[LOS_MAX_L];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = LOS_THREADS / 32;
     const double q = M.q_int[iq], tau0 = M.tau0;
     const double* TimePoints = M.tau;
     if (tid == 0) s_firstfail = ntime + 1;
     if (tid < M.n_tau_regions) s_tau_regions[tid] = M.tau_regions[tid];
+    {
+        const double BessIntBoost = M.AccuracyBoost * M.BessIntBoost;
+        for (int j = tid; j < n_l; j += LOS_THREADS) {
+            const int l = B.l[j];
+            s_xlim[j] = fmax(0.0, l - 4.2 * pow((double)l, 1.0 / 3.0));
+            s_xlmax1[j] = 80 * l * BessIntBoost;
+            s_qmax_int[j] = (l > 850 ? l : 850) * 3 * BessIntBoost / tau0 * 1.2;
+            // UseLimber (cmbmain.f90:1619-1636): negative = integrate phi by Bessels at this l, else the Limber prefactor
+            s_limfac[j] = l > 400 * pow(M.AccuracyBoost * M.LimberBoost, 0.5) ? sqrt(3.1415926535897932384626433832795 / 2 / (l + 0.5)) : -1.0;
+        }
+    }
     __syncthreads();
     // ---- InterpolateSources, cmbmain.f90:1351-1480 ----
     const bool tensors = M.is_tensor != 0;   // cmbmain.f90:1391-1403
@@ -159,7 +183,6 @@ cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
     int llmax = (int)llround(q * tau0);
     if (llmax < 15) llmax = 17;
     else llmax = (int)llround(q * (tau0 + 6.0 * 3.1415926535897932384626433832795 / q));
-    const double BessIntBoost = M.AccuracyBoost * M.BessIntBoost;
     double* Dout = M.Delta + (size_t)nsrc * n_l * iq;
     for (int j = 1 + warp; j <= n_l; j += nwarp) {
         const int l = B.l[j - 1];
@@ -167,10 +190,8 @@ cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
         bool active = l <= llmax;
         double tmin = 0, tmax = 0;
         if (active) {
-            const double xlim = fmax(0.0, l - 4.2 * pow((double)l, 1.0 / 3.0));
-            const double xlmax1 = 80 * l * BessIntBoost;
-            tmin = fmax(TimePoints[1], tau0 - xlmax1 / q);
-            tmax = tau0 - xlim / q;
+            tmin = fmax(TimePoints[1], tau0 - s_xlmax1[j - 1] / q);
+            tmax = tau0 - s_xlim[j - 1] / q;
             if (tmax < TimePoints[1]) active = false;
         }
         if (active) {
@@ -178,34 +199,42 @@ cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
             const int n1 = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, tmin);
             int n2 = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, tmax);
             if (n2 > SourceSteps) n2 = SourceSteps;
-            bool DoInt = true;
-            if (nsrc > 2) {
-                const double qmax_int = (l > 850 ? l : 850) * 3 * BessIntBoost / tau0 * 1.2;
-                DoInt = tensors || q < qmax_int;   // DoInt = .not. CP%WantScalars .or. IV%q < qmax_int
-            }
+            const bool DoInt = nsrc <= 2 || tensors || q < s_qmax_int[j - 1];   // DoInt = .not. CP%WantScalars .or. IV%q < qmax_int
             if (DoInt) {
                 for (int n = n1 + lane; n <= n2; n += 32) {
                     const double a2 = left_weight[n - 1];
-                    const double2* h = reinterpret_cast<const double2*>(H + 4 * (size_t)(bes_index[n - 1] - 1));
-                    const double2 h0 = __ldg(h), h1 = __ldg(h + 1);
-                    double J_l = h0.x + a2 * (h0.y + a2 * (h1.x + a2 * h1.y));
+                    double c0, c1, c2, c3;
+                    ld_horner(H + 4 * (size_t)(bes_index[n - 1] - 1), c0, c1, c2, c3);
+                    double J_l = c0 + a2 * (c1 + a2 * (c2 + a2 * c3));
                     J_l = J_l * dtau_s[n - 1];
                     s0 = s0 + Source_q[n - 1] * J_l;
                     s1 = s1 + Source_q[max_n_tau + n - 1] * J_l;
                     if (nsrc > 2) s2 = s2 + Source_q[2 * (size_t)max_n_tau + n - 1] * J_l;
                 }
-                s0 = warp_sum(s0); s1 = warp_sum(s1);
-                if (nsrc > 2) s2 = warp_sum(s2);
+                // Three sums, one butterfly: a reduce-scatter over the xor tree (16, 8, 4, 2, 1) leaves s0 in lane 0, s1 in
+                // lane 8 and s2 in lane 16 with 6 instead of 15 double shuffles -- the same additions as the plain butterfly, so
+                // the result is bit-identical and deterministic.
+                {
+                    const bool up = lane & 16;
+                    double a = (up ? s2 : s0) + __shfl_xor_sync(FULL, up ? s0 : s2, 16);
+                    double b = (up ? 0.0 : s1) + __shfl_xor_sync(FULL, up ? s1 : 0.0, 16);
+                    const bool mid = lane & 8;
+                    double c = (mid ? b : a) + __shfl_xor_sync(FULL, mid ? a : b, 8);
+                    c += __shfl_xor_sync(FULL, c, 4);
+                    c += __shfl_xor_sync(FULL, c, 2);
+                    c += __shfl_xor_sync(FULL, c, 1);
+                    s0 = __shfl_sync(FULL, c, 0); s1 = __shfl_sync(FULL, c, 8); s2 = __shfl_sync(FULL, c, 16);
+                }
             }
             if (nsrc > 2 && !tensors) {  // UseLimber, cmbmain.f90:1619-1636, 1821-1832 (scalars only)
-                const bool limber = l > 400 * pow(M.AccuracyBoost * M.LimberBoost, 0.5);
-                if (!DoInt || limber) {
+                const double limfac = s_limfac[j - 1];
+                if (!DoInt || limfac > 0) {
                     double xf = tau0 - (l + 0.5) / q;
                     if (xf < M.tau_highest && xf > M.tau_lowest) {
                         const int n = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, xf);
                         xf = (xf - TimePoints[n - 1]) / (TimePoints[n] - TimePoints[n - 1]);
                         s2 = (Source_q[2 * (size_t)max_n_tau + n - 1] * (1 - xf) + xf * Source_q[2 * (size_t)max_n_tau + n]) *
-                             sqrt(3.1415926535897932384626433832795 / 2 / (l + 0.5)) / q;
+                             (limfac > 0 ? limfac : sqrt(3.1415926535897932384626433832795 / 2 / (l + 0.5))) / q;
                     } else s2 = 0;
                 }
             }
@@ -342,9 +371,9 @@ cb_los_win_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
             double acc = 0;
             for (int n = na + lane; n <= nb; n += 32) {
                 const double a2 = left_weight[n - 1];
-                const double2* h = reinterpret_cast<const double2*>(H + 4 * (size_t)(bes_index[n - 1] - 1));
-                const double2 h0 = __ldg(h), h1 = __ldg(h + 1);
-                double J_l = h0.x + a2 * (h0.y + a2 * (h1.x + a2 * h1.y));
+                double c0, c1, c2, c3;
+                ld_horner(H + 4 * (size_t)(bes_index[n - 1] - 1), c0, c1, c2, c3);
+                double J_l = c0 + a2 * (c1 + a2 * (c2 + a2 * c3));
                 J_l = J_l * __ldg(&M.dtau[n - 1]);
                 acc = acc + source_q(n, s) * J_l;
             }
