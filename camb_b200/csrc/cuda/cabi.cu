@@ -16,7 +16,7 @@
 // evolve.cu
 void cb_mode_size(const DModel& M, double q, int transfer_only, int* nvar, int* maxl);
 cudaError_t cb_evolve_launch(const DModel*, const DModeItem*, int n_items, int nv, int maxl, int lanes_per_mode, int lean,
-                             unsigned int*, int*, int n_sm, cudaStream_t, int* grid_out);
+                             unsigned int*, int*, int n_sm, cudaStream_t, int* grid_out, int block_cap);
 // evolve_tensor.cu
 void cb_tensor_mode_size(const DModel& M, int* nvart, int* maxl);
 cudaError_t cb_evolve_tensor_launch(const DModel*, const DModeItem*, int n_items, int nv, int maxl, unsigned int*, int*, int n_sm,
@@ -424,13 +424,22 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
     int lean = 1;   // every model massless-nu LCDM: the kernel variant without massive-nu / dark-energy code
     for (int m = 0; m < n_models; m++) if (dm[m]->h.Num_Nu_massive != 0 || !dm[m]->h.de_is_cc || dm[m]->h.num_redshiftwindows > 0) lean = 0;
     int lanes = ctx->lanes_per_mode;
-    if (lanes != 8 && lanes != 16 && lanes != 32) lanes = n_items >= 16 * ctx->n_sm ? 8 : 32;
+    if (lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) lanes = n_items >= 16 * ctx->n_sm ? 8 : 32;
     CK(cudaEventRecord(ctx->stage_ev[0][0], ctx->stream));
     CK(cudaEventRecord(ctx->fork, ctx->stream));
-    for (int c = 0; c < CB_N_CLASSES; c++) {
-        ctx->last_grid[c] = 0;
+    // Launch order and block caps of the slab classes (experiment knobs CAMB_B200_ORDER / CAMB_B200_CAPS)
+    int order_desc = 0, caps[CB_N_CLASSES] = {};
+    if (const char* o = getenv("CAMB_B200_ORDER")) order_desc = atoi(o);
+    if (const char* cp = getenv("CAMB_B200_CAPS")) {
+        int i = 0;
+        for (const char* p = cp; *p && i < CB_N_CLASSES; i++) { caps[i] = atoi(p); while (*p && *p != ',') p++; if (*p == ',') p++; }
+    }
+    for (int cc = 0; cc < CB_N_CLASSES; cc++) ctx->last_grid[cc] = 0;
+    for (int cc = 0; cc < CB_N_CLASSES; cc++) {
+        const int c = order_desc ? CB_N_CLASSES - 1 - cc : cc;
         const int n_c = (int)cls_items[c].size();
         if (n_c == 0) continue;
+        if (const char* only = getenv("CAMB_B200_ONLY_CLASS")) if (atoi(only) != c) continue;   // timing experiments: one slab class alone
         // the scratch EvolutionVars of a layout switch aliases two stage vectors (evolve.cu)
         const int nv = std::max(cls_nv[c], 32);
         CK(cudaStreamWaitEvent(ctx->class_stream[c], ctx->fork, 0));
@@ -438,7 +447,7 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
                              ? cb_evolve_tensor_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, cls_nv[c], cls_maxl[c], ctx->d_counter + c,
                                                        ctx->d_error, ctx->n_sm, ctx->class_stream[c], &ctx->last_grid[c])
                              : cb_evolve_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, nv, cls_maxl[c], lanes, lean, ctx->d_counter + c,
-                                                ctx->d_error, ctx->n_sm, ctx->class_stream[c], &ctx->last_grid[c]);
+                                                ctx->d_error, ctx->n_sm, ctx->class_stream[c], &ctx->last_grid[c], caps[c]);
         if (le != cudaSuccess) { ctx->err = std::string("evolve launch: ") + cudaGetErrorString(le); return CB_ERR_CUDA; }
         ctx->launches++;
         CK(cudaEventRecord(ctx->class_done[c], ctx->class_stream[c]));
@@ -672,7 +681,7 @@ int cb_set_option(cb_ctx* ctx, const char* name, double value) {
     if (!ctx) return CB_ERR_NO_DEVICE;
     if (!strcmp(name, "lanes_per_mode")) {
         const int v = (int)value;
-        if (v != 0 && v != 8 && v != 16 && v != 32) { ctx->err = "lanes_per_mode must be 0 (automatic), 8, 16 or 32"; return CB_ERR_UNSUPPORTED_PARAMS; }
+        if (v != 0 && v != 4 && v != 8 && v != 16 && v != 32) { ctx->err = "lanes_per_mode must be 0 (automatic), 4, 8, 16 or 32"; return CB_ERR_UNSUPPORTED_PARAMS; }
         ctx->lanes_per_mode = v;
         return 0;
     }

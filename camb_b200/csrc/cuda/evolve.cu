@@ -1170,11 +1170,11 @@ __device__ __forceinline__ bool attempt_start(const MHot& H, const EVs& E, Ctl& 
     const double h = trial_x - x;
     __syncwarp(gm);   // every lane has read the control block
     if (lane == 0) { C.css = css; C.h = h; C.trial_x = trial_x; C.hmin = hmin; }
-    if (lane < 6) {
-        const double ts = x + c_dp_c[lane + 1] * h;
+    for (int st = lane; st < 6; st += G) {   // one stage time per lane (two per lane in a 4-lane group)
+        const double ts = x + c_dp_c[st + 1] * h;
         double a, cs2, opac, dopac = 0;
         thermo_values(H, ts, a, cs2, opac, dopac, E.TightCoupling != 0);
-        double* t = C.th[lane];
+        double* t = C.th[st];
         t[0] = cs2; t[1] = opac; t[2] = a; t[3] = dopac; t[4] = 1.0 / ts;
     }
     return true;
@@ -1236,7 +1236,9 @@ __device__ __forceinline__ void attempt_finish(const DModel& M, EVs& E, Ctl& C, 
 
 }  // namespace
 
-#define WARPS_PER_BLOCK 2
+// Warps per block: two for the 8..32-lane groups, one for 4-lane groups (eight modes per warp) so that a block is
+// always eight modes or fewer and the slab classes of cabi.cu keep their meaning.
+#define WPB(G_) ((G_) >= 8 ? 2 : 1)
 #ifndef EVOLVE_MIN_BLOCKS
 #define EVOLVE_MIN_BLOCKS 6   /* 64 threads x 6 blocks: <= 168 registers per thread */
 #endif
@@ -1250,7 +1252,7 @@ __device__ __forceinline__ void attempt_finish(const DModel& M, EVs& E, Ctl& C, 
 // Dynamic shared memory per group: [Ctl][MHot][EVs][denlk, denlk2, polfack: 3*(maxl+1)][NVEC*nv],
 // padded so that consecutive groups start 64 bytes apart modulo 128.
 template <int G, bool LEAN>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, EVOLVE_MIN_BLOCKS)
+__global__ void __launch_bounds__(WPB(G) * 32, EVOLVE_MIN_BLOCKS)
 cb_evolve_kernel(const DModel* __restrict__ models, const DModeItem* __restrict__ items, int n_items, int nv, int maxl,
                  unsigned long long slab_bytes, unsigned int* counter, int* error_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1396,10 +1398,10 @@ void cb_mode_size(const DModel& M, double q, int transfer_only, int* nvar, int* 
 
 template <int G, bool LEAN>
 static cudaError_t launch_g(const DModel* d_models, const DModeItem* d_items, int n_items, int nv, int maxl, unsigned int* d_counter,
-                            int* d_error, int n_sm, cudaStream_t stream, int* grid_out) {
+                            int* d_error, int n_sm, cudaStream_t stream, int* grid_out, int block_cap) {
     constexpr int MPW = 32 / G;
     const size_t slab = cb_evolve_slab_bytes(nv, maxl);
-    const size_t smem = slab * MPW * WARPS_PER_BLOCK;
+    const size_t smem = slab * MPW * WPB(G);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(cb_evolve_kernel<G, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1408,15 +1410,16 @@ static cudaError_t launch_g(const DModel* d_models, const DModeItem* d_items, in
         if (e != cudaSuccess) return e;
     }
     int nb = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cb_evolve_kernel<G, LEAN>, WARPS_PER_BLOCK * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cb_evolve_kernel<G, LEAN>, WPB(G) * 32, smem);
     if (e != cudaSuccess) return e;
     if (const char* mb = getenv("CAMB_B200_MAXBLOCKS")) nb = nb < atoi(mb) ? nb : atoi(mb);
+    if (block_cap > 0 && nb > block_cap) nb = block_cap;   // leave room for the other slab classes running beside this one
     if (nb < 1) nb = 1;
-    const int per_block = MPW * WARPS_PER_BLOCK;
+    const int per_block = MPW * WPB(G);
     int grid = (n_items + per_block - 1) / per_block;
     if (grid > n_sm * nb) grid = n_sm * nb;
     if (grid_out) *grid_out = grid;
-    cb_evolve_kernel<G, LEAN><<<grid, WARPS_PER_BLOCK * 32, smem, stream>>>(d_models, d_items, n_items, nv, maxl, (unsigned long long)slab,
+    cb_evolve_kernel<G, LEAN><<<grid, WPB(G) * 32, smem, stream>>>(d_models, d_items, n_items, nv, maxl, (unsigned long long)slab,
                                                                       d_counter, d_error);
     return cudaGetLastError();
 }
@@ -1424,9 +1427,10 @@ static cudaError_t launch_g(const DModel* d_models, const DModeItem* d_items, in
 // lanes_per_mode: 8 (throughput: four modes share a warp's instruction stream) or 32 (latency:
 // one mode per warp, for launches with fewer modes than the GPU has warp slots).
 cudaError_t cb_evolve_launch(const DModel* d_models, const DModeItem* d_items, int n_items, int nv, int maxl, int lanes_per_mode, int lean,
-                             unsigned int* d_counter, int* d_error, int n_sm, cudaStream_t stream, int* grid_out) {
-#define CB_LAUNCH(G_) (lean ? launch_g<G_, true>(d_models, d_items, n_items, nv, maxl, d_counter, d_error, n_sm, stream, grid_out) \
-                            : launch_g<G_, false>(d_models, d_items, n_items, nv, maxl, d_counter, d_error, n_sm, stream, grid_out))
+                             unsigned int* d_counter, int* d_error, int n_sm, cudaStream_t stream, int* grid_out, int block_cap) {
+#define CB_LAUNCH(G_) (lean ? launch_g<G_, true>(d_models, d_items, n_items, nv, maxl, d_counter, d_error, n_sm, stream, grid_out, block_cap) \
+                            : launch_g<G_, false>(d_models, d_items, n_items, nv, maxl, d_counter, d_error, n_sm, stream, grid_out, block_cap))
+    if (lanes_per_mode == 4) return CB_LAUNCH(4);
     if (lanes_per_mode == 8) return CB_LAUNCH(8);
     if (lanes_per_mode == 16) return CB_LAUNCH(16);
     return CB_LAUNCH(32);

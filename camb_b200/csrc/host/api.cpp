@@ -154,6 +154,8 @@ int cbh_scalar_power_at(cbh_state* s, int n, const double* k, double* out) {
     return 0;
 }
 
+double cbh_omnuh2_from_mass(double mass_eV, double degeneracy, double number, double TCMB) { return nu_omnuh2_from_mass(mass_eV, degeneracy, number, TCMB); }
+
 int cbh_get_derived(cbh_state* s, double out[13]) {
     const Derived& D = s->S.derived;
     if (!s->S.has_derived) return 1;

@@ -43,6 +43,8 @@ def load_host_lib():
         lib.cbh_get_ls.argtypes = [C.c_void_p, c_int_p, C.POINTER(c_int_p)]
         lib.cbh_get_pows.argtypes = [C.c_void_p, C.c_int, c_double_p]
         lib.cbh_scalar_power_at.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p]
+        lib.cbh_omnuh2_from_mass.restype = C.c_double
+        lib.cbh_omnuh2_from_mass.argtypes = [C.c_double] * 4
         lib.cbh_get_derived.argtypes = [C.c_void_p, C.c_double * 13]
         lib.cbh_get_background.argtypes = [C.c_void_p, C.c_double * 16]
         lib.cbh_interp_cl.argtypes = [C.c_void_p, c_double_p, c_double_p]
@@ -62,6 +64,26 @@ def default_params():
 
 def _dp(a):
     return a.ctypes.data_as(c_double_p)
+
+
+def set_neutrino_masses(p, mnu, nnu=3.044, num_massive_neutrinos=1, standard_neutrino_neff=3.044):
+    """CAMBparams_SetNeutrinoMasses (fortran/model.f90:364-405) with the degenerate hierarchy
+    (CAMBparams_SetNeutrinoHierarchyBase :260-298): what `set_cosmology(mnu=...)` does in the reference's Python API."""
+    if mnu == 0:
+        p.omnuh2, p.Num_Nu_massive, p.Nu_mass_eigenstates, p.Num_Nu_massless, p.share_delta_neff = 0.0, 0, 0, nnu, 0
+        return p
+    neff_massive = num_massive_neutrinos * standard_neutrino_neff / 3
+    p.Num_Nu_massive, p.Nu_mass_eigenstates, p.share_delta_neff = num_massive_neutrinos, 1, 0
+    if nnu > neff_massive:
+        p.Num_Nu_massless = nnu - neff_massive
+    else:
+        p.Num_Nu_massless, neff_massive = 0.0, nnu
+    p.Nu_mass_numbers[0] = num_massive_neutrinos
+    p.Nu_mass_degeneracies[0] = neff_massive
+    mass = mnu / num_massive_neutrinos
+    p.omnuh2 = load_host_lib().cbh_omnuh2_from_mass(mass, neff_massive, float(num_massive_neutrinos), p.TCMB)
+    p.Nu_mass_fractions[0] = 1.0
+    return p
 
 
 DERIVED_NAMES = ["age", "zstar", "rstar", "thetastar", "DAstar", "zdrag", "rdrag", "kd", "thetad", "zeq", "keq",

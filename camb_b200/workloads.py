@@ -179,3 +179,29 @@ def lensing_window_params(z=1089.0, sigma=30.0, lmax=400, limber=False):
     _set_windows(p, [("lensing", z, sigma, 1.0, 0.0)])
     p.SourceTerms.limber_windows = 1 if limber else 0
     return p
+
+
+def sigma8_anchor_params(anchor, notebook=False):
+    """`notebook=True`: the CAMBdemo.ipynb variant (mnu 0.06, kmax 2, redshifts [0.8, 0], the default RECFAST set).
+    The parameter set of the reference's sigma8 known-answer test (camb/tests/camb_test.py:800-823), from the
+    committed fixture tests/golden/sigma8_anchor.json: CAMBparams() defaults + set_cosmology(H0, ombh2, omch2, mnu) +
+    InitPower(ns, As) + RECFAST 'planck' set + set_matter_power(redshifts, kmax=1.2) (which turns high_precision on)."""
+    from .host import set_neutrino_masses
+    a = dict(anchor["params"])
+    if notebook:
+        a.update(anchor["notebook"]["params"])
+    p = default_params()
+    p.H0, p.ombh2, p.omch2, p.TCMB, p.Yhe = a["H0"], a["ombh2"], a["omch2"], a["TCMB"], a["YHe"]
+    set_neutrino_masses(p, a["mnu"], nnu=a["nnu"], num_massive_neutrinos=a["num_massive_neutrinos"])
+    p.As, p.ns = a["As"], a["ns"]
+    if a["recfast_approx_model"] == "planck":   # camb/recombination.py:11-23; "cosmorec" is the library default (:24-35)
+        p.RECFAST_fudge, p.RECFAST_fudge_He, p.RECFAST_He_rate_correction = 1.125, 0.86, 0
+        p.AGauss1, p.AGauss2, p.zGauss1, p.zGauss2, p.wGauss1, p.wGauss2 = -0.14, 0.079, 7.28, 6.73, 0.18, 0.33
+    p.use_optical_depth, p.redshift = 0, a["reion_redshift_default"]
+    p.Max_l, p.Max_eta_k, p.DoLensing = 2500, 5000.0, 1
+    p.WantTransfer, p.transfer_high_precision, p.transfer_kmax = 1, 1, a["transfer_kmax"]
+    zs = sorted(a["redshifts"], reverse=True)
+    p.transfer_PK_num_redshifts = len(zs)
+    for i, z in enumerate(zs):
+        p.transfer_PK_redshifts[i] = z
+    return p

@@ -31,6 +31,9 @@ int cbh_get_ls(cbh_state* s, int* n_l, const int** l);
 int cbh_get_pows(cbh_state* s, int tensor, double* pows);     /* InitPower at q_int [n_q] */
 /* InitPower%ScalarPower at arbitrary wavenumbers (the Limber sums of CalcLimberScalCls, cmbmain.f90:387). */
 int cbh_scalar_power_at(cbh_state* s, int n, const double* k, double* out);
+/* ThermalNuBackground%omnuh2_from_mass (massive_neutrinos.f90:245-262), the forward map CAMBparams_SetNeutrinoMasses uses
+ * (model.f90:364-405). */
+double cbh_omnuh2_from_mass(double mass_eV, double degeneracy, double number, double TCMB);
 int cbh_get_derived(cbh_state* s, double out[13]);            /* ThermoDerivedParams order */
 int cbh_get_background(cbh_state* s, double out[16]);         /* tau0,taurst,taurend,tau_maxvis,dtaurec,scale,... */
 /* InterpolateClArr (results.f90:1706-1743): iCl[n_l] -> all_Cl[lmin..ls(n_l)] */
