@@ -35,3 +35,27 @@ def sigma8_and_fsigma8(hs, transfer):
     s8 = sigma_r(hs, transfer, 8.0)
     sv = sigma_r(hs, transfer, 8.0, TRANSFER_TOT, TRANSFER_NEWT_VEL_CDM, root=False)
     return s8, sv / s8
+
+
+def matter_power(hs, transfer, var1=TRANSFER_TOT, var2=TRANSFER_TOT, hubble_units=True):
+    """`Transfer_GetUnsplinedPower` (fortran/results.f90:3472-3513): P(k) = 2 pi^2/k^3 T_1 T_2 P_R(k) at the transfer
+    wavenumbers, in (Mpc/h)^3 when hubble_units.  Returns (kh [n_k], P [n_z, n_k]) in the order of `transfer`."""
+    tr = np.asarray(transfer, dtype=np.float64)
+    kh = tr[0, :, TRANSFER_KH]
+    h = hs.params.H0 / 100.0
+    k = kh * h
+    pk = tr[:, :, var1] * tr[:, :, var2] * (k * np.pi * 2 * np.pi * hs.scalar_power_at(k))[None, :]
+    return kh, pk * h ** 3 if hubble_units else pk
+
+
+def matter_power_interp(hs, transfer, minkh=1e-4, maxkh=1.0, npoints=100):
+    """`Transfer_GetMatterPowerData` + `Transfer_GetMatterPowerD` (fortran/results.f90:3559-3616, 3700-3790): natural cubic
+    spline of log P in log(k/h), evaluated on a regular grid in log(k/h) -- what `get_matter_power_spectrum` returns."""
+    from scipy.interpolate import CubicSpline
+    kh, pk = matter_power(hs, transfer)
+    lk = np.log(kh)
+    out_kh = minkh * np.exp(np.arange(npoints) * (np.log(maxkh / minkh) / (npoints - 1)))
+    res = np.empty((pk.shape[0], npoints))
+    for i in range(pk.shape[0]):
+        res[i] = np.exp(CubicSpline(lk, np.log(pk[i]), bc_type="natural")(np.log(out_kh)))
+    return out_kh, res

@@ -31,7 +31,10 @@ out = {
                "redshifts": [3.1, 0.17, 0.0], "transfer_kmax": 1.2, "transfer_high_precision": True,
                "recfast_approx_model": "planck", "reion_redshift_default": 10.0},
     "expected": {"sigma8": {"3.1": 0.24686, "0.0": 0.80044}, "fsigma8": {"3.1": 0.2431, "0.0": 0.424712},
-                 "places_in_reference_test": 3},
+                 "places_in_reference_test": 3,
+                 # camb/tests/camb_test.py:812-829 (2 decimal places there): pk = get_matter_power_spectrum(1e-4, 1, 20) at the
+                 # highest redshift, third-last k; pk2 = get_linear_matter_power_spectrum() at z = 0.17, fourth-last transfer k
+                 "pk_interp_z3.1_khindex-3_of_20": 51.924, "pk_linear_z0.17_kindex-4": 56.454},
     "notebook": {"source": "docs/CAMBdemo.ipynb cell 8 (:335, CAMB 2.0.0 output): camb.set_params(H0=67.5, ombh2=0.022, omch2=0.122, ns=0.965) "
                            "-> mnu 0.06, As 2e-9, default (cosmorec-fit) RECFAST set, default reionization; set_matter_power(redshifts=[0., 0.8], kmax=2.0)",
                  "params": {"mnu": 0.06, "transfer_kmax": 2.0, "redshifts": [0.8, 0.0], "recfast_approx_model": "cosmorec"},

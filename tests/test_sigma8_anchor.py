@@ -1,7 +1,8 @@
 """The reference's own known answers for the matter-transfer outputs of loops A / A' (the one place where the tree
 holds 1e-4-grade numbers for this path): sigma_8 and f*sigma_8 of camb/tests/camb_test.py:800-823 (asserted there to
 3 decimal places, quoted to 5 digits) and the 8-digit sigma_8 pair printed in docs/CAMBdemo.ipynb cell 8 (CAMB 2.0.0).
-The stand-in host + oracle reproduce them to 6e-5 and 4e-5; the tests enforce 2e-4 / 1e-4.  The GPU test puts the
+The stand-in host + oracle reproduce them to 6e-5 and 4e-5 (tests enforce 2e-4 / 1e-4), and the two P(k) samples of the
+same reference test to 3e-6 (linear, at a transfer wavenumber) and 3e-5 (splined).  The GPU test puts the
 CUDA path through the same check via the C-ABI."""
 import json
 import os
@@ -10,7 +11,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from camb_b200.transfer import sigma8_and_fsigma8
+from camb_b200.transfer import matter_power, matter_power_interp, sigma8_and_fsigma8
 from camb_b200.workloads import sigma8_anchor_params
 from conftest import ROOT, host_state
 
@@ -28,6 +29,12 @@ def _check(hs, tr, notebook):
         exp = ANCHOR["expected"]
         assert abs(s8[0] / exp["sigma8"]["3.1"] - 1) < 2e-4 and abs(s8[2] / exp["sigma8"]["0.0"] - 1) < 2e-4, s8
         assert abs(fs8[0] / exp["fsigma8"]["3.1"] - 1) < 3e-4 and abs(fs8[2] / exp["fsigma8"]["0.0"] - 1) < 2e-4, fs8
+        # P(k): the linear spectrum at the fourth-last transfer wavenumber (k/h = 0.9927, z = 0.17) is quoted to 5 digits
+        # (rounding 9e-6): enforced at 3e-5, achieved 3e-6 -- this also pins the transfer k grid point for point
+        kh, pk = matter_power(hs, tr)
+        assert abs(pk[1][-4] / exp["pk_linear_z0.17_kindex-4"] - 1) < 3e-5, pk[1][-4]
+        _, pki = matter_power_interp(hs, tr, 1e-4, 1.0, 20)
+        assert abs(pki[0][-3] / exp["pk_interp_z3.1_khindex-3_of_20"] - 1) < 1e-4, pki[0][-3]
     return s8
 
 
