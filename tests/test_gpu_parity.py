@@ -369,3 +369,51 @@ def test_kshard_subsets_and_q_slices_compose(ctx):
         ctx.destroy_model(dm)
     one = ShardedBoltzmann(GpuBackend(ctx), 0, 1).cls(hs)
     assert np.array_equal(one, icl_full)
+
+
+def test_ragged_batch_and_call_order_errors(ctx):
+    """Edge cases of the boundary: (i) a batch whose members differ in n_k, n_tau, n_src and physics (massless LCDM with and
+    without the lensing source, massive-nu w0wa PPF) gives, member by member, the bits of the one-at-a-time calls (the
+    massive member forces the full kernel variant for everyone); (ii) calls out of order and mismatched kinds are errors,
+    not silent garbage."""
+    import ctypes as C
+    from camb_b200._cdefs import c_double_p
+    ps = [planck2018_params(lmax=600, lensing=True, massless=True), planck2018_params(lmax=600, lensing=False, massless=True),
+          synthetic_lcdm_batch(1, seed=3, lmax=600, extended=True)[0]]
+    hss = [HostState(p) for p in ps]
+    assert len({hs.n_src for hs in hss}) == 2 and len({hs.n_tau for hs in hss}) >= 2
+    assert all(np.array_equal(hs.ls, hss[0].ls) for hs in hss)       # one Bessel table per context: same l sampling
+    ctx.set_bessel(hss[0])
+    dms = [ctx.create_model(hs) for hs in hss]
+    try:
+        # (ii) before anything was evolved
+        nq = (C.c_int * 1)(len(hss[0].q_int))
+        q_p = (c_double_p * 1)(hss[0].q_int.ctypes.data_as(c_double_p))
+        dq_p = (c_double_p * 1)(hss[0].dq_int.ctypes.data_as(c_double_p))
+        e = ctx._lib.cb_project(ctx._h, 1, (C.c_void_p * 1)(dms[0]), nq, q_p, dq_p, (c_double_p * 1)())
+        assert e == 5 and b"no sources" in ctx._lib.cb_last_error(ctx._h)
+        pw = hss[0].scalar_power()
+        e = ctx._lib.cb_cl(ctx._h, 1, (C.c_void_p * 1)(dms[0]), 0, (c_double_p * 1)(pw.ctypes.data_as(c_double_p)), (c_double_p * 1)())
+        assert e == 5 and b"cb_project first" in ctx._lib.cb_last_error(ctx._h)
+        with pytest.raises(CAMBError):
+            ctx.set_option("lanes_per_mode", 7)
+        with pytest.raises(CAMBError):
+            ctx.set_option("no_such_option", 1)
+        # (i)
+        ctx.evolve(hss, dms, want_sources=False, want_stats=False)
+        ctx.project(hss, dms, want_delta=False)
+        batch = ctx.cl(hss, dms)
+        assert [b.shape[1] for b in batch] == [6, 3, 6]
+        for i, hs in enumerate(hss):
+            ctx.evolve([hs], [dms[i]], want_sources=False, want_stats=False)
+            ctx.project([hs], [dms[i]], want_delta=False)
+            one = ctx.cl([hs], [dms[i]])[0]
+            if i == 2:
+                assert np.array_equal(one, batch[i])
+            else:   # alone, the massless members run the lean kernel variant: same arithmetic, possibly different contraction
+                assert max(cl_err(one, batch[i])) < 1e-11
+        e = ctx._lib.cb_cl_array(ctx._h, 1, (C.c_void_p * 1)(dms[1]), (c_double_p * 1)(), (c_double_p * 1)())
+        assert e == 5   # iCl_Array needs the lensing source (NumSources > 2)
+    finally:
+        for dm in dms:
+            ctx.destroy_model(dm)
