@@ -404,8 +404,7 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
     items.reserve(n_items);
     int cls_off[CB_N_CLASSES];
     for (int c = 0; c < CB_N_CLASSES; c++) {
-        // largest k first (cmbmain.f90:205-206: descending q with dynamic scheduling)
-        std::stable_sort(cls_items[c].begin(), cls_items[c].end(), [](const DModeItem& a, const DModeItem& b) { return a.q > b.q; });
+        // already largest k first (cmbmain.f90:205-206: descending q with dynamic scheduling): the binning pass kept the order
         cls_off[c] = (int)items.size();
         items.insert(items.end(), cls_items[c].begin(), cls_items[c].end());
     }

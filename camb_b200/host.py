@@ -109,6 +109,7 @@ class HostState:
         self.tau = np.ctypeslib.as_array(m.tau, shape=(m.n_tau,))
         self.dtau = np.ctypeslib.as_array(m.dtau, shape=(m.n_tau,))
         self._bessel = None
+        self._pows = [None, None]
         nl = C.c_int()
         lp = c_int_p()
         lib.cbh_get_ls(self._h, C.byref(nl), C.byref(lp))
