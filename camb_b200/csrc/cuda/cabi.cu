@@ -426,19 +426,24 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
     if (lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) lanes = n_items >= 16 * ctx->n_sm ? 8 : 32;
     CK(cudaEventRecord(ctx->stage_ev[0][0], ctx->stream));
     CK(cudaEventRecord(ctx->fork, ctx->stream));
-    // Launch order and block caps of the slab classes (experiment knobs CAMB_B200_ORDER / CAMB_B200_CAPS)
+    // Launch order and block caps of the slab classes.  The scheduling experiments of DESIGN.md 4.1 (profiles/r01o, r01p)
+    // are compiled in only with -DCB_TUNING_KNOBS: CAMB_B200_ORDER, CAMB_B200_CAPS, CAMB_B200_ONLY_CLASS.
     int order_desc = 0, caps[CB_N_CLASSES] = {};
+#ifdef CB_TUNING_KNOBS
     if (const char* o = getenv("CAMB_B200_ORDER")) order_desc = atoi(o);
     if (const char* cp = getenv("CAMB_B200_CAPS")) {
         int i = 0;
         for (const char* p = cp; *p && i < CB_N_CLASSES; i++) { caps[i] = atoi(p); while (*p && *p != ',') p++; if (*p == ',') p++; }
     }
+#endif
     for (int cc = 0; cc < CB_N_CLASSES; cc++) ctx->last_grid[cc] = 0;
     for (int cc = 0; cc < CB_N_CLASSES; cc++) {
         const int c = order_desc ? CB_N_CLASSES - 1 - cc : cc;
         const int n_c = (int)cls_items[c].size();
         if (n_c == 0) continue;
+#ifdef CB_TUNING_KNOBS
         if (const char* only = getenv("CAMB_B200_ONLY_CLASS")) if (atoi(only) != c) continue;   // timing experiments: one slab class alone
+#endif
         // the scratch EvolutionVars of a layout switch aliases two stage vectors (evolve.cu)
         const int nv = std::max(cls_nv[c], 32);
         CK(cudaStreamWaitEvent(ctx->class_stream[c], ctx->fork, 0));

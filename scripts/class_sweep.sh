@@ -1,4 +1,5 @@
 #!/bin/bash
+# needs a library built with -DCB_TUNING_KNOBS (make cuda NVFLAGS+=-DCB_TUNING_KNOBS)
 # Duration of every slab class of the evolve stage when it runs alone (bench batch), at 6 and 3 resident blocks per SM.
 out=gpurun_out/${1:-classes}.log
 : > $out

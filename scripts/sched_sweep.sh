@@ -1,4 +1,5 @@
 #!/bin/bash
+# needs a library built with -DCB_TUNING_KNOBS (make cuda NVFLAGS+=-DCB_TUNING_KNOBS)
 # Co-scheduling of the evolve slab classes: launch order (descending slab first) and blocks-per-SM caps per class.
 out=gpurun_out/${1:-sched}.log
 : > $out
