@@ -19,8 +19,6 @@ cudaError_t cb_evolve_launch(const DModel*, const DModeItem*, int n_items, int n
                              unsigned int*, int*, int n_sm, cudaStream_t, int* grid_out, int block_cap);
 // evolve_tensor.cu
 void cb_tensor_mode_size(const DModel& M, int* nvart, int* maxl);
-cudaError_t cb_evolve_soa_launch(const DModel*, const DModeItem*, int n_items, int nv, int lean, unsigned int*, int*, int n_sm, cudaStream_t,
-                                 int* grid_out);
 cudaError_t cb_evolve_tensor_launch(const DModel*, const DModeItem*, int n_items, int nv, int maxl, unsigned int*, int*, int n_sm,
                                     cudaStream_t, int* grid_out);
 // project.cu
@@ -41,11 +39,9 @@ double cb_fp64_peak_measure(int n_sm, cudaStream_t st, int reps);
 // tables), so that every launch sizes its per-mode slab for its own class.  The limits are the slab sizes at
 // which 6, 5, 4 and 3 blocks of eight modes fit one SM's 227 KB (1 KB per block is reserved by the system).
 // The last class holds tensor modes (their own kernel, evolve_tensor.cu).
-#define CB_N_CLASSES 7
+#define CB_N_CLASSES 6
 #define CB_TENSOR_CLASS 5
-#define CB_SOA_CLASS 6            /* mode-per-lane kernel (lanes_per_mode = 1): scalar modes with <= CB_SOA_MAX_NV equations, no transfer outputs */
-#define CB_SOA_MAX_NV 48          /* two warps x [8][nv][32] doubles must fit 227 KB */
-static const size_t kClassSlabLimit[5] = {4714, 5683, 7136, 9557, ~size_t(0)};
+static const size_t kClassSlabLimit[CB_N_CLASSES - 1] = {4714, 5683, 7136, 9557, ~size_t(0)};
 size_t cb_evolve_slab_bytes(int nv, int maxl);   // evolve.cu
 
 struct cb_dmodel {
@@ -387,17 +383,11 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
     // class whose slab, grown to hold it, stays inside that class's limit -- so the high-k bulk (45-ish equations, 14
     // multipoles) keeps the smallest slab and the few deep low-k hierarchies land in the larger classes.
     std::stable_sort(all_items.begin(), all_items.end(), [](const DModeItem& a, const DModeItem& b) { return a.q > b.q; });
-    int lanes = ctx->lanes_per_mode;
-    if (lanes != 1 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) lanes = (int)all_items.size() >= 16 * ctx->n_sm ? 8 : 32;
-    const bool soa = lanes == 1;   // mode-per-lane kernel for the eligible modes, 8-lane groups for the rest
-    if (soa) lanes = 8;
     for (DModeItem& it : all_items) {
         const int ml = it.transfer_only >> 8;
         it.transfer_only &= 0xff;
         int c = 0;
-        const DModel& Dm = dm[it.model]->h;
-        if (Dm.is_tensor) c = CB_TENSOR_CLASS;
-        else if (soa && it.nvar <= CB_SOA_MAX_NV && ml <= 96 && !it.transfer_only && Dm.num_transfer_redshifts == 0) c = CB_SOA_CLASS;
+        if (dm[it.model]->h.is_tensor) c = CB_TENSOR_CLASS;
         else
             for (;; c++) {
                 const size_t grown = cb_evolve_slab_bytes(std::max(std::max(cls_nv[c], it.nvar), 32), std::max(cls_maxl[c], ml));
@@ -432,6 +422,8 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
     CK(cudaMemsetAsync(ctx->d_error, 0, sizeof(int), ctx->stream));
     int lean = 1;   // every model massless-nu LCDM: the kernel variant without massive-nu / dark-energy code
     for (int m = 0; m < n_models; m++) if (dm[m]->h.Num_Nu_massive != 0 || !dm[m]->h.de_is_cc || dm[m]->h.num_redshiftwindows > 0) lean = 0;
+    int lanes = ctx->lanes_per_mode;
+    if (lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) lanes = n_items >= 16 * ctx->n_sm ? 8 : 32;
     CK(cudaEventRecord(ctx->stage_ev[0][0], ctx->stream));
     CK(cudaEventRecord(ctx->fork, ctx->stream));
     // Launch order and block caps of the slab classes.  The scheduling experiments of DESIGN.md 4.1 (profiles/r01o, r01p)
@@ -455,10 +447,7 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
         // the scratch EvolutionVars of a layout switch aliases two stage vectors (evolve.cu)
         const int nv = std::max(cls_nv[c], 32);
         CK(cudaStreamWaitEvent(ctx->class_stream[c], ctx->fork, 0));
-        cudaError_t le = c == CB_SOA_CLASS
-                             ? cb_evolve_soa_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, cls_nv[c], lean, ctx->d_counter + c, ctx->d_error,
-                                                    ctx->n_sm, ctx->class_stream[c], &ctx->last_grid[c])
-                         : c == CB_TENSOR_CLASS
+        cudaError_t le = c == CB_TENSOR_CLASS
                              ? cb_evolve_tensor_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, cls_nv[c], cls_maxl[c], ctx->d_counter + c,
                                                        ctx->d_error, ctx->n_sm, ctx->class_stream[c], &ctx->last_grid[c])
                              : cb_evolve_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, nv, cls_maxl[c], lanes, lean, ctx->d_counter + c,
@@ -696,7 +685,7 @@ int cb_set_option(cb_ctx* ctx, const char* name, double value) {
     if (!ctx) return CB_ERR_NO_DEVICE;
     if (!strcmp(name, "lanes_per_mode")) {
         const int v = (int)value;
-        if (v != 0 && v != 1 && v != 4 && v != 8 && v != 16 && v != 32) { ctx->err = "lanes_per_mode must be 0 (automatic), 1, 4, 8, 16 or 32"; return CB_ERR_UNSUPPORTED_PARAMS; }
+        if (v != 0 && v != 4 && v != 8 && v != 16 && v != 32) { ctx->err = "lanes_per_mode must be 0 (automatic), 4, 8, 16 or 32"; return CB_ERR_UNSUPPORTED_PARAMS; }
         ctx->lanes_per_mode = v;
         return 0;
     }

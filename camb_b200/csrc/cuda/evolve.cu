@@ -229,14 +229,11 @@ CB_COLD __host__ __device__ void get_num_eqns(const DModel& M, EVs& E) {
 }
 
 // CopyScalarVariableArray, equations.f90:703-791.  Executed by lane 0 (rare: ~10 per mode).
-// YS: stride between consecutive elements of y / yout (1: a mode's own contiguous vectors; 32: the mode-per-lane kernel's
-// [element][lane] layout).
-template <int YS>
 CB_COLD __device__ void copy_scalar_array(const DModel& M, const double* y, double* yout, const EVs& E, const EVs& O) {
-#define Y(i) y[((i)-1) * YS]
-#define YO(i) yout[((i)-1) * YS]
+#define Y(i) y[(i)-1]
+#define YO(i) yout[(i)-1]
     int lmax, l;
-    for (int i = 0; i < O.nvar; i++) yout[i * YS] = 0;
+    for (int i = 0; i < O.nvar; i++) yout[i] = 0;
     for (int i = 1; i <= 4; i++) YO(i) = Y(i);
     for (int i = 0; i < M.de_nperturb; i++) YO(O.w_ix + i) = Y(E.w_ix + i);
     if (!E.no_phot && !O.no_phot) {
@@ -284,14 +281,10 @@ CB_COLD __device__ void copy_scalar_array(const DModel& M, const double* y, doub
 }
 
 // ---------------- momentum integrals (equations.f90:1178-1356); warp-uniform ----------------
-#define AY(i) ay[((i)-1) * YS]
-#define AYP(i) ayp[((i)-1) * YS]
+#define AY(i) ay[(i)-1]
+#define AYP(i) ayp[(i)-1]
 
-// 1/(2l+1) and (l+3)(l-1)/(l+1): with them denlk(l) = (c_denl[l] k) l etc. are formed on the fly, bit for bit as `initial`
-// tabulates them, when a mode has no private coefficient table (mode-per-lane kernel).
-__constant__ double c_denl[CBD_MAX_L_EVOLVE + 1], c_polfac[CBD_MAX_L_EVOLVE + 1];
-
-template <int YS, class MT>
+template <class MT>
 __device__ void nu_integrate_L012(const MT& M, const EVs& E, const double* ay, double a, int nu_i, double& drhonu,
                                   double& fnu, double& dpnu, double& pinu) {
     double am = a * M.nu_masses[nu_i];
@@ -327,19 +320,15 @@ __device__ void nu_integrate_L012(const MT& M, const EVs& E, const double* ay, d
 // `th` (may be null) holds cs2b, opacity, a, dopacity evaluated ahead of time for this tau.
 // LEAN = true compiles the massive-neutrino and dark-energy-perturbation code out (launches whose
 // models are all massless-nu LCDM): a shorter, branch-poorer instruction stream for the common case.
-template <int G, bool LEAN, int YS = 1, bool CONSTL = false>
-__device__ __forceinline__ void derivs(const MHot& M_, EVs& E, const double* __restrict__ denlk_, const double* __restrict__ denlk2_,
-                                       const double* __restrict__ polfack_, double tau, const double* ay, double* ayp, int lane,
+template <int G, bool LEAN>
+__device__ __forceinline__ void derivs(const MHot& M_, EVs& E, const double* __restrict__ denlk, const double* __restrict__ denlk2,
+                                       const double* __restrict__ polfack, double tau, const double* ay, double* ayp, int lane,
                                        unsigned gm, int out_mode, const double* th, double* src_out, float* tr_out, int q_ix = 0,
                                        int jstep = 0) {
     const MHot& M = M_;
     const bool de_is_cc = LEAN ? true : (M.de_is_cc != 0);
     const double k = E.k, k2 = E.k2;
     const bool tight = E.TightCoupling, no_nu = E.no_nu, no_phot = E.no_phot;
-    // multipole coupling coefficients: the mode's own table, or formed from the constant tables (same bits)
-    auto denlk = [&](int l) { return CONSTL ? (c_denl[l] * k) * l : denlk_[l]; };
-    auto denlk2 = [&](int l) { return CONSTL ? (c_denl[l] * k) * (l + 1) : denlk2_[l]; };
-    auto polfack = [&](int l) { return CONSTL ? (c_polfac[l] * k) * c_denl[l] : polfack_[l]; };
     double a, cs2, opacity, dopacity = 0;
     if (th) { cs2 = th[0]; opacity = th[1]; a = th[2]; dopacity = th[3]; }
     else thermo_values(M, tau, a, cs2, opacity, dopacity, tight);
@@ -490,7 +479,7 @@ __device__ __forceinline__ void derivs(const MHot& M_, EVs& E, const double* __r
     }
     double polter = 0;
     if (!no_phot) {
-        qgdot = 4.0 / 3 * (-vbdot - adotoa * vb + delta_p_b * k) / pb43 + denlk(1) * clxg - denlk2(1) * pig;
+        qgdot = 4.0 / 3 * (-vbdot - adotoa * vb + delta_p_b * k) / pb43 + denlk[1] * clxg - denlk2[1] * pig;
         const int g = E.g_ix;
         if (tight) {
             if (lane == 0) { AYP(g) = clxgdot; AYP(g + 1) = qgdot; }
@@ -498,29 +487,16 @@ __device__ __forceinline__ void derivs(const MHot& M_, EVs& E, const double* __r
             const int lmaxg = E.lmaxg, pol = E.polind, lmaxgpol = E.lmaxgpol;
             const double E2 = AY(pol + 2);
             polter = pig * 0.1 + 9.0 / 15 * E2;
-            pigdot = denlk(2) * qg - denlk2(2) * AY(g + 3) - opacity * (pig - polter) + 8.0 / 15.0 * k * sigma;
+            pigdot = denlk[2] * qg - denlk2[2] * AY(g + 3) - opacity * (pig - polter) + 8.0 / 15.0 * k * sigma;
             // interior multipoles are one uniform formula; the l = 0, 1, 2 and truncation entries are
             // written by lane 0 (no per-element branching inside the lane-strided loops)
-            if constexpr (G == 1) {   // mode-per-lane: serial loops, unrolled so that the loads of four multipoles are in flight
-#pragma unroll 4
-                for (int l = 3; l < lmaxg; l++) {
-                    const int ix = g + l;
-                    AYP(ix) = (denlk(l) * AY(ix - 1) - denlk2(l) * AY(ix + 1)) - opacity * AY(ix);
-                }
-#pragma unroll 4
-                for (int l = 3; l < lmaxgpol; l++) {
-                    const int ix = pol + l;
-                    AYP(ix) = -opacity * AY(ix) + (denlk(l) * AY(ix - 1) - polfack(l) * AY(ix + 1));
-                }
-            } else {
-                for (int l = 3 + lane; l < lmaxg; l += G) {
-                    const int ix = g + l;
-                    AYP(ix) = (denlk(l) * AY(ix - 1) - denlk2(l) * AY(ix + 1)) - opacity * AY(ix);
-                }
-                for (int l = 3 + lane; l < lmaxgpol; l += G) {
-                    const int ix = pol + l;
-                    AYP(ix) = -opacity * AY(ix) + (denlk(l) * AY(ix - 1) - polfack(l) * AY(ix + 1));
-                }
+            for (int l = 3 + lane; l < lmaxg; l += G) {
+                const int ix = g + l;
+                AYP(ix) = (denlk[l] * AY(ix - 1) - denlk2[l] * AY(ix + 1)) - opacity * AY(ix);
+            }
+            for (int l = 3 + lane; l < lmaxgpol; l += G) {
+                const int ix = pol + l;
+                AYP(ix) = -opacity * AY(ix) + (denlk[l] * AY(ix - 1) - polfack[l] * AY(ix + 1));
             }
             if (lane == 0) {
                 AYP(g) = clxgdot; AYP(g + 1) = qgdot; AYP(g + 2) = pigdot;
@@ -535,24 +511,16 @@ __device__ __forceinline__ void derivs(const MHot& M_, EVs& E, const double* __r
     if (!no_nu) {
         const int r = E.r_ix;
         const double clxrdot = -k * (4.0 / 3.0 * z + qr);
-        qrdot = denlk(1) * clxr - denlk2(1) * pir;
+        qrdot = denlk[1] * clxr - denlk2[1] * pir;
         if (E.high_ktau) {
             pirdot = -3 * pir * cothxor - clxrdot;
             if (lane == 0) { AYP(r) = clxrdot; AYP(r + 1) = qrdot; AYP(r + 2) = pirdot; }
         } else {
             const int lmaxnr = E.lmaxnr;
-            pirdot = denlk(2) * qr - denlk2(2) * AY(r + 3) + 8.0 / 15.0 * k * sigma;
-            if constexpr (G == 1) {
-#pragma unroll 4
-                for (int l = 3; l < lmaxnr; l++) {
-                    const int ix = r + l;
-                    AYP(ix) = (denlk(l) * AY(ix - 1) - denlk2(l) * AY(ix + 1));
-                }
-            } else {
-                for (int l = 3 + lane; l < lmaxnr; l += G) {
-                    const int ix = r + l;
-                    AYP(ix) = (denlk(l) * AY(ix - 1) - denlk2(l) * AY(ix + 1));
-                }
+            pirdot = denlk[2] * qr - denlk2[2] * AY(r + 3) + 8.0 / 15.0 * k * sigma;
+            for (int l = 3 + lane; l < lmaxnr; l += G) {
+                const int ix = r + l;
+                AYP(ix) = (denlk[l] * AY(ix - 1) - denlk2[l] * AY(ix + 1));
             }
             if (lane == 0) {
                 AYP(r) = clxrdot; AYP(r + 1) = qrdot; AYP(r + 2) = pirdot;
@@ -580,12 +548,12 @@ __device__ __forceinline__ void derivs(const MHot& M_, EVs& E, const double* __r
                 const double v = 1.0 / sqrt(1.0 + aq * aq);
                 double r;
                 if (l == 0) r = -k * (4.0 / 3.0 * z + v * AY(ind + 1));
-                else if (l == 1) r = v * (denlk(1) * AY(ind - 1) - denlk2(1) * AY(ind + 1));
+                else if (l == 1) r = v * (denlk[1] * AY(ind - 1) - denlk2[1] * AY(ind + 1));
                 else if (lt == 2) {  // l == 2 == lt: -ayprime(l=0) - 3 cothxor y
                     double yp0 = -k * (4.0 / 3.0 * z + v * AY(ind - 1));
                     r = -yp0 - 3 * cothxor * AY(ind);
-                } else if (l == 2) r = v * (denlk(2) * AY(ind - 1) - denlk2(2) * AY(ind + 1)) + k * 8.0 / 15.0 * sigma;
-                else if (l < lt) r = v * (denlk(l) * AY(ind - 1) - denlk2(l) * AY(ind + 1));
+                } else if (l == 2) r = v * (denlk[2] * AY(ind - 1) - denlk2[2] * AY(ind + 1)) + k * 8.0 / 15.0 * sigma;
+                else if (l < lt) r = v * (denlk[l] * AY(ind - 1) - denlk2[l] * AY(ind + 1));
                 else r = k * v * AY(ind - 1) - (lt + 1) * cothxor * AY(ind);
                 AYP(ind) = r;
             }
@@ -597,7 +565,7 @@ __device__ __forceinline__ void derivs(const MHot& M_, EVs& E, const double* __r
             const int ind = p0 + l, ind2 = r0 + l;
             double v;
             if (l == 0) v = +k * a2 * qr - k * AY(ind + 1);
-            else if (l < lp) v = -a2 * (denlk(l) * AY(ind2 - 1) - denlk2(l) * AY(ind2 + 1)) + (denlk(l) * AY(ind - 1) - denlk2(l) * AY(ind + 1));
+            else if (l < lp) v = -a2 * (denlk[l] * AY(ind2 - 1) - denlk2[l] * AY(ind2 + 1)) + (denlk[l] * AY(ind - 1) - denlk2[l] * AY(ind + 1));
             else v = k * (AY(ind - 1) - a2 * AY(ind2 - 1)) - (lp + 1) * cothxor * AY(ind);
             AYP(ind) = v;
         }
@@ -633,7 +601,7 @@ __device__ __forceinline__ void derivs(const MHot& M_, EVs& E, const double* __r
                     pinu = AY(E.nu_ix[nu_i] + 3);
                     pinudot = AYP(E.nu_ix[nu_i] + 3);
                 } else {
-                    nu_integrate_L012<YS>(M, E, ay, a, nu_i, clx, qn, dpnu, pinu);
+                    nu_integrate_L012(M, E, ay, a, nu_i, clx, qn, dpnu, pinu);
                     clx = clx / rhonu;
                     pinu = pinu / rhonu;
                     double rhonudot = nu_drho(a * M.nu_masses[nu_i], adotoa);
@@ -796,19 +764,18 @@ __device__ __forceinline__ int next_nu_nq(const MT& M, int nq) {
 }
 
 // initial, equations.f90:1891-2112 (adiabatic and the four isocurvature modes, initial_vector; flat); lane 0
-template <int YS>
 CB_COLD __device__ void initial_conditions(const DModel& M, EVs& E, double* denlk, double* denlk2, double* polfack, double* y, double tau,
                                    const DModeItem& it) {
     const double k = E.q;
     E.k = k; E.k2 = E.q * E.q; E.kinv = 1.0 / k; E.k2inv = 1.0 / E.k2;
-    for (int j = 1; denlk && j <= E.MaxlNeeded; j++) {   // no private table in the mode-per-lane kernel (c_denl / c_polfac)
+    for (int j = 1; j <= E.MaxlNeeded; j++) {
         double denl = 1.0 / (2 * j + 1);
         denlk[j] = denl * k * j;
         denlk2[j] = denl * k * 1.0 * (j + 1);
         polfack[j] = j >= 2 ? ((double)((j + 3) * (j - 1)) / (j + 1)) * k * 1.0 * denl : 0.0;
     }
     E.TightSwitchoffTime = it.tight_switchoff;
-    for (int i = 0; i < E.nvar; i++) y[(i) * YS] = 0;
+    for (int i = 0; i < E.nvar; i++) y[i] = 0;
     const double x = k * tau, x2 = x * x, x3 = x2 * x;
     double rhomass = 0;
     for (int i = 0; i < M.Nu_mass_eigenstates; i++) rhomass += M.grhormass[i];
@@ -870,17 +837,17 @@ CB_COLD __device__ void initial_conditions(const DModel& M, EVs& E, double* denl
     const double i_clxg = initvec[I_CLXG], i_clxr = initvec[I_CLXR], i_clxc = initvec[I_CLXC], i_clxb = initvec[I_CLXB];
     const double i_qg = initvec[I_QG], i_qr = initvec[I_QR], i_vb = initvec[I_VB], i_pir = initvec[I_PIR], i_eta = initvec[I_ETA];
     const double i_aj3r = initvec[I_AJ3R];
-    y[(0) * YS] = -i_eta * k / 2; y[(1) * YS] = i_clxc; y[(2) * YS] = i_clxb; y[(3) * YS] = i_vb;
-    y[(E.g_ix - 1) * YS] = i_clxg; y[(E.g_ix) * YS] = i_qg;
-    y[(E.r_ix - 1) * YS] = i_clxr; y[(E.r_ix) * YS] = i_qr; y[(E.r_ix + 1) * YS] = i_pir;
-    if (E.lmaxnr > 2) y[(E.r_ix + 2) * YS] = i_aj3r;
+    y[0] = -i_eta * k / 2; y[1] = i_clxc; y[2] = i_clxb; y[3] = i_vb;
+    y[E.g_ix - 1] = i_clxg; y[E.g_ix] = i_qg;
+    y[E.r_ix - 1] = i_clxr; y[E.r_ix] = i_qr; y[E.r_ix + 1] = i_pir;
+    if (E.lmaxnr > 2) y[E.r_ix + 2] = i_aj3r;
     if (M.Num_Nu_massive == 0) return;
     for (int nu_i = 0; nu_i < M.Nu_mass_eigenstates; nu_i++) {
         E.MassiveNuApproxTime[nu_i] = it.nu_massive_approx_time[nu_i];
         int ind = E.nu_ix[nu_i];
         for (int i = 1; i <= E.nq[nu_i]; i++) {
-            y[(ind - 1) * YS] = y[(E.r_ix - 1) * YS]; y[(ind) * YS] = y[(E.r_ix) * YS]; y[(ind + 1) * YS] = y[(E.r_ix + 1) * YS];
-            if (E.lmaxnu_tau[nu_i] > 2) y[(ind + 2) * YS] = i_aj3r;
+            y[ind - 1] = y[E.r_ix - 1]; y[ind] = y[E.r_ix]; y[ind + 1] = y[E.r_ix + 1];
+            if (E.lmaxnu_tau[nu_i] > 2) y[ind + 2] = i_aj3r;
             ind = ind + E.lmaxnu_tau[nu_i] + 1;
         }
     }
@@ -937,13 +904,12 @@ CB_COLD __device__ void plan_switches(const MT& M, const EVs& E, Ctl& C) {
 
 // ... and applies the switch that fires at C.next_switch (same if-chain order as the reference,
 // equations.f90:339-441).  Lane 0 of the group; layout changes go through the scratch slots.
-template <int YS>
-CB_COLD __device__ void apply_switch(const DModel& M, EVs& E, Ctl& C, const Vecs& V, EVs* scratch = nullptr) {
+CB_COLD __device__ void apply_switch(const DModel& M, EVs& E, Ctl& C, const Vecs& V) {
     const int n_eig = M.Num_Nu_massive != 0 ? M.Nu_mass_eigenstates : 0;
     const double noSwitch = M.tau0 + 1, next_switch = C.next_switch, tau = C.tau;
     double* y = V.y;
     double* yout = V.k4;
-    EVs& EO = scratch ? *scratch : *reinterpret_cast<EVs*>(V.k5);   // the scratch EvolutionVars: a dead stage vector, or the caller's
+    EVs& EO = *reinterpret_cast<EVs*>(V.k5);
     int which;
     if (next_switch == C.t_tight) which = 0;
     else if (next_switch == C.t_ktau) which = 1;
@@ -977,27 +943,27 @@ CB_COLD __device__ void apply_switch(const DModel& M, EVs& E, Ctl& C, const Vecs
             if (!E.MassiveNuApprox[nu_i] && next_switch == E.MassiveNuApproxTime[nu_i]) {
                 EO.MassiveNuApprox[nu_i] = 1;
                 setup_indices(M, EO);
-                copy_scalar_array<YS>(M, y, yout, E, EO);
+                copy_scalar_array(M, y, yout, E, EO);
                 double rhonu, pnu, clxnu, qnu, dpnu, pinu;
                 nu_rho_P(a * M.nu_masses[nu_i], rhonu, pnu);
-                nu_integrate_L012<YS>(M, E, y, a, nu_i, clxnu, qnu, dpnu, pinu);
-                yout[(EO.nu_ix[nu_i] - 1) * YS] = clxnu / rhonu;
-                yout[(EO.nu_ix[nu_i]) * YS] = dpnu / rhonu;
-                yout[(EO.nu_ix[nu_i] + 1) * YS] = qnu / rhonu;
-                yout[(EO.nu_ix[nu_i] + 2) * YS] = pinu / rhonu;
+                nu_integrate_L012(M, E, y, a, nu_i, clxnu, qnu, dpnu, pinu);
+                yout[EO.nu_ix[nu_i] - 1] = clxnu / rhonu;
+                yout[EO.nu_ix[nu_i]] = dpnu / rhonu;
+                yout[EO.nu_ix[nu_i] + 1] = qnu / rhonu;
+                yout[EO.nu_ix[nu_i] + 2] = pinu / rhonu;
                 // Nu_Intvsq, equations.f90:1328-1356
                 double G11 = 0, G30 = 0, am = a * M.nu_masses[nu_i];
                 int indx = E.nu_ix[nu_i];
                 for (int iq = 1; iq <= E.nq[nu_i]; iq++) {
                     double aq = am / M.nu_q[iq - 1], v = 1.0 / sqrt(1.0 + aq * aq);
-                    G11 = G11 + M.nu_int_kernel[iq - 1] * y[(indx) * YS] * v * v;
-                    if (E.lmaxnu_tau[nu_i] > 2) G30 = G30 + M.nu_int_kernel[iq - 1] * y[(indx + 2) * YS] * v * v;
+                    G11 = G11 + M.nu_int_kernel[iq - 1] * y[indx] * v * v;
+                    if (E.lmaxnu_tau[nu_i] > 2) G30 = G30 + M.nu_int_kernel[iq - 1] * y[indx + 2] * v * v;
                     indx = indx + E.lmaxnu_tau[nu_i] + 1;
                 }
                 EO.G11[nu_i] = G11 * a * a * a / rhonu;
                 EO.G30[nu_i] = G30 * a * a * a / rhonu;
                 E = EO;
-                for (int i = 0; i < E.nvar; i++) y[(i) * YS] = yout[(i) * YS];
+                for (int i = 0; i < E.nvar; i++) y[i] = yout[i];
                 break;
             }
         }
@@ -1005,19 +971,19 @@ CB_COLD __device__ void apply_switch(const DModel& M, EVs& E, Ctl& C, const Vecs
     else { EO.no_phot = 1; }
     if (docopy) {
         setup_indices(M, EO);
-        copy_scalar_array<YS>(M, y, yout, E, EO);
+        copy_scalar_array(M, y, yout, E, EO);
         E = EO;
-        for (int i = 0; i < E.nvar; i++) y[(i) * YS] = yout[(i) * YS];
+        for (int i = 0; i < E.nvar; i++) y[i] = yout[i];
         if (which == 0) {  // tight-coupling values, equations.f90:349-363
             double a, cs2, opacity, dopacity;
             thermo_values(M, tau, a, cs2, opacity, dopacity, true);
             const double kk = E.k, op2 = opacity * opacity;
-            y[(E.g_ix + 2 - 1) * YS] = E.pig;
-            y[(E.g_ix + 3 - 1) * YS] = (3.0 / 7.0) * y[(E.g_ix + 2 - 1) * YS] * (kk / opacity) * (1.0 + dopacity / op2) +
+            y[E.g_ix + 2 - 1] = E.pig;
+            y[E.g_ix + 3 - 1] = (3.0 / 7.0) * y[E.g_ix + 2 - 1] * (kk / opacity) * (1.0 + dopacity / op2) +
                                 (3.0 / 7.0) * E.pigdot * (kk / op2) * (-1.0);
-            y[(E.polind + 2 - 1) * YS] = E.pig / 4 + E.pigdot * (1.0 / opacity) * (-5.0 / 8.0 - (25.0 / 16.0) * dopacity / op2) +
+            y[E.polind + 2 - 1] = E.pig / 4 + E.pigdot * (1.0 / opacity) * (-5.0 / 8.0 - (25.0 / 16.0) * dopacity / op2) +
                                   E.pig * (kk / opacity) * (kk / opacity) * (-5.0 / 56.0);
-            y[(E.polind + 3 - 1) * YS] = (3.0 / 7.0) * (kk / opacity) * y[(E.polind + 2 - 1) * YS] * (1.0 + dopacity / op2) +
+            y[E.polind + 3 - 1] = (3.0 / 7.0) * (kk / opacity) * y[E.polind + 2 - 1] * (1.0 + dopacity / op2) +
                                   (3.0 / 7.0) * (kk / op2) * ((E.pigdot / 4.0) * (1.0 + (5.0 / 2.0) * dopacity / op2)) * (-1.0);
         }
     }
@@ -1042,10 +1008,9 @@ __device__ __forceinline__ void dp45_begin(Ctl& C, double xend) {
 // attempt (PH_STEP), an output evaluation (PH_OUTPUT) or there is no work left (PH_EXIT).
 // CalcScalarSources cmbmain.f90:998-1074 / GetTransfer :1167-1188 unrolled into a state machine;
 // rows skipped by the high-k*tau early-out stay zero (LinearSrc is cleared before the launch).
-template <int YS>
 CB_COLD __device__ void advance_schedule(const DModel* __restrict__ models, const DModeItem* __restrict__ items, int n_items,
                                  unsigned int* counter, int* error_flag, EVs& E, Ctl& C, MHot& H, double* denlk, double* denlk2,
-                                 double* polfack, const Vecs& V, EVs* scratch = nullptr) {
+                                 double* polfack, const Vecs& V) {
     for (;;) {
         if (C.phase == PH_FETCH) {
             const unsigned item = atomicAdd(counter, 1u);
@@ -1061,7 +1026,7 @@ CB_COLD __device__ void advance_schedule(const DModel* __restrict__ models, cons
             E.w_ix = E.r_ix = E.g_ix = E.polind = E.nu_pert_ix = 0; E.lmaxnu_pert = 0; E.NuMethod = 1;
             get_num_eqns(M, E);
             const double taustart = get_tau_start(M, it.q);
-            initial_conditions<YS>(M, E, denlk, denlk2, polfack, V.y, taustart, it);
+            initial_conditions(M, E, denlk, denlk2, polfack, V.y, taustart, it);
             C.max_step_size = 0; C.current_step_size = 0; C.estimated_error = 0; C.previous_xend = 0;
             C.xend_reached = 0; C.first_derivative_valid = 0; C.successive_failures = 0;
             C.steps = 0; C.attempts = 0; C.neq_evals = 0; C.nderivs = 0;
@@ -1130,7 +1095,7 @@ CB_COLD __device__ void advance_schedule(const DModel* __restrict__ models, cons
             const double smallTime = fmin(C.tau, 1 / E.k) / 100;
             double xend;
             if (C.next_switch < C.goal) {
-                if (!(C.next_switch > C.tau + smallTime)) { apply_switch<YS>(MG, E, C, V, scratch); continue; }
+                if (!(C.next_switch > C.tau + smallTime)) { apply_switch(MG, E, C, V); continue; }
                 xend = C.next_switch; C.seg_switch = 1;
             } else { xend = C.goal; C.seg_switch = 0; }
             // GaugeInterface_ScalEv, equations.f90:212-234
@@ -1252,7 +1217,7 @@ __device__ __forceinline__ void attempt_finish(const DModel& M, EVs& E, Ctl& C, 
                 C.xend_reached = 1;
                 C.first_derivative_valid = 1;
                 if (C.seg_switch) {
-                    apply_switch<1>(M, E, C, V);
+                    apply_switch(M, E, C, V);
                     C.phase = PH_PLAN;
                 } else if (C.out_kind != OUT_NONE) {
                     C.phase = PH_OUTPUT;
@@ -1321,7 +1286,7 @@ cb_evolve_kernel(const DModel* __restrict__ models, const DModeItem* __restrict_
         int out_mode = OUT_NONE;
         if (t == 0) {
             if (lane == 0 && (C.phase == PH_FETCH || C.phase == PH_NEXT_GOAL || C.phase == PH_PLAN))
-                advance_schedule<1>(models, items, n_items, counter, error_flag, E, C, H, denlk, denlk2, polfack, V);
+                advance_schedule(models, items, n_items, counter, error_flag, E, C, H, denlk, denlk2, polfack, V);
             __syncwarp(gm);
             const int phase = C.phase;
             if (__all_sync(FULL, phase == PH_EXIT)) break;
@@ -1410,199 +1375,6 @@ cb_evolve_kernel(const DModel* __restrict__ models, const DModeItem* __restrict_
     }
 }
 
-// =====================================================================================================================
-// Mode-per-lane variant (lanes_per_mode = 1): every lane of a warp owns one k-mode, 32 modes share one instruction
-// stream.  The lane-group kernel above spends most of its issue slots on work that all lanes of a group repeat (the
-// scalar part of derivs, step control) or that one lane does alone (the l = 0, 1, 2 and truncation entries); here every
-// instruction advances 32 modes.  What makes that possible:
-//  * state vectors in shared memory as [vector][element][lane]: element i of lane L is word (i*32 + L), so whatever
-//    element each lane touches (the layouts differ from mode to mode) the 32 accesses fall in 32 different 8-byte
-//    words of one row -- no bank conflicts beyond the two wavefronts a 64-bit access always takes;
-//  * the multipole coefficients k l/(2l+1) ... are formed from two constant tables (the lanes walk l together, so the
-//    constant cache broadcasts), the per-mode control block, EvolutionVars and model constants are per-thread;
-//  * the same warp-synchronous trip loop: trip 0 serves single evaluations (first derivative of a segment, source
-//    output), trips 1..6 the stages of one Runge-Kutta attempt for every lane that is stepping.
-// Used for batches of scalar models without transfer outputs (the benchmark's regime); everything else takes the
-// lane-group kernel.  Same arithmetic per mode, so the same step sequences and the same bits as G = 8/16/32 up to FMA
-// contraction.
-#define SOA_WARPS 2
-#define SOA_MAXL 96            /* deepest multipole of an eligible mode (per-thread scratch in the cold paths) */
-
-template <bool LEAN>
-__global__ void __launch_bounds__(SOA_WARPS * 32, 1)
-cb_evolve_soa_kernel(const DModel* __restrict__ models, const DModeItem* __restrict__ items, int n_items, int nv, unsigned int* counter,
-                     int* error_flag) {
-    extern __shared__ __align__(16) double soa_sm[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned self = 1u << lane;
-    double* W = soa_sm + (size_t)warp * NVEC * nv * 32 + lane;      // this lane's column of the warp's [vector][element][lane] block
-    const size_t vs = (size_t)nv * 32;                               // words between vectors
-    const Vecs V(W, (int)vs);                                        // V.y[i*32], V.k1[i*32] ... (stride 32)
-    Ctl C;
-    MHot H;
-    EVs E, Escratch;
-    C.phase = PH_FETCH;
-    for (;;) {
-        // ---- control: fetch a mode, next output time, switch plan (per lane; rare and short next to the trips)
-        if (C.phase == PH_FETCH || C.phase == PH_NEXT_GOAL || C.phase == PH_PLAN)
-            advance_schedule<32>(models, items, n_items, counter, error_flag, E, C, H, nullptr, nullptr, nullptr, V, &Escratch);
-        if (__all_sync(FULL, C.phase == PH_EXIT)) break;
-        for (int t = 0; t <= 6; t++) {
-            bool active;
-            const double* in = V.y;
-            double* out = V.k3;
-            const double* th = nullptr;
-            double tev = 0;
-            int out_mode = OUT_NONE;
-            if (t == 0) {
-                active = C.phase == PH_OUTPUT || (C.phase == PH_STEP && C.s == 0);
-                if (!__any_sync(FULL, active)) continue;
-                if (active) {
-                    tev = C.tau;
-                    if (C.phase == PH_STEP) out = V.k1;
-                    else {
-                        for (int i = 0; i < E.nvar; i++) out[i * 32] = 0;
-                        out_mode = C.out_kind;
-                    }
-                }
-            } else {
-                active = C.phase == PH_STEP && C.s == 1;
-                if (t == 1) {
-                    if (!__any_sync(FULL, active)) break;
-                    if (active) {   // attempt_start: RungeKuttaDP45.f90:230-302, per lane
-                        const int n = E.neq;
-                        const double eps = 2.220446049250313e-16, tiny = 2.2250738585072014e-308;
-                        const double x = C.tau, xend = C.seg_end, tol = C.tol1;
-                        double temp = 0;
-                        _Pragma("unroll 4") for (int i = 0; i < n; i++) temp = fmax(temp, fabs(V.y[i * 32]));
-                        const double wny = fmin(temp, 1.0);
-                        const double hmin = 10.0 * fmax(tiny, eps * fmax(wny / tol, fabs(x)));
-                        const double hmax = C.max_step_size != 0 ? fabs(C.max_step_size) : 20.0;
-                        if (hmin > hmax) { C.ind = -2; atomicExch(error_flag, CB_ERR_EVOLUTION); C.phase = PH_FETCH; active = false; }
-                        else {
-                            double css = C.current_step_size;
-                            const double est = C.estimated_error;
-                            const bool first = C.ind <= 2, shrink = tol < 54.19228098697693 * est;  // (2/0.9)^5
-                            const double p = pow(first ? tol : tol / est, 1.0 / 5.0);
-                            if (first) css = hmax * p;
-                            else if (C.successive_failures <= 1) {
-                                temp = 2.0 * css;
-                                if (shrink) temp = 0.9 * p * css;
-                                css = fmax(temp, 0.5 * css);
-                            } else css = 0.5 * css;
-                            css = fmin(css, hmax);
-                            css = fmax(css, hmin);
-                            temp = fabs(xend - x);
-                            double trial_x;
-                            if (css < temp && (temp > 1.2 * css || temp > hmax)) {
-                                css = fmin(css, 0.5 * temp);
-                                trial_x = x + copysign(css, xend - x);
-                            } else { css = temp; trial_x = xend; }
-                            C.css = css; C.h = trial_x - x; C.trial_x = trial_x; C.hmin = hmin;
-#pragma unroll
-                            for (int st = 0; st < 6; st++) {   // thermo look-ups of the six stage times, issued together
-                                const double ts = x + c_dp_c[st + 1] * C.h;
-                                double a, cs2, opac, dopac = 0;
-                                thermo_values(H, ts, a, cs2, opac, dopac, E.TightCoupling != 0);
-                                C.th[st][0] = cs2; C.th[st][1] = opac; C.th[st][2] = a; C.th[st][3] = dopac; C.th[st][4] = 1.0 / ts;
-                            }
-                        }
-                    }
-                }
-                if (active) {
-                    const double h = C.h;
-                    const int n = E.neq;
-                    double* yt = V.yt;
-                    const double *k1 = V.k1, *k2 = V.k2, *k3 = V.k3, *k4 = V.k4, *k5 = V.k5, *k6 = V.k6, *y0 = V.y;
-                    switch (t) {
-                        case 1:
-                            _Pragma("unroll 4") for (int i = 0; i < n * 32; i += 32) yt[i] = fma(h, c_dp_a[1][0] * k1[i], y0[i]);
-                            break;
-                        case 2:
-                            _Pragma("unroll 4") for (int i = 0; i < n * 32; i += 32) yt[i] = fma(h, fma(c_dp_a[2][1], k2[i], c_dp_a[2][0] * k1[i]), y0[i]);
-                            break;
-                        case 3:
-                            _Pragma("unroll 4") for (int i = 0; i < n * 32; i += 32)
-                                yt[i] = fma(h, fma(c_dp_a[3][2], k3[i], fma(c_dp_a[3][1], k2[i], c_dp_a[3][0] * k1[i])), y0[i]);
-                            break;
-                        case 4:
-                            _Pragma("unroll 4") for (int i = 0; i < n * 32; i += 32)
-                                yt[i] = fma(h, fma(c_dp_a[4][3], k4[i], fma(c_dp_a[4][2], k3[i], fma(c_dp_a[4][1], k2[i], c_dp_a[4][0] * k1[i]))), y0[i]);
-                            break;
-                        case 5:
-                            _Pragma("unroll 4") for (int i = 0; i < n * 32; i += 32)
-                                yt[i] = fma(h, fma(c_dp_a[5][4], k5[i], fma(c_dp_a[5][3], k4[i], fma(c_dp_a[5][2], k3[i],
-                                            fma(c_dp_a[5][1], k2[i], c_dp_a[5][0] * k1[i])))), y0[i]);
-                            break;
-                        default:
-                            _Pragma("unroll 4") for (int i = 0; i < n * 32; i += 32)
-                                yt[i] = fma(h, fma(c_dp_a[6][5], k6[i], fma(c_dp_a[6][4], k5[i], fma(c_dp_a[6][3], k4[i],
-                                            fma(c_dp_a[6][2], k3[i], c_dp_a[6][0] * k1[i])))), y0[i]);
-                            break;
-                    }
-                    in = yt;
-                    out = t == 6 ? V.k2 : W + (size_t)(t + 1) * vs;
-                    tev = C.tau + c_dp_c[t] * h;
-                    th = C.th[t - 1];
-                }
-            }
-            if (active) {
-                double srcs[3];
-                derivs<1, LEAN, 32, true>(H, E, nullptr, nullptr, nullptr, tev, in, out, 0, self, out_mode, th,
-                                          out_mode == OUT_SRC ? srcs : nullptr, nullptr, LEAN ? 0 : C.q_ix, LEAN ? 0 : C.j);
-                C.nderivs++;
-                if (t == 0) {
-                    if (C.phase == PH_STEP) { C.s = 1; C.neq_evals += E.neq; }
-                    else {
-                        double* S = H.LinearSrc;
-                        const int n3 = H.n_src < 3 ? H.n_src : 3;
-                        for (int i = 0; i < n3; i++) S[C.q_ix + (size_t)H.n_k * (i + (size_t)H.n_src * (C.j - 1))] = srcs[i];
-                        C.stage = C.next_stage;
-                        C.phase = PH_NEXT_GOAL;
-                    }
-                } else {
-                    C.neq_evals += E.neq;
-                    if (t == 6) {   // attempt_finish: RungeKuttaDP45.f90:330-347, per lane
-                        const int n = E.neq;
-                        double temp = 0;
-                        _Pragma("unroll 4") for (int i = 0; i < n * 32; i += 32) {
-                            double e = c_dp_a[0][0] * V.k1[i];
-                            e = fma(c_dp_a[0][1], V.k2[i], e); e = fma(c_dp_a[0][2], V.k3[i], e); e = fma(c_dp_a[0][3], V.k4[i], e);
-                            e = fma(c_dp_a[0][4], V.k5[i], e); e = fma(c_dp_a[0][5], V.k6[i], e);
-                            temp = fmax(temp, fabs(e) / fmax(1.0, fabs(V.y[i])));
-                        }
-                        const double css = C.css, est = temp * css, xend = C.seg_end, trial_x = C.trial_x;
-                        const bool accept = !(est > C.tol1);
-                        if (accept)
-                            _Pragma("unroll 4") for (int i = 0; i < n * 32; i += 32) { V.y[i] = V.yt[i]; V.k1[i] = V.k2[i]; }
-                        C.current_step_size = css;
-                        C.estimated_error = est;
-                        C.attempts++;
-                        if (accept) {
-                            C.tau = trial_x;
-                            C.steps++;
-                            C.successive_failures = 0;
-                            if (trial_x == xend) {
-                                C.ind = 3; C.previous_xend = xend; C.xend_reached = 1; C.first_derivative_valid = 1;
-                                if (C.seg_switch) { apply_switch<32>(models[C.model], E, C, V, &Escratch); C.phase = PH_PLAN; }
-                                else if (C.out_kind != OUT_NONE) C.phase = PH_OUTPUT;
-                                else { C.stage = C.next_stage; C.phase = PH_NEXT_GOAL; }
-                            } else C.ind = 6;
-                        } else {
-                            C.ind = 6;
-                            C.successive_failures++;
-                            if (css <= C.hmin) { C.ind = -3; atomicExch(error_flag, CB_ERR_EVOLUTION); C.phase = PH_FETCH; }
-                        }
-                    }
-                }
-            }
-            if (t == 0 && (C.phase == PH_NEXT_GOAL || C.phase == PH_PLAN))   // after an output: line the lane up for this cycle's attempt
-                advance_schedule<32>(models, items, n_items, counter, error_flag, E, C, H, nullptr, nullptr, nullptr, V, &Escratch);
-            __syncwarp();
-        }
-    }
-}
-
 // ---------------- host-side helpers used by cabi.cu ----------------
 size_t cb_evolve_slab_bytes(int nv, int maxl) {
     const size_t ctl_bytes = (sizeof(Ctl) + 15) & ~size_t(15), hot_bytes = (sizeof(MHot) + 15) & ~size_t(15),
@@ -1649,40 +1421,6 @@ static cudaError_t launch_g(const DModel* d_models, const DModeItem* d_items, in
     if (grid_out) *grid_out = grid;
     cb_evolve_kernel<G, LEAN><<<grid, WPB(G) * 32, smem, stream>>>(d_models, d_items, n_items, nv, maxl, (unsigned long long)slab,
                                                                       d_counter, d_error);
-    return cudaGetLastError();
-}
-
-// Mode-per-lane launch: nv = the largest number of equations among the items (one [8][nv][32] block per warp).
-static bool g_soa_constants = false;
-cudaError_t cb_evolve_soa_launch(const DModel* d_models, const DModeItem* d_items, int n_items, int nv, int lean, unsigned int* d_counter,
-                                 int* d_error, int n_sm, cudaStream_t stream, int* grid_out) {
-    if (!g_soa_constants) {
-        double denl[CBD_MAX_L_EVOLVE + 1], polfac[CBD_MAX_L_EVOLVE + 1];
-        denl[0] = 0; polfac[0] = 0;
-        for (int j = 1; j <= CBD_MAX_L_EVOLVE; j++) {
-            denl[j] = 1.0 / (2 * j + 1);
-            polfac[j] = j >= 2 ? ((double)((j + 3) * (j - 1)) / (j + 1)) : 0.0;
-        }
-        cudaError_t e = cudaMemcpyToSymbol(c_denl, denl, sizeof(denl));
-        if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_polfac, polfac, sizeof(polfac));
-        if (e != cudaSuccess) return e;
-        g_soa_constants = true;
-    }
-    const size_t smem = sizeof(double) * SOA_WARPS * NVEC * (size_t)nv * 32;
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = lean ? cudaFuncSetAttribute(cb_evolve_soa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                         : cudaFuncSetAttribute(cb_evolve_soa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int nb = 0;
-    e = lean ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cb_evolve_soa_kernel<true>, SOA_WARPS * 32, smem)
-             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cb_evolve_soa_kernel<false>, SOA_WARPS * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (nb < 1) nb = 1;
-    int grid = (n_items + SOA_WARPS * 32 - 1) / (SOA_WARPS * 32);
-    if (grid > n_sm * nb) grid = n_sm * nb;
-    if (grid_out) *grid_out = grid;
-    if (lean) cb_evolve_soa_kernel<true><<<grid, SOA_WARPS * 32, smem, stream>>>(d_models, d_items, n_items, nv, d_counter, d_error);
-    else cb_evolve_soa_kernel<false><<<grid, SOA_WARPS * 32, smem, stream>>>(d_models, d_items, n_items, nv, d_counter, d_error);
     return cudaGetLastError();
 }
 
