@@ -301,6 +301,8 @@ def main():
                        "l2": "inputs larger than L2 (per-step working set %.0f MB)" % (
                            (los_bytes + sum(model_h2d_bytes(hs) for hs in hss)) / 1e6)},
             "k_modes_per_sec": world * n_modes * args.steps / (ms_max * 1e-3),
+            # BASELINE.json's second metric: Boltzmann k-modes/s of stages 1-2 alone (this rank's evolve stage, CUDA events)
+            "k_modes_per_sec_evolve_stage": world * n_modes / (t_ev / args.steps * 1e-3),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "clocks": clocks,
