@@ -1,0 +1,44 @@
+"""Small end-to-end invocations of every kernel for compute-sanitizer (memcheck / racecheck): one low-resolution
+cosmology per model kind.  Usage: compute-sanitizer --tool memcheck python scripts/sanitize.py"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from camb_b200.gpu import GpuContext
+from camb_b200.host import HostState
+from camb_b200.workloads import (isocurvature_params, lensing_window_params, params_counts_config4, planck2018_params,
+                                 tensor_params)
+
+ctx = GpuContext(0)
+
+
+def scalar(hs, lanes):
+    ctx.set_option("lanes_per_mode", lanes)
+    ctx.set_bessel(hs)
+    dm = ctx.create_model(hs)
+    ctx.evolve([hs], [dm])
+    if hs.model.WantTransfer:
+        ctx.evolve([hs], [dm], transfer_only=True)
+    ctx.project([hs], [dm])
+    if hs.model.num_redshiftwindows:
+        ctx.cl_windows([hs], [dm])
+    else:
+        ctx.cl([hs], [dm])
+        if hs.n_src == 3 and hs.model.WantScalars:
+            ctx.cl_array([hs], [dm])
+    ctx.destroy_model(dm)
+    print("ok", hs.n_src, lanes, flush=True)
+
+
+p = planck2018_params(lmax=150, lensing=True, massless=False, want_transfer=True)
+p.transfer_kmax = 0.5
+scalar(HostState(p), 8)
+scalar(HostState(planck2018_params(lmax=150, lensing=True, massless=True)), 32)
+scalar(HostState(planck2018_params(lmax=150, lensing=False, massless=True)), 4)
+scalar(HostState(isocurvature_params(vector=[1, 0.2, 0.1, 0.1, 0.1], lmax=150)), 16)
+scalar(HostState(tensor_params(lmax_tensor=150, k_eta_max_tensor=400, massless=False)), 0)
+scalar(HostState(params_counts_config4(lmax=100)), 8)
+scalar(HostState(lensing_window_params(lmax=100, limber=False)), 8)
+ctx.close()
+print("sanitize run complete")
