@@ -260,6 +260,7 @@ def main():
             ctx.destroy_model(x)
         return out
 
+    ctx.set_option("async_model_upload", 1)   # the host tables outlive the step (as CAMBdata's allocatables outlive cmbmain)
     e2e_step()
     barrier()
     t0 = time.perf_counter()

@@ -77,6 +77,7 @@ struct cb_ctx {
     cudaStream_t class_stream[CB_N_CLASSES] = {};
     cudaEvent_t class_done[CB_N_CLASSES] = {}, fork = nullptr;
     int lanes_per_mode = 0;              // 0 = automatic
+    int async_model_upload = 0;          // cb_model_create returns without waiting for its host->device copies
     cudaEvent_t stage_ev[4][2] = {};     // per-stage kernel brackets of the last calls (evolve, spline-k, LOS, C_l)
     DModel* h_models = nullptr;   size_t cap_h_models = 0;   // page-locked staging
     DModeItem* h_items = nullptr; size_t cap_h_items = 0;
@@ -286,7 +287,8 @@ int cb_model_create(cb_ctx* ctx, const cb_model* m, cb_dmodel** out) {
         }
         D.windows[i] = w;
     }
-    CK(cudaStreamSynchronize(ctx->stream));
+    // the copies are stream-ordered before every later call; waiting here only frees the caller's arrays for reuse
+    if (!ctx->async_model_upload) CK(cudaStreamSynchronize(ctx->stream));
     *out = dm;
     return 0;
 }
@@ -689,6 +691,7 @@ int cb_set_option(cb_ctx* ctx, const char* name, double value) {
         ctx->lanes_per_mode = v;
         return 0;
     }
+    if (!strcmp(name, "async_model_upload")) { ctx->async_model_upload = value != 0; return 0; }
     ctx->err = std::string("unknown option ") + name;
     return CB_ERR_UNSUPPORTED_PARAMS;
 }
