@@ -28,10 +28,18 @@ camb_b200/libcambhost.so: $(HOST_SRC) $(HOST_HDR)
 oracle/liboracle.so: $(ORACLE_SRC) $(ORACLE_HDR)
 	$(CC) $(CFLAGS) -shared -o $@ $(ORACLE_SRC) -lm
 
-camb_b200/libcambb200.so: $(CUDA_SRC) $(CUDA_HDR)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CUDA_SRC) -lcudart 2> camb_b200/csrc/cuda/ptxas.log || (cat camb_b200/csrc/cuda/ptxas.log; exit 1)
+# one object per .cu (no relocatable device code: kernels share headers only), so touching one kernel rebuilds one file
+CUDA_OBJ  := $(patsubst camb_b200/csrc/cuda/%.cu,build/cuda/%.o,$(CUDA_SRC))
+
+build/cuda/%.o: camb_b200/csrc/cuda/%.cu $(CUDA_HDR)
+	@mkdir -p build/cuda
+	$(NVCC) $(NVFLAGS) -c -o $@ $< 2> build/cuda/$*.ptxas.log || (cat build/cuda/$*.ptxas.log; exit 1)
+
+camb_b200/libcambb200.so: $(CUDA_OBJ)
+	$(NVCC) $(ARCH) -shared -o $@ $(CUDA_OBJ) -lcudart
+	@cat build/cuda/*.ptxas.log > camb_b200/csrc/cuda/ptxas.log
 
 clean:
-	rm -f camb_b200/libcambhost.so oracle/liboracle.so camb_b200/libcambb200.so camb_b200/csrc/cuda/ptxas.log
+	rm -rf build camb_b200/libcambhost.so oracle/liboracle.so camb_b200/libcambb200.so camb_b200/csrc/cuda/ptxas.log
 
 .PHONY: all host oracle cuda clean

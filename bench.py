@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "lcdm_cl_sets_per_sec_lmax2500"
 UNIT = "C_l sets/s"
-WORKLOAD = "planck2018_lcdm_box_massless_nu_T+E+phi_lmax2500_keta6250"
+WORKLOAD = "planck2018_lcdm_box_massless_nu_T+E+phi_lmax2500_keta6250_lensed"
 
 
 def env_int(name, default):
@@ -100,8 +100,19 @@ def oracle_cl_sets(hss, nthreads, budget_s, min_sets=1):
     import oracle_lib as O
     t0 = time.perf_counter()
     n = modes = 0
+    from camb_b200 import lensing as L
+    from camb_b200.workloads import synthetic_highl_template
+
+    class OracleLens:          # the CPU restatement of the theta loops behind the same host code
+        def lens_contrib(self, plan, spectra, out=None):
+            for i, sp in enumerate(spectra):
+                out[i] = O.lens_contrib(plan, sp, nthreads=nthreads)
+            return list(out)
+
+    plan, template = L.plan_for(hss[0]), synthetic_highl_template()
     for hs in hss:
-        O.cls_from_params(hs, nthreads=nthreads)
+        icl, _ = O.cls_from_params(hs, nthreads=nthreads)
+        L.lens_cls_from_icl(OracleLens(), plan, [hs], [icl], template, nthreads=1)
         n += 1
         modes += len(hs.source_q())
         if time.perf_counter() - t0 > budget_s and n >= min_sets:
@@ -207,12 +218,21 @@ def main():
     dms = [ctx.create_model(hs) for hs in hss]
     n_modes = sum(len(hs.source_q()) for hs in hss)
 
+    # lens_Cls: the batch is projected against one Bessel table (hss[0]'s l sampling), so one plan; the high-L template is
+    # synthetic here (the reference's data file does not travel), it only shapes the tail above Max_l
+    from camb_b200 import lensing as L
+    from camb_b200.workloads import synthetic_highl_template
+    plan, template = L.plan_for(hss[0]), synthetic_highl_template()
+
     def step(want_stats=False):
         _, _, st = ctx.evolve(hss, dms, want_sources=False, want_stats=want_stats)
         t_ev = ctx.timings_ms()["evolve"]
         ctx.project(hss, dms, want_delta=False)
         icl = ctx.cl(hss, dms)
-        return icl, st, t_ev, ctx.timings_ms()
+        tm = ctx.timings_ms()
+        _, lensed = L.lens_cls_from_icl(ctx, plan, hss, icl, template, ls_owner=hss[0])
+        tm["lens"] = ctx.last_lens_ms()
+        return lensed, st, t_ev, tm
 
     def barrier():
         if world > 1:
@@ -233,10 +253,10 @@ def main():
     sampler.start()
     barrier()
     ctx.timer_start()
-    t_ev = t_los = t_spl = t_cl = 0.0
+    t_ev = t_los = t_spl = t_cl = t_lens = 0.0
     for _ in range(args.steps):
         icl, _, tev, tm = step(False)
-        t_ev += tev; t_los += tm["los"]; t_spl += tm["spline_k"]; t_cl += tm["cl"]
+        t_ev += tev; t_los += tm["los"]; t_spl += tm["spline_k"]; t_cl += tm["cl"]; t_lens += tm["lens"]
     ms = ctx.timer_stop()
     barrier()
     clocks = sampler.stop()
@@ -249,13 +269,14 @@ def main():
 
     # ---- e2e: host buffers -> C-ABI -> host results, copies inside the timed region ----
     h2d = sum(model_h2d_bytes(hs) for hs in hss) + sum(8 * (3 * len(hs.q_int) + len(hs.source_q())) for hs in hss)
-    d2h = sum(8 * len(hs.ls) * 6 for hs in hss)
+    h2d += B * 8 * 4 * (plan.lmax + 1)
+    d2h = sum(8 * len(hs.ls) * 6 for hs in hss) + B * 8 * 4 * (plan.lmax_lensed + 1)
 
     def e2e_step():
         d = [ctx.create_model(hs) for hs in hss]
         ctx.evolve(hss, d, want_sources=False, want_stats=False)
         ctx.project(hss, d, want_delta=False)
-        out = ctx.cl(hss, d)
+        _, out = L.lens_cls_from_icl(ctx, plan, hss, ctx.cl(hss, d), template, ls_owner=hss[0])
         for x in d:
             ctx.destroy_model(x)
         return out
@@ -299,6 +320,8 @@ def main():
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sets_per_gpu_per_step": B, "k_modes_per_set": n_modes / B,
+                       "lensing": "lens_Cls default method (CorrFuncFullSkyApodized), %d angles x l <= %d, lensed output to l = %d; "
+                                  "synthetic high-L template" % (plan.c.npoints - 1, plan.lmax, plan.lmax_lensed),
                        "l2": "inputs larger than L2 (per-step working set %.0f MB)" % (
                            (los_bytes + sum(model_h2d_bytes(hs) for hs in hss)) / 1e6)},
             "k_modes_per_sec": world * n_modes * args.steps / (ms_max * 1e-3),
@@ -310,7 +333,7 @@ def main():
             "roofline": {"bound": "fp64", "kernel": "cb_evolve_kernel", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": ach / fp64_peak if fp64_peak else None, "traffic": traffic.get("cb_evolve_kernel_dram_bytes_per_launch"),
                          "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                         "ms_per_launch": ev_ms, "share_of_step": t_ev / (t_ev + t_los + t_spl + t_cl),
+                         "ms_per_launch": ev_ms, "share_of_step": t_ev / (t_ev + t_los + t_spl + t_cl + t_lens),
                          "derivs_evals_per_launch": evals, "algorithmic_flops_per_launch": ode_flops},
             "roofline_los": {"bound": "hbm", "kernel": "cb_los_kernel", "achieved": los_bytes / (los_ms * 1e-3) / 1e9,
                              "peak": hbm_peak, "unit": "GB/s", "frac": los_bytes / (los_ms * 1e-3) / 1e9 / hbm_peak,
@@ -319,8 +342,9 @@ def main():
                              "gather_bytes_per_launch": gather_bytes, "l2_gather_gbs": gather_bytes / (los_ms * 1e-3) / 1e9,
                              "note": "working set is L2-resident: the kernel is bound by the 32-byte Bessel-record gathers through L1/L2 "
                                      "(l2_gather_gbs), not by HBM",
-                             "ms_per_launch": los_ms, "share_of_step": t_los / (t_ev + t_los + t_spl + t_cl)},
-            "stage_ms_per_step": {"evolve": ev_ms, "spline_k": t_spl / args.steps, "los": los_ms, "cl": t_cl / args.steps},
+                             "ms_per_launch": los_ms, "share_of_step": t_los / (t_ev + t_los + t_spl + t_cl + t_lens)},
+            "stage_ms_per_step": {"evolve": ev_ms, "spline_k": t_spl / args.steps, "los": los_ms, "cl": t_cl / args.steps,
+                                  "lens": t_lens / args.steps},
         }
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1

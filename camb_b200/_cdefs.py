@@ -48,6 +48,14 @@ class cb_window(C.Structure):
                     "comoving_density_ev")]
 
 
+class cb_lens_plan(C.Structure):
+    _fields_ = [("variant", C.c_int), ("lmin", C.c_int), ("lmax", C.c_int), ("lmax_lensed", C.c_int), ("npoints", C.c_int),
+                ("dtheta", C.c_double), ("apodize_point_width", C.c_int), ("interp_fac", C.c_int),
+                ("short_integral_range", C.c_int), ("imin", C.c_int), ("xvals", C.POINTER(C.c_double)),
+                ("weights", C.POINTER(C.c_double)), ("theta_max", C.c_double), ("apodize_theta_width", C.c_double),
+                ("xtaper_start", C.c_double)]
+
+
 class cb_params(C.Structure):
     _fields_ = [
         ("WantCls", C.c_int), ("WantTransfer", C.c_int), ("WantScalars", C.c_int), ("WantTensors", C.c_int),

@@ -29,6 +29,7 @@ void cb_los_launch(const DModel*, int, const DBessel&, int, int, size_t, cudaStr
 cudaError_t cb_los_win_launch(const DModel*, int, const DBessel&, int, int, cudaStream_t);
 void cb_cl_launch(const DModel*, int, const DBessel&, cudaStream_t);
 void cb_cl_array_launch(const DModel*, int, const DBessel&, double* const*, cudaStream_t);
+#include "lensing.cuh"
 void cb_limber_launch(const DModel*, int, const DBessel&, int, double* const*, cudaStream_t);
 void cb_cl_windows_launch(const DModel*, int, const DBessel&, double* const*, double* const*, double* const*, cudaStream_t);
 // peak.cu
@@ -82,6 +83,9 @@ struct cb_ctx {
     DModel* h_models = nullptr;   size_t cap_h_models = 0;   // page-locked staging
     DModeItem* h_items = nullptr; size_t cap_h_items = 0;
     int last_grid[CB_N_CLASSES] = {};
+    LensTab* d_lens_tab = nullptr; int lens_tab_n = 0;       // per-l constants of the lensing kernels, grown on demand
+    cudaEvent_t lens_ev[2] = {};
+    bool lens_timed = false;
 };
 
 #define CK(call)                                                                                  \
@@ -174,6 +178,8 @@ void cb_destroy(cb_ctx* ctx) {
     if (ctx->d_scratch_ptrs) cudaFree(ctx->d_scratch_ptrs);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     if (ctx->d_error) cudaFree(ctx->d_error);
+    if (ctx->d_lens_tab) cudaFree(ctx->d_lens_tab);
+    for (cudaEvent_t e : ctx->lens_ev) if (e) cudaEventDestroy(e);
     for (int c = 0; c < CB_N_CLASSES; c++) {
         if (ctx->class_stream[c]) cudaStreamDestroy(ctx->class_stream[c]);
         if (ctx->class_done[c]) cudaEventDestroy(ctx->class_done[c]);
@@ -667,6 +673,86 @@ int cb_cl_windows(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const double*
             CK(cudaMemcpyAsync(iCl_Array[m], dm[m]->d_icl_array, sizeof(double) * (size_t)n_l * n * n, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int cb_lens_contrib(cb_ctx* ctx, int n_sets, const cb_lens_plan* P, const double* const* spectra, double* const* lens_contrib) {
+    if (!ctx) return CB_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    if (!P || n_sets <= 0 || !spectra || !lens_contrib) { ctx->err = "cb_lens_contrib: null argument"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    if ((P->variant != CB_LENS_APODIZED && P->variant != CB_LENS_FULL) || (P->lmin != 1 && P->lmin != 2) || P->lmax < 4 ||
+        P->lmax_lensed < P->lmin || P->lmax_lensed > P->lmax || P->npoints < 2) {
+        ctx->err = "cb_lens_contrib: inconsistent plan (variant, lmin in {1,2}, lmin <= lmax_lensed <= lmax, npoints)";
+        return CB_ERR_UNSUPPORTED_PARAMS;
+    }
+    LensArgs A{};
+    A.variant = P->variant; A.lmin = P->lmin; A.lmax = P->lmax; A.lmax_lensed = P->lmax_lensed; A.npoints = P->npoints;
+    std::vector<void*> owned;
+    auto release = [&]() { for (void* p : owned) dev_free(ctx, p); };
+    if (P->variant == CB_LENS_APODIZED) {
+        if (!(P->dtheta > 0) || P->interp_fac < 1 || (P->short_integral_range && P->apodize_point_width < 1)) {
+            ctx->err = "cb_lens_contrib: apodized plan needs dtheta > 0, interp_fac >= 1, apodize_point_width >= 1";
+            return CB_ERR_UNSUPPORTED_PARAMS;
+        }
+        A.first = 1; A.last = P->npoints - 1;
+        A.dtheta = P->dtheta; A.apodize_point_width = P->apodize_point_width; A.interp_fac = P->interp_fac;
+        A.short_integral_range = P->short_integral_range;
+    } else {
+        if (!P->xvals || !P->weights || P->imin < 1 || P->imin > P->npoints) {
+            ctx->err = "cb_lens_contrib: full plan needs xvals, weights and 1 <= imin <= npoints";
+            return CB_ERR_UNSUPPORTED_PARAMS;
+        }
+        A.first = P->imin; A.last = P->npoints;
+        double *dx = nullptr, *dw = nullptr;
+        if (int e = upload(ctx, P->xvals, (size_t)P->npoints, &dx, &owned)) { release(); return e; }
+        if (int e = upload(ctx, P->weights, (size_t)P->npoints, &dw, &owned)) { release(); return e; }
+        A.xvals = dx; A.weights = dw;
+        A.theta_max = P->theta_max; A.apodize_theta_width = P->apodize_theta_width; A.xtaper_start = P->xtaper_start;
+    }
+    if (ctx->lens_tab_n < P->lmax + 1) {
+        if (ctx->d_lens_tab) dev_free(ctx, ctx->d_lens_tab);
+        ctx->d_lens_tab = nullptr; ctx->lens_tab_n = 0;
+        CK(dev_alloc(ctx, (void**)&ctx->d_lens_tab, sizeof(LensTab) * (size_t)(P->lmax + 1)));
+        ctx->lens_tab_n = P->lmax + 1;
+        cb_lens_tab_launch(ctx->d_lens_tab, ctx->lens_tab_n, ctx->stream);
+        ctx->launches++;
+    }
+    A.tab = ctx->d_lens_tab;
+    const size_t ld = 4 * ((size_t)P->lmax + 1), n_out = 4 * ((size_t)P->lmax_lensed + 1);
+    const int n_warps = cb_lens_warps(A);
+    double *d_spec = nullptr, *d_part = nullptr, *d_out = nullptr;
+    cudaError_t ce = dev_alloc(ctx, (void**)&d_spec, sizeof(double) * ld * n_sets);
+    if (ce == cudaSuccess) { owned.push_back(d_spec); ce = dev_alloc(ctx, (void**)&d_part, sizeof(double) * n_out * n_warps * n_sets); }
+    if (ce == cudaSuccess) { owned.push_back(d_part); ce = dev_alloc(ctx, (void**)&d_out, sizeof(double) * n_out * n_sets); }
+    if (ce != cudaSuccess) { release(); ctx->err = std::string("cb_lens_contrib: ") + cudaGetErrorString(ce); return CB_ERR_CUDA; }
+    owned.push_back(d_out);
+    for (int m = 0; m < n_sets; m++) {
+        ce = cudaMemcpyAsync(d_spec + ld * m, spectra[m], sizeof(double) * ld, cudaMemcpyHostToDevice, ctx->stream);
+        if (ce != cudaSuccess) { release(); ctx->err = std::string("cb_lens_contrib: ") + cudaGetErrorString(ce); return CB_ERR_CUDA; }
+    }
+    A.spectra = d_spec; A.partial = d_part;
+    if (!ctx->lens_ev[0]) { CK(cudaEventCreate(&ctx->lens_ev[0])); CK(cudaEventCreate(&ctx->lens_ev[1])); }
+    cudaEventRecord(ctx->lens_ev[0], ctx->stream);
+    cb_lens_launch(A, n_sets, d_out, ctx->stream);
+    cudaEventRecord(ctx->lens_ev[1], ctx->stream);
+    ctx->lens_timed = true;
+    ctx->launches += 2;
+    ce = cudaGetLastError();
+    for (int m = 0; m < n_sets && ce == cudaSuccess; m++)
+        ce = cudaMemcpyAsync(lens_contrib[m], d_out + n_out * m, sizeof(double) * n_out, cudaMemcpyDeviceToHost, ctx->stream);
+    release();
+    if (ce != cudaSuccess) { ctx->err = std::string("cb_lens_contrib: ") + cudaGetErrorString(ce); return CB_ERR_CUDA; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int cb_last_lens_timing(cb_ctx* ctx, double* ms) {
+    if (!ctx || !ms) return CB_ERR_NO_DEVICE;
+    *ms = 0;
+    if (!ctx->lens_timed) return 0;
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, ctx->lens_ev[0], ctx->lens_ev[1]));
+    *ms = f;
     return 0;
 }
 

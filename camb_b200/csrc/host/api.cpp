@@ -179,6 +179,115 @@ int cbh_interp_cl(cbh_state* s, const double* iCl, double* all_Cl) {
     return 0;
 }
 
+// InterpolateCls of the four lensing inputs (results.f90:1745-1824 -> InterpolateClArr) followed by
+// SetLensingPotentialSpectrum (lensing.f90:179-189) and PrepareLensedCLSpectra (lensing.f90:280-336), curved-sky weights.
+static int lens_spectra_impl(const HostState& S, const std::vector<int>& ls, const double* iCl, int n_cl, const double* highL, int lmax,
+                             int ee_taper, double* cl_scalar, double* spectra) {
+    const int n_l = (int)ls.size(), lmin = S.CP.Min_l, Max_l = ls.back();
+    if (n_cl < 4 || lmax < Max_l) return 1;
+    std::vector<double> col(n_l), all(Max_l - lmin + 1);
+    for (int c = 0; c < 4; c++) {
+        for (int i = 0; i < n_l; i++) col[i] = iCl[(size_t)i * n_cl + c];
+        // lSamples%init (results.f90:1517-1520): template on for C_Temp, C_E, C_Cross, l-rescaled when the acoustic scale moved > 1%
+        if (highL && c < 3 && S.CP.use_cl_spline_template)
+            InterpolateClArrTemplated(ls, col.data(), lmin, all.data(), n_l, highL + c, 4, std::fabs(S.scale - 1.0) > 0.01 ? S.scale : 1.0);
+        else
+            InterpolateClArr(ls, col.data(), lmin, all.data(), n_l);
+        for (int l = 0; l < lmin; l++) cl_scalar[(size_t)l * 4 + c] = 0;
+        for (int l = lmin; l <= Max_l; l++) cl_scalar[(size_t)l * 4 + c] = all[l - lmin];
+    }
+    const size_t ld = (size_t)lmax + 1;
+    double *Cphil3 = spectra, *CTT = spectra + ld, *CEE = spectra + 2 * ld, *CTE = spectra + 3 * ld;
+    for (size_t i = 0; i < 4 * ld; i++) spectra[i] = 0;
+    auto clw = [](int l) { return (2.0 * l + 1) / (4 * M_PI) * (2 * M_PI) / ((double)l * (l + 1)); };
+    auto phw = [](int l) { return (l + 0.5) / ((double)(l + 1) * l); };
+    for (int l = lmin; l <= Max_l; l++) {
+        const double* c = cl_scalar + (size_t)l * 4;
+        const double cpp = c[3] * ((double)(l + 1) * (l + 1)) / ((double)l * l) / (2 * M_PI);
+        Cphil3[l] = cpp * phw(l);
+        const double fac = clw(l);
+        CTT[l] = c[0] * fac;
+        CEE[l] = c[1] * fac;
+        if (ee_taper) {
+            double t = std::max(0.0, std::min(1.0, (l - 2.0) / 18.0));
+            CEE[l] *= t * t * (3.0 - 2.0 * t);
+        }
+        CTE[l] = c[2] * fac;
+    }
+    if (Max_l >= 10 && Cphil3[10] > 1e-7) return 2;       // AmplitudeError
+    if (lmax > Max_l) {
+        if (!highL) return 3;
+        const double* tM = highL + (size_t)Max_l * 4;
+        const double sc = clw(Max_l);
+        const double fac2 = CTT[Max_l] / (sc * tM[0]), fac3 = CEE[Max_l] / (sc * tM[1]);
+        const double te = std::sqrt(std::max(0.0, fac2 * fac3)), facp = Cphil3[Max_l] / (phw(Max_l) * tM[3]);
+        for (int l = Max_l + 1; l <= lmax; l++) {
+            const double* t = highL + (size_t)l * 4;
+            const double scl = clw(l);
+            Cphil3[l] = t[3] * facp * phw(l);
+            CTT[l] = t[0] * fac2 * scl;
+            CEE[l] = t[1] * fac3 * scl;
+            CTE[l] = t[2] * te * scl;
+        }
+        if (Cphil3[Max_l + 1] > 1e-7) return 4;
+    }
+    return 0;
+}
+
+int cbh_lens_spectra(cbh_state* s, const double* iCl, int n_cl, const double* highL, int lmax, int ee_taper, double* cl_scalar,
+                     double* spectra) {
+    return lens_spectra_impl(s->S, s->S.ls, iCl, n_cl, highL, lmax, ee_taper, cl_scalar, spectra);
+}
+
+// The same for a batch (one OpenMP thread per cosmology): contiguous cl_scalar (n, Max_l+1, 4) and spectra (n, 4, lmax+1).
+// ls_owner, when given, is the state whose l sampling every iCl[i] is on (a batch projected against one Bessel table).
+int cbh_lens_spectra_batch(int n, cbh_state* const* s, cbh_state* ls_owner, const double* const* iCl, int n_cl, const double* highL, int lmax,
+                           int ee_taper, double* cl_scalar, double* spectra, int nthreads) {
+    if (n <= 0) return 1;
+    const int Max_l = ls_owner ? ls_owner->S.ls.back() : s[0]->S.ls.back();
+    for (int i = 0; i < n; i++)
+        if (!ls_owner && s[i]->S.ls.back() != Max_l) return 1;
+    int err = 0;
+#pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1)
+    for (int i = 0; i < n; i++) {
+        const int e = lens_spectra_impl(s[i]->S, ls_owner ? ls_owner->S.ls : s[i]->S.ls, iCl[i], n_cl, highL, lmax, ee_taper,
+                                        cl_scalar + (size_t)i * (Max_l + 1) * 4, spectra + (size_t)i * 4 * ((size_t)lmax + 1));
+        if (e) {
+#pragma omp atomic write
+            err = e;
+        }
+    }
+    return err;
+}
+
+// Cl_lensed = lens_contrib * l(l+1)/OutputDenominator * 2pi [* dtheta] + unlensed (lensing.f90:660-672, 910-936);
+// lens_contrib, Cl_lensed (n, lmax_lensed+1, 4); cl_scalar (n, Max_l+1, 4) columns C_Temp, C_E, C_Cross, C_Phi.
+int cbh_lens_assemble_batch(int n, const cb_lens_plan* P, const double* lens_contrib, const double* cl_scalar, int Max_l, double* Cl_lensed,
+                            int nthreads) {
+    const int lout = P->lmax_lensed;
+    if (n <= 0 || lout > Max_l) return 1;
+#pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1)
+    for (int i = 0; i < n; i++) {
+        const double* c = lens_contrib + (size_t)i * (lout + 1) * 4;
+        const double* u = cl_scalar + (size_t)i * (Max_l + 1) * 4;
+        double* o = Cl_lensed + (size_t)i * (lout + 1) * 4;
+        for (int l = 0; l <= lout; l++) {
+            double* ol = o + 4 * (size_t)l;
+            if (l < P->lmin) { ol[0] = ol[1] = ol[2] = ol[3] = 0; continue; }
+            double fac = (double)l * (l + 1);
+            if (P->variant == CB_LENS_APODIZED) fac *= P->dtheta;
+            const double* cl = c + 4 * (size_t)l;
+            const double* ul = u + 4 * (size_t)l;
+            if (l == 1 && P->variant == CB_LENS_FULL) { ol[0] = cl[0] * 2.0 + ul[0]; ol[1] = ul[1]; ol[2] = 0; ol[3] = ul[2]; continue; }
+            ol[0] = cl[0] * fac + ul[0];
+            ol[1] = cl[1] * fac + ul[1];
+            ol[2] = cl[2] * fac;
+            ol[3] = cl[3] * fac + ul[2];
+        }
+    }
+    return 0;
+}
+
 double cbh_dtauda(cbh_state* s, double a) { return s->S.dtauda(a); }
 double cbh_xe(cbh_state* s, double a) { return s->S.rec.x_e(a); }
 

@@ -172,5 +172,7 @@ struct HostState {
 
 // results.f90:1706-1743 InterpolateClArr (plain cubic spline in l)
 void InterpolateClArr(const std::vector<int>& ls, const double* iCl, int lmin, double* all_Cl, int max_ind);
+void InterpolateClArrTemplated(const std::vector<int>& ls, const double* iCl, int lmin, double* all_Cl, int max_ind, const double* tmpl,
+                               int tmpl_stride, double template_scale);
 
 }  // namespace cbh

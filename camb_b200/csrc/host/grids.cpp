@@ -404,6 +404,41 @@ void InterpolateClArr(const std::vector<int>& ls, const double* iCl, int lmin, d
     }
 }
 
+// results.f90:1745-1824 InterpolateClArrTemplated: spline only the difference to the (l-rescaled) high-L template column
+// `tmpl` (indexed by l, 1..lmax_extrap), used for C_Temp, C_E, C_Cross when CP%use_cl_spline_template.
+void InterpolateClArrTemplated(const std::vector<int>& ls, const double* iCl, int lmin, double* all_Cl, int max_ind, const double* tmpl,
+                               int tmpl_stride, double template_scale) {
+    const int lmax_extrap = 8000;
+    if (!tmpl) { InterpolateClArr(ls, iCl, lmin, all_Cl, max_ind); return; }
+    auto T = [&](int l) { return tmpl[(size_t)l * tmpl_stride]; };
+    int maxdelta = max_ind;
+    std::vector<double> delta(ls.size()), tcl;
+    if (template_scale == 1.0) {
+        while (ls[maxdelta - 1] > lmax_extrap) maxdelta--;
+        for (int i = 0; i < maxdelta; i++) delta[i] = iCl[i] - T(ls[i]);
+        InterpolateClArr(ls, delta.data(), lmin, all_Cl, maxdelta);
+        for (int il = lmin; il <= ls[maxdelta - 1]; il++) all_Cl[il - lmin] += T(il);
+    } else {
+        while (maxdelta > 1 && ls[maxdelta - 1] / template_scale > lmax_extrap) maxdelta--;
+        if (ls[maxdelta - 1] / template_scale > lmax_extrap) { InterpolateClArr(ls, iCl, lmin, all_Cl, max_ind); return; }
+        tcl.resize(ls[maxdelta - 1] + 1);
+        for (int il = lmin; il <= ls[maxdelta - 1]; il++) {
+            const double tl = il / template_scale;
+            if (tl <= 1.0) tcl[il] = T(1);
+            else if (tl >= lmax_extrap) tcl[il] = T(lmax_extrap);
+            else { const int lo = (int)tl; const double frac = tl - lo; tcl[il] = (1.0 - frac) * T(lo) + frac * T(lo + 1); }
+        }
+        for (int i = 0; i < maxdelta; i++) delta[i] = iCl[i] - tcl[ls[i]];
+        InterpolateClArr(ls, delta.data(), lmin, all_Cl, maxdelta);
+        for (int il = lmin; il <= ls[maxdelta - 1]; il++) all_Cl[il - lmin] += tcl[il];
+    }
+    if (maxdelta < max_ind) {   // no template up there: plain spline, overlapped by two samples
+        std::vector<double> tmp(ls[max_ind - 1] - lmin + 1);
+        InterpolateClArr(ls, iCl, lmin, tmp.data(), max_ind);
+        for (int il = ls[maxdelta - 3]; il <= ls[max_ind - 1]; il++) all_Cl[il - lmin] = tmp[il - lmin];
+    }
+}
+
 void HostState::fill_model(cb_model& m) const {
     std::memset(&m, 0, sizeof(m));
     m.grhog = grhog; m.grhor = grhor; m.grhornomass = grhornomass; m.grhob = grhob; m.grhoc = grhoc; m.grhov = grhov; m.grhok = grhok;

@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-from ._cdefs import cb_bessel, cb_model, cb_modes, c_double_p, c_float_p, c_int_p
+from ._cdefs import cb_bessel, cb_lens_plan, cb_model, cb_modes, c_double_p, c_float_p, c_int_p
 from .host import CAMBError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -22,7 +22,8 @@ SYMBOLS = ["cb_create", "cb_destroy", "cb_last_error", "cb_device_count", "cb_se
            "cb_model_destroy", "cb_evolve", "cb_set_sources", "cb_project", "cb_cl", "cb_last_timings",
            "cb_launch_count", "cb_abi_sizeof", "cb_timer_start", "cb_timer_stop", "cb_fp64_peak",
            "cb_host_alloc", "cb_host_free", "cb_device_buffer", "cb_set_option", "cb_host_register",
-           "cb_host_unregister", "cb_cl_array", "cb_cl_windows"]
+           "cb_host_unregister", "cb_cl_array", "cb_cl_windows", "cb_lens_contrib",
+           "cb_last_lens_timing"]
 
 
 def load_gpu_lib():
@@ -50,6 +51,8 @@ def load_gpu_lib():
         lib.cb_cl_array.argtypes = [C.c_void_p, C.c_int, c_void_pp, C.POINTER(c_double_p), C.POINTER(c_double_p)]
         lib.cb_cl_windows.argtypes = [C.c_void_p, C.c_int, c_void_pp, C.POINTER(c_double_p), C.POINTER(c_double_p),
                                       C.POINTER(c_double_p), C.POINTER(c_double_p)]
+        lib.cb_lens_contrib.argtypes = [C.c_void_p, C.c_int, C.POINTER(cb_lens_plan), C.POINTER(c_double_p), C.POINTER(c_double_p)]
+        lib.cb_last_lens_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         lib.cb_last_timings.argtypes = [C.c_void_p, C.c_double * 4]
         lib.cb_launch_count.restype = C.c_longlong
         lib.cb_launch_count.argtypes = [C.c_void_p]
@@ -218,6 +221,27 @@ class GpuContext:
         a_p = (c_double_p * n)(*[_dp(a) for a in arr])
         self._check(self._lib.cb_cl_windows(self._h, n, dm_arr, p_p, lp_p, i_p, a_p))
         return [o.T.copy() for o in icl], arr
+
+    def lens_contrib(self, plan, spectra, out=None):
+        """Theta loops of the lensed-C_l correlation functions: spectra[i] (4, lmax+1) -> lens_contrib[i] (lmax_lensed+1, 4);
+        `out` (n, lmax_lensed+1, 4), when given, receives the results in place."""
+        n = len(spectra)
+        for a in spectra:
+            assert a.shape == (4, plan.lmax + 1) and a.flags.c_contiguous and a.dtype == np.float64
+        if out is None:
+            res = [np.zeros((plan.lmax_lensed + 1, 4)) for _ in range(n)]
+        else:
+            assert out.shape == (n, plan.lmax_lensed + 1, 4) and out.flags.c_contiguous and out.dtype == np.float64
+            res = list(out)
+        s_p = (c_double_p * n)(*[_dp(a) for a in spectra])
+        o_p = (c_double_p * n)(*[_dp(a) for a in res])
+        self._check(self._lib.cb_lens_contrib(self._h, n, C.byref(plan.c), s_p, o_p))
+        return res
+
+    def last_lens_ms(self):
+        ms = C.c_double()
+        self._check(self._lib.cb_last_lens_timing(self._h, C.byref(ms)))
+        return ms.value
 
     def pin_host_tables(self, hs):
         """Page-lock the host's boundary tables in place (what a Fortran host would do with its

@@ -48,6 +48,10 @@ def load_host_lib():
         lib.cbh_get_derived.argtypes = [C.c_void_p, C.c_double * 13]
         lib.cbh_get_background.argtypes = [C.c_void_p, C.c_double * 16]
         lib.cbh_interp_cl.argtypes = [C.c_void_p, c_double_p, c_double_p]
+        lib.cbh_lens_spectra.argtypes = [C.c_void_p, c_double_p, C.c_int, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p]
+        lib.cbh_lens_spectra_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(c_double_p), C.c_int, c_double_p, C.c_int,
+                                               C.c_int, c_double_p, c_double_p, C.c_int]
+        lib.cbh_lens_assemble_batch.argtypes = [C.c_int, C.c_void_p, c_double_p, c_double_p, C.c_int, c_double_p, C.c_int]
         lib.cbh_dtauda.restype = C.c_double
         lib.cbh_dtauda.argtypes = [C.c_void_p, C.c_double]
         lib.cbh_xe.restype = C.c_double
@@ -193,6 +197,23 @@ class HostState:
             self._lib.cbh_interp_cl(self._h, _dp(col), _dp(tmp))
             out[lmin:, c] = tmp
         return out
+
+    def lens_spectra(self, iCl, template, lmax, ee_taper=True):
+        """InterpolateCls (templated for TT, EE, TE when a template is given) + PrepareLensedCLSpectra (lensing.f90:280-336):
+        iCl (n_l, >=4) -> (Cl_scalar (Max_l+1, 4), spectra (4, lmax+1) for cb_lens_contrib)."""
+        iCl = np.ascontiguousarray(iCl, dtype=np.float64)
+        Max_l = int(self.ls[-1])
+        cl = np.empty((Max_l + 1, 4))
+        sp = np.empty((4, lmax + 1))
+        if template is not None:
+            assert template.flags.c_contiguous and template.shape[1] == 4 and template.shape[0] > lmax
+        err = self._lib.cbh_lens_spectra(self._h, _dp(iCl), iCl.shape[1], _dp(template) if template is not None else None, int(lmax),
+                                         int(bool(ee_taper)), _dp(cl), _dp(sp))
+        if err:
+            raise CAMBError({1: "lens_spectra: bad arguments", 2: "You need to normalize realistically to use lensing",
+                             3: "lens_spectra: lmax > Max_l needs the high-L template",
+                             4: "You need to normalize the high-L template so it is dimensionless"}.get(err, "lens_spectra"), err)
+        return cl, sp
 
     def dtauda(self, a):
         return self._lib.cbh_dtauda(self._h, float(a))

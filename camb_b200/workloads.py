@@ -205,3 +205,24 @@ def sigma8_anchor_params(anchor, notebook=False):
     for i, z in enumerate(zs):
         p.transfer_PK_redshifts[i] = z
     return p
+
+
+def analytic_cmb_cls(lmax):
+    """Analytic CMB-like spectra (lmax+1, 4): TT, EE, TE, PP with the l(l+1)/2pi ([L(L+1)]^2/2pi for PP) factors,
+    dimensionless, zero below l = 2.  Used as lensing test input and, on machines without the reference's
+    HighLExtrapTemplate_lenspotentialCls.dat, as a stand-in for that template's tail shape (config.f90:93-116)."""
+    l = np.arange(lmax + 1, dtype=float)
+    ph = np.pi * l / 301.0
+    damp_t = np.exp(-(l / 1350.0) ** 1.25)
+    tt = 9e-10 * (0.12 + np.cos(ph - 0.6) ** 2 * (0.45 + 0.55 * np.exp(-(l / 900.0)))) * damp_t * (l / (l + 25.0)) + 1.5e-10 / (1 + (l / 12.0) ** 2)
+    ee = 7e-12 * (0.05 + np.sin(ph - 0.55) ** 2) * (l / 700.0) ** 1.5 * np.exp(-(l / 1500.0) ** 1.6) * 4.0 + 6e-15 * np.exp(-((l - 4.0) / 3.0) ** 2)
+    te = 0.55 * np.sqrt(tt * ee) * np.sin(2 * ph - 1.3)
+    pp = 1.6e-7 * (l / 40.0) ** 1.2 / (1.0 + (l / 40.0) ** 2.45)
+    out = np.stack([tt, ee, te, pp], axis=1)
+    out[:2] = 0
+    return out
+
+
+def synthetic_highl_template():
+    """Stand-in for highL_CL_template (l = 0..8000; columns TT, EE, TE, PP) where the reference's data file is not available."""
+    return np.ascontiguousarray(analytic_cmb_cls(8000))

@@ -199,6 +199,35 @@ int  cb_cl_array(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const double* 
 int  cb_cl_windows(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const double* const* pows, const double* const* limber_pows,
                    double* const* iCl, double* const* iCl_Array);
 
+/* CMB lensing of the C_l: the OpenMP loops over the angle theta of
+ * CorrFuncFullSkyApodized (lensing.f90:338-678, the default: lensing_method_curv_corr) and CorrFuncFullSky
+ * (lensing.f90:680-941, AccurateBB / lensing_method_curv_corr_full).  The plan carries the SHARED scalars of those
+ * parallel regions (lensing.f90:449-452, 776-780); the host keeps PrepareLensedCLSpectra (:280-336) before the call and
+ * the final l(l+1)/OutputDenominator scaling (:660-672, 922-936) after it. */
+#define CB_LENS_APODIZED 0
+#define CB_LENS_FULL     1
+typedef struct cb_lens_plan {
+    int variant;                 /* CB_LENS_APODIZED or CB_LENS_FULL */
+    int lmin, lmax;              /* CP%Min_l (1 or 2) and LensingExtrapLmax (lensing.f90:161-177) */
+    int lmax_lensed;             /* CLout%lmax_lensed (InitLensedClArrays, lensing.f90:230-247) */
+    int npoints;
+    /* CB_LENS_APODIZED: theta_i = i*dtheta, i = 1..npoints-1 (lensing.f90:396-411) */
+    double dtheta;
+    int apodize_point_width, interp_fac, short_integral_range;
+    /* CB_LENS_FULL: Gauss-Legendre points i = imin..npoints (1-based), ascending x (lensing.f90:718-741) */
+    int imin;
+    const double* xvals;         /* [npoints] */
+    const double* weights;       /* [npoints] */
+    double theta_max, apodize_theta_width, xtaper_start;
+} cb_lens_plan;
+
+/* spectra[i]      double (4, lmax + 1), l fastest, rows Cphil3, CTT, CEE, CTE of PrepareLensedCLSpectra (entries below lmin ignored)
+ * lens_contrib[i] double (lmax_lensed + 1, 4): sum over theta (the reference's sum over threads of lens_contrib(:, l, thread))
+ *                 for CT_Temp, CT_E, CT_B, CT_Cross; rows below lmin are zero. */
+int  cb_lens_contrib(cb_ctx* ctx, int n_sets, const cb_lens_plan* plan, const double* const* spectra, double* const* lens_contrib);
+/* Device time of the two kernels of the last cb_lens_contrib call, ms (CUDA events on the launching stream). */
+int  cb_last_lens_timing(cb_ctx* ctx, double* ms);
+
 /* Kernel timing of the last call of each stage, ms, measured with CUDA events on
  * the launching stream: [0] evolve, [1] spline-k, [2] LOS, [3] C_l. */
 int  cb_last_timings(const cb_ctx* ctx, double ms[4]);

@@ -38,6 +38,20 @@ int cbh_get_derived(cbh_state* s, double out[13]);            /* ThermoDerivedPa
 int cbh_get_background(cbh_state* s, double out[16]);         /* tau0,taurst,taurend,tau_maxvis,dtaurec,scale,... */
 /* InterpolateClArr (results.f90:1706-1743): iCl[n_l] -> all_Cl[lmin..ls(n_l)] */
 int cbh_interp_cl(cbh_state* s, const double* iCl, double* all_Cl);
+/* Host side of lens_Cls before the theta loops: InterpolateCls of TT, EE, TE, PhiPhi (results.f90:1745-1824),
+ * SetLensingPotentialSpectrum (lensing.f90:179-189) and PrepareLensedCLSpectra (lensing.f90:280-336).
+ *   iCl (n_l, n_cl) row-major with columns C_Temp, C_E, C_Cross, C_Phi first; highL (>= lmax+1, 4) TT, EE, TE, PP template
+ *   rows indexed by l (config.f90:93-116), may be NULL when lmax == Max_l;  cl_scalar (Max_l+1, 4);  spectra (4, lmax+1)
+ *   as cb_lens_contrib takes it.  Returns 2 for the reference's AmplitudeError, 4 for an undimensioned template. */
+int cbh_lens_spectra(cbh_state* s, const double* iCl, int n_cl, const double* highL, int lmax, int ee_taper, double* cl_scalar,
+                     double* spectra);
+/* Batch forms (OpenMP over cosmologies sharing Max_l): cl_scalar (n, Max_l+1, 4), spectra (n, 4, lmax+1) contiguous; and the
+ * ls_owner (or NULL): the state whose l sampling all iCl[i] are on, for a batch projected against one Bessel table;
+ * final assembly of Cl_lensed (n, lmax_lensed+1, 4) = TT, EE, BB, TE from lens_contrib (lensing.f90:660-672, 910-936). */
+int cbh_lens_spectra_batch(int n, cbh_state* const* s, cbh_state* ls_owner, const double* const* iCl, int n_cl, const double* highL,
+                           int lmax, int ee_taper, double* cl_scalar, double* spectra, int nthreads);
+int cbh_lens_assemble_batch(int n, const cb_lens_plan* plan, const double* lens_contrib, const double* cl_scalar, int Max_l,
+                            double* Cl_lensed, int nthreads);
 double cbh_dtauda(cbh_state* s, double a);
 double cbh_xe(cbh_state* s, double a);
 

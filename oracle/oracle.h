@@ -39,6 +39,11 @@ int oracle_cl_windows(const cb_model* M, const cb_bessel* B, int n_q, const doub
                       const double* Delta_p_l_k, const double* LimbSrc, const int* n1n2, const double* limber_pows, double* iCl,
                       double* iCl_Array);
 
+/* CMB lensing theta loops (lensing.f90:449-657 and :776-908): spectra (4, lmax+1) -> lens_contrib (lmax_lensed+1, 4);
+ * OpenMP over theta with per-thread accumulators like the reference. */
+int oracle_lens_apodized(const cb_lens_plan* plan, const double* spectra, double* lens_contrib, int nthreads);
+int oracle_lens_full(const cb_lens_plan* plan, const double* spectra, double* lens_contrib, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

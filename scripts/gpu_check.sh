@@ -18,6 +18,6 @@ tail -c 600 $OUT/${TAG}_bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --batch 16 --no-cpu-baseline > $OUT/${TAG}_ncu_bench.log 2>&1
 # full capture of the two main kernels on a small run (smoke: one cosmology, lmax 600)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"cb_evolve_kernel|cb_los_kernel" -c 2 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"cb_evolve_kernel|cb_los_kernel|cb_lens_kernel" -c 3 \
     -o $OUT/${TAG}_prof -f python bench.py --steps 1 --warmup 3 --batch 8 --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
 ls -la $OUT

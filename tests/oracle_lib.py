@@ -139,6 +139,19 @@ def cl_windows(hs, delta, limb_src, n1n2, pows=None):
     return icl.T.copy(), arr
 
 
+def lens_contrib(plan, spectra, nthreads=1):
+    """Theta loops of the lensed-C_l correlation functions on the CPU: spectra (4, lmax+1) -> (lmax_lensed+1, 4)."""
+    from camb_b200._cdefs import cb_lens_plan
+    lib = load()
+    fn = lib.oracle_lens_full if plan.variant == 1 else lib.oracle_lens_apodized
+    fn.argtypes = [C.POINTER(cb_lens_plan), c_double_p, c_double_p, C.c_int]
+    sp = np.ascontiguousarray(spectra, dtype=np.float64)
+    assert sp.shape == (4, plan.lmax + 1)
+    out = np.zeros((plan.lmax_lensed + 1, 4))
+    assert fn(C.byref(plan.c), _dp(sp), _dp(out), int(nthreads)) == 0
+    return out
+
+
 def cls_windows_from_params(hs, nthreads=1):
     src, tr, stats = evolve(hs, nthreads=nthreads)
     q_src = hs.source_q()
