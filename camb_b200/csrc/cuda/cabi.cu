@@ -83,7 +83,7 @@ struct cb_ctx {
     DModel* h_models = nullptr;   size_t cap_h_models = 0;   // page-locked staging
     DModeItem* h_items = nullptr; size_t cap_h_items = 0;
     int last_grid[CB_N_CLASSES] = {};
-    LensTab* d_lens_tab = nullptr; int lens_tab_n = 0;       // per-l constants of the lensing kernels, grown on demand
+    LensTab* d_lens_tab = nullptr; LensTab2* d_lens_tab2 = nullptr; int lens_tab_n = 0;       // per-l constants of the lensing kernels, grown on demand
     cudaEvent_t lens_ev[2] = {};
     bool lens_timed = false;
 };
@@ -179,6 +179,7 @@ void cb_destroy(cb_ctx* ctx) {
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     if (ctx->d_error) cudaFree(ctx->d_error);
     if (ctx->d_lens_tab) cudaFree(ctx->d_lens_tab);
+    if (ctx->d_lens_tab2) cudaFree(ctx->d_lens_tab2);
     for (cudaEvent_t e : ctx->lens_ev) if (e) cudaEventDestroy(e);
     for (int c = 0; c < CB_N_CLASSES; c++) {
         if (ctx->class_stream[c]) cudaStreamDestroy(ctx->class_stream[c]);
@@ -711,13 +712,15 @@ int cb_lens_contrib(cb_ctx* ctx, int n_sets, const cb_lens_plan* P, const double
     }
     if (ctx->lens_tab_n < P->lmax + 1) {
         if (ctx->d_lens_tab) dev_free(ctx, ctx->d_lens_tab);
-        ctx->d_lens_tab = nullptr; ctx->lens_tab_n = 0;
+        if (ctx->d_lens_tab2) dev_free(ctx, ctx->d_lens_tab2);
+        ctx->d_lens_tab = nullptr; ctx->d_lens_tab2 = nullptr; ctx->lens_tab_n = 0;
         CK(dev_alloc(ctx, (void**)&ctx->d_lens_tab, sizeof(LensTab) * (size_t)(P->lmax + 1)));
+        CK(dev_alloc(ctx, (void**)&ctx->d_lens_tab2, sizeof(LensTab2) * (size_t)(P->lmax + 1)));
         ctx->lens_tab_n = P->lmax + 1;
-        cb_lens_tab_launch(ctx->d_lens_tab, ctx->lens_tab_n, ctx->stream);
+        cb_lens_tab_launch(ctx->d_lens_tab, ctx->d_lens_tab2, ctx->lens_tab_n, ctx->stream);
         ctx->launches++;
     }
-    A.tab = ctx->d_lens_tab;
+    A.tab = ctx->d_lens_tab; A.tab2 = ctx->d_lens_tab2;
     const size_t ld = 4 * ((size_t)P->lmax + 1), n_out = 4 * ((size_t)P->lmax_lensed + 1);
     const int n_warps = cb_lens_warps(A);
     double *d_spec = nullptr, *d_part = nullptr, *d_out = nullptr;

@@ -20,9 +20,11 @@ struct Angle {
     double x, theta, sinth, sin2, rsin2, fac1, fac2;
 };
 
-__device__ __forceinline__ void legendre_step(int l, double inv_l, const Angle& a, double& pmm, double& pmmp1, double& Pl, double& dPl) {
-    Pl = ((2 * l - 1) * a.x * pmmp1 - (l - 1) * pmm) * inv_l;
-    dPl = l * (pmmp1 - a.x * Pl) * a.rsin2;
+// dl runs along with l as a double (exactly l): no integer conversions in the serial chain
+__device__ __forceinline__ void legendre_step(double& dl, double inv_l, const Angle& a, double& pmm, double& pmmp1, double& Pl, double& dPl) {
+    dl += 1.0;
+    Pl = ((2.0 * dl - 1.0) * a.x * pmmp1 - (dl - 1.0) * pmm) * inv_l;
+    dPl = dl * (pmmp1 - a.x * Pl) * a.rsin2;
     pmm = pmmp1;
     pmmp1 = Pl;
 }
@@ -44,31 +46,30 @@ __device__ __forceinline__ void spin2_rows(const LensTab& t, const Angle& a, dou
 }
 
 // one sampled l of the apodized method's correlation sums (lensing.f90:515-626)
-__device__ __forceinline__ void apodized_term(int l, const LensTab& t, const Angle& a, double Pl, double dPl, double sigmasq, double Cg2,
+__device__ __forceinline__ void apodized_term(int l, const LensTab& t, const LensTab2& u, const Angle& a, double Pl, double dPl, double sigmasq, double Cg2,
                                               double sc, double ctt, double cee, double cte, double corr[4]) {
     const double x = a.x, sinth = a.sinth, fac1 = a.fac1, fac2 = a.fac2;
     const double llp1 = t.lf, lf2 = t.lf2;
-    const double rootllp1 = sqrt(llp1), rootfac1 = sqrt(lf2);
-    const double rootfac2 = l >= 2 ? sqrt((double)(l + 3) * (double)(l - 2)) : 0.0;
+    const double rootllp1 = u.rootllp1, rootfac1 = u.rootfac1, rootfac2 = u.rootfac2;
     const double d11 = fac1 * dPl * t.ilf + Pl, dm11 = fac2 * dPl * t.ilf - Pl;
     double d2m2 = 0, d22 = 0, d20 = 0, d1m2 = 0, d12 = 0, d1m3 = 0, d2m3 = 0, d3m3 = 0, d13 = 0, d04 = 0, d2m4 = 0, d4m4 = 0, rootfac3 = 0;
     if (l >= 2) {
         spin2_rows<CB_LENS_APODIZED>(t, a, Pl, dPl, d22, d2m2, d20);
-        d1m2 = sinth / rootfac1 * (dPl - 2 / fac1 * dm11);
-        d12 = sinth / rootfac1 * (dPl - 2 / fac2 * d11);
+        d1m2 = sinth * u.irootfac1 * (dPl - 2 / fac1 * dm11);
+        d12 = sinth * u.irootfac1 * (dPl - 2 / fac2 * d11);
     }
     if (l >= 3) {
         const double sinfac = 4 / sinth;
-        d1m3 = (-(x + 0.5) * d1m2 * sinfac - lf2 * dm11 / rootfac1) / rootfac2;
-        d2m3 = (-fac2 * d2m2 * sinfac - rootfac1 * d1m2) / rootfac2;
-        d3m3 = (-(x + 1.5) * d2m3 * sinfac - rootfac1 * d1m3) / rootfac2;
-        d13 = ((x - 0.5) * d12 * sinfac - lf2 * d11 / rootfac1) / rootfac2;
+        d1m3 = (-(x + 0.5) * d1m2 * sinfac - lf2 * dm11 * u.irootfac1) * u.irootfac2;
+        d2m3 = (-fac2 * d2m2 * sinfac - rootfac1 * d1m2) * u.irootfac2;
+        d3m3 = (-(x + 1.5) * d2m3 * sinfac - rootfac1 * d1m3) * u.irootfac2;
+        d13 = ((x - 0.5) * d12 * sinfac - lf2 * d11 * u.irootfac1) * u.irootfac2;
     }
     if (l >= 4) {
-        rootfac3 = sqrt((double)(l - 3) * (double)(l + 4));
-        d04 = ((-llp1 + (18 * x * x + 6) * a.rsin2) * d20 - 6 * x * lf2 * dPl * t.ilroot) / (rootfac2 * rootfac3);
-        d2m4 = (-(6 * x + 4) * d2m3 / sinth - rootfac2 * d2m2) / rootfac3;
-        d4m4 = (-7 / 5.0 * (llp1 - 6) * d2m2 + 12 / 5.0 * (-llp1 + (9 * x + 26) / fac1) * d3m3) / (llp1 - 12);
+        rootfac3 = u.rootfac3;
+        d04 = ((-llp1 + (18 * x * x + 6) * a.rsin2) * d20 - 6 * x * lf2 * dPl * t.ilroot) * (u.irootfac2 * u.irootfac3);
+        d2m4 = (-(6 * x + 4) * d2m3 / sinth - rootfac2 * d2m2) * u.irootfac3;
+        d4m4 = (-7 / 5.0 * (llp1 - 6) * d2m2 + 12 / 5.0 * (-llp1 + (9 * x + 26) / fac1) * d3m3) * u.ilfm12;
     }
     const double X000 = exp(-llp1 * sigmasq / 4);
     const double X022 = X000 * (1 + sigmasq);
@@ -92,7 +93,7 @@ __device__ __forceinline__ void apodized_term(int l, const LensTab& t, const Ang
 }
 
 // one l (>= 2) of the full method's correlation sums (lensing.f90:859-898)
-__device__ __forceinline__ void full_term(int l, const LensTab& t, const Angle& a, double Pl, double dPl, double facexp, double Cg2,
+__device__ __forceinline__ void full_term(int l, const LensTab& t, const LensTab2& u, const Angle& a, double Pl, double dPl, double facexp, double Cg2,
                                           double ctt, double cee, double cte, double corr[4]) {
     const double x = a.x, sinth = a.sinth, fac1 = a.fac1, fac2 = a.fac2;
     const double lf = t.lf, lf2 = t.lf2;
@@ -107,8 +108,8 @@ __device__ __forceinline__ void full_term(int l, const LensTab& t, const Angle& 
     corr[3] += cte * (facexp - 1) * d20 + fTE * (c2fac * d11 / 2 + 3 * c2fac2 * d20 / 8);
     if (l >= 3) {
         const double sinfac = 4 / sinth;
-        const double rootfac1 = sqrt(lf2), irootfac1 = 1 / rootfac1;
-        const double rootfac2 = sqrt((double)(l + 3) * (double)(l - 2)), irootfac2 = 1 / rootfac2, rootrat = rootfac1 * irootfac2;
+        const double rootfac1 = u.rootfac1, irootfac1 = u.irootfac1;
+        const double rootfac2 = u.rootfac2, irootfac2 = u.irootfac2, rootrat = rootfac1 * irootfac2;
         const double d1m2 = sinth * irootfac1 * (dPl - 2 / fac1 * dm11);
         const double d12 = sinth * irootfac1 * (dPl - 2 / fac2 * d11);
         const double d1m3 = -(x + 0.5) * sinfac * d1m2 * irootfac2 - rootrat * dm11;
@@ -119,10 +120,10 @@ __device__ __forceinline__ void full_term(int l, const LensTab& t, const Angle& 
         corr[2] += fEE * c2fac * d3m3 / 2;
         corr[3] += fTE * c2fac * d1m3 / 2;
         if (l >= 4) {
-            const double irootfac3 = 1 / sqrt((double)(l - 3) * (double)(l + 4));
+            const double irootfac3 = u.irootfac3;
             const double d04 = ((-lf + (18 * x * x + 6) * a.rsin2) * d20 - 6 * x * lf2 * dPl * t.ilroot) * (irootfac2 * irootfac3);
             const double d2m4 = (-((6 * x + 4) / sinth) * d2m3 - rootfac2 * d2m2) * irootfac3;
-            const double d4m4 = (-7.0 / 5.0 * (lf - 6) * d2m2 + 12.0 / 5.0 * (-lf + (9 * x + 26) / fac1) * d3m3) * (1 / (lf - 12));
+            const double d4m4 = (-7.0 / 5.0 * (lf - 6) * d2m2 + 12.0 / 5.0 * (-lf + (9 * x + 26) / fac1) * d3m3) * u.ilfm12;
             corr[1] += fEE * c2fac2 * d04 / 4;
             corr[2] += fEE * c2fac2 * d4m4 / 8;
             corr[3] += fTE * c2fac2 * d2m4 / 8;
@@ -136,21 +137,31 @@ __device__ __forceinline__ void full_term(int l, const LensTab& t, const Angle& 
 constexpr int CH = 64;
 struct Stage {
     LensTab tab[CH];
+    LensTab2 tab2[CH];
     double spec[4][CH];
 };
 struct Prefetch {
     double2 t[CH * 4 / 32];
+    double2 t2[CH * 4 / 32];
     double s[4][CH / 32];
 };
 
 template <bool SPEC>
-__device__ __forceinline__ void prefetch_chunk(Prefetch& R, const LensTab* __restrict__ T, const double* __restrict__ spectra, size_t ld,
-                                               int l0, int lmax, int lane) {
+__device__ __forceinline__ void prefetch_chunk(Prefetch& R, const LensTab* __restrict__ T, const LensTab2* __restrict__ T2,
+                                               const double* __restrict__ spectra, size_t ld, int l0, int lmax, int lane) {
     const double2* src = reinterpret_cast<const double2*>(T + l0);
 #pragma unroll
     for (int k = 0; k < CH * 4 / 32; k++) {
         const int e = k * 32 + lane;
         R.t[k] = (l0 + e / 4 <= lmax) ? __ldg(src + e) : make_double2(0.0, 0.0);
+    }
+    if (SPEC && T2) {
+        const double2* src2 = reinterpret_cast<const double2*>(T2 + l0);
+#pragma unroll
+        for (int k = 0; k < CH * 4 / 32; k++) {
+            const int e = k * 32 + lane;
+            R.t2[k] = (l0 + e / 4 <= lmax) ? __ldg(src2 + e) : make_double2(0.0, 0.0);
+        }
     }
     if (SPEC) {
 #pragma unroll
@@ -163,11 +174,16 @@ __device__ __forceinline__ void prefetch_chunk(Prefetch& R, const LensTab* __res
     }
 }
 
-template <bool SPEC>
+template <bool SPEC, bool WITH2 = false>
 __device__ __forceinline__ void commit_chunk(Stage& S, const Prefetch& R, int lane) {
     double2* dst = reinterpret_cast<double2*>(S.tab);
 #pragma unroll
     for (int k = 0; k < CH * 4 / 32; k++) dst[k * 32 + lane] = R.t[k];
+    if (SPEC && WITH2) {
+        double2* dst2 = reinterpret_cast<double2*>(S.tab2);
+#pragma unroll
+        for (int k = 0; k < CH * 4 / 32; k++) dst2[k * 32 + lane] = R.t2[k];
+    }
     if (SPEC) {
 #pragma unroll
         for (int c = 0; c < 4; c++)
@@ -185,6 +201,7 @@ __global__ void __launch_bounds__(32) cb_lens_kernel(LensArgs A) {
     const size_t ld = (size_t)lmax + 1;
     const double* __restrict__ spectra = A.spectra + (size_t)set * 4 * ld;      // rows Cphil3, CTT, CEE, CTE
     const LensTab* __restrict__ T = A.tab;
+    const LensTab2* __restrict__ T2 = A.tab2;
     Prefetch R;
 
     // this lane's angle; lanes past the end redo the last angle with zero weight
@@ -216,19 +233,19 @@ __global__ void __launch_bounds__(32) cb_lens_kernel(LensArgs A) {
     // pass 1: sigma^2(theta) and C_gl,2(theta)
     double sigmasq = 0, Cg2 = 0;
     {
-        double pmm = 1, pmmp1 = a.x, Pl, dPl;
-        prefetch_chunk<true>(R, T, spectra, ld, 0, lmax, lane);
+        double pmm = 1, pmmp1 = a.x, Pl, dPl, dl = 1.0;
+        prefetch_chunk<true>(R, T, nullptr, spectra, ld, 0, lmax, lane);
         for (int l0 = 0; l0 <= lmax; l0 += CH) {
             __syncwarp();
             commit_chunk<true>(S, R, lane);
             __syncwarp();
-            if (l0 + CH <= lmax) prefetch_chunk<true>(R, T, spectra, ld, l0 + CH, lmax, lane);
+            if (l0 + CH <= lmax) prefetch_chunk<true>(R, T, nullptr, spectra, ld, l0 + CH, lmax, lane);
             const int n = min(CH, lmax + 1 - l0);
             for (int lj = 0; lj < n; lj++) {
                 const int l = l0 + lj;
                 const double c = S.spec[0][lj];
                 if (l >= 2) {
-                    legendre_step(l, S.tab[lj].inv_l, a, pmm, pmmp1, Pl, dPl);
+                    legendre_step(dl, S.tab[lj].inv_l, a, pmm, pmmp1, Pl, dPl);
                     const double u = dPl * S.tab[lj].ilf;
                     sigmasq += (1 - (a.fac1 * u + Pl)) * c;
                     Cg2 += (a.fac2 * u - Pl) * c;
@@ -243,37 +260,39 @@ __global__ void __launch_bounds__(32) cb_lens_kernel(LensArgs A) {
     // pass 2: the four lensed-minus-unlensed correlation functions at this angle
     double corr[4] = {0, 0, 0, 0};
     {
-        double pmm = 1, pmmp1 = a.x, Pl, dPl;
+        double pmm = 1, pmmp1 = a.x, Pl, dPl, dl = 1.0;
         int j = 0;
-        const int half = A.interp_fac / 2;
+        // sampled multipoles of the correlation sums: every l <= 15, then l = 15 + half (+ k interp_fac) (lensing.f90:416-421)
+        int next_sample = 15 + (A.interp_fac / 2 > 0 ? A.interp_fac / 2 : A.interp_fac);
         const double expsig = exp(-sigmasq);
         double expl = expsig, facexp = expsig;
-        prefetch_chunk<true>(R, T, spectra, ld, 0, lmax, lane);
+        prefetch_chunk<true>(R, T, T2, spectra, ld, 0, lmax, lane);
         for (int l0 = 0; l0 <= lmax; l0 += CH) {
             __syncwarp();
-            commit_chunk<true>(S, R, lane);
+            commit_chunk<true, true>(S, R, lane);
             __syncwarp();
-            if (l0 + CH <= lmax) prefetch_chunk<true>(R, T, spectra, ld, l0 + CH, lmax, lane);
+            if (l0 + CH <= lmax) prefetch_chunk<true>(R, T, T2, spectra, ld, l0 + CH, lmax, lane);
             const int n = min(CH, lmax + 1 - l0);
             for (int lj = 0; lj < n; lj++) {
                 const int l = l0 + lj;
                 if (l >= 2) {
-                    legendre_step(l, S.tab[lj].inv_l, a, pmm, pmmp1, Pl, dPl);
+                    legendre_step(dl, S.tab[lj].inv_l, a, pmm, pmmp1, Pl, dPl);
                     if (VARIANT == CB_LENS_APODIZED) {
-                        if (l <= 15 || (l - 15) % A.interp_fac == half) {
+                        if (l <= 15 || l == next_sample) {
+                            if (l > 15) next_sample += A.interp_fac;
                             j++;
                             const double sc = j > 14 ? (double)A.interp_fac : 1.0;
-                            apodized_term(l, S.tab[lj], a, Pl, dPl, sigmasq, Cg2, sc, S.spec[1][lj], S.spec[2][lj], S.spec[3][lj], corr);
+                            apodized_term(l, S.tab[lj], S.tab2[lj], a, Pl, dPl, sigmasq, Cg2, sc, S.spec[1][lj], S.spec[2][lj], S.spec[3][lj], corr);
                         }
                     } else {
                         expl *= expsig;
                         facexp *= expl;
-                        full_term(l, S.tab[lj], a, Pl, dPl, facexp, Cg2, S.spec[1][lj], S.spec[2][lj], S.spec[3][lj], corr);
+                        full_term(l, S.tab[lj], S.tab2[lj], a, Pl, dPl, facexp, Cg2, S.spec[1][lj], S.spec[2][lj], S.spec[3][lj], corr);
                     }
                 } else if (l == 1 && lmin == 1) {
                     if (VARIANT == CB_LENS_APODIZED) {
                         j = 1;
-                        apodized_term(1, S.tab[lj], a, a.x, 1.0, sigmasq, Cg2, 1.0, S.spec[1][lj], S.spec[2][lj], S.spec[3][lj], corr);
+                        apodized_term(1, S.tab[lj], S.tab2[lj], a, a.x, 1.0, sigmasq, Cg2, 1.0, S.spec[1][lj], S.spec[2][lj], S.spec[3][lj], corr);
                     } else {
                         const double c2fac = Cg2;                 // lfacs(1) Cg2 / 2
                         corr[0] = S.spec[1][lj] * ((facexp - 1) * a.x + facexp * c2fac * (dm11_1 + c2fac * a.x / 4));
@@ -298,13 +317,13 @@ __global__ void __launch_bounds__(32) cb_lens_kernel(LensArgs A) {
     }
     if (!live) { w1 = 0; w2 = 0; w3 = 0; w4 = 0; }
     double* __restrict__ out = A.partial + ((size_t)set * gridDim.x + warp) * (size_t)(lout + 1) * 4;
-    double pmm = 1, pmmp1 = a.x, Pl, dPl;
-    prefetch_chunk<false>(R, T, spectra, ld, 0, lout, lane);
+    double pmm = 1, pmmp1 = a.x, Pl, dPl, dl = 1.0;
+    prefetch_chunk<false>(R, T, nullptr, spectra, ld, 0, lout, lane);
     for (int c0 = 0; c0 <= lout; c0 += CH) {
         __syncwarp();
         commit_chunk<false>(S, R, lane);
         __syncwarp();
-        if (c0 + CH <= lout) prefetch_chunk<false>(R, T, spectra, ld, c0 + CH, lout, lane);
+        if (c0 + CH <= lout) prefetch_chunk<false>(R, T, nullptr, spectra, ld, c0 + CH, lout, lane);
         for (int l0 = c0; l0 < c0 + CH && l0 <= lout; l0 += TL) {
 #pragma unroll 1
             for (int lj = 0; lj < TL; lj++) {
@@ -312,7 +331,7 @@ __global__ void __launch_bounds__(32) cb_lens_kernel(LensArgs A) {
                 double cT = 0, cE = 0, cB = 0, cX = 0;
                 if (l >= 2 && l <= lout) {
                     const LensTab& t = S.tab[l - c0];
-                    legendre_step(l, t.inv_l, a, pmm, pmmp1, Pl, dPl);
+                    legendre_step(dl, t.inv_l, a, pmm, pmmp1, Pl, dPl);
                     double d22, d2m2, d20;
                     spin2_rows<VARIANT>(t, a, Pl, dPl, d22, d2m2, d20);
                     const double T2 = w2 * d22, T4 = w3 * d2m2;
@@ -350,7 +369,7 @@ __global__ void cb_lens_reduce_kernel(const double* __restrict__ partial, int n_
     out[(size_t)set * n_per_set + e] = s;
 }
 
-__global__ void cb_lens_tab_kernel(LensTab* T, int n) {
+__global__ void cb_lens_tab_kernel(LensTab* T, LensTab2* T2, int n) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n) return;
     LensTab t;
@@ -364,12 +383,22 @@ __global__ void cb_lens_tab_kernel(LensTab* T, int n) {
     t.ilroot = l > 1 ? 1.0 / sqrt(lf * lf2) : 0.0;
     t.theta_cut = l > 1 ? 0.244949 / sqrt(3.0 * lf - 8.0) : 0.0;
     T[l] = t;
+    LensTab2 u;
+    u.rootfac1 = l > 1 ? sqrt(lf2) : 0.0;
+    u.irootfac1 = l > 1 ? 1.0 / sqrt(lf2) : 0.0;
+    u.rootfac2 = l > 2 ? sqrt((double)(l + 3) * (double)(l - 2)) : 0.0;
+    u.irootfac2 = l > 2 ? 1.0 / sqrt((double)(l + 3) * (double)(l - 2)) : 0.0;
+    u.rootfac3 = l > 3 ? sqrt((double)(l - 3) * (double)(l + 4)) : 0.0;
+    u.irootfac3 = l > 3 ? 1.0 / sqrt((double)(l - 3) * (double)(l + 4)) : 0.0;
+    u.ilfm12 = l > 3 ? 1.0 / (lf - 12.0) : 0.0;
+    u.rootllp1 = sqrt(lf);
+    T2[l] = u;
 }
 
 }  // namespace
 
-void cb_lens_tab_launch(LensTab* d_tab, int n, cudaStream_t st) {
-    cb_lens_tab_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_tab, n);
+void cb_lens_tab_launch(LensTab* d_tab, LensTab2* d_tab2, int n, cudaStream_t st) {
+    cb_lens_tab_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_tab, d_tab2, n);
 }
 
 int cb_lens_warps(const LensArgs& A) { return (A.last - A.first + 1 + 31) / 32; }

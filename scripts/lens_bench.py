@@ -18,6 +18,13 @@ from lensing_inputs import analytic_cls, cl_scalar_from_analytic  # noqa: E402
 LS = np.array(list(range(2, 2600, 50)) + [2600, 2650])
 ctx = GpuContext(0)
 rows = []
+if "--profile" in sys.argv:      # one launch of each method at the bench batch, for ncu
+    for kw in ({}, dict(variant=L.LENS_FULL)):
+        plan = L.LensPlan(2650, LS, **kw)
+        cls = analytic_cls(plan.lmax)
+        sp = np.ascontiguousarray(L.prepare_spectra(cl_scalar_from_analytic(cls), cls[:, 3], 2, plan.lmax, plan.lmax, plan.ee_taper, None))
+        ctx.lens_contrib(plan, [sp] * 64)
+    sys.exit(0)
 for name, kw in (("apodized_default", {}), ("gauss_legendre_short", dict(variant=L.LENS_FULL)), ("gauss_legendre_full", dict(AccurateBB=True))):
     plan = L.LensPlan(2650, LS, **kw)
     cls = analytic_cls(plan.lmax)
