@@ -230,7 +230,7 @@ def main():
         ctx.project(hss, dms, want_delta=False)
         icl = ctx.cl(hss, dms)
         tm = ctx.timings_ms()
-        _, lensed = L.lens_cls_from_icl(ctx, plan, hss, icl, template, ls_owner=hss[0])
+        _, lensed = L.lens_cls_from_icl(ctx, plan, hss, icl, template, ls_owner=hss[0], reuse_buffers=True)
         tm["lens"] = ctx.last_lens_ms()
         return lensed, st, t_ev, tm
 
@@ -257,6 +257,7 @@ def main():
     for _ in range(args.steps):
         icl, _, tev, tm = step(False)
         t_ev += tev; t_los += tm["los"]; t_spl += tm["spline_k"]; t_cl += tm["cl"]; t_lens += tm["lens"]
+    icl = icl.copy()       # the lensed C_l of the resident path (the host buffers are reused by the e2e steps below)
     ms = ctx.timer_stop()
     barrier()
     clocks = sampler.stop()
@@ -276,7 +277,7 @@ def main():
         d = [ctx.create_model(hs) for hs in hss]
         ctx.evolve(hss, d, want_sources=False, want_stats=False)
         ctx.project(hss, d, want_delta=False)
-        _, out = L.lens_cls_from_icl(ctx, plan, hss, ctx.cl(hss, d), template, ls_owner=hss[0])
+        _, out = L.lens_cls_from_icl(ctx, plan, hss, ctx.cl(hss, d), template, ls_owner=hss[0], reuse_buffers=True)
         for x in d:
             ctx.destroy_model(x)
         return out
@@ -289,7 +290,7 @@ def main():
         out = e2e_step()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    assert np.array_equal(out[0], icl[0]), "e2e path and resident path disagree"
+    assert np.array_equal(out[0], icl[0]) and np.all(icl[:, 2:, 0] > 0), "e2e path and resident path disagree"
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

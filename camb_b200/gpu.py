@@ -254,6 +254,10 @@ class GpuContext:
             if addr:
                 self._lib.cb_host_register(addr, 8 * cnt)   # best effort: an unpinned table is still copied correctly
 
+    def pin_array(self, a):
+        """Page-lock a numpy array in place (best effort) so its copies are asynchronous DMA; the array must outlive the context use."""
+        self._lib.cb_host_register(a.ctypes.data, a.nbytes)
+
     def set_option(self, name, value):
         self._check(self._lib.cb_set_option(self._h, name.encode(), float(value)))
 

@@ -219,10 +219,12 @@ def plan_for(hs, variant=None):
                     accuracy_target=int(p.AccuracyTarget), variant=variant)
 
 
-def lens_cls_from_icl(ctx, plan, hss, icls, template, nthreads=None, ls_owner=None):
+def lens_cls_from_icl(ctx, plan, hss, icls, template, nthreads=None, ls_owner=None, reuse_buffers=False):
     """Loop C output -> lensed C_l for a batch sharing one l sampling: host InterpolateCls + PrepareLensedCLSpectra (C++ host,
     OpenMP over cosmologies), one cb_lens_contrib call, host assembly.  `ls_owner`: the host state whose l sampling the
     iCl are on when the whole batch was projected against one Bessel table (set_bessel); default each state's own.
+    `reuse_buffers`: keep the (page-locked) host arrays on the plan and hand the same ones back on the next call with this
+    batch size -- for a loop that consumes each result before the next step.
     Returns (Cl_scalar (n, Max_l+1, 4), Cl_lensed (n, lmax_lensed+1, 4))."""
     import os
     from .host import CAMBError, c_double_p, load_host_lib
@@ -232,8 +234,16 @@ def lens_cls_from_icl(ctx, plan, hss, icls, template, nthreads=None, ls_owner=No
     icls = [np.ascontiguousarray(a, dtype=np.float64) for a in icls]
     n_cl = icls[0].shape[1]
     assert all(a.shape == (len((ls_owner or hs).ls), n_cl) for a, hs in zip(icls, hss))
-    cl = np.empty((n, Max_l + 1, 4))
-    sp = np.empty((n, 4, plan.lmax + 1))
+    ws = getattr(plan, "_ws", {}).get(n) if reuse_buffers else None
+    if ws is None:
+        ws = [np.empty((n, Max_l + 1, 4)), np.empty((n, 4, plan.lmax + 1)), np.empty((n, plan.lmax_lensed + 1, 4)),
+              np.empty((n, plan.lmax_lensed + 1, 4))]
+        if reuse_buffers:
+            if hasattr(ctx, "pin_array"):
+                for a in ws[1:3]:
+                    ctx.pin_array(a)            # the arrays that cross PCIe
+            plan._ws = {**getattr(plan, "_ws", {}), n: ws}
+    cl, sp, contrib, lensed = ws
     dp = lambda a: a.ctypes.data_as(c_double_p)   # noqa: E731
     if template is not None:
         assert template.flags.c_contiguous and template.shape[1] == 4 and template.shape[0] > plan.lmax
@@ -243,8 +253,6 @@ def lens_cls_from_icl(ctx, plan, hss, icls, template, nthreads=None, ls_owner=No
     if err:
         raise CAMBError({2: "You need to normalize realistically to use lensing", 3: "lensing needs the high-L template above Max_l",
                          4: "You need to normalize the high-L template so it is dimensionless"}.get(err, "lens_spectra_batch: bad arguments"), err)
-    contrib = np.empty((n, plan.lmax_lensed + 1, 4))
     ctx.lens_contrib(plan, list(sp), out=contrib)
-    lensed = np.empty_like(contrib)
     lib.cbh_lens_assemble_batch(n, C.byref(plan.c), dp(contrib), dp(cl), Max_l, dp(lensed), nthreads)
     return cl, lensed
