@@ -83,6 +83,9 @@ struct cb_ctx {
     DModel* h_models = nullptr;   size_t cap_h_models = 0;   // page-locked staging
     DModeItem* h_items = nullptr; size_t cap_h_items = 0;
     int last_grid[CB_N_CLASSES] = {};
+    // many small host arrays travel as one page-locked block and one PCIe copy each way (pieces move device-to-device)
+    double *h_in = nullptr, *d_in = nullptr, *h_out = nullptr, *d_out = nullptr;
+    size_t cap_in = 0, cap_out = 0, used_in = 0;
     LensTab* d_lens_tab = nullptr; LensTab2* d_lens_tab2 = nullptr; int lens_tab_n = 0;       // per-l constants of the lensing kernels, grown on demand
     cudaEvent_t lens_ev[2] = {};
     bool lens_timed = false;
@@ -119,6 +122,42 @@ static int ensure(cb_ctx* ctx, T** p, size_t* cap, size_t n) {
     *p = nullptr;
     CK(dev_alloc(ctx, (void**)p, n * sizeof(T)));
     *cap = n;
+    return 0;
+}
+
+// Staging of small arrays.  Safe to reuse between entry points because each one ends with a stream synchronisation.
+static int stage_reserve(cb_ctx* ctx, size_t n_in, size_t n_out) {
+    if (n_in > ctx->cap_in) {
+        if (ctx->h_in) cudaFreeHost(ctx->h_in);
+        if (ctx->d_in) cudaFree(ctx->d_in);
+        ctx->h_in = ctx->d_in = nullptr; ctx->cap_in = 0;
+        CK(cudaHostAlloc((void**)&ctx->h_in, sizeof(double) * n_in, cudaHostAllocDefault));
+        CK(cudaMalloc((void**)&ctx->d_in, sizeof(double) * n_in));
+        ctx->cap_in = n_in;
+    }
+    if (n_out > ctx->cap_out) {
+        if (ctx->h_out) cudaFreeHost(ctx->h_out);
+        if (ctx->d_out) cudaFree(ctx->d_out);
+        ctx->h_out = ctx->d_out = nullptr; ctx->cap_out = 0;
+        CK(cudaHostAlloc((void**)&ctx->h_out, sizeof(double) * n_out, cudaHostAllocDefault));
+        CK(cudaMalloc((void**)&ctx->d_out, sizeof(double) * n_out));
+        ctx->cap_out = n_out;
+    }
+    ctx->used_in = 0;
+    return 0;
+}
+// queue src (host) -> dst (device): packed now, moved by stage_upload
+struct StagePiece { double* dst; size_t off, n; };
+static void stage_add(cb_ctx* ctx, std::vector<StagePiece>& pieces, double* dst, const double* src, size_t n) {
+    memcpy(ctx->h_in + ctx->used_in, src, sizeof(double) * n);
+    pieces.push_back({dst, ctx->used_in, n});
+    ctx->used_in += n;
+}
+static int stage_upload(cb_ctx* ctx, const std::vector<StagePiece>& pieces) {
+    if (pieces.empty()) return 0;
+    CK(cudaMemcpyAsync(ctx->d_in, ctx->h_in, sizeof(double) * ctx->used_in, cudaMemcpyHostToDevice, ctx->stream));
+    for (const StagePiece& p : pieces)
+        CK(cudaMemcpyAsync(p.dst, ctx->d_in + p.off, sizeof(double) * p.n, cudaMemcpyDeviceToDevice, ctx->stream));
     return 0;
 }
 
@@ -178,6 +217,10 @@ void cb_destroy(cb_ctx* ctx) {
     if (ctx->d_scratch_ptrs) cudaFree(ctx->d_scratch_ptrs);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     if (ctx->d_error) cudaFree(ctx->d_error);
+    if (ctx->h_in) cudaFreeHost(ctx->h_in);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->d_in) cudaFree(ctx->d_in);
+    if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_lens_tab) cudaFree(ctx->d_lens_tab);
     if (ctx->d_lens_tab2) cudaFree(ctx->d_lens_tab2);
     for (cudaEvent_t e : ctx->lens_ev) if (e) cudaEventDestroy(e);
@@ -331,6 +374,12 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
     CK(cudaSetDevice(ctx->device));
     std::vector<DModeItem> cls_items[CB_N_CLASSES], all_items;
     int cls_nv[CB_N_CLASSES] = {}, cls_maxl[CB_N_CLASSES] = {};
+    std::vector<StagePiece> pieces;
+    {
+        size_t tot = 0;
+        for (int m = 0; m < n_models; m++) tot += (size_t)std::max(modes[m].n_k, 0);
+        if (int e = stage_reserve(ctx, tot, 0)) return e;
+    }
     for (int m = 0; m < n_models; m++) {
         cb_dmodel* d = dm[m];
         const cb_modes& md = modes[m];
@@ -349,7 +398,7 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
                 if (int e = ensure(ctx, &d->d_scratch, &c3, ns)) return e;
                 d->cap_src = ns;
             }
-            CK(cudaMemcpyAsync(d->d_q_src, md.q, sizeof(double) * n_k, cudaMemcpyHostToDevice, ctx->stream));
+            stage_add(ctx, pieces, d->d_q_src, md.q, (size_t)n_k);
             // row tau_1 is never written by the reference (allocated zero, cmbmain.f90:777-778) and the rows
             // after a mode's k*tau early-out are zero (:1034-1037): the kernel writes only live entries
             CK(cudaMemsetAsync(d->d_src, 0, sizeof(double) * ns, ctx->stream));
@@ -409,6 +458,7 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
     int n_items = 0;
     for (int c = 0; c < CB_N_CLASSES; c++) n_items += (int)cls_items[c].size();
     if (n_items == 0) return 0;
+    if (int e = stage_upload(ctx, pieces)) return e;
     std::vector<DModeItem> items;
     items.reserve(n_items);
     int cls_off[CB_N_CLASSES];
@@ -515,6 +565,12 @@ int cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q, 
     const int n_l = ctx->bess.n_l;
     int max_cols = 0, max_nq = 0, max_ntau = 0, max_nsrc = 0;
     std::vector<double*> scr(n_models);
+    std::vector<StagePiece> pieces;
+    {
+        size_t tot = 0;
+        for (int m = 0; m < n_models; m++) tot += 2 * (size_t)std::max(n_q[m], 0);
+        if (int e = stage_reserve(ctx, tot, 0)) return e;
+    }
     for (int m = 0; m < n_models; m++) {
         cb_dmodel* d = dm[m];
         DModel& D = d->h;
@@ -534,13 +590,14 @@ int cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q, 
         size_t nd = (size_t)D.n_src * n_l * nq;
         if (nd > d->cap_delta) { if (d->d_delta) dev_free(ctx, d->d_delta); d->d_delta = nullptr; d->cap_delta = 0; }
         if (int e = ensure(ctx, &d->d_delta, &d->cap_delta, nd)) return e;
-        CK(cudaMemcpyAsync(d->d_q_int, q_int[m], sizeof(double) * nq, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(d->d_dq_int, dq[m], sizeof(double) * nq, cudaMemcpyHostToDevice, ctx->stream));
+        stage_add(ctx, pieces, d->d_q_int, q_int[m], (size_t)nq);
+        stage_add(ctx, pieces, d->d_dq_int, dq[m], (size_t)nq);
         D.n_q = nq; D.q_int = d->d_q_int; D.dq_int = d->d_dq_int; D.pows = d->d_pows; D.Delta = d->d_delta;
         max_cols = std::max(max_cols, D.n_src * D.n_tau);
         max_nq = std::max(max_nq, nq); max_ntau = std::max(max_ntau, D.n_tau); max_nsrc = std::max(max_nsrc, D.n_src);
         scr[m] = d->d_scratch;
     }
+    if (int e = stage_upload(ctx, pieces)) return e;
     if (int e = push_models(ctx, n_models, dm)) return e;
     if (int e = ensure(ctx, &ctx->d_scratch_ptrs, &ctx->cap_scr, (size_t)n_models)) return e;
     CK(cudaMemcpyAsync(ctx->d_scratch_ptrs, scr.data(), sizeof(double*) * n_models, cudaMemcpyHostToDevice, ctx->stream));
@@ -579,6 +636,12 @@ int cb_cl(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, int tensor, const dou
     if (!ctx) return CB_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
     const int n_l = ctx->bess.n_l;
+    std::vector<StagePiece> pieces;
+    {
+        size_t tot_in = 0, tot_out = 0;
+        for (int m = 0; m < n_models; m++) { tot_in += (size_t)std::max(dm[m]->h.n_q, 0); tot_out += (size_t)n_l * dm[m]->n_cl; }
+        if (int e = stage_reserve(ctx, tot_in, tot_out)) return e;
+    }
     for (int m = 0; m < n_models; m++) {
         cb_dmodel* d = dm[m];
         DModel& D = d->h;
@@ -588,18 +651,30 @@ int cb_cl(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, int tensor, const dou
         size_t nc = (size_t)n_l * d->n_cl;
         if (nc > d->cap_icl) { if (d->d_icl) dev_free(ctx, d->d_icl); d->d_icl = nullptr; d->cap_icl = 0; }
         if (int e = ensure(ctx, &d->d_icl, &d->cap_icl, nc)) return e;
-        CK(cudaMemcpyAsync(d->d_pows, pows[m], sizeof(double) * D.n_q, cudaMemcpyHostToDevice, ctx->stream));
+        stage_add(ctx, pieces, d->d_pows, pows[m], (size_t)D.n_q);
         D.iCl = d->d_icl;
     }
+    if (int e = stage_upload(ctx, pieces)) return e;
     if (int e = push_models(ctx, n_models, dm)) return e;
     CK(cudaEventRecord(ctx->stage_ev[3][0], ctx->stream));
     cb_cl_launch(ctx->d_models, n_models, ctx->bess, ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->stage_ev[3][1], ctx->stream));
-    for (int m = 0; m < n_models; m++)
-        if (iCl && iCl[m]) CK(cudaMemcpyAsync(iCl[m], dm[m]->d_icl, sizeof(double) * (size_t)n_l * dm[m]->n_cl, cudaMemcpyDeviceToHost, ctx->stream));
+    size_t off = 0;
+    for (int m = 0; m < n_models; m++) {
+        const size_t n = (size_t)n_l * dm[m]->n_cl;
+        if (iCl && iCl[m]) CK(cudaMemcpyAsync(ctx->d_out + off, dm[m]->d_icl, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+        off += n;
+    }
+    if (iCl && off) CK(cudaMemcpyAsync(ctx->h_out, ctx->d_out, sizeof(double) * off, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    off = 0;
+    for (int m = 0; m < n_models; m++) {
+        const size_t n = (size_t)n_l * dm[m]->n_cl;
+        if (iCl && iCl[m]) memcpy(iCl[m], ctx->h_out + off, sizeof(double) * n);
+        off += n;
+    }
     return 0;
 }
 

@@ -151,9 +151,13 @@ class HostState:
         return self._bessel
 
     def scalar_power(self):
-        out = np.zeros(len(self.q_int))
-        self._lib.cbh_get_pows(self._h, 0, _dp(out))
-        return out
+        """InitPower%ScalarPower on the integration grid (cmbmain.f90:3199); computed once per cosmology."""
+        if self._pows[0] is None:
+            out = np.zeros(len(self.q_int))
+            self._lib.cbh_get_pows(self._h, 0, _dp(out))
+            out.flags.writeable = False
+            self._pows[0] = out
+        return self._pows[0]
 
     def scalar_power_at(self, k):
         k = np.ascontiguousarray(k, dtype=np.float64)
@@ -169,9 +173,12 @@ class HostState:
         return np.where(chi[None, :] > 0, self.scalar_power_at(k), 0.0)
 
     def tensor_power(self):
-        out = np.zeros(len(self.q_int))
-        self._lib.cbh_get_pows(self._h, 1, _dp(out))
-        return out
+        if self._pows[1] is None:
+            out = np.zeros(len(self.q_int))
+            self._lib.cbh_get_pows(self._h, 1, _dp(out))
+            out.flags.writeable = False
+            self._pows[1] = out
+        return self._pows[1]
 
     def derived(self):
         d = (C.c_double * 13)()
