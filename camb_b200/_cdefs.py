@@ -53,7 +53,7 @@ class cb_lens_plan(C.Structure):
                 ("dtheta", C.c_double), ("apodize_point_width", C.c_int), ("interp_fac", C.c_int),
                 ("short_integral_range", C.c_int), ("imin", C.c_int), ("xvals", C.POINTER(C.c_double)),
                 ("weights", C.POINTER(C.c_double)), ("theta_max", C.c_double), ("apodize_theta_width", C.c_double),
-                ("xtaper_start", C.c_double)]
+                ("xtaper_start", C.c_double), ("theta_first", C.c_int), ("theta_last", C.c_int)]
 
 
 class cb_params(C.Structure):

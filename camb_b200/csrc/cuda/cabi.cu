@@ -785,6 +785,16 @@ int cb_lens_contrib(cb_ctx* ctx, int n_sets, const cb_lens_plan* P, const double
         A.xvals = dx; A.weights = dw;
         A.theta_max = P->theta_max; A.apodize_theta_width = P->apodize_theta_width; A.xtaper_start = P->xtaper_start;
     }
+    if (P->theta_last > 0) {        // a theta slice of the loop (multi-GPU sharding)
+        A.first = std::max(A.first, P->theta_first);
+        A.last = std::min(A.last, P->theta_last);
+    }
+    if (A.last < A.first) {         // this rank's slice holds no angle of the method's range
+        for (int m = 0; m < n_sets; m++) memset(lens_contrib[m], 0, sizeof(double) * 4 * ((size_t)P->lmax_lensed + 1));
+        release();
+        CK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
     if (ctx->lens_tab_n < P->lmax + 1) {
         if (ctx->d_lens_tab) dev_free(ctx, ctx->d_lens_tab);
         if (ctx->d_lens_tab2) dev_free(ctx, ctx->d_lens_tab2);

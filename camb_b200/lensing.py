@@ -178,6 +178,24 @@ class LensPlan:
                 c.imin, c.apodize_theta_width, c.xtaper_start, c.theta_max = 1, 0.0, -1.0, np.pi
         self.c = c
 
+    def theta_range(self):
+        """(first, last) loop indices of the method's angles (lensing.f90:451, 781)."""
+        return (1, self.c.npoints - 1) if self.variant == LENS_APODIZED else (self.c.imin, self.c.npoints)
+
+    def theta_slice(self, rank, world):
+        """A copy of the plan restricted to rank's contiguous share of the angles (the reference's !$OMP DO split over ranks)."""
+        first, last = self.theta_range()
+        n = last - first + 1
+        lo, hi = first + (n * rank) // world, first + (n * (rank + 1)) // world - 1
+        p = LensPlan.__new__(LensPlan)
+        p.__dict__.update(self.__dict__)
+        p.c = cb_lens_plan.from_buffer_copy(self.c)
+        if hi < lo:
+            lo, hi = last + 1, last + 1          # an empty share: nothing inside the method's range
+        p.c.theta_first, p.c.theta_last = lo, hi
+        p.__dict__.pop("_ws", None)
+        return p
+
     def spectra(self, cl_scalar, template, cpp=None):
         if cpp is None:
             cpp = lensing_potential_spectrum(cl_scalar, self.lmin, self.Max_l)

@@ -7,7 +7,9 @@
            InterpolateSources (:1413-1472) need every source k, and x + 0 is exact, so the gathered
            array is bit-identical to the single-GPU one;
   loop B   every rank projects a contiguous, cost-balanced slice of the integration wavenumbers;
-  loop C   partial sums over the slice, then ONE all-reduce(sum) of iCl (n_l x 3|6 doubles).
+  loop C   partial sums over the slice, then ONE all-reduce(sum) of iCl (n_l x 3|6 doubles);
+  lensing  (lensed_cls) every rank integrates a contiguous share of the angles theta -- the reference's `!$OMP DO` over i
+           (lensing.f90:451, 781) -- and ONE all-reduce(sum) of lens_contrib ((lmax_lensed+1) x 4 doubles) merges them.
 
 The collectives go through torch.distributed: NCCL over NVLink on the device buffers the C-ABI exposes
 (cb_device_buffer), gloo in the CPU tests, where `backend` is a stand-in that computes with the oracle so
@@ -81,6 +83,10 @@ class GpuBackend:
         self.ctx.cl([hs], [dm], [pows[lo:hi]])
         return self._view(dm, CB_BUF_ICL, self.torch.float64)
 
+    def lens_contrib(self, plan, spectra):
+        out = self.ctx.lens_contrib(plan, [spectra])[0]
+        return self.torch.from_numpy(out).to(self.torch.device("cuda", self.ctx.device))
+
     def sync(self):
         self.torch.cuda.synchronize()
 
@@ -120,3 +126,16 @@ class ShardedBoltzmann:
         finally:
             self.b.end(dm)
         return out
+
+    def lensed_cls(self, hs, template, pows=None, plan=None):
+        """(iCl, Cl_scalar (Max_l+1, 4), Cl_lensed (lmax_lensed+1, 4)), identical on every rank: cls() followed by lens_Cls with
+        the theta loop shared out over the ranks."""
+        from . import lensing as L
+        icl = self.cls(hs, pows)
+        plan = plan or L.plan_for(hs)
+        cl, sp = hs.lens_spectra(icl, template, plan.lmax, plan.ee_taper)        # cheap and identical on every rank
+        part = self.b.lens_contrib(plan.theta_slice(self.rank, self.world), np.ascontiguousarray(sp))
+        self.b.sync()
+        self._allreduce(part)
+        self.b.sync()
+        return icl, cl, plan.assemble(self.b.to_numpy(part), cl)

@@ -219,6 +219,10 @@ typedef struct cb_lens_plan {
     const double* xvals;         /* [npoints] */
     const double* weights;       /* [npoints] */
     double theta_max, apodize_theta_width, xtaper_start;
+    /* theta-sharding (the reference's !$OMP DO over i): when theta_last > 0 this call integrates only the
+     * angles theta_first <= i <= theta_last (the loop index of lensing.f90:451 / :781, 1-based), clipped to the method's own
+     * range; lens_contrib of the slices add up to the full result.  0, 0 = all angles. */
+    int theta_first, theta_last;
 } cb_lens_plan;
 
 /* spectra[i]      double (4, lmax + 1), l fastest, rows Cphil3, CTT, CEE, CTE of PrepareLensedCLSpectra (entries below lmin ignored)

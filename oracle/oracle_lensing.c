@@ -66,7 +66,7 @@ int oracle_lens_apodized(const cb_lens_plan* pl, const double* spectra, double* 
     }
 #pragma omp for schedule(static)
     for (int i = 1; i <= pl->npoints - 1; i++) {
-        if (!w.P) continue;
+        if (!w.P || (pl->theta_last > 0 && (i < pl->theta_first || i > pl->theta_last))) continue;
         const double theta = i * pl->dtheta, x = cos(theta), sinth = sin(theta), halfsinth = sinth / 2;
         double pmm = 1, pmmp1 = x, Cg2 = 0, sigmasq = 0;
         if (lmin == 1) {                                         /* lensing.f90:469-478 */
@@ -195,7 +195,7 @@ int oracle_lens_full(const cb_lens_plan* pl, const double* spectra, double* lens
     }
 #pragma omp for schedule(static)
     for (int i = pl->imin; i <= pl->npoints; i++) {
-        if (!w.P) continue;
+        if (!w.P || (pl->theta_last > 0 && (i < pl->theta_first || i > pl->theta_last))) continue;
         const double x = pl->xvals[i - 1];
         double weight = pl->weights[i - 1];
         const double theta = acos(x);

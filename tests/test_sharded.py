@@ -59,6 +59,9 @@ class OracleBackend:
         icl = self.O.cl(hs, delta, pows, q_slice=(lo, hi))          # (n_l, n_cl)
         return self.torch.from_numpy(np.ascontiguousarray(icl.T))   # the device layout: (n_cl, n_l) C order
 
+    def lens_contrib(self, plan, spectra):
+        return self.torch.from_numpy(self.O.lens_contrib(plan, spectra, nthreads=2))
+
     def sync(self):
         pass
 
@@ -75,10 +78,12 @@ def _worker(rank, world, port, out):
         from camb_b200.host import HostState
         hs = HostState(planck2018_params(lmax=500, lensing=True, massless=True))
         be = OracleBackend()
-        icl = ShardedBoltzmann(be, rank, world).cls(hs)
+        from camb_b200.workloads import synthetic_highl_template
+        icl, _, lensed = ShardedBoltzmann(be, rank, world).lensed_cls(hs, synthetic_highl_template())
         if rank == 0:
             np.save(out, icl)
             np.save(out + ".src.npy", be.src.numpy())
+            np.save(out + ".lensed.npy", lensed)
     finally:
         dist.destroy_process_group()
 
@@ -100,6 +105,15 @@ def test_two_rank_gloo_matches_unsharded(tmp_path):
     assert np.array_equal(src, aux["src"])                      # the gather is exact
     assert icl.shape == ref.shape
     assert np.allclose(icl, ref, rtol=1e-12, atol=0)            # partial sums re-associate the q sum
+    # lens_Cls with the theta loop split over the two ranks == the unsharded one on the same (sharded) iCl
+    from camb_b200 import lensing as L
+    from camb_b200.workloads import synthetic_highl_template
+    plan = L.plan_for(hs)
+    cl, sp = hs.lens_spectra(icl, synthetic_highl_template(), plan.lmax, plan.ee_taper)
+    lensed_ref = plan.assemble(O.lens_contrib(plan, sp), cl)
+    lensed = np.load(out + ".lensed.npy")
+    assert lensed.shape == lensed_ref.shape
+    assert np.allclose(lensed, lensed_ref, rtol=1e-12, atol=1e-30)
 
 
 def test_single_rank_is_the_plain_chain():
