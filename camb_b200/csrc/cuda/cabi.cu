@@ -935,6 +935,8 @@ size_t cb_abi_sizeof(int which) {
         case 3: return sizeof(cb_bessel);
         case 4: return sizeof(cb_range);
         case 5: return sizeof(cb_accuracy);
+        case 6: return sizeof(cb_lens_plan);
+        case 7: return sizeof(cb_window);
     }
     return 0;
 }

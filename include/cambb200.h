@@ -262,7 +262,7 @@ void  cb_host_unregister(void* p);
 enum { CB_BUF_LINEARSRC = 0, CB_BUF_DELTA = 1, CB_BUF_ICL = 2, CB_BUF_TRANSFER = 3 };
 int  cb_device_buffer(cb_ctx* ctx, cb_dmodel* dm, int which, void** ptr, size_t* bytes);
 /* sizeof() of the boundary structs as this library was compiled, for binding checks:
- * 0 cb_params, 1 cb_model, 2 cb_modes, 3 cb_bessel, 4 cb_range, 5 cb_accuracy. */
+ * 0 cb_params, 1 cb_model, 2 cb_modes, 3 cb_bessel, 4 cb_range, 5 cb_accuracy, 6 cb_lens_plan, 7 cb_window. */
 size_t cb_abi_sizeof(int which);
 
 #ifdef __cplusplus

@@ -36,7 +36,7 @@ def test_struct_sizes_match_c_side():
     lib.cb_abi_sizeof.restype = C.c_size_t
     lib.cb_abi_sizeof.argtypes = [C.c_int]
     for which, cls in enumerate([_cdefs.cb_params, _cdefs.cb_model, _cdefs.cb_modes, _cdefs.cb_bessel, _cdefs.cb_range,
-                                 _cdefs.cb_accuracy]):
+                                 _cdefs.cb_accuracy, _cdefs.cb_lens_plan, _cdefs.cb_window]):
         assert lib.cb_abi_sizeof(which) == C.sizeof(cls), cls.__name__
 
 
