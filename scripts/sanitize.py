@@ -31,14 +31,37 @@ def scalar(hs, lanes):
     print("ok", hs.n_src, lanes, flush=True)
 
 
+LENS_ONLY = "--lens-only" in sys.argv      # racecheck of the lensing kernels alone (the whole script takes > 10 min under racecheck)
 p = planck2018_params(lmax=150, lensing=True, massless=False, want_transfer=True)
 p.transfer_kmax = 0.5
-scalar(HostState(p), 8)
-scalar(HostState(planck2018_params(lmax=150, lensing=True, massless=True)), 32)
-scalar(HostState(planck2018_params(lmax=150, lensing=False, massless=True)), 4)
-scalar(HostState(isocurvature_params(vector=[1, 0.2, 0.1, 0.1, 0.1], lmax=150)), 16)
-scalar(HostState(tensor_params(lmax_tensor=150, k_eta_max_tensor=400, massless=False)), 0)
-scalar(HostState(params_counts_config4(lmax=100)), 8)
-scalar(HostState(lensing_window_params(lmax=100, limber=False)), 8)
+if not LENS_ONLY:
+    scalar(HostState(p), 8)
+if not LENS_ONLY:
+    scalar(HostState(planck2018_params(lmax=150, lensing=True, massless=True)), 32)
+if not LENS_ONLY:
+    scalar(HostState(planck2018_params(lmax=150, lensing=False, massless=True)), 4)
+if not LENS_ONLY:
+    scalar(HostState(isocurvature_params(vector=[1, 0.2, 0.1, 0.1, 0.1], lmax=150)), 16)
+if not LENS_ONLY:
+    scalar(HostState(tensor_params(lmax_tensor=150, k_eta_max_tensor=400, massless=False)), 0)
+if not LENS_ONLY:
+    scalar(HostState(params_counts_config4(lmax=100)), 8)
+if not LENS_ONLY:
+    scalar(HostState(lensing_window_params(lmax=100, limber=False)), 8)
+# lensing of the C_l: both methods, lmin 1 and 2, a batch of two, a theta slice
+import numpy as np
+from camb_b200 import lensing as L
+from camb_b200.workloads import analytic_cmb_cls
+for variant in (L.LENS_APODIZED, L.LENS_FULL):
+    for lmin in (2, 1):
+        plan = L.LensPlan(400, np.array(list(range(2, 400, 25)) + [350, 400]), lmin=lmin, variant=variant)
+        cls = analytic_cmb_cls(plan.lmax)
+        cs = cls.copy()
+        ell = np.arange(len(cls), dtype=float)
+        cs[2:, 3] = cls[2:, 3] * 2 * np.pi * ell[2:] ** 2 / (ell[2:] + 1) ** 2
+        sp = np.ascontiguousarray(L.prepare_spectra(cs, cls[:, 3], lmin, plan.lmax, plan.lmax, plan.ee_taper, None))
+        ctx.lens_contrib(plan, [sp, sp])
+        ctx.lens_contrib(plan.theta_slice(1, 3), [sp])
+        print("ok lens", variant, lmin, flush=True)
 ctx.close()
 print("sanitize run complete")
