@@ -78,6 +78,7 @@ struct cb_ctx {
     cudaStream_t class_stream[CB_N_CLASSES] = {};
     cudaEvent_t class_done[CB_N_CLASSES] = {}, fork = nullptr;
     int lanes_per_mode = 0;              // 0 = automatic
+    int class_lanes[CB_N_CLASSES] = {};  // per slab-size class override of the lane width (0 = lanes_per_mode)
     int async_model_upload = 0;          // cb_model_create returns without waiting for its host->device copies
     cudaEvent_t stage_ev[4][2] = {};     // per-stage kernel brackets of the last calls (evolve, spline-k, LOS, C_l)
     DModel* h_models = nullptr;   size_t cap_h_models = 0;   // page-locked staging
@@ -509,7 +510,7 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
         cudaError_t le = c == CB_TENSOR_CLASS
                              ? cb_evolve_tensor_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, cls_nv[c], cls_maxl[c], ctx->d_counter + c,
                                                        ctx->d_error, ctx->n_sm, ctx->class_stream[c], &ctx->last_grid[c])
-                             : cb_evolve_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, nv, cls_maxl[c], lanes, lean, ctx->d_counter + c,
+                             : cb_evolve_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, nv, cls_maxl[c], ctx->class_lanes[c] ? ctx->class_lanes[c] : lanes, lean, ctx->d_counter + c,
                                                 ctx->d_error, ctx->n_sm, ctx->class_stream[c], &ctx->last_grid[c], caps[c]);
         if (le != cudaSuccess) { ctx->err = std::string("evolve launch: ") + cudaGetErrorString(le); return CB_ERR_CUDA; }
         ctx->launches++;
@@ -859,6 +860,12 @@ long long cb_launch_count(const cb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int cb_set_option(cb_ctx* ctx, const char* name, double value) {
     if (!ctx) return CB_ERR_NO_DEVICE;
+    if (!strncmp(name, "lanes_class", 11) && name[11] >= '0' && name[11] < '0' + CB_TENSOR_CLASS && !name[12]) {
+        const int v = (int)value;
+        if (v != 0 && v != 4 && v != 8 && v != 16 && v != 32) { ctx->err = "lanes_classN must be 0 (follow lanes_per_mode), 4, 8, 16 or 32"; return CB_ERR_UNSUPPORTED_PARAMS; }
+        ctx->class_lanes[name[11] - '0'] = v;
+        return 0;
+    }
     if (!strcmp(name, "lanes_per_mode")) {
         const int v = (int)value;
         if (v != 0 && v != 4 && v != 8 && v != 16 && v != 32) { ctx->err = "lanes_per_mode must be 0 (automatic), 4, 8, 16 or 32"; return CB_ERR_UNSUPPORTED_PARAMS; }

@@ -240,6 +240,8 @@ long long cb_launch_count(const cb_ctx* ctx);
 /* Tuning knobs.  "lanes_per_mode": lanes of a warp that own one k-mode in cb_evolve: 8 (four modes
  * share a warp's instruction stream: throughput, for batches), 16, 32 (one mode per warp: latency,
  * for a single cosmology) or 0 = chosen from the number of modes in the call (default).
+ * "lanes_class0" ... "lanes_class4": the same per slab-size class of cb_evolve (0 = follow lanes_per_mode; experiments only,
+ * 8 everywhere is the measured optimum).
  * "async_model_upload" = 1: cb_model_create queues its host->device copies and returns; the caller keeps the cb_model arrays
  * alive and unchanged until the next cb_evolve / cb_project / cb_cl* call on the context returns (a Fortran host's
  * allocatables outlive cmbmain anyway).  Default 0: the arrays may be freed as soon as cb_model_create returns. */
