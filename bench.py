@@ -223,6 +223,7 @@ def main():
     from camb_b200 import lensing as L
     from camb_b200.workloads import synthetic_highl_template
     plan, template = L.plan_for(hss[0]), synthetic_highl_template()
+    host_threads = max(1, min(16, (os.cpu_count() or 1) // world))     # the ranks of one box share its host cores
 
     def step(want_stats=False):
         _, _, st = ctx.evolve(hss, dms, want_sources=False, want_stats=want_stats)
@@ -230,7 +231,7 @@ def main():
         ctx.project(hss, dms, want_delta=False)
         icl = ctx.cl(hss, dms)
         tm = ctx.timings_ms()
-        _, lensed = L.lens_cls_from_icl(ctx, plan, hss, icl, template, ls_owner=hss[0], reuse_buffers=True)
+        _, lensed = L.lens_cls_from_icl(ctx, plan, hss, icl, template, ls_owner=hss[0], reuse_buffers=True, nthreads=host_threads)
         tm["lens"] = ctx.last_lens_ms()
         return lensed, st, t_ev, tm
 
@@ -277,7 +278,7 @@ def main():
         d = [ctx.create_model(hs) for hs in hss]
         ctx.evolve(hss, d, want_sources=False, want_stats=False)
         ctx.project(hss, d, want_delta=False)
-        _, out = L.lens_cls_from_icl(ctx, plan, hss, ctx.cl(hss, d), template, ls_owner=hss[0], reuse_buffers=True)
+        _, out = L.lens_cls_from_icl(ctx, plan, hss, ctx.cl(hss, d), template, ls_owner=hss[0], reuse_buffers=True, nthreads=host_threads)
         for x in d:
             ctx.destroy_model(x)
         return out
