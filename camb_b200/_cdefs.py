@@ -31,7 +31,8 @@ CB_MAX_WINDOWS = 8
 
 class cb_source_window(C.Structure):
     _fields_ = [("source_type", C.c_int), ("redshift", C.c_double), ("sigma", C.c_double), ("bias", C.c_double),
-                ("dlog10Ndm", C.c_double)]
+                ("dlog10Ndm", C.c_double), ("n_table", C.c_int), ("z_table", C.POINTER(C.c_double)),
+                ("W_table", C.POINTER(C.c_double))]
 
 
 class cb_source_terms(C.Structure):

@@ -211,11 +211,51 @@ double HostState::TensorPower(double k) const {  // InitialPower.f90:147-173 (fl
 }
 
 double RedWin::count_obs_window_z(double z, double& winamp) const {
+    if (!zt.empty()) {   // TSplinedSourceWindow_count_obs_window_z, SourceWindows.f90:282-305
+        double v = 0;
+        const int n = (int)zt.size();
+        if (!(z > zt[n - 1] || z < zt[0])) {
+            int lo = 0, hi = n - 1;
+            while (hi - lo > 1) { const int mid = (lo + hi) / 2; if (zt[mid] > z) hi = mid; else lo = mid; }
+            const double h = zt[hi] - zt[lo], a0 = (zt[hi] - z) / h, b0 = (z - zt[lo]) / h;
+            v = a0 * Wt[lo] + b0 * Wt[hi] + ((a0 * a0 * a0 - a0) * ddWt[lo] + (b0 * b0 * b0 - b0) * ddWt[hi]) * (h * h) / 6;
+        }
+        winamp = v / maxwin;
+        return v;
+    }
     const double root2pi = 2.506628274;
     double dz = z - w_redshift;
     winamp = std::exp(-(dz / w_sigma) * (dz / w_sigma) / 2);
     return winamp / w_sigma / root2pi;
 }
+void RedWin::GetScales(double& zpeak, double& sigma_z, double& zpeakstart, double& zpeakend) const {
+    if (zt.empty()) {   // TGaussianSourceWindow_GetScales
+        sigma_z = w_sigma; zpeak = w_redshift; zpeakstart = w_redshift + sigma_z * 3; zpeakend = std::fmax(0.0, w_redshift - sigma_z * 3);
+        return;
+    }
+    const int n = (int)zt.size();
+    const std::vector<double>&z = zt, &w = Wt;
+    const double zstart = z[n - 1], zend = z[0];
+    zpeak = z[std::max_element(w.begin(), w.end()) - w.begin()];
+    zpeakstart = zstart;
+    for (int i = n - 1; i >= 0; i--) if (w[i] > maxwin / 15) { zpeakstart = z[i]; break; }
+    zpeakend = zend;
+    for (int i = 0; i < n; i++) if (w[i] > maxwin / 15) { if (zpeakstart > z[i]) zpeakend = z[i]; break; }
+    double z1 = 0;
+    sigma_z = (zpeakstart - zpeakend) / 3;
+    for (int i = 0; i < n; i++) {
+        if (w[i] > maxwin / 2 && z1 == 0) z1 = z[i];
+        else if (w[i] < maxwin / 2 && z1 != 0) { sigma_z = std::fmin(sigma_z, z[i] - z1); z1 = 0; }
+    }
+    for (int i = 0; i < n; i++) {
+        if (w[i] < maxwin * 0.45) {
+            const double targ = w[i] + maxwin / 2;
+            for (int j = i + 1; j < n; j++) if (w[j] >= targ) { sigma_z = std::fmin(sigma_z, (z[j] - z[i]) / 0.85); break; }
+            for (int j = i - 1; j >= 0; j--) if (w[j] >= targ) { sigma_z = std::fmin(sigma_z, (z[i] - z[j]) / 0.85); break; }
+        }
+    }
+}
+
 double RedWin::Window_f_a(double a, double& winamp) const { return count_obs_window_z(1 / a - 1, winamp) / (a * a); }
 
 double HostState::WindowKmaxForL(const RedWin& W, int ell) const {
@@ -346,8 +386,16 @@ int HostState::SetParams(const cb_params& P) {  // results.f90:332-627 (flat, no
                 return error;
             }
             W.kind = sw.source_type; W.w_redshift = sw.redshift; W.w_sigma = sw.sigma; W.bias = sw.bias; W.dlog10Ndm = sw.dlog10Ndm;
-            // TGaussianSourceWindow_GetScales, SourceWindows.f90:213-226
-            double sigma_z = sw.sigma, zpeak = sw.redshift, zpeakstart = sw.redshift + sigma_z * 3, zpeakend = std::fmax(0.0, sw.redshift - sigma_z * 3);
+            if (sw.n_table > 0) {   // TSplinedSourceWindow_SetTable, SourceWindows.f90:243-262
+                if (sw.n_table < 5 || !sw.z_table || !sw.W_table) { fail(CB_ERR_UNSUPPORTED_PARAMS, "splined source window needs >= 5 ascending redshifts"); return error; }
+                W.zt.assign(sw.z_table, sw.z_table + sw.n_table);
+                W.Wt.assign(sw.W_table, sw.W_table + sw.n_table);
+                W.ddWt.resize(sw.n_table);
+                spline(W.zt.data(), W.Wt.data(), sw.n_table, SPLINE_DANGLE, SPLINE_DANGLE, W.ddWt.data());
+                W.maxwin = *std::max_element(W.Wt.begin(), W.Wt.end());
+            }
+            double sigma_z, zpeak, zpeakstart, zpeakend;
+            W.GetScales(zpeak, sigma_z, zpeakstart, zpeakend);
             W.Redshift = zpeak;
             W.tau = TimeOfz(zpeak, 1e-4);
             W.sigma_tau = sigma_z * dtauda(1 / (1 + zpeak)) / ((1 + zpeak) * (1 + zpeak));

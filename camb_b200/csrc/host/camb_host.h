@@ -64,6 +64,8 @@ struct Thermo {  // results.f90 TThermoData
 struct RedWin {  // SourceWindows.f90:72-84 TRedWin + its TGaussianSourceWindow (:22-30) + CalWins temporaries
     int kind = CB_WINDOW_COUNTS;
     double w_redshift = 0, w_sigma = 0, bias = 1, dlog10Ndm = 0;
+    std::vector<double> zt, Wt, ddWt;   // TSplinedSourceWindow table + natural-spline second derivatives
+    double maxwin = 0;
     double Redshift = 0, tau = 0, tau_start = 0, tau_end = 0, tau_peakstart = 0, tau_peakend = 0, sigma_tau = 0, chi0 = 0, chimin = 0;
     int mag_index = 0;
     std::vector<double> winF, wing, wing2, wingtau, dwing, dwing2, dwingtau, ddwing, ddwing2, ddwingtau, winV, dwinV, ddwinV, win_lens,
@@ -73,6 +75,7 @@ struct RedWin {  // SourceWindows.f90:72-84 TRedWin + its TGaussianSourceWindow 
     std::vector<double> awin_lens, dawin_lens;
     double count_obs_window_z(double z, double& winamp) const;   // SourceWindows.f90:156-171
     double Window_f_a(double a, double& winamp) const;           // :173-190 (counts / lensing)
+    void GetScales(double& zpeak, double& sigma_z, double& zpeakstart, double& zpeakend) const;   // :192-205, 307-363
 };
 
 struct Derived {

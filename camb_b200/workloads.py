@@ -207,6 +207,39 @@ def sigma8_anchor_params(anchor, notebook=False):
     return p
 
 
+def splined_counts_anchor_params(anchor, lmax=4000):
+    """The parameter set of the reference's sharp-window known-answer test (camb/tests/camb_test.py:1226-1241):
+    CAMBparams() defaults + RECFAST 'planck' set + set_cosmology(H0=67.5, ombh2=0.022, omch2=0.122) (mnu 0.06) +
+    InitPower(As=2e-9, ns=0.965) + set_for_lmax(4000, lens_potential_accuracy=0) + one SplinedSourceWindow (Tukey window,
+    alpha 0.1, over 2000 redshifts in [1.9689, 2.1057), counts) with the default SourceTerms (counts_redshift on).
+    Returns (params, keep) -- `keep` holds the table arrays the params point to."""
+    from .host import set_neutrino_masses
+    p = sigma8_anchor_params(anchor)
+    set_neutrino_masses(p, 0.06, nnu=anchor["params"]["nnu"], num_massive_neutrinos=anchor["params"]["num_massive_neutrinos"])
+    p.WantTransfer, p.transfer_high_precision, p.transfer_PK_num_redshifts = 0, 0, 0
+    p.DoLensing, p.lens_output_margin = 1, 200
+    p.Max_l = lmax + 200                     # set_for_lmax: max_l = lmax + lens_output_margin, max_eta_k = 2.5 max_l (model.py:1053-1058)
+    p.Max_eta_k = 2.5 * p.Max_l
+    zs = np.arange(1.9689, 2.1057, (2.1057 - 1.9689) / 2000)
+    n = len(zs)
+    # scipy.signal.windows.tukey(n, alpha=0.1), symmetric
+    a = 0.1
+    x = np.arange(n, dtype=float)
+    width = int(np.floor(a * (n - 1) / 2.0))
+    W = np.ones(n)
+    n1 = x[:width + 1]
+    W[:width + 1] = 0.5 * (1 + np.cos(np.pi * (-1 + 2.0 * n1 / a / (n - 1))))
+    n3 = x[n - width - 1:]
+    W[n - width - 1:] = 0.5 * (1 + np.cos(np.pi * (-2.0 / a + 1 + 2.0 * n3 / a / (n - 1))))
+    zs, W = np.ascontiguousarray(zs), np.ascontiguousarray(W)
+    _set_windows(p, [("counts", 0.0, 0.0, 1.0, 0.0)])
+    w = p.SourceWindows[0]
+    w.n_table = n
+    w.z_table = zs.ctypes.data_as(type(w.z_table))
+    w.W_table = W.ctypes.data_as(type(w.W_table))
+    return p, (zs, W)
+
+
 def analytic_cmb_cls(lmax):
     """Analytic CMB-like spectra (lmax+1, 4): TT, EE, TE, PP with the l(l+1)/2pi ([L(L+1)]^2/2pi for PP) factors,
     dimensionless, zero below l = 2.  Used as lensing test input and, on machines without the reference's

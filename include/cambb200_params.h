@@ -52,6 +52,12 @@ enum { CB_WINDOW_21CM = 1, CB_WINDOW_COUNTS = 2, CB_WINDOW_LENSING = 3 };
 typedef struct cb_source_window {
     int source_type;               /* CB_WINDOW_COUNTS or CB_WINDOW_LENSING (21cm is out of scope) */
     double redshift, sigma, bias, dlog10Ndm;
+    /* TSplinedSourceWindow (SourceWindows.f90:32-44, 282-363): when n_table > 0 the window is the natural cubic spline of
+     * W_table over z_table (ascending z; the total observed count distribution, not normalised) with the constant `bias`;
+     * redshift and sigma are then ignored (GetScales derives them from the table). */
+    int n_table;
+    const double* z_table;
+    const double* W_table;
 } cb_source_window;
 typedef struct cb_source_terms {
     int limber_windows, limber_phi_lmin;
