@@ -372,6 +372,8 @@ void HostState::GenerateBessels(double max_etak) {  // bessels.f90:64-113, 140-2
         for (int i = 1; i <= std::max(min_ix - 1, 1); i++) kv[i - 1] = 0;
         spline(BessRanges.points.data(), kv.data(), nx, SPLINE_DANGLE, dend[j], y2.data());
         double* H = &bessel_horner[(size_t)4 * (nx - 1) * j];
+        // intervals 1..max(min_ix-1, 1) are zeroed first (the array starts zero here) and the fill below starts at
+        // max(1, min_ix-1), so the last of them is overwritten -- the reference's order, bessels.f90:215-222
         for (int i = std::max(1, min_ix - 1); i <= nx - 1; i++) {  // spline_horner_coeffs, bessels.f90:48-62
             double h2over6 = (BessRanges.points[i] - BessRanges.points[i - 1]);
             h2over6 = h2over6 * h2over6 / 6;
@@ -380,7 +382,6 @@ void HostState::GenerateBessels(double max_etak) {  // bessels.f90:64-113, 140-2
             double* h = &H[4 * (i - 1)];
             h[0] = c1; h[1] = c2; h[2] = c3; h[3] = c4;
         }
-        for (int i = 1; i <= std::max(min_ix - 1, 1); i++) { double* h = &H[4 * (i - 1)]; h[0] = h[1] = h[2] = h[3] = 0; }
     }
     bess_regions_c.clear();
     for (int i = 0; i < BessRanges.count; i++) {
