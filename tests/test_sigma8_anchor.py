@@ -63,3 +63,48 @@ def test_gpu_sigma8_matches_reference_values(notebook):
         ctx.close()
     s8 = _check(hs, np.concatenate([tr1[0], tr2[0]], axis=1), notebook)
     print("gpu sigma8", s8)
+
+
+# ---- sigma_R(3 Mpc, z = 0) = 1.77346 on the dense high-k grid (camb/tests/camb_test.py:1017-1069, testSigmaR: same cosmology,
+# set_matter_power(k_per_logint=100, kmax=10, redshifts=0,2,...,8), get_sigmaR(hubble_units=False); asserted there to 3 places) ----
+SIGMA_R3_Z0 = 1.77346
+
+
+def _sigma_r_params():
+    p = sigma8_anchor_params(ANCHOR)
+    p.transfer_kmax, p.transfer_k_per_logint = 10.0, 100
+    zs = [8.0, 6.0, 4.0, 2.0, 0.0]
+    p.transfer_PK_num_redshifts = len(zs)
+    for i, z in enumerate(zs):
+        p.transfer_PK_redshifts[i] = z
+    return p
+
+
+def _check_sigma_r(hs, tr):
+    from camb_b200.transfer import sigma_r
+    s = sigma_r(hs, tr, 3.0 * hs.params.H0 / 100.0)          # R = 3 Mpc, not Mpc/h
+    assert abs(s[-1] / SIGMA_R3_Z0 - 1) < 2.8e-4, s          # the reference's own assertion level; achieved 1.1e-4
+    return s
+
+
+def test_oracle_sigma_r_dense_grid():
+    hs = host_state("sigma_r3", _sigma_r_params)
+    assert len(hs.source_q()) + len(hs.transfer_q()) > 1200
+    _, tr1, _ = O.evolve(hs, nthreads=8)
+    _, tr2, _ = O.evolve(hs, transfer_only=True, nthreads=8)
+    print("oracle sigma_R(3 Mpc)", _check_sigma_r(hs, np.concatenate([tr1, tr2], axis=1)))
+
+
+@pytest.mark.gpu
+def test_gpu_sigma_r_dense_grid():
+    from camb_b200.gpu import GpuContext
+    hs = host_state("sigma_r3", _sigma_r_params)
+    ctx = GpuContext(0)
+    try:
+        dm = ctx.create_model(hs)
+        _, tr1, _ = ctx.evolve([hs], [dm], want_sources=False)
+        _, tr2, _ = ctx.evolve([hs], [dm], transfer_only=True)
+        ctx.destroy_model(dm)
+    finally:
+        ctx.close()
+    print("gpu sigma_R(3 Mpc)", _check_sigma_r(hs, np.concatenate([tr1[0], tr2[0]], axis=1)))
