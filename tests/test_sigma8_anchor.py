@@ -108,3 +108,59 @@ def test_gpu_sigma_r_dense_grid():
     finally:
         ctx.close()
     print("gpu sigma_R(3 Mpc)", _check_sigma_r(hs, np.concatenate([tr1[0], tr2[0]], axis=1)))
+
+
+# ---- baryon-CDM relative velocity at z = 200 ... 1090 (docs/CAMBdemo.ipynb cells 51-52, printed to 3 significant figures):
+# CAMBparams() + set_cosmology(H0=67.5, ombh2=0.022, omch2=0.122) + ns 0.965 + set_matter_power(redshifts=[200, 500, 800, 1090],
+# kmax=10, k_per_logint=30); rms of the Transfer_vel_baryon_cdm power over 300 log-spaced k in [1e-3, 10] / Mpc ----
+VBC_PRINTED = {200.0: ("2.04e-05", "6.11"), 500.0: ("5.03e-05", "15.1"), 800.0: ("7.89e-05", "23.6"), 1090.0: ("9.67e-05", "29")}
+TRANSFER_VEL_BARYON_CDM = 12
+
+
+def _vbc_params():
+    p = sigma8_anchor_params(ANCHOR, notebook=True)
+    p.transfer_kmax, p.transfer_k_per_logint = 10.0, 30
+    zs = sorted(VBC_PRINTED, reverse=True)
+    p.transfer_PK_num_redshifts = len(zs)
+    for i, z in enumerate(zs):
+        p.transfer_PK_redshifts[i] = z
+    return p
+
+
+def _check_vbc(hs, tr):
+    from scipy.interpolate import CubicSpline
+    kh, pk = matter_power(hs, tr, var1=TRANSFER_VEL_BARYON_CDM, var2=TRANSFER_VEL_BARYON_CDM, hubble_units=False)
+    k = kh * hs.params.H0 / 100.0
+    order = np.argsort(k)
+    k, pk = k[order], pk[:, order]
+    k, pk = k[k > 0], pk[:, k > 0]
+    ks = np.logspace(-3, 1, 300)
+    out = {}
+    for i, z in enumerate(sorted(VBC_PRINTED, reverse=True)):
+        curly = np.exp(CubicSpline(np.log(k), np.log(pk[i]))(np.log(ks))) * ks ** 3 / (2 * np.pi ** 2)
+        rms = np.sqrt(curly[1:-1].dot((ks[2:] - ks[:-2]) / 2 / ks[1:-1]))
+        out[z] = rms
+        assert (f"{rms:.3g}", "%.3g" % (rms * 299792)) == VBC_PRINTED[z], (z, rms)     # the notebook's own print format
+    return out
+
+
+def test_oracle_relative_velocity_matches_notebook():
+    hs = host_state("vbc", _vbc_params)
+    _, tr1, _ = O.evolve(hs, nthreads=8)
+    _, tr2, _ = O.evolve(hs, transfer_only=True, nthreads=8)
+    print("oracle v_bc rms", _check_vbc(hs, np.concatenate([tr1, tr2], axis=1)))
+
+
+@pytest.mark.gpu
+def test_gpu_relative_velocity_matches_notebook():
+    from camb_b200.gpu import GpuContext
+    hs = host_state("vbc", _vbc_params)
+    ctx = GpuContext(0)
+    try:
+        dm = ctx.create_model(hs)
+        _, tr1, _ = ctx.evolve([hs], [dm], want_sources=False)
+        _, tr2, _ = ctx.evolve([hs], [dm], transfer_only=True)
+        ctx.destroy_model(dm)
+    finally:
+        ctx.close()
+    print("gpu v_bc rms", _check_vbc(hs, np.concatenate([tr1[0], tr2[0]], axis=1)))
