@@ -58,5 +58,5 @@ def test_product_package_does_not_touch_the_oracle():
         for fn in fns:
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dp, fn)).read()
-                for bad in ("liboracle", "oracle_lib", "import oracle", "from oracle", "oracle.h", "oracle_evolve", "oracle_project"):
+                for bad in ("liboracle", "oracle_lib", "import oracle", "from oracle", "oracle.h", "oracle_evolve", "oracle_project", "oracle_lens"):
                     assert bad not in txt, (os.path.join(dp, fn), bad)
