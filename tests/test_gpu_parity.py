@@ -417,3 +417,24 @@ def test_ragged_batch_and_call_order_errors(ctx):
     finally:
         for dm in dms:
             ctx.destroy_model(dm)
+
+
+def test_integrator_failure_is_reported_like_the_reference(ctx):
+    """A tolerance the step-size control cannot meet (IntTolBoost = 100: RungeKuttaDP45 runs into its minimum step,
+    RungeKuttaDP45.f90 'step size underflow' -> GlobalError error_evolution = 4) comes back as error 4 from the device
+    integrator and from the oracle alike -- no hang, no partial result -- and the context stays usable."""
+    p = planck2018_params(lmax=300, lensing=False, massless=True)
+    p.Accuracy.IntTolBoost = 100.0
+    hs = HostState(p)
+    with pytest.raises(RuntimeError, match="error 4"):
+        O.evolve(hs, nthreads=4)
+    dm = ctx.create_model(hs)
+    with pytest.raises(CAMBError) as e:
+        ctx.evolve([hs], [dm])
+    assert e.value.code == 4
+    ctx.destroy_model(dm)
+    hs2 = host_state("after_failure", lambda: planck2018_params(lmax=300, lensing=False, massless=True))
+    dm2 = ctx.create_model(hs2)
+    _, _, st = ctx.evolve([hs2], [dm2])
+    assert st[0][:, 0].min() > 100
+    ctx.destroy_model(dm2)
