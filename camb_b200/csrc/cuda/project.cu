@@ -111,6 +111,7 @@ cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
     // per-l constants of DoFlatIntegration (x limits, the phi column's DoInt and Limber switches): evaluated once per CTA
     // instead of once per (warp, l) -- pow() and sqrt() leave the l loop
     __shared__ double s_xlim[LOS_MAX_L], s_xlmax1[LOS_MAX_L], s_qmax_int[LOS_MAX_L], s_limfac[LOS_MAX_L];
+    __shared__ int s_n1[LOS_MAX_L], s_n2[LOS_MAX_L];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = LOS_THREADS / 32;
     const double q = M.q_int[iq], tau0 = M.tau0;
     const double* TimePoints = M.tau;
@@ -183,22 +184,30 @@ cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
     int llmax = (int)llround(q * tau0);
     if (llmax < 15) llmax = 17;
     else llmax = (int)llround(q * (tau0 + 6.0 * 3.1415926535897932384626433832795 / q));
+    // time-step window [n1, n2] of every l (cmbmain.f90:1702-1716): one thread per l, instead of all 32 lanes of the warp
+    // that owns the l repeating the two region look-ups (divisions, a log in the log-spaced regions)
+    for (int j = 1 + tid; j <= n_l; j += LOS_THREADS) {
+        int n1 = -1, n2 = 0;                       // n1 < 0: this l takes no part at this q
+        if (B.l[j - 1] <= llmax) {
+            const double tmin = fmax(TimePoints[1], tau0 - s_xlmax1[j - 1] / q);
+            const double tmax = tau0 - s_xlim[j - 1] / q;
+            if (!(tmax < TimePoints[1])) {
+                n1 = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, tmin);
+                n2 = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, tmax);
+                if (n2 > SourceSteps) n2 = SourceSteps;
+            }
+        }
+        s_n1[j - 1] = n1; s_n2[j - 1] = n2;
+    }
+    __syncthreads();
     double* Dout = M.Delta + (size_t)nsrc * n_l * iq;
     for (int j = 1 + warp; j <= n_l; j += nwarp) {
         const int l = B.l[j - 1];
         double s0 = 0, s1 = 0, s2 = 0;
-        bool active = l <= llmax;
-        double tmin = 0, tmax = 0;
-        if (active) {
-            tmin = fmax(TimePoints[1], tau0 - s_xlmax1[j - 1] / q);
-            tmax = tau0 - s_xlim[j - 1] / q;
-            if (tmax < TimePoints[1]) active = false;
-        }
+        const int n1 = s_n1[j - 1], n2 = s_n2[j - 1];
+        const bool active = n1 >= 0;
         if (active) {
             const double* H = B.horner + (size_t)4 * (B.nx - 1) * (j - 1);
-            const int n1 = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, tmin);
-            int n2 = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, tmax);
-            if (n2 > SourceSteps) n2 = SourceSteps;
             const bool DoInt = nsrc <= 2 || tensors || q < s_qmax_int[j - 1];   // DoInt = .not. CP%WantScalars .or. IV%q < qmax_int
             if (DoInt) {
                 for (int n = n1 + lane; n <= n2; n += 32) {
