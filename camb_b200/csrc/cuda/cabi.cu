@@ -17,6 +17,8 @@
 void cb_mode_size(const DModel& M, double q, int transfer_only, int* nvar, int* maxl);
 cudaError_t cb_evolve_launch(const DModel*, const DModeItem*, int n_items, int nv, int maxl, int lanes_per_mode, int lean,
                              unsigned int*, int*, int n_sm, cudaStream_t, int* grid_out, int block_cap);
+cudaError_t cb_debug_derivs_launch(const DModel* d_model, double q, double tau, const int* flags4, const double* d_y, int n, int nv,
+                                   int maxl, int lanes, int lean, double* d_yprime, double* d_sources, int* d_status, cudaStream_t stream);
 // evolve_tensor.cu
 void cb_tensor_mode_size(const DModel& M, int* nvart, int* maxl);
 cudaError_t cb_evolve_tensor_launch(const DModel*, const DModeItem*, int n_items, int nv, int maxl, unsigned int*, int*, int n_sm,
@@ -932,6 +934,44 @@ int cb_device_buffer(cb_ctx* ctx, cb_dmodel* dm, int which, void** ptr, size_t* 
     }
     ctx->err = "cb_device_buffer: unknown buffer id";
     return CB_ERR_UNSUPPORTED_PARAMS;
+}
+
+// One evaluation of the device `derivs` + source output at a given state (parity tests against the reference-authored
+// per-evaluation fixture).  lanes: 8 or 32; lean: the massless-nu LCDM template variant (refused for other models).
+int cb_debug_derivs(cb_ctx* ctx, cb_dmodel* dm, double q, double tau, const int* flags4, const double* y, int n, int lanes, int lean,
+                    double* yprime, double* sources) {
+    if (!ctx || !dm) return CB_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    const DModel& D = dm->h;
+    if (D.is_tensor) { ctx->err = "cb_debug_derivs: scalar models only"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    if (lean && (D.Num_Nu_massive != 0 || !D.de_is_cc || D.num_redshiftwindows > 0)) {
+        ctx->err = "cb_debug_derivs: the lean variant is for massless-neutrino LCDM models";
+        return CB_ERR_UNSUPPORTED_PARAMS;
+    }
+    int nv = 0, maxl = 0;
+    cb_mode_size(D, q, 0, &nv, &maxl);
+    if (n < 1 || n > nv || maxl > CBD_MAX_L_EVOLVE) { ctx->err = "cb_debug_derivs: bad state size"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    DModel* d_model = nullptr;
+    double *d_y = nullptr, *d_out = nullptr;
+    int* d_status = nullptr;
+    CK(cudaMalloc(&d_model, sizeof(DModel)));
+    CK(cudaMalloc(&d_y, sizeof(double) * nv));
+    CK(cudaMalloc(&d_out, sizeof(double) * (nv + 3)));
+    CK(cudaMalloc(&d_status, sizeof(int) * 2));
+    int rc = 0, status[2] = {0, 1};
+    cudaError_t e = cudaMemcpyAsync(d_model, &D, sizeof(DModel), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_y, y, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cb_debug_derivs_launch(d_model, q, tau, flags4, d_y, n, nv, maxl, lanes, lean, d_out, d_out + nv, d_status, ctx->stream);
+    if (e == cudaSuccess) { ctx->launches++; e = cudaMemcpyAsync(status, d_status, sizeof(status), cudaMemcpyDeviceToHost, ctx->stream); }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && status[1] == 0) {
+        e = cudaMemcpy(yprime, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(sources, d_out + nv, sizeof(double) * 3, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_model); cudaFree(d_y); cudaFree(d_out); cudaFree(d_status);
+    if (e != cudaSuccess) { ctx->err = std::string("cb_debug_derivs: ") + cudaGetErrorString(e); return CB_ERR_CUDA; }
+    if (status[1] != 0) { ctx->err = "cb_debug_derivs: n does not match the layout the flags select"; rc = CB_ERR_UNSUPPORTED_PARAMS; }
+    return rc;
 }
 
 size_t cb_abi_sizeof(int which) {

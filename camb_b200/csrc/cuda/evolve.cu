@@ -1375,6 +1375,67 @@ cb_evolve_kernel(const DModel* __restrict__ models, const DModeItem* __restrict_
     }
 }
 
+// One evaluation of `derivs` with the source output branch at a given state, through the same templates the
+// evolve kernel instantiates (cb_debug_derivs: the per-evaluation parity tests against the reference-authored
+// fixture tests/golden/symbolic_derivs.json).  One lane group of G lanes; shared memory: [MHot][EVs][3 x (maxl + 1)][y][y'].
+template <int G, bool LEAN>
+__global__ void cb_debug_derivs_kernel(const DModel* __restrict__ model, double q, double tau, int f_tight, int f_no_nu, int f_no_phot,
+                                       int f_ktau, const double* __restrict__ y_in, int n, int nv, int maxl, double* yprime,
+                                       double* sources, int* status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const unsigned gm = G == 32 ? FULL : ((1u << G) - 1u);
+    const size_t hot_bytes = (sizeof(MHot) + 15) & ~size_t(15), ev_bytes = (sizeof(EVs) + 15) & ~size_t(15);
+    MHot& H = *reinterpret_cast<MHot*>(smem_raw);
+    EVs& E = *reinterpret_cast<EVs*>(smem_raw + hot_bytes);
+    double* denlk = reinterpret_cast<double*>(smem_raw + hot_bytes + ev_bytes);
+    double* denlk2 = denlk + (maxl + 1);
+    double* polfack = denlk2 + (maxl + 1);
+    double* y = polfack + (maxl + 1);
+    double* yp = y + nv;
+    if (lane == 0) {
+        const DModel& M = *model;
+        fill_hot(H, M);
+        memset(&E, 0, sizeof(E));
+        E.q = q; E.NuMethod = 1;
+        get_num_eqns(M, E);
+        DModeItem it;
+        memset(&it, 0, sizeof(it));
+        it.q = q; it.tight_switchoff = M.tau0 + 1;
+        initial_conditions(M, E, denlk, denlk2, polfack, y, get_tau_start(M, q), it);
+        E.TightCoupling = f_tight; E.no_nu = f_no_nu; E.no_phot = f_no_phot; E.high_ktau = f_ktau;
+        setup_indices(M, E);
+        status[0] = E.neq; status[1] = E.neq == n ? 0 : 1;
+        for (int i = 0; i < nv; i++) { y[i] = (i < n && E.neq == n) ? y_in[i] : 0.0; yp[i] = 0.0; }
+    }
+    __syncwarp(gm);
+    if (E.neq != n) return;
+    double srcs[3] = {0, 0, 0};
+    derivs<G, LEAN>(H, E, denlk, denlk2, polfack, tau, y, yp, lane, gm, OUT_SRC, nullptr, srcs, nullptr, 0, 2);
+    __syncwarp(gm);
+    if (lane == 0) {
+        for (int i = 0; i < n; i++) yprime[i] = yp[i];
+        for (int i = 0; i < 3; i++) sources[i] = i < H.n_src ? srcs[i] : 0.0;
+    }
+}
+
+cudaError_t cb_debug_derivs_launch(const DModel* d_model, double q, double tau, const int* flags4, const double* d_y, int n, int nv,
+                                   int maxl, int lanes, int lean, double* d_yprime, double* d_sources, int* d_status, cudaStream_t stream) {
+    const size_t hot_bytes = (sizeof(MHot) + 15) & ~size_t(15), ev_bytes = (sizeof(EVs) + 15) & ~size_t(15);
+    const size_t smem = hot_bytes + ev_bytes + sizeof(double) * (3 * (size_t)(maxl + 1) + 2 * (size_t)nv);
+#define CB_DBG(G_, L_)                                                                                                        \
+    do {                                                                                                                        \
+        cudaError_t e = cudaFuncSetAttribute(cb_debug_derivs_kernel<G_, L_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                                                         \
+        cb_debug_derivs_kernel<G_, L_><<<1, G_, smem, stream>>>(d_model, q, tau, flags4[0], flags4[1], flags4[2], flags4[3], d_y, n, nv, \
+                                                                 maxl, d_yprime, d_sources, d_status);                          \
+    } while (0)
+    if (lanes == 8) { if (lean) CB_DBG(8, true); else CB_DBG(8, false); }
+    else { if (lean) CB_DBG(32, true); else CB_DBG(32, false); }
+#undef CB_DBG
+    return cudaGetLastError();
+}
+
 // ---------------- host-side helpers used by cabi.cu ----------------
 size_t cb_evolve_slab_bytes(int nv, int maxl) {
     const size_t ctl_bytes = (sizeof(Ctl) + 15) & ~size_t(15), hot_bytes = (sizeof(MHot) + 15) & ~size_t(15),

@@ -23,7 +23,7 @@ SYMBOLS = ["cb_create", "cb_destroy", "cb_last_error", "cb_device_count", "cb_se
            "cb_launch_count", "cb_abi_sizeof", "cb_timer_start", "cb_timer_stop", "cb_fp64_peak",
            "cb_host_alloc", "cb_host_free", "cb_device_buffer", "cb_set_option", "cb_host_register",
            "cb_host_unregister", "cb_cl_array", "cb_cl_windows", "cb_lens_contrib",
-           "cb_last_lens_timing"]
+           "cb_last_lens_timing", "cb_debug_derivs"]
 
 
 def load_gpu_lib():
@@ -66,6 +66,8 @@ def load_gpu_lib():
         lib.cb_host_register.argtypes = [C.c_void_p, C.c_size_t]
         lib.cb_host_unregister.argtypes = [C.c_void_p]
         lib.cb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        lib.cb_debug_derivs.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, c_int_p, c_double_p, C.c_int, C.c_int,
+                                        C.c_int, c_double_p, c_double_p]
         lib.cb_abi_sizeof.restype = C.c_size_t
         lib.cb_abi_sizeof.argtypes = [C.c_int]
         _lib = lib
@@ -106,6 +108,15 @@ class GpuContext:
         dm = C.c_void_p()
         self._check(self._lib.cb_model_create(self._h, C.byref(hs.model), C.byref(dm)))
         return dm
+
+    def debug_derivs(self, dm, q, tau, y, flags=(0, 0, 0, 0), lanes=32, lean=False):
+        """One device evaluation of `derivs` + the source output branch (cb_debug_derivs): (yprime, sources[3])."""
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        yp, src = np.zeros(len(y)), np.zeros(3)
+        f = (C.c_int * 4)(*[int(x) for x in flags])
+        self._check(self._lib.cb_debug_derivs(self._h, dm, float(q), float(tau), f, _dp(y), len(y), int(lanes), int(bool(lean)),
+                                              _dp(yp), _dp(src)))
+        return yp, src
 
     def destroy_model(self, dm):
         self._lib.cb_model_destroy(self._h, dm)

@@ -46,6 +46,13 @@ int oracle_cl_windows(const cb_model* M, const cb_bessel* B, int n_q, const doub
 int oracle_lens_apodized(const cb_lens_plan* plan, const double* spectra, double* lens_contrib, int nthreads);
 int oracle_lens_full(const cb_lens_plan* plan, const double* spectra, double* lens_contrib, int nthreads);
 
+/* Debug entry points for the per-evaluation fixtures (oracle_evolve.c, end of file): the state of one mode at given
+ * times, and one evaluation of derivs + output at a given state. */
+int oracle_debug_states(const cb_model* M, const cb_modes* modes, int q_ix, int n_times, const double* times, int ld,
+                        double* y_out, int* layout_out);
+int oracle_debug_derivs(const cb_model* M, double q, double tau, const int* flags4, const double* y_in, int n, double* yprime,
+                        double* sources, double* aux, int* layout);
+
 #ifdef __cplusplus
 }
 #endif

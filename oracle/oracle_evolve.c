@@ -1827,3 +1827,89 @@ int oracle_evolve(const cb_model* M, const cb_modes* modes, double* LinearSrc, f
     }
     return err;
 }
+
+/* =====================================================================================
+ * Debug entry points for the per-evaluation fixtures (tests/golden/make_symbolic_fixture.py,
+ * tests/test_symbolic_fixture.py): the state of one mode at requested times, and one `derivs`
+ * evaluation (with the source output branch) at a given state.  TEST INFRASTRUCTURE ONLY.
+ * layout[16] = {neq, nvar, g_ix, polind, r_ix, w_ix, lmaxg, lmaxgpol, lmaxnr, TightCoupling,
+ *               no_nu_multpoles, no_phot_multpoles, high_ktau_neutrino_approx, 0, 0, 0}
+ * aux[16]    = {a, adotoa, grhob_t, grhoc_t, grhog_t, grhor_t, grhov_t, cs2b, opacity, dopacity,
+ *               ddopacity, visibility, dvisibility, ddvisibility, exptau, 0}
+ * ===================================================================================== */
+static void debug_layout(const EVars* EV, int* layout) {
+    memset(layout, 0, 16 * sizeof(int));
+    layout[0] = EV->ScalEqsToPropagate; layout[1] = EV->nvar; layout[2] = EV->g_ix; layout[3] = EV->polind;
+    layout[4] = EV->r_ix; layout[5] = EV->w_ix; layout[6] = EV->lmaxg; layout[7] = EV->lmaxgpol; layout[8] = EV->lmaxnr;
+    layout[9] = EV->TightCoupling; layout[10] = EV->no_nu_multpoles; layout[11] = EV->no_phot_multpoles;
+    layout[12] = EV->high_ktau_neutrino_approx;
+}
+
+/* Evolves mode q_ix with the production schedule code (initial, EvolveScal) to each of `times` (ascending) and
+ * records y (ld doubles per time, zero padded) and the layout in force there. */
+int oracle_debug_states(const cb_model* M, const cb_modes* modes, int q_ix, int n_times, const double* times, int ld,
+                        double* y_out, int* layout_out) {
+    nu_consts_init();
+    EVars EV;
+    memset(&EV, 0, sizeof(EV));
+    EV.M = M; EV.q = modes->q[q_ix]; EV.q2 = EV.q * EV.q; EV.TransferOnly = 0; EV.fcn = derivs;
+    double tau = get_tau_start(M, EV.q);
+    get_num_eqns(&EV);
+    const int nvar = EV.nvar;
+    if (nvar > ld) return CB_ERR_UNSUPPORTED_PARAMS;
+    double* w = (double*)calloc((size_t)nvar * 9, sizeof(double));
+    double* y = (double*)calloc(nvar, sizeof(double));
+    double* yout = (double*)calloc(nvar, sizeof(double));
+    RKSettings rk;
+    memset(&rk, 0, sizeof(rk));
+    initial(&EV, y, tau, modes->tight_switchoff[q_ix], modes->nu_massive_approx_time + (size_t)q_ix * CB_MAX_NU);
+    int ind = 1, err = 0;
+    double tol1 = 1.0e-4 / exp(M->AccuracyBoost * M->IntTolBoost - 1);
+    for (int i = 0; i < n_times && !err; i++) {
+        err = EvolveScal(&EV, &tau, y, times[i], tol1, &ind, &rk, w, yout);
+        for (int j = 0; j < ld; j++) y_out[(size_t)ld * i + j] = j < nvar ? y[j] : 0.0;
+        debug_layout(&EV, layout_out + 16 * i);
+    }
+    free(w); free(y); free(yout);
+    return err;
+}
+
+/* One evaluation of `derivs` + `output` for wavenumber q at time tau on the state y (n = layout[0] entries in the
+ * layout the four approximation flags select).  sources: n_src values; aux: background / ionization values at tau. */
+int oracle_debug_derivs(const cb_model* M, double q, double tau, const int* flags4, const double* y_in, int n, double* yprime,
+                        double* sources, double* aux, int* layout) {
+    nu_consts_init();
+    EVars EV;
+    memset(&EV, 0, sizeof(EV));
+    EV.M = M; EV.q = q; EV.q2 = q * q; EV.TransferOnly = 0; EV.fcn = derivs;
+    get_num_eqns(&EV);
+    double* y = (double*)calloc(EV.nvar, sizeof(double));
+    double* yp = (double*)calloc(EV.nvar, sizeof(double));
+    double nuapprox[CB_MAX_NU] = {0};
+    initial(&EV, y, get_tau_start(M, q), M->tau0 + 1, nuapprox);   /* per-l coefficients, k buffers */
+    EV.TightCoupling = flags4[0]; EV.no_nu_multpoles = flags4[1]; EV.no_phot_multpoles = flags4[2];
+    EV.high_ktau_neutrino_approx = flags4[3];
+    int maxeq;
+    setup_indices(&EV, &maxeq);
+    if (layout) debug_layout(&EV, layout);
+    if (n != EV.ScalEqsToPropagate) { free(y); free(yp); return CB_ERR_UNSUPPORTED_PARAMS; }
+    for (int i = 0; i < EV.nvar; i++) y[i] = i < n ? y_in[i] : 0.0;
+    double src[3 + 2 * CB_MAX_WINDOWS];
+    output(&EV, y, 2, tau, src, yp);
+    for (int i = 0; i < n; i++) yprime[i] = yp[i];
+    for (int s = 0; s < M->n_src && s < 3; s++) sources[s] = src[s];
+    if (aux) {
+        double a, opac, dopac, ddopac, vis, dvis, ddvis, expmmu, cs2, grhov_t, w_de, a1;
+        ionization_functions(M, tau, &a, &opac, &dopac, &ddopac, &vis, &dvis, &ddvis, &expmmu);
+        thermo_values(M, tau, &a1, &cs2, &opac, &dopac);
+        de_background(M, a, &grhov_t, &w_de);
+        double a2 = a * a;
+        double grho = M->grhob / a + M->grhoc / a + M->grhornomass / a2 + M->grhog / a2 + grhov_t;
+        memset(aux, 0, 16 * sizeof(double));
+        aux[0] = a; aux[1] = sqrt(grho / 3); aux[2] = M->grhob / a; aux[3] = M->grhoc / a; aux[4] = M->grhog / a2;
+        aux[5] = M->grhornomass / a2; aux[6] = grhov_t; aux[7] = cs2; aux[8] = opac; aux[9] = dopac; aux[10] = ddopac;
+        aux[11] = vis; aux[12] = dvis; aux[13] = ddvis; aux[14] = expmmu;
+    }
+    free(y); free(yp);
+    return 0;
+}
