@@ -14,11 +14,15 @@
 #include "dmodel.cuh"
 
 // evolve.cu
-void cb_mode_size(const DModel& M, double q, int transfer_only, int* nvar, int* maxl);
+void cb_mode_size(const DModel& M, double q, int transfer_only, int* nvar, int* maxl, int* lmax3);
 cudaError_t cb_evolve_launch(const DModel*, const DModeItem*, int n_items, int nv, int maxl, int lanes_per_mode, int lean,
                              unsigned int*, int*, int n_sm, cudaStream_t, int* grid_out, int block_cap);
 cudaError_t cb_debug_derivs_launch(const DModel* d_model, double q, double tau, const int* flags4, const double* d_y, int n, int nv,
                                    int maxl, int lanes, int lean, double* d_yprime, double* d_sources, int* d_status, cudaStream_t stream);
+// evolve_reg.cu
+int cb_reg_class(int lmaxg, int lmaxgpol, int lmaxnr);
+cudaError_t cb_evolve_reg_launch(int reg_class, const DModel*, const DModeItem*, int n_items, unsigned int*, int*, int n_sm, cudaStream_t,
+                                 int* grid_out);
 // evolve_tensor.cu
 void cb_tensor_mode_size(const DModel& M, int* nvart, int* maxl);
 cudaError_t cb_evolve_tensor_launch(const DModel*, const DModeItem*, int n_items, int nv, int maxl, unsigned int*, int*, int n_sm,
@@ -42,9 +46,11 @@ double cb_fp64_peak_measure(int n_sm, cudaStream_t st, int reps);
 // tables), so that every launch sizes its per-mode slab for its own class.  The limits are the slab sizes at
 // which 6, 5, 4 and 3 blocks of eight modes fit one SM's 227 KB (1 KB per block is reserved by the system).
 // The last class holds tensor modes (their own kernel, evolve_tensor.cu).
-#define CB_N_CLASSES 6
+// Classes 6, 7, 8 are the three static layouts of the register-resident kernel (evolve_reg.cu): lean launches only.
+#define CB_N_CLASSES 9
 #define CB_TENSOR_CLASS 5
-static const size_t kClassSlabLimit[CB_N_CLASSES - 1] = {4714, 5683, 7136, 9557, ~size_t(0)};
+#define CB_REG_CLASS0 6
+static const size_t kClassSlabLimit[5] = {4714, 5683, 7136, 9557, ~size_t(0)};
 size_t cb_evolve_slab_bytes(int nv, int maxl);   // evolve.cu
 
 struct cb_dmodel {
@@ -82,6 +88,7 @@ struct cb_ctx {
     int lanes_per_mode = 0;              // 0 = automatic
     int class_lanes[CB_N_CLASSES] = {};  // per slab-size class override of the lane width (0 = lanes_per_mode)
     int async_model_upload = 0;          // cb_model_create returns without waiting for its host->device copies
+    int use_reg_kernel = 1;              // lean launches: modes that fit a static layout run the register-resident kernel
     cudaEvent_t stage_ev[4][2] = {};     // per-stage kernel brackets of the last calls (evolve, spline-k, LOS, C_l)
     DModel* h_models = nullptr;   size_t cap_h_models = 0;   // page-locked staging
     DModeItem* h_items = nullptr; size_t cap_h_items = 0;
@@ -193,6 +200,7 @@ int cb_create(int device, cb_ctx** out) {
     }
     cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming);
     if (const char* e = getenv("CAMB_B200_LANES")) ctx->lanes_per_mode = atoi(e);
+    if (const char* e = getenv("CAMB_B200_REG")) ctx->use_reg_kernel = atoi(e);
     {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -376,6 +384,8 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
     if (!ctx) return CB_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
     std::vector<DModeItem> cls_items[CB_N_CLASSES], all_items;
+    int lean = 1;   // every model massless-nu LCDM: the kernel variants without massive-nu / dark-energy code
+    for (int m = 0; m < n_models; m++) if (dm[m]->h.Num_Nu_massive != 0 || !dm[m]->h.de_is_cc || dm[m]->h.num_redshiftwindows > 0 || dm[m]->h.is_tensor) lean = 0;
     int cls_nv[CB_N_CLASSES] = {}, cls_maxl[CB_N_CLASSES] = {};
     std::vector<StagePiece> pieces;
     {
@@ -432,9 +442,10 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
             it.model = m; it.q_ix = i; it.transfer_only = md.transfer_only; it.q = md.q[i];
             it.tight_switchoff = md.tight_switchoff[i];
             for (int j = 0; j < CB_MAX_NU; j++) it.nu_massive_approx_time[j] = md.nu_massive_approx_time[(size_t)i * CB_MAX_NU + j];
-            int ml;
+            int ml, lm3[3] = {0, 0, 0};
             if (D.is_tensor) cb_tensor_mode_size(D, &it.nvar, &ml);
-            else cb_mode_size(D, it.q, it.transfer_only, &it.nvar, &ml);
+            else cb_mode_size(D, it.q, it.transfer_only, &it.nvar, &ml, lm3);
+            it.lmaxg = lm3[0]; it.lmaxgpol = lm3[1]; it.lmaxnr = lm3[2];
             if (ml > CBD_MAX_L_EVOLVE) { ctx->err = "Need to increase max_l_evolve"; return CB_ERR_UNSUPPORTED_PARAMS; }
             it.transfer_only |= ml << 8;   // deepest multipole rides along until the binning pass below
             all_items.push_back(it);
@@ -448,7 +459,10 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
         const int ml = it.transfer_only >> 8;
         it.transfer_only &= 0xff;
         int c = 0;
+        int rc = (lean && ctx->use_reg_kernel) ? cb_reg_class(it.lmaxg, it.lmaxgpol, it.lmaxnr) : -1;
+        if (rc == 1 && ctx->use_reg_kernel == 2) rc = -1;   // experiment: the 16-lane layout's modes through the general kernel
         if (dm[it.model]->h.is_tensor) c = CB_TENSOR_CLASS;
+        else if (rc >= 0) { cls_items[CB_REG_CLASS0 + rc].push_back(it); continue; }
         else
             for (;; c++) {
                 const size_t grown = cb_evolve_slab_bytes(std::max(std::max(cls_nv[c], it.nvar), 32), std::max(cls_maxl[c], ml));
@@ -482,8 +496,6 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
     CK(cudaMemcpyAsync(ctx->d_items, ctx->h_items, sizeof(DModeItem) * n_items, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int) * CB_N_CLASSES, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_error, 0, sizeof(int), ctx->stream));
-    int lean = 1;   // every model massless-nu LCDM: the kernel variant without massive-nu / dark-energy code
-    for (int m = 0; m < n_models; m++) if (dm[m]->h.Num_Nu_massive != 0 || !dm[m]->h.de_is_cc || dm[m]->h.num_redshiftwindows > 0) lean = 0;
     int lanes = ctx->lanes_per_mode;
     if (lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) lanes = n_items >= 16 * ctx->n_sm ? 8 : 32;
     CK(cudaEventRecord(ctx->stage_ev[0][0], ctx->stream));
@@ -500,7 +512,9 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
 #endif
     for (int cc = 0; cc < CB_N_CLASSES; cc++) ctx->last_grid[cc] = 0;
     for (int cc = 0; cc < CB_N_CLASSES; cc++) {
-        const int c = order_desc ? CB_N_CLASSES - 1 - cc : cc;
+        // the register classes go first (deep low-k layout, then the bulk): their modes are the longest serial chains
+        static const int kOrder[CB_N_CLASSES] = {CB_REG_CLASS0 + 1, CB_REG_CLASS0, CB_REG_CLASS0 + 2, 0, 1, 2, 3, 4, CB_TENSOR_CLASS};
+        const int c = order_desc ? CB_N_CLASSES - 1 - cc : kOrder[cc];
         const int n_c = (int)cls_items[c].size();
         if (n_c == 0) continue;
 #ifdef CB_TUNING_KNOBS
@@ -509,7 +523,10 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
         // the scratch EvolutionVars of a layout switch aliases two stage vectors (evolve.cu)
         const int nv = std::max(cls_nv[c], 32);
         CK(cudaStreamWaitEvent(ctx->class_stream[c], ctx->fork, 0));
-        cudaError_t le = c == CB_TENSOR_CLASS
+        cudaError_t le = c >= CB_REG_CLASS0
+                             ? cb_evolve_reg_launch(c - CB_REG_CLASS0, ctx->d_models, ctx->d_items + cls_off[c], n_c, ctx->d_counter + c, ctx->d_error,
+                                                    ctx->n_sm, ctx->class_stream[c], &ctx->last_grid[c])
+                         : c == CB_TENSOR_CLASS
                              ? cb_evolve_tensor_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, cls_nv[c], cls_maxl[c], ctx->d_counter + c,
                                                        ctx->d_error, ctx->n_sm, ctx->class_stream[c], &ctx->last_grid[c])
                              : cb_evolve_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, nv, cls_maxl[c], ctx->class_lanes[c] ? ctx->class_lanes[c] : lanes, lean, ctx->d_counter + c,
@@ -875,6 +892,7 @@ int cb_set_option(cb_ctx* ctx, const char* name, double value) {
         return 0;
     }
     if (!strcmp(name, "async_model_upload")) { ctx->async_model_upload = value != 0; return 0; }
+    if (!strcmp(name, "use_reg_kernel")) { ctx->use_reg_kernel = (int)value; return 0; }
     ctx->err = std::string("unknown option ") + name;
     return CB_ERR_UNSUPPORTED_PARAMS;
 }
@@ -949,7 +967,7 @@ int cb_debug_derivs(cb_ctx* ctx, cb_dmodel* dm, double q, double tau, const int*
         return CB_ERR_UNSUPPORTED_PARAMS;
     }
     int nv = 0, maxl = 0;
-    cb_mode_size(D, q, 0, &nv, &maxl);
+    cb_mode_size(D, q, 0, &nv, &maxl, nullptr);
     if (n < 1 || n > nv || maxl > CBD_MAX_L_EVOLVE) { ctx->err = "cb_debug_derivs: bad state size"; return CB_ERR_UNSUPPORTED_PARAMS; }
     DModel* d_model = nullptr;
     double *d_y = nullptr, *d_out = nullptr;

@@ -85,6 +85,7 @@ struct DModeItem {
     int q_ix;        // 0-based mode index inside that model's mode list
     int transfer_only;
     int nvar;        // worst-case number of equations (GetNumEqns), sizes the smem slab
+    int lmaxg, lmaxgpol, lmaxnr;   // hierarchy depths of GetNumEqns (equations.f90:933-995), for the register kernel's static layout
     double q;
     double tight_switchoff;
     double nu_massive_approx_time[CB_MAX_NU];

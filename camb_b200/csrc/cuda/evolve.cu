@@ -1446,7 +1446,7 @@ size_t cb_evolve_slab_bytes(int nv, int maxl) {
 }
 
 // GetNumEqns on the host for one mode: sizes the shared-memory slab and orders the queue.
-void cb_mode_size(const DModel& M, double q, int transfer_only, int* nvar, int* maxl) {
+void cb_mode_size(const DModel& M, double q, int transfer_only, int* nvar, int* maxl, int* lmax3) {
     EVs E;
     memset(&E, 0, sizeof(E));
     E.q = q;
@@ -1455,6 +1455,7 @@ void cb_mode_size(const DModel& M, double q, int transfer_only, int* nvar, int* 
     get_num_eqns(M, E);
     *nvar = E.nvar;
     *maxl = E.MaxlNeeded;
+    if (lmax3) { lmax3[0] = E.lmaxg; lmax3[1] = E.lmaxgpol; lmax3[2] = E.lmaxnr; }
 }
 
 template <int G, bool LEAN>

@@ -13,10 +13,39 @@ _lib = None
 c_ll_p = C.POINTER(C.c_longlong)
 
 
+_fast = False
+
+
+def use_fast(on=True):
+    """Select the throughput build of the oracle (bench.py's CPU arms): -O3 -march=native with FMA contraction, as
+    the reference's own build flags (fortran/Makefile:103).  The parity tests keep the default -O2 -ffp-contract=off
+    build, an arithmetic path independent of the CUDA code."""
+    global _fast, _lib
+    if bool(on) != _fast:
+        _fast, _lib = bool(on), None
+
+
+def _fast_path():
+    """oracle/liboracle_fast.so is built with the portable -march=x86-64-v3; a -march=native build for the cores
+    this process runs on is made on first use (a few seconds of gcc) and preferred when it works."""
+    import subprocess
+    d = os.path.join(_ROOT, "oracle")
+    native = os.path.join(d, "liboracle_native.so")
+    srcs = [os.path.join(d, f) for f in ("oracle_evolve.c", "oracle_lensing.c", "oracle_project.c")]
+    try:
+        if not os.path.exists(native) or any(os.path.getmtime(f) > os.path.getmtime(native) for f in srcs):
+            subprocess.run(["gcc", "-O3", "-march=native", "-std=c11", "-fPIC", "-fopenmp", "-shared", "-o", native] + srcs + ["-lm"],
+                           check=True, capture_output=True, timeout=300)
+        C.CDLL(native)
+        return native
+    except Exception:
+        return os.path.join(d, "liboracle_fast.so")
+
+
 def load():
     global _lib
     if _lib is None:
-        path = os.path.join(_ROOT, "oracle", "liboracle.so")
+        path = _fast_path() if _fast else os.path.join(_ROOT, "oracle", "liboracle.so")
         if not os.path.exists(path):
             raise ImportError(f"{path} not built; run `make oracle`")
         lib = C.CDLL(path)
