@@ -35,6 +35,16 @@ METRIC = "lcdm_cl_sets_per_sec_lmax2500"
 UNIT = "C_l sets/s"
 WORKLOAD = "planck2018_lcdm_box_massless_nu_T+E+phi_lmax2500_keta6250_lensed"
 
+# --workload: the default is the configuration BASELINE.json's metric is quoted on (configs[1] with its "massless neutrinos"
+# override); the others are BASELINE.json's configs[0] and configs[4] as SURVEY.md 8(d) specifies them, and the latency of
+# one cosmology.  Every workload is a batch of `--batch` synthetic parameter sets per GPU per step.
+WORKLOADS = {
+    "lcdm_massless": dict(name=WORKLOAD, lensing=True),
+    "config1_massive": dict(name="params_ini_box_one_massive_nu_T+E_lmax2500_keta6250_unlensed", lensing=False),
+    "config5_mnu_w0wa": dict(name="planck2018_box_mnu+w0wa_ppf_T+E_lmax2500_keta6250_unlensed", lensing=False),
+    "single_cosmology": dict(name="planck_2018_massless_nu_T+E+phi_lmax2500_lensed_one_cosmology", lensing=True),
+}
+
 
 def env_int(name, default):
     try:
@@ -87,36 +97,64 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_batch(n, seed):
+def build_batch(n, seed, workload="lcdm_massless"):
     from camb_b200.host import HostState
-    from camb_b200.workloads import synthetic_lcdm_batch
-    ps = synthetic_lcdm_batch(n, seed=seed, lmax=2500, lensing=True, massless=True)
+    from camb_b200.workloads import planck2018_params, synthetic_config1_batch, synthetic_lcdm_batch
+    if workload == "config1_massive":
+        ps = synthetic_config1_batch(n, seed=seed)
+    elif workload == "config5_mnu_w0wa":
+        ps = synthetic_lcdm_batch(n, seed=seed, lmax=2500, lensing=False, extended=True)
+    elif workload == "single_cosmology":
+        ps = [planck2018_params(lmax=2500, lensing=True, massless=True) for _ in range(n)]
+    else:
+        ps = synthetic_lcdm_batch(n, seed=seed, lmax=2500, lensing=True, massless=True)
     return [HostState(p) for p in ps]
 
 
-def oracle_cl_sets(hss, nthreads, budget_s, min_sets=1):
-    """Time the oracle chain on a bounded sample of the batch; returns (sets, seconds, k_modes)."""
+def oracle_cl_sets(hss, nthreads, budget_s, min_sets=1, lensing=True, per_set_threads=False):
+    """Time the CPU restatement of the path on a bounded sample of the batch; returns (sets, seconds, k_modes).
+    Default: whole parameter sets in parallel, one thread each (a thread pool over ctypes calls, which release the
+    GIL) -- the way a batch runs on CPU cores; `per_set_threads`: one set at a time with OpenMP over its k-modes (the
+    reference's own single-cosmology parallelisation, cmbmain.f90:205-209)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import concurrent.futures as cf
     import oracle_lib as O
-    t0 = time.perf_counter()
-    n = modes = 0
     from camb_b200 import lensing as L
-    from camb_b200.workloads import synthetic_highl_template
+    O.use_fast(True)          # -O3 -march=native build, as the reference's Makefile (fortran/Makefile:103)
+    template = L.default_highl_template()
+    plan = L.plan_for(hss[0]) if lensing else None
+    inner = nthreads if per_set_threads else 1
 
     class OracleLens:          # the CPU restatement of the theta loops behind the same host code
         def lens_contrib(self, plan, spectra, out=None):
             for i, sp in enumerate(spectra):
-                out[i] = O.lens_contrib(plan, sp, nthreads=nthreads)
+                out[i] = O.lens_contrib(plan, sp, nthreads=inner)
             return list(out)
 
-    plan, template = L.plan_for(hss[0]), synthetic_highl_template()
-    for hs in hss:
-        icl, _ = O.cls_from_params(hs, nthreads=nthreads)
-        L.lens_cls_from_icl(OracleLens(), plan, [hs], [icl], template, nthreads=1)
-        n += 1
-        modes += len(hs.source_q())
-        if time.perf_counter() - t0 > budget_s and n >= min_sets:
-            break
+    def one(hs):
+        icl, _ = O.cls_from_params(hs, nthreads=inner)
+        if lensing:
+            L.lens_cls_from_icl(OracleLens(), plan, [hs], [icl], template, nthreads=1)
+        return len(hs.source_q())
+
+    t0 = time.perf_counter()
+    n = modes = 0
+    if per_set_threads:
+        for hs in hss:
+            modes += one(hs)
+            n += 1
+            if time.perf_counter() - t0 > budget_s and n >= min_sets:
+                break
+    else:
+        with cf.ThreadPoolExecutor(max_workers=nthreads) as ex:
+            i = 0
+            while i < len(hss):
+                chunk = hss[i:i + nthreads]
+                modes += sum(ex.map(one, chunk))
+                n += len(chunk)
+                i += len(chunk)
+                if time.perf_counter() - t0 > budget_s and n >= min_sets:
+                    break
     return n, time.perf_counter() - t0, modes
 
 
@@ -125,26 +163,30 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = max(1, min(args.batch, 4))
-    hss = build_batch(per_step, seed=20261017)
+    wl = WORKLOADS[args.workload]
+    per_step = 1 if args.workload == "single_cosmology" else max(1, min(args.batch, 2 * cores))
+    hss = build_batch(per_step, seed=20261017, workload=args.workload)
     for hs in hss:
         hs.bessel()
+    single = args.workload == "single_cosmology"
     for _ in range(args.warmup):
-        oracle_cl_sets(hss, cores, 1e9)
+        oracle_cl_sets(hss, cores, 1e9, lensing=wl["lensing"], per_set_threads=single)
     t0 = time.perf_counter()
     sets = modes = 0
     for _ in range(args.steps):
-        n, _, m = oracle_cl_sets(hss, cores, 1e9)
+        n, _, m = oracle_cl_sets(hss, cores, 1e9, lensing=wl["lensing"], per_set_threads=single)
         sets += n
         modes += m
     dt = time.perf_counter() - t0
     v = sets / dt
-    sample = f"{per_step} of the batch's parameter sets per step, OpenMP over k-modes, {cores} threads"
+    sample = (f"{per_step} of the batch's parameter sets per step, " +
+              ("OpenMP over the k-modes of the one cosmology" if single else "one thread per parameter set") +
+              f", {cores} threads, oracle built -O3 -march=native")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sets_per_step": per_step,
+        "config": {"workload": wl["name"], "sets_per_step": per_step,
                    "note": "CPU restatement of the reference path (oracle port); the Fortran reference cannot be built in this image"},
         "k_modes_per_sec": modes / dt,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -184,19 +226,55 @@ def model_h2d_bytes(hs):
     return 8 * (m.nthermo * (16 + 7) + 2 * m.n_tau) + 8 * max(0, m.num_transfer_redshifts)
 
 
+def one_cosmology_latency(ctx, reps=5):
+    """Wall-clock latency of ONE planck_2018 cosmology (massless neutrinos, lensed) through the C-ABI with host buffers:
+    model upload, evolve, project, C_l, lens_Cls.  Best evolve path per stage (the library chooses the kernel by the
+    number of modes in the call)."""
+    import torch
+    from camb_b200 import lensing as L
+    from camb_b200.host import HostState
+    from camb_b200.workloads import planck2018_params
+    hs = HostState(planck2018_params(lmax=2500, lensing=True, massless=True))
+    ctx.set_bessel(hs)
+    plan, template = L.plan_for(hs), L.default_highl_template()
+    out = {}
+    for label, opt in (("mode_per_lane", 3), ("lane_group_32", 0)):
+        ctx.set_option("use_reg_kernel", opt)
+        best = 1e30
+        for _ in range(reps + 1):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            dm = ctx.create_model(hs)
+            ctx.evolve([hs], [dm], want_sources=False, want_stats=False)
+            ctx.project([hs], [dm], want_delta=False)
+            icl = ctx.cl([hs], [dm])
+            L.lens_cls_from_icl(ctx, plan, [hs], icl, template, nthreads=1)
+            ctx.destroy_model(dm)
+            torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        out[label] = 1e3 * best
+    ctx.set_option("use_reg_kernel", 3)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="lcdm_massless", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=env_int("CAMB_B200_BATCH", 64), help="parameter sets per GPU per step")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the one-cosmology latency measurement")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.warmup < 3:
         args.warmup = 3
+    wl = WORKLOADS[args.workload]
+    if args.workload == "single_cosmology":
+        args.batch = 1
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -211,18 +289,20 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = GpuContext(local)
     B = args.batch
-    hss = build_batch(B, seed=20261017 + 1000 * rank)       # every rank its own parameter sets
+    lensing = wl["lensing"]
+    hss = build_batch(B, seed=20261017 + 1000 * rank, workload=args.workload)       # every rank its own parameter sets
     ctx.set_bessel(hss[0])
     for hs in hss:
         ctx.pin_host_tables(hs)
     dms = [ctx.create_model(hs) for hs in hss]
     n_modes = sum(len(hs.source_q()) for hs in hss)
+    lean = all(hs.model.Num_Nu_massive == 0 and hs.model.de_is_cosmological_constant for hs in hss)
 
-    # lens_Cls: the batch is projected against one Bessel table (hss[0]'s l sampling), so one plan; the high-L template is
-    # synthetic here (the reference's data file does not travel), it only shapes the tail above Max_l
+    # lens_Cls: the batch is projected against one Bessel table (hss[0]'s l sampling), so one plan; the
+    # high-L template is the reference's own table (package data, camb_b200/data)
     from camb_b200 import lensing as L
-    from camb_b200.workloads import synthetic_highl_template
-    plan, template = L.plan_for(hss[0]), synthetic_highl_template()
+    plan = L.plan_for(hss[0]) if lensing else None
+    template = L.default_highl_template() if lensing else None
     host_threads = max(1, min(16, (os.cpu_count() or 1) // world))     # the ranks of one box share its host cores
 
     def step(want_stats=False):
@@ -231,9 +311,12 @@ def main():
         ctx.project(hss, dms, want_delta=False)
         icl = ctx.cl(hss, dms)
         tm = ctx.timings_ms()
-        _, lensed = L.lens_cls_from_icl(ctx, plan, hss, icl, template, ls_owner=hss[0], reuse_buffers=True, nthreads=host_threads)
-        tm["lens"] = ctx.last_lens_ms()
-        return lensed, st, t_ev, tm
+        tm["lens"] = 0.0
+        res = np.stack(icl)
+        if lensing:
+            _, res = L.lens_cls_from_icl(ctx, plan, hss, icl, template, ls_owner=hss[0], reuse_buffers=True, nthreads=host_threads)
+            tm["lens"] = ctx.last_lens_ms()
+        return res, st, t_ev, tm
 
     def barrier():
         if world > 1:
@@ -246,7 +329,6 @@ def main():
     # algorithmic work of the ODE kernel from the integrator's own counters
     evals = sum(int(s[:, 0].sum()) for s in st)
     neq_evals = sum(int(s[:, 2].sum()) for s in st)
-    attempts = sum(int(s[:, 3].sum()) for s in st)
     neq_attempts = neq_evals / 6.0                       # 6 integrator derivs calls per attempt (FSAL)
     ode_flops = 5.0 * neq_evals + 200.0 * evals + 70.0 * neq_attempts
     launches0 = ctx.launch_count()
@@ -258,7 +340,7 @@ def main():
     for _ in range(args.steps):
         icl, _, tev, tm = step(False)
         t_ev += tev; t_los += tm["los"]; t_spl += tm["spline_k"]; t_cl += tm["cl"]; t_lens += tm["lens"]
-    icl = icl.copy()       # the lensed C_l of the resident path (the host buffers are reused by the e2e steps below)
+    icl = icl.copy()       # the result of the resident path (the host buffers are reused by the e2e steps below)
     ms = ctx.timer_stop()
     barrier()
     clocks = sampler.stop()
@@ -269,16 +351,26 @@ def main():
     ms_max = float(t.item())
     value = world * B * args.steps / (ms_max * 1e-3)
 
-    # ---- e2e: host buffers -> C-ABI -> host results, copies inside the timed region ----
+    # ---- e2e: host buffers -> C-ABI -> host results, copies inside the timed region.  What the drop-in API hands back
+    # is read back every step: iCl AND Delta_p_l_k (results.py:541 reads it from the host), plus the lensed C_l.
     h2d = sum(model_h2d_bytes(hs) for hs in hss) + sum(8 * (3 * len(hs.q_int) + len(hs.source_q())) for hs in hss)
-    h2d += B * 8 * 4 * (plan.lmax + 1)
-    d2h = sum(8 * len(hs.ls) * 6 for hs in hss) + B * 8 * 4 * (plan.lmax_lensed + 1)
+    d2h = sum(8 * len(hs.ls) * (6 if hs.n_src > 2 else 3) for hs in hss)
+    d2h += sum(8 * hs.n_src * len(hss[0].ls) * len(hs.q_int) for hs in hss)
+    if lensing:
+        h2d += B * 8 * 4 * (plan.lmax + 1)
+        d2h += B * 8 * 4 * (plan.lmax_lensed + 1)
+    delta_host = [np.zeros((len(hs.q_int), len(hss[0].ls), hs.n_src)) for hs in hss]
+    for a in delta_host:
+        ctx.pin_array(a)
 
     def e2e_step():
         d = [ctx.create_model(hs) for hs in hss]
         ctx.evolve(hss, d, want_sources=False, want_stats=False)
-        ctx.project(hss, d, want_delta=False)
-        _, out = L.lens_cls_from_icl(ctx, plan, hss, ctx.cl(hss, d), template, ls_owner=hss[0], reuse_buffers=True, nthreads=host_threads)
+        ctx.project(hss, d, want_delta=True, out=delta_host)
+        res = ctx.cl(hss, d)
+        out = np.stack(res)
+        if lensing:
+            _, out = L.lens_cls_from_icl(ctx, plan, hss, res, template, ls_owner=hss[0], reuse_buffers=True, nthreads=host_threads)
         for x in d:
             ctx.destroy_model(x)
         return out
@@ -291,11 +383,16 @@ def main():
         out = e2e_step()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    assert np.array_equal(out[0], icl[0]) and np.all(icl[:, 2:, 0] > 0), "e2e path and resident path disagree"
+    assert np.array_equal(out[0], icl[0]) and np.all(np.abs(delta_host[0]).max(axis=(0, 2)) > 0), "e2e path and resident path disagree"
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(t.item())
+
+    latency = None
+    if rank == 0 and not args.no_latency:
+        latency = one_cosmology_latency(ctx)
+        ctx.set_bessel(hss[0])
 
     if rank == 0:
         peaks = {}
@@ -312,48 +409,53 @@ def main():
         los_bytes = 32.0 * (b.nx - 1) * b.n_l + sum(
             8.0 * (2 * len(hs.source_q()) * hs.n_src * hs.n_tau + hs.n_src * len(hs.ls) * len(hs.q_int)) for hs in hss)
         gather_bytes = 32.0 * sum(los_gather_evals(hs) for hs in hss)
-        traffic = {}
-        try:   # DRAM bytes per launch of the two kernels from the committed `ncu --set full` capture of this command
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        except Exception:
-            pass
+        tot = t_ev + t_los + t_spl + t_cl + t_lens
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sets_per_gpu_per_step": B, "k_modes_per_set": n_modes / B,
-                       "lensing": "lens_Cls default method (CorrFuncFullSkyApodized), %d angles x l <= %d, lensed output to l = %d; "
-                                  "synthetic high-L template" % (plan.c.npoints - 1, plan.lmax, plan.lmax_lensed),
+            "config": {"workload": wl["name"], "sets_per_gpu_per_step": B, "k_modes_per_set": n_modes / B,
+                       "lensing": ("lens_Cls default method (CorrFuncFullSkyApodized), %d angles x l <= %d, lensed output to l = %d; "
+                                   "the reference's high-L template" % (plan.c.npoints - 1, plan.lmax, plan.lmax_lensed)) if lensing else "none",
                        "l2": "inputs larger than L2 (per-step working set %.0f MB)" % (
                            (los_bytes + sum(model_h2d_bytes(hs) for hs in hss)) / 1e6)},
             "k_modes_per_sec": world * n_modes * args.steps / (ms_max * 1e-3),
             # BASELINE.json's second metric: Boltzmann k-modes/s of stages 1-2 alone (this rank's evolve stage, CUDA events)
             "k_modes_per_sec_evolve_stage": world * n_modes / (t_ev / args.steps * 1e-3),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "returns": "iCl, Delta_p_l_k" + (", lensed C_l" if lensing else "")},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "kernel": "cb_evolve_kernel", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": ach / fp64_peak if fp64_peak else None, "traffic": traffic.get("cb_evolve_kernel_dram_bytes_per_launch"),
+            "roofline": {"bound": "fp64", "kernel": "cb_evolve_mpl_kernel (+ cb_evolve_reg_kernel for the deep low-k hierarchies)" if lean else "cb_evolve_kernel",
+                         "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": ach / fp64_peak if fp64_peak else None, "traffic": None,
                          "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                         "ms_per_launch": ev_ms, "share_of_step": t_ev / (t_ev + t_los + t_spl + t_cl + t_lens),
+                         "ms_per_launch": ev_ms, "share_of_step": t_ev / tot,
                          "derivs_evals_per_launch": evals, "algorithmic_flops_per_launch": ode_flops},
             "roofline_los": {"bound": "hbm", "kernel": "cb_los_kernel", "achieved": los_bytes / (los_ms * 1e-3) / 1e9,
                              "peak": hbm_peak, "unit": "GB/s", "frac": los_bytes / (los_ms * 1e-3) / 1e9 / hbm_peak,
-                             "traffic": traffic.get("cb_los_kernel_dram_bytes_per_launch"),
+                             "traffic": None,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",
                              "gather_bytes_per_launch": gather_bytes, "l2_gather_gbs": gather_bytes / (los_ms * 1e-3) / 1e9,
                              "note": "working set is L2-resident: the kernel is bound by the 32-byte Bessel-record gathers through L1/L2 "
                                      "(l2_gather_gbs), not by HBM",
-                             "ms_per_launch": los_ms, "share_of_step": t_los / (t_ev + t_los + t_spl + t_cl + t_lens)},
+                             "ms_per_launch": los_ms, "share_of_step": t_los / tot},
             "stage_ms_per_step": {"evolve": ev_ms, "spline_k": t_spl / args.steps, "los": los_ms, "cl": t_cl / args.steps,
                                   "lens": t_lens / args.steps},
         }
+        if latency:
+            line["latency_ms"] = {"one_planck2018_cosmology_1gpu": min(latency.values()), "by_evolve_path": latency,
+                                  "note": "wall clock through the C-ABI with host buffers, best of 5"}
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            n, secs, m = oracle_cl_sets(hss, cores, args.cpu_budget)
+            sample_sets = hss[:max(1, min(B, 2 * cores))]
+            n, secs, m = oracle_cl_sets(sample_sets, cores, args.cpu_budget, lensing=lensing, per_set_threads=(B == 1))
             line["cpu_baseline"] = {"value": n / secs, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"first {n} parameter sets of the batch, {secs:.1f} s, OpenMP over k-modes",
+                                    "sample": f"first {n} parameter sets of the batch, {secs:.1f} s, one thread per parameter set, "
+                                              "oracle built -O3 -march=native",
                                     "k_modes_per_sec": m / secs}
+            n2, secs2, _ = oracle_cl_sets(hss[:4], cores, min(args.cpu_budget, 6.0), lensing=lensing, per_set_threads=True)
+            line["cpu_baseline"]["per_cosmology_openmp_value"] = n2 / secs2   # the reference's own parallelisation: one set at a time
         print(json.dumps(line))
     for dm in dms:
         ctx.destroy_model(dm)

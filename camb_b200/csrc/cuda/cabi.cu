@@ -23,6 +23,19 @@ cudaError_t cb_debug_derivs_launch(const DModel* d_model, double q, double tau, 
 int cb_reg_class(int lmaxg, int lmaxgpol, int lmaxnr);
 cudaError_t cb_evolve_reg_launch(int reg_class, const DModel*, const DModeItem*, int n_items, unsigned int*, int*, int n_sm, cudaStream_t,
                                  int* grid_out);
+// tmem_probe.cu
+cudaError_t cb_tmem_probe_launch(int n_blocks, int* d_mismatches, long long* d_cycles, cudaStream_t stream);
+// evolve_mpl.cu
+int cb_mpl_class(int lmaxg, int lmaxgpol, int lmaxnr);
+cudaError_t cb_evolve_mpl_launch(const DModel* d_models, const DModeItem* d_items_a, int n_a, const DModeItem* d_items_c, int n_c,
+                                 unsigned int* d_counter_a, unsigned int* d_counter_c, int* d_error, int n_sm, cudaStream_t stream,
+                                 int* grid_out);
+cudaError_t cb_debug_derivs_mpl_launch(const DModel* d_model, double q, double tau, const int* flags4, const int* lmax3, const double* d_y,
+                                       int n, double* d_yprime, double* d_sources, cudaStream_t stream);
+#ifdef CB_TRACE
+void cb_trace_mpl_begin(int q_ix, int cap); void cb_trace_mpl_end(const char* path);
+void cb_trace_reg_begin(int q_ix, int cap); void cb_trace_reg_end(const char* path);
+#endif
 // evolve_tensor.cu
 void cb_tensor_mode_size(const DModel& M, int* nvart, int* maxl);
 cudaError_t cb_evolve_tensor_launch(const DModel*, const DModeItem*, int n_items, int nv, int maxl, unsigned int*, int*, int n_sm,
@@ -46,8 +59,11 @@ double cb_fp64_peak_measure(int n_sm, cudaStream_t st, int reps);
 // tables), so that every launch sizes its per-mode slab for its own class.  The limits are the slab sizes at
 // which 6, 5, 4 and 3 blocks of eight modes fit one SM's 227 KB (1 KB per block is reserved by the system).
 // The last class holds tensor modes (their own kernel, evolve_tensor.cu).
-// Classes 6, 7, 8 are the three static layouts of the register-resident kernel (evolve_reg.cu): lean launches only.
-#define CB_N_CLASSES 9
+// Classes 6, 7, 8 are the three static layouts of the register-resident kernel (evolve_reg.cu), 9 and 10 the two classes
+// of the mode-per-lane kernel (evolve_mpl.cu, one launch for both): lean launches only.
+#define CB_N_CLASSES 11
+#define CB_MPL_CLASS_A 9
+#define CB_MPL_CLASS_C 10
 #define CB_TENSOR_CLASS 5
 #define CB_REG_CLASS0 6
 static const size_t kClassSlabLimit[5] = {4714, 5683, 7136, 9557, ~size_t(0)};
@@ -88,7 +104,10 @@ struct cb_ctx {
     int lanes_per_mode = 0;              // 0 = automatic
     int class_lanes[CB_N_CLASSES] = {};  // per slab-size class override of the lane width (0 = lanes_per_mode)
     int async_model_upload = 0;          // cb_model_create returns without waiting for its host->device copies
-    int use_reg_kernel = 1;              // lean launches: modes that fit a static layout run the register-resident kernel
+    // lean launches: 0 = the general kernel only; 1 = register kernel for every mode that fits a static layout; 2 = the same
+    // but the 16-lane layout's modes through the general kernel; 3 (default) = mode-per-lane kernel for the 48-element
+    // classes, register kernel for the deep low-k hierarchies
+    int use_reg_kernel = 3;
     cudaEvent_t stage_ev[4][2] = {};     // per-stage kernel brackets of the last calls (evolve, spline-k, LOS, C_l)
     DModel* h_models = nullptr;   size_t cap_h_models = 0;   // page-locked staging
     DModeItem* h_items = nullptr; size_t cap_h_items = 0;
@@ -461,6 +480,10 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
         int c = 0;
         int rc = (lean && ctx->use_reg_kernel) ? cb_reg_class(it.lmaxg, it.lmaxgpol, it.lmaxnr) : -1;
         if (rc == 1 && ctx->use_reg_kernel == 2) rc = -1;   // experiment: the 16-lane layout's modes through the general kernel
+        if (lean && ctx->use_reg_kernel == 3) {
+            const int mc = cb_mpl_class(it.lmaxg, it.lmaxgpol, it.lmaxnr);
+            if (mc >= 0) { cls_items[mc == 0 ? CB_MPL_CLASS_A : CB_MPL_CLASS_C].push_back(it); continue; }
+        }
         if (dm[it.model]->h.is_tensor) c = CB_TENSOR_CLASS;
         else if (rc >= 0) { cls_items[CB_REG_CLASS0 + rc].push_back(it); continue; }
         else
@@ -494,6 +517,9 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
     }
     memcpy(ctx->h_items, items.data(), sizeof(DModeItem) * n_items);
     CK(cudaMemcpyAsync(ctx->d_items, ctx->h_items, sizeof(DModeItem) * n_items, cudaMemcpyHostToDevice, ctx->stream));
+#ifdef CB_TRACE
+    if (const char* tq = getenv("CAMB_B200_TRACE")) { cb_trace_mpl_begin(atoi(tq), 4096); cb_trace_reg_begin(atoi(tq), 4096); }
+#endif
     CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int) * CB_N_CLASSES, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_error, 0, sizeof(int), ctx->stream));
     int lanes = ctx->lanes_per_mode;
@@ -513,9 +539,11 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
     for (int cc = 0; cc < CB_N_CLASSES; cc++) ctx->last_grid[cc] = 0;
     for (int cc = 0; cc < CB_N_CLASSES; cc++) {
         // the register classes go first (deep low-k layout, then the bulk): their modes are the longest serial chains
-        static const int kOrder[CB_N_CLASSES] = {CB_REG_CLASS0 + 1, CB_REG_CLASS0, CB_REG_CLASS0 + 2, 0, 1, 2, 3, 4, CB_TENSOR_CLASS};
+        static const int kOrder[CB_N_CLASSES] = {CB_MPL_CLASS_A, CB_MPL_CLASS_C, CB_REG_CLASS0 + 1, CB_REG_CLASS0, CB_REG_CLASS0 + 2, 0, 1, 2, 3, 4, CB_TENSOR_CLASS};
         const int c = order_desc ? CB_N_CLASSES - 1 - cc : kOrder[cc];
-        const int n_c = (int)cls_items[c].size();
+        int n_c = (int)cls_items[c].size();
+        if (c == CB_MPL_CLASS_C) continue;                                   // launched together with class A
+        if (c == CB_MPL_CLASS_A) n_c += (int)cls_items[CB_MPL_CLASS_C].size();
         if (n_c == 0) continue;
 #ifdef CB_TUNING_KNOBS
         if (const char* only = getenv("CAMB_B200_ONLY_CLASS")) if (atoi(only) != c) continue;   // timing experiments: one slab class alone
@@ -523,7 +551,12 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
         // the scratch EvolutionVars of a layout switch aliases two stage vectors (evolve.cu)
         const int nv = std::max(cls_nv[c], 32);
         CK(cudaStreamWaitEvent(ctx->class_stream[c], ctx->fork, 0));
-        cudaError_t le = c >= CB_REG_CLASS0
+        cudaError_t le = c == CB_MPL_CLASS_A
+                             ? cb_evolve_mpl_launch(ctx->d_models, ctx->d_items + cls_off[CB_MPL_CLASS_A], (int)cls_items[CB_MPL_CLASS_A].size(),
+                                                    ctx->d_items + cls_off[CB_MPL_CLASS_C], (int)cls_items[CB_MPL_CLASS_C].size(),
+                                                    ctx->d_counter + CB_MPL_CLASS_A, ctx->d_counter + CB_MPL_CLASS_C, ctx->d_error, ctx->n_sm,
+                                                    ctx->class_stream[c], &ctx->last_grid[c])
+                         : c >= CB_REG_CLASS0
                              ? cb_evolve_reg_launch(c - CB_REG_CLASS0, ctx->d_models, ctx->d_items + cls_off[c], n_c, ctx->d_counter + c, ctx->d_error,
                                                     ctx->n_sm, ctx->class_stream[c], &ctx->last_grid[c])
                          : c == CB_TENSOR_CLASS
@@ -550,6 +583,12 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
             CK(cudaMemcpyAsync(stats[m], d->d_stats, sizeof(long long) * 4 * (size_t)D.n_k, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
+#ifdef CB_TRACE
+    if (getenv("CAMB_B200_TRACE")) {
+        cb_trace_mpl_end(ctx->use_reg_kernel == 3 ? "gpurun_out/trace_mpl.bin" : "gpurun_out/trace_mpl_unused.bin");
+        cb_trace_reg_end(ctx->use_reg_kernel == 1 ? "gpurun_out/trace_reg.bin" : "gpurun_out/trace_reg_unused.bin");
+    }
+#endif
     if (herr) { ctx->err = "RungeKuttaDP45 error: step size underflow in the device integrator"; return herr; }
     return 0;
 }
@@ -966,8 +1005,12 @@ int cb_debug_derivs(cb_ctx* ctx, cb_dmodel* dm, double q, double tau, const int*
         ctx->err = "cb_debug_derivs: the lean variant is for massless-neutrino LCDM models";
         return CB_ERR_UNSUPPORTED_PARAMS;
     }
-    int nv = 0, maxl = 0;
-    cb_mode_size(D, q, 0, &nv, &maxl, nullptr);
+    int nv = 0, maxl = 0, lmax3[3] = {0, 0, 0};
+    cb_mode_size(D, q, 0, &nv, &maxl, lmax3);
+    if (lanes == 1 && (!lean || cb_mpl_class(lmax3[0], lmax3[1], lmax3[2]) < 0)) {
+        ctx->err = "cb_debug_derivs: the mode-per-lane kernel takes lean models and modes of its two size classes";
+        return CB_ERR_UNSUPPORTED_PARAMS;
+    }
     if (n < 1 || n > nv || maxl > CBD_MAX_L_EVOLVE) { ctx->err = "cb_debug_derivs: bad state size"; return CB_ERR_UNSUPPORTED_PARAMS; }
     DModel* d_model = nullptr;
     double *d_y = nullptr, *d_out = nullptr;
@@ -979,7 +1022,12 @@ int cb_debug_derivs(cb_ctx* ctx, cb_dmodel* dm, double q, double tau, const int*
     int rc = 0, status[2] = {0, 1};
     cudaError_t e = cudaMemcpyAsync(d_model, &D, sizeof(DModel), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_y, y, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cb_debug_derivs_launch(d_model, q, tau, flags4, d_y, n, nv, maxl, lanes, lean, d_out, d_out + nv, d_status, ctx->stream);
+    if (e == cudaSuccess && lanes == 1) {
+        e = cudaMemsetAsync(d_out, 0, sizeof(double) * (nv + 3), ctx->stream);
+        if (e == cudaSuccess) e = cb_debug_derivs_mpl_launch(d_model, q, tau, flags4, lmax3, d_y, n, d_out, d_out + nv, ctx->stream);
+        status[1] = 0;
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_status, 0, sizeof(int) * 2, ctx->stream);
+    } else if (e == cudaSuccess) e = cb_debug_derivs_launch(d_model, q, tau, flags4, d_y, n, nv, maxl, lanes, lean, d_out, d_out + nv, d_status, ctx->stream);
     if (e == cudaSuccess) { ctx->launches++; e = cudaMemcpyAsync(status, d_status, sizeof(status), cudaMemcpyDeviceToHost, ctx->stream); }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess && status[1] == 0) {
@@ -990,6 +1038,28 @@ int cb_debug_derivs(cb_ctx* ctx, cb_dmodel* dm, double q, double tau, const int*
     if (e != cudaSuccess) { ctx->err = std::string("cb_debug_derivs: ") + cudaGetErrorString(e); return CB_ERR_CUDA; }
     if (status[1] != 0) { ctx->err = "cb_debug_derivs: n does not match the layout the flags select"; rc = CB_ERR_UNSUPPORTED_PARAMS; }
     return rc;
+}
+
+// Self-test of the Tensor-Memory vector storage (tmem.cuh) the mode-per-lane evolve kernel relies on: pattern write /
+// read-back through every column of every lane on n_blocks SMs; cycles[0..1] = SM cycles per 8-double load / store.
+int cb_tmem_probe(cb_ctx* ctx, int n_blocks, int* mismatches, long long* cycles) {
+    if (!ctx) return CB_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    int* d_bad = nullptr;
+    long long* d_cyc = nullptr;
+    CK(cudaMalloc(&d_bad, sizeof(int)));
+    CK(cudaMalloc(&d_cyc, 3 * sizeof(long long)));
+    CK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(d_cyc, 0, 3 * sizeof(long long), ctx->stream));
+    cudaError_t e = cb_tmem_probe_launch(n_blocks > 0 ? n_blocks : ctx->n_sm, d_bad, d_cyc, ctx->stream);
+    if (e == cudaSuccess) { ctx->launches++; e = cudaStreamSynchronize(ctx->stream); }
+    long long cyc[3] = {0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(mismatches, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(cyc, d_cyc, sizeof(cyc), cudaMemcpyDeviceToHost);
+    cudaFree(d_bad); cudaFree(d_cyc);
+    if (e != cudaSuccess) { ctx->err = std::string("cb_tmem_probe: ") + cudaGetErrorString(e); return CB_ERR_CUDA; }
+    if (cycles) { cycles[0] = cyc[0]; cycles[1] = cyc[1]; }
+    return 0;
 }
 
 size_t cb_abi_sizeof(int which) {

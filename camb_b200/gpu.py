@@ -23,7 +23,7 @@ SYMBOLS = ["cb_create", "cb_destroy", "cb_last_error", "cb_device_count", "cb_se
            "cb_launch_count", "cb_abi_sizeof", "cb_timer_start", "cb_timer_stop", "cb_fp64_peak",
            "cb_host_alloc", "cb_host_free", "cb_device_buffer", "cb_set_option", "cb_host_register",
            "cb_host_unregister", "cb_cl_array", "cb_cl_windows", "cb_lens_contrib",
-           "cb_last_lens_timing", "cb_debug_derivs"]
+           "cb_last_lens_timing", "cb_debug_derivs", "cb_tmem_probe"]
 
 
 def load_gpu_lib():
@@ -68,6 +68,7 @@ def load_gpu_lib():
         lib.cb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         lib.cb_debug_derivs.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, c_int_p, c_double_p, C.c_int, C.c_int,
                                         C.c_int, c_double_p, c_double_p]
+        lib.cb_tmem_probe.argtypes = [C.c_void_p, C.c_int, c_int_p, C.POINTER(C.c_longlong)]
         lib.cb_abi_sizeof.restype = C.c_size_t
         lib.cb_abi_sizeof.argtypes = [C.c_int]
         _lib = lib
@@ -117,6 +118,13 @@ class GpuContext:
         self._check(self._lib.cb_debug_derivs(self._h, dm, float(q), float(tau), f, _dp(y), len(y), int(lanes), int(bool(lean)),
                                               _dp(yp), _dp(src)))
         return yp, src
+
+    def tmem_probe(self, n_blocks=0):
+        """(mismatches, cycles per 8-double TMEM load, per store) of the Tensor-Memory self-test (cb_tmem_probe)."""
+        bad = C.c_int(-1)
+        cyc = (C.c_longlong * 2)()
+        self._check(self._lib.cb_tmem_probe(self._h, int(n_blocks), C.byref(bad), cyc))
+        return bad.value, int(cyc[0]), int(cyc[1])
 
     def destroy_model(self, dm):
         self._lib.cb_model_destroy(self._h, dm)
@@ -169,8 +177,9 @@ class GpuContext:
         src = np.ascontiguousarray(src)
         self._check(self._lib.cb_set_sources(self._h, dm, len(q_src), _dp(q_src), _dp(src)))
 
-    def project(self, hss, dms, want_delta=True, q_slices=None):
-        """`q_slices` (q-sharding of loop B): per cosmology a (lo, hi) slice of the integration grid."""
+    def project(self, hss, dms, want_delta=True, q_slices=None, out=None):
+        """`q_slices` (q-sharding of loop B): per cosmology a (lo, hi) slice of the integration grid.
+        `out`: list of (n_q, n_l, n_src) arrays to receive Delta_p_l_k in place (e.g. page-locked and reused by the caller)."""
         n = len(hss)
         dm_arr = (C.c_void_p * n)(*dms)
         sl = [slice(None)] * n if q_slices is None else [slice(lo, hi) for lo, hi in q_slices]
@@ -179,10 +188,12 @@ class GpuContext:
         nq = (C.c_int * n)(*[len(q) for q in qs])
         q_p = (c_double_p * n)(*[_dp(a) for a in qs])
         dq_p = (c_double_p * n)(*[_dp(a) for a in dqs])
-        out, out_p = [], (c_double_p * n)()
+        given, out, out_p = out, [], (c_double_p * n)()
         for i, hs in enumerate(hss):
             if want_delta:
-                a = np.zeros((len(qs[i]), self.n_l, hs.model.n_src))
+                shape = (len(qs[i]), self.n_l, hs.model.n_src)
+                a = given[i] if given is not None else np.zeros(shape)
+                assert a.shape == shape and a.flags.c_contiguous and a.dtype == np.float64
                 out.append(a)
                 out_p[i] = _dp(a)
             else:

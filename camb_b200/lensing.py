@@ -31,6 +31,25 @@ def load_highl_template(path):
     return out
 
 
+_default_template = None
+
+
+def default_highl_template():
+    """highL_CL_template of the reference host (config.f90:93-116): the file named by CAMB_HIGHL_TEMPLATE (a CAMB
+    installation's HighLExtrapTemplate_lenspotentialCls.dat) or the copy of its four used columns shipped as package data
+    (camb_b200/data/highl_template.npz, made by tests/golden/make_template_fixture.py)."""
+    global _default_template
+    if _default_template is None:
+        import os
+        path = os.environ.get("CAMB_HIGHL_TEMPLATE")
+        if path:
+            _default_template = np.ascontiguousarray(load_highl_template(path))
+        else:
+            f = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "highl_template.npz")
+            _default_template = np.ascontiguousarray(np.load(f)["template"])
+    return _default_template
+
+
 def lensing_extrap_lmax(Max_l, lens_output_margin, lens_accuracy_boost, accuracy_target=1):
     output_lmax = Max_l - lens_output_margin
     margin = EXTRAP_MARGIN

@@ -114,6 +114,23 @@ def synthetic_lcdm_batch(n, seed=20261017, lmax=2500, lensing=True, massless=Tru
     return out
 
 
+def synthetic_config1_batch(n, seed=20261017):
+    """BASELINE.json configs[0] as a batch: the params.ini cosmology (one massive neutrino, n_src = 2, no lensing, lmax 2500,
+    k_eta_max 6250) with the SURVEY.md 8(d) box around it for the five LCDM parameters."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        p = params_ini_config1()
+        p.ombh2 = rng.uniform(0.0205, 0.0240)
+        p.omch2 = rng.uniform(0.105, 0.135)
+        p.H0 = rng.uniform(60.0, 76.0)
+        p.optical_depth = rng.uniform(0.03, 0.09)
+        p.ns = rng.uniform(0.92, 1.00)
+        p.As = np.exp(rng.uniform(2.9, 3.2)) * 1e-10
+        out.append(p)
+    return out
+
+
 def tensor_params(r=0.1, nt=0.0, lmax_tensor=600, k_eta_max_tensor=1200.0, massless=True, accuracy_boost=1.0):
     """The tensor pass of CAMB_GetResults (camb.f90:85-104: WantScalars=F, WantTransfer=F) on the
     planck_2018.ini cosmology: tensor T/E/B sources, C_l^{TT,EE,BB,TE} to Max_l_tensor."""

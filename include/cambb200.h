@@ -266,11 +266,16 @@ int  cb_device_buffer(cb_ctx* ctx, cb_dmodel* dm, int which, void** ptr, size_t*
 /* Test hook: ONE evaluation of the device `derivs` (equations.f90:2273-2949) with its source output branch (:2775-2947)
  * for wavenumber q at conformal time tau on the state y(1:n), in the layout SetupScalarArrayIndices gives for the four
  * approximation flags flags4 = {TightCoupling, no_nu_multpoles, no_phot_multpoles, high_ktau_neutrino_approx}.  Runs the
- * same template instances as cb_evolve (lanes = 8 or 32 lanes per mode; lean = 1: the massless-neutrino LCDM variant).
+ * same template instances as cb_evolve (lanes = 8 or 32 lanes per mode; lean = 1: the massless-neutrino LCDM variant;
+ * lanes = 1: the derivs of the mode-per-lane kernel, lean models and modes of its size classes only).
  *   yprime double[n]; sources double[3] (T, E, lensing potential).
  * Used by the parity tests against tests/golden/symbolic_derivs.json (values authored by the reference's camb/symbolic.py). */
 int  cb_debug_derivs(cb_ctx* ctx, cb_dmodel* dm, double q, double tau, const int* flags4, const double* y, int n, int lanes, int lean,
                      double* yprime, double* sources);
+/* Test hook: self-test of the Tensor-Memory vector storage of the mode-per-lane evolve kernel (tmem.cuh): pattern write /
+ * read-back of every thread's private TMEM row on n_blocks SMs (0 = all); cycles[0], cycles[1] = SM cycles per 8-double
+ * tcgen05.ld / tcgen05.st. */
+int  cb_tmem_probe(cb_ctx* ctx, int n_blocks, int* mismatches, long long* cycles);
 /* sizeof() of the boundary structs as this library was compiled, for binding checks:
  * 0 cb_params, 1 cb_model, 2 cb_modes, 3 cb_bessel, 4 cb_range, 5 cb_accuracy, 6 cb_lens_plan, 7 cb_window. */
 size_t cb_abi_sizeof(int which);

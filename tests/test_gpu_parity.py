@@ -438,3 +438,11 @@ def test_integrator_failure_is_reported_like_the_reference(ctx):
     _, _, st = ctx.evolve([hs2], [dm2])
     assert st[0][:, 0].min() > 100
     ctx.destroy_model(dm2)
+
+
+def test_tensor_memory_vector_storage_selftest(ctx):
+    """tmem.cuh (tcgen05.ld / tcgen05.st as thread-private vector storage of the mode-per-lane evolve kernel): every thread's
+    256-double row written and read back on every SM."""
+    bad, cyc_ld, cyc_st = ctx.tmem_probe()
+    print("TMEM probe: mismatches", bad, "cycles per 8-double load", cyc_ld, "store", cyc_st)
+    assert bad == 0

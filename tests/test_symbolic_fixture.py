@@ -88,7 +88,7 @@ def test_oracle_derivs_and_sources_match_symbolic(fixture):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("lanes,lean", [(32, False), (8, False), (8, True), (32, True)])
+@pytest.mark.parametrize("lanes,lean", [(32, False), (8, False), (8, True), (32, True), (1, True)])
 def test_cuda_derivs_and_sources_match_symbolic(fixture, lanes, lean):
     from camb_b200.gpu import GpuContext
     ctx = GpuContext(0)
@@ -99,6 +99,8 @@ def test_cuda_derivs_and_sources_match_symbolic(fixture, lanes, lean):
             hs = host_state("sym_" + st["cosmo"], COSMOS[st["cosmo"]])
             if st["cosmo"] not in dms:
                 dms[st["cosmo"]] = ctx.create_model(hs)
+            if lanes == 1 and st["layout"]["lmaxg"] not in (11, 13, 24):
+                continue   # the mode-per-lane kernel has two size classes; the deep low-k hierarchies run the lane-group kernel
             yp, src = ctx.debug_derivs(dms[st["cosmo"]], st["q"], st["tau"], st["y"], lanes=lanes, lean=lean)
             worst = max(worst, check_state(st, yp, src, f"cuda G={lanes} lean={lean}"))
     finally:
