@@ -238,7 +238,7 @@ def one_cosmology_latency(ctx, reps=5):
     ctx.set_bessel(hs)
     plan, template = L.plan_for(hs), L.default_highl_template()
     out = {}
-    for label, opt in (("mode_per_lane", 3), ("lane_group_32", 0)):
+    for label, opt in (("register_lane_groups", 1), ("mode_per_lane_tmem", 3), ("general_32_lanes", 0)):
         ctx.set_option("use_reg_kernel", opt)
         best = 1e30
         for _ in range(reps + 1):
@@ -253,7 +253,7 @@ def one_cosmology_latency(ctx, reps=5):
             torch.cuda.synchronize()
             best = min(best, time.perf_counter() - t0)
         out[label] = 1e3 * best
-    ctx.set_option("use_reg_kernel", 3)
+    ctx.set_option("use_reg_kernel", 1)
     return out
 
 
@@ -426,7 +426,7 @@ def main():
                     "returns": "iCl, Delta_p_l_k" + (", lensed C_l" if lensing else "")},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "kernel": "cb_evolve_mpl_kernel (+ cb_evolve_reg_kernel for the deep low-k hierarchies)" if lean else "cb_evolve_kernel",
+            "roofline": {"bound": "fp64", "kernel": "cb_evolve_reg_kernel (three static layouts)" if lean else "cb_evolve_kernel",
                          "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": ach / fp64_peak if fp64_peak else None, "traffic": None,
                          "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",

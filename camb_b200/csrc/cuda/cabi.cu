@@ -104,10 +104,11 @@ struct cb_ctx {
     int lanes_per_mode = 0;              // 0 = automatic
     int class_lanes[CB_N_CLASSES] = {};  // per slab-size class override of the lane width (0 = lanes_per_mode)
     int async_model_upload = 0;          // cb_model_create returns without waiting for its host->device copies
-    // lean launches: 0 = the general kernel only; 1 = register kernel for every mode that fits a static layout; 2 = the same
-    // but the 16-lane layout's modes through the general kernel; 3 (default) = mode-per-lane kernel for the 48-element
-    // classes, register kernel for the deep low-k hierarchies
-    int use_reg_kernel = 3;
+    // lean launches: 0 = the general kernel only; 1 (default) = register kernel for every mode that fits a static layout;
+    // 2 = the same but the 16-lane layout's modes through the general kernel; 3 = mode-per-lane Tensor-Memory kernel for the
+    // 48-element classes, register kernel for the deep low-k hierarchies (equal throughput at >= 192 sets per call,
+    // slower below: DESIGN.md section 4.1)
+    int use_reg_kernel = 1;
     cudaEvent_t stage_ev[4][2] = {};     // per-stage kernel brackets of the last calls (evolve, spline-k, LOS, C_l)
     DModel* h_models = nullptr;   size_t cap_h_models = 0;   // page-locked staging
     DModeItem* h_items = nullptr; size_t cap_h_items = 0;

@@ -80,6 +80,7 @@ __constant__ double m_dp_c[7] = {0, 1.0 / 5.0, 3.0 / 10.0, 4.0 / 5.0, 8.0 / 9.0,
 // for what does not fit (the cold half).
 struct MCtl {
     const DModel* M;
+    double grhob, grhoc, grhornomass, grhog, grhov, g_over_b, b_over_g;   // the model constants derivs reads at every evaluation
     double max_step_size, current_step_size, estimated_error, previous_xend;
     double tau, goal, seg_end, next_switch, tol1;
     double t_tight, t_ktau, t_no_nu;
@@ -103,6 +104,7 @@ struct Store {
 };
 
 __device__ __forceinline__ int m_imax(int a, int b) { return a > b ? a : b; }
+__device__ __noinline__ double div_out_of_line(double a, double b) { return a / b; }
 
 __device__ __forceinline__ int ref_neq(const MCtl& C) {   // SetupScalarArrayIndices, equations.f90:585-701 (statistics)
     int n = 4;
@@ -203,7 +205,7 @@ __device__ void plan_switches_mpl(const DModel& M, MCtl& C) {   // equations.f90
 // The switch that fires at C.next_switch (if-chain order of equations.f90:339-441).  Nothing moves in the static layout:
 // flags change, dropped multipoles are zeroed and the tight-coupling seeds (:349-363) written by the warp-uniform patch
 // step that follows the schedule (ymod).
-__device__ void apply_switch_mpl(MCtl& C) {
+__device__ __noinline__ void apply_switch_mpl(MCtl& C) {
     const DModel& M = *C.M;
     const double noSwitch = M.tau0 + 1, next_switch = C.next_switch, tau = C.tau;
     int which;
@@ -246,7 +248,7 @@ __device__ __forceinline__ void dp45_begin_mpl(MCtl& C, double xend) {   // Rung
 // CalcScalarSources cmbmain.f90:998-1074 / GetTransfer :1167-1188 as a state machine, advanced per lane until the mode
 // needs a Runge-Kutta attempt, an output evaluation, or the queue is empty.
 template <class L>
-__device__ void advance_schedule_mpl(const DModel* __restrict__ models, const DModeItem* __restrict__ items, int n_items,
+__device__ __noinline__ void advance_schedule_mpl(const DModel* __restrict__ models, const DModeItem* __restrict__ items, int n_items,
                                      unsigned int* counter, int* error_flag, MCtl& C, const Store& S, int debug_single) {
     for (;;) {
         if (C.phase == PH_FETCH) {
@@ -256,6 +258,8 @@ __device__ void advance_schedule_mpl(const DModel* __restrict__ models, const DM
             const DModeItem& it = items[item];
             const DModel& M = models[it.model];
             C.M = &M;
+            C.grhob = M.grhob; C.grhoc = M.grhoc; C.grhornomass = M.grhornomass; C.grhog = M.grhog; C.grhov = M.grhov;
+            C.g_over_b = M.grhog / M.grhob; C.b_over_g = 0.75 / (M.grhog / M.grhob);
             C.q_ix = it.q_ix; C.transfer_only = it.transfer_only;
             C.q = it.q; C.k = it.q; C.k2 = it.q * it.q; C.kinv = 1.0 / it.q; C.k2inv = 1.0 / C.k2;
             C.lmaxg = it.lmaxg; C.lmaxgpol = it.lmaxgpol; C.lmaxnr = it.lmaxnr;
@@ -401,40 +405,30 @@ __device__ __forceinline__ void store_vec_block(const Store& S, int v, int b, co
     }
 }
 
-// Stage input of evaluation T (0: the state itself; 1..6: y + h sum_j a_Tj k_j, RungeKuttaDP45.f90:306-324), all 48
-// elements into registers.  Same nesting of the multiply-adds as the lane-group kernels.
-template <int T>
-__device__ __forceinline__ void stage_input(const Store& S, double h, double (&in)[NV]) {
+// Stage input of evaluation t (0: the state itself; 1..6: y + h sum_j a_tj k_j, RungeKuttaDP45.f90:306-324), all 48
+// elements into registers.  ONE code path for the seven evaluations: the coefficients of the row come from constant
+// memory (zeros for the stages a row does not use -- fma(0, k, acc) returns acc exactly, so the result has the bits of
+// the reference's nesting a_t1 k1 first, highest stage last), which keeps the hot loop inside the instruction cache.
+__device__ __forceinline__ void stage_input(const Store& S, int t, double h, double (&in)[NV]) {
+    const double c1 = m_dp_a[t][0], c2 = m_dp_a[t][1], c3 = m_dp_a[t][2], c4 = m_dp_a[t][3], c5 = m_dp_a[t][4], c6 = m_dp_a[t][5];
+    const double hh = t == 0 ? 0.0 : h;
 #pragma unroll
     for (int b = 0; b < NB; b++) {
-        double y[8], k1[8], k2[8], k3[8], k4[8], k5[8], k6[8];
-        tmem::Raw8 qy, q1, q2, q3, q4, q5, q6;
-        load_issue(S, VY, b, qy);
-        if (T >= 1) load_issue(S, VK1, b, q1);
-        if (T >= 2 && T <= 5) load_issue(S, VK2, b, q2);
-        if (T >= 3) load_issue(S, VK3, b, q3);
-        if (T >= 4) load_issue(S, VK4, b, q4);
+        double y[8], k1[8], k2[8], k3[8], k4[8];
+        tmem::Raw8 qy, q1, q2, q3, q4;
+        tmem::ld8_issue(S.col(VY, b), qy); tmem::ld8_issue(S.col(VK1, b), q1); tmem::ld8_issue(S.col(VK2, b), q2);
+        tmem::ld8_issue(S.col(VK3, b), q3); tmem::ld8_issue(S.col(VK4, b), q4);
         tmem::wait_ld();
-        load_take(S, VY, b, qy, y);
-        if (T >= 1) load_take(S, VK1, b, q1, k1);
-        if (T >= 2 && T <= 5) load_take(S, VK2, b, q2, k2);
-        if (T >= 3) load_take(S, VK3, b, q3, k3);
-        if (T >= 4) load_take(S, VK4, b, q4, k4);
-        if (T >= 5) load_take(S, VK5, b, q5, k5);
-        if (T >= 6) load_take(S, VK6, b, q6, k6);
+        tmem::ld8_take(qy, y); tmem::ld8_take(q1, k1); tmem::ld8_take(q2, k2); tmem::ld8_take(q3, k3); tmem::ld8_take(q4, k4);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            double v;
-            if (T == 0) v = y[i];
-            else if (T == 1) v = fma(h, m_dp_a[1][0] * k1[i], y[i]);
-            else if (T == 2) v = fma(h, fma(m_dp_a[2][1], k2[i], m_dp_a[2][0] * k1[i]), y[i]);
-            else if (T == 3) v = fma(h, fma(m_dp_a[3][2], k3[i], fma(m_dp_a[3][1], k2[i], m_dp_a[3][0] * k1[i])), y[i]);
-            else if (T == 4) v = fma(h, fma(m_dp_a[4][3], k4[i], fma(m_dp_a[4][2], k3[i], fma(m_dp_a[4][1], k2[i], m_dp_a[4][0] * k1[i]))), y[i]);
-            else if (T == 5)
-                v = fma(h, fma(m_dp_a[5][4], k5[i], fma(m_dp_a[5][3], k4[i], fma(m_dp_a[5][2], k3[i], fma(m_dp_a[5][1], k2[i], m_dp_a[5][0] * k1[i])))), y[i]);
-            else
-                v = fma(h, fma(m_dp_a[6][5], k6[i], fma(m_dp_a[6][4], k5[i], fma(m_dp_a[6][3], k4[i], fma(m_dp_a[6][2], k3[i], m_dp_a[6][0] * k1[i])))), y[i]);
-            in[8 * b + i] = v;
+            double acc = c1 * k1[i];
+            acc = fma(c2, k2[i], acc);
+            acc = fma(c3, k3[i], acc);
+            acc = fma(c4, k4[i], acc);
+            acc = fma(c5, S.s(VK5, 8 * b + i), acc);
+            acc = fma(c6, S.s(VK6, 8 * b + i), acc);
+            in[8 * b + i] = fma(hh, acc, y[i]);
         }
     }
 }
@@ -527,13 +521,14 @@ __device__ __forceinline__ void derivs_preamble(const double (&in)[NV], MCtl& C,
     const double k = C.k, kinv = C.kinv, k2inv = C.k2inv;
     double a, cs2, opacity, dopacity = 0;
     thermo_values(M, tau, a, cs2, opacity, dopacity, true);
-    const double ainv = 1.0 / a, a2inv = ainv * ainv;
-    const double grhob_t = M.grhob * ainv, grhoc_t = M.grhoc * ainv, grhor_t = M.grhornomass * a2inv, grhog_t = M.grhog * a2inv;
-    const double grhov_t = M.grhov * (a * a);
+    const double ainv = __drcp_rn(a), a2inv = ainv * ainv;
+    const double grhob_t = C.grhob * ainv, grhoc_t = C.grhoc * ainv, grhor_t = C.grhornomass * a2inv, grhog_t = C.grhog * a2inv;
+    const double grhov_t = C.grhov * (a * a);
     const double grho_matter = grhob_t + grhoc_t;
     const double grho = grho_matter + grhor_t + grhog_t + grhov_t;
     const double adotoa = sqrt(grho * (1.0 / 3.0));
-    const double cothxor = 1.0 / tau;
+    const double adotoa_inv = __drcp_rn(adotoa);   // one reciprocal for the divisions by adotoa (an ulp per quotient, as evolve_reg.cu)
+    const double cothxor = __drcp_rn(tau);
     const double etak = in[0], clxc = in[1], clxb = in[2], vb = in[3];
     double clxg = in[4], qg = in[5], pig = in[6];
     const double E2 = in[L::SE];
@@ -543,7 +538,7 @@ __device__ __forceinline__ void derivs_preamble(const double (&in)[NV], MCtl& C,
     double dgrho = dgrho_matter;
     double z = 0, dz = 0;
     if (no_nu) {
-        z = (0.5 * dgrho * kinv + etak) / adotoa;
+        z = (0.5 * dgrho * kinv + etak) * adotoa_inv;
         dz = -adotoa * z - 0.5 * dgrho * kinv;
         clxr = -4 * dz * kinv;
         qr = -4.0 / 3 * z;
@@ -551,7 +546,7 @@ __device__ __forceinline__ void derivs_preamble(const double (&in)[NV], MCtl& C,
     }
     if (no_phot) {
         if (!no_nu) {
-            z = (0.5 * dgrho * kinv + etak) / adotoa;
+            z = (0.5 * dgrho * kinv + etak) * adotoa_inv;
             dz = -adotoa * z - 0.5 * dgrho * kinv;
             clxg = -4 * dz * kinv - 4 * kinv * opacity * (vb + z);
             qg = -4.0 / 3 * z;
@@ -560,9 +555,8 @@ __device__ __forceinline__ void derivs_preamble(const double (&in)[NV], MCtl& C,
     } else if (tight) pig = 0;
     dgrho = dgrho + grhog_t * clxg + grhor_t * clxr;
     dgq = dgq + grhog_t * qg + grhor_t * qr;
-    const double g_over_b = M.grhog / M.grhob;
-    const double photbar = g_over_b * ainv, pb43 = 4.0 / 3 * photbar;
-    z = (0.5 * dgrho * kinv + etak) / adotoa;
+    const double photbar = C.g_over_b * ainv, pb43 = 4.0 / 3 * photbar, pb43_inv = C.b_over_g * a;
+    z = (0.5 * dgrho * kinv + etak) * adotoa_inv;
     const double sigma = (z + 1.5 * dgq * k2inv);
     const double clxcdot = -k * z, clxbdot = -k * (z + vb), clxgdot = -k * (4.0 / 3.0 * z + qg);
     const double delta_p_b = cs2 * clxb;
@@ -570,25 +564,26 @@ __device__ __forceinline__ void derivs_preamble(const double (&in)[NV], MCtl& C,
     if (tight) {
         const double gpres = (grhor_t + grhog_t) * (1.0 / 3.0) - grhov_t;
         const double adotdota = (adotoa * adotoa - gpres) / 2;
-        pig = 32.0 / 45 / opacity * k * (sigma + vb);
-        const double slip = -(2 * adotoa / (1 + pb43) + dopacity / opacity) * (vb - 3.0 / 4 * qg) +
-                            (-adotdota * vb - k / 2 * adotoa * clxg + k * (cs2 * clxbdot - clxgdot / 4)) / (opacity * (1 + pb43));
+        const double opinv = __drcp_rn(opacity), op1 = __drcp_rn(1 + pb43);
+        pig = 32.0 / 45 * opinv * k * (sigma + vb);
+        const double slip = -(2 * adotoa * op1 + dopacity * opinv) * (vb - 3.0 / 4 * qg) +
+                            (-adotdota * vb - k / 2 * adotoa * clxg + k * (cs2 * clxbdot - clxgdot / 4)) * (opinv * op1);
         const double dgs = grhog_t * pig + grhor_t * pir;
-        sigmadot = -2 * adotoa * sigma - dgs / k + etak;
+        sigmadot = -2 * adotoa * sigma - dgs * kinv + etak;
         qgdot = k * (clxg / 4.0 - pig / 2.0) + opacity * slip;
-        pig = 32.0 / 45 / opacity * k * (sigma + 3.0 * qg / 4.0) * (1 + (dopacity * 11.0 / 6.0 / (opacity * opacity))) +
-              (32.0 / 45.0 / (opacity * opacity)) * k * (sigmadot + 3.0 * qgdot / 4.0) * (-11.0 / 6.0);
-        pigdot = -(32.0 / 45.0) * (dopacity / (opacity * opacity)) * k * (sigma + 3.0 * qg / 4.0) *
-                     (1 + dopacity * 11.0 / 6.0 / (opacity * opacity)) +
-                 (32.0 / 45.0 / opacity) * k * (sigmadot + 3.0 * qgdot / 4.0) * (1 + (11.0 / 6.0) * (dopacity / (opacity * opacity)));
-        vbdot = (-adotoa * vb + cs2 * k * clxb + k / 4 * pb43 * (clxg - 2 * 1.0 * pig)) / (1 + pb43);
-        vbdot = vbdot + pb43 / (1 + pb43) * slip;
+        const double dop2 = dopacity * (opinv * opinv);
+        pig = 32.0 / 45 * opinv * k * (sigma + 3.0 * qg / 4.0) * (1 + (dop2 * 11.0 / 6.0)) +
+              (32.0 / 45.0 * (opinv * opinv)) * k * (sigmadot + 3.0 * qgdot / 4.0) * (-11.0 / 6.0);
+        pigdot = -(32.0 / 45.0) * dop2 * k * (sigma + 3.0 * qg / 4.0) * (1 + dop2 * 11.0 / 6.0) +
+                 (32.0 / 45.0 * opinv) * k * (sigmadot + 3.0 * qgdot / 4.0) * (1 + (11.0 / 6.0) * dop2);
+        vbdot = (-adotoa * vb + cs2 * k * clxb + k / 4 * pb43 * (clxg - 2 * 1.0 * pig)) * op1;
+        vbdot = vbdot + pb43 * op1 * slip;
         if (live) { C.pig = pig; C.pigdot = pigdot; }   // the side effect of derivs the tight-coupling switch reads (equations.f90:2517, 2526)
     } else {
         vbdot = -adotoa * vb + k * delta_p_b - photbar * opacity * (4.0 / 3 * vb - qg);
     }
     const double denl1k = m_denl[1] * k;
-    qgdot = 4.0 / 3 * (-vbdot - adotoa * vb + delta_p_b * k) / pb43 + (denl1k * 1.0) * clxg - (denl1k * 1.0 * 2.0) * pig;
+    qgdot = 4.0 / 3 * (-vbdot - adotoa * vb + delta_p_b * k) * pb43_inv + (denl1k * 1.0) * clxg - (denl1k * 1.0 * 2.0) * pig;
     const double polter = pig * 0.1 + 9.0 / 15 * E2;
     const double clxrdot = -k * (4.0 / 3.0 * z + qr);
     R.etakdot = 0.5 * dgq; R.clxcdot = clxcdot; R.clxbdot = clxbdot; R.vbdot = vbdot; R.clxgdot = clxgdot; R.qgdot = qgdot;
@@ -605,10 +600,21 @@ __device__ __forceinline__ void derivs_preamble(const double (&in)[NV], MCtl& C,
 }
 
 // Output branch of derivs, equations.f90:2775-2947: sources (out_mode 1) or the 13 transfer variables (2), per lane.
-template <class L>
-__device__ void derivs_output(const double (&in)[NV], const MCtl& C, double tau, int fl, const Rows& R, const Pre& P, const RowOut& O,
-                              int out_mode, double* src_out = nullptr) {
-    const DModel& M = *C.M;
+// (Out of line: its arguments travel in one block, so that the caller's state stays in registers.)
+struct OutArgs {
+    const DModel* M;
+    double k, k2, grhov, tau;
+    int q_ix, j, itf, fl, out_mode;
+    double* src_out;
+    Rows R; Pre P; RowOut O;
+};
+__device__ __noinline__ void derivs_output(const OutArgs& A) {
+    const DModel& M = *A.M;
+    const Rows& R = A.R; const Pre& P = A.P; const RowOut& O = A.O;
+    const int fl = A.fl, out_mode = A.out_mode;
+    const double tau = A.tau;
+    double* src_out = A.src_out;
+    struct { double k, k2, grhov; int q_ix, j, itf; } C = {A.k, A.k2, A.grhov, A.q_ix, A.j, A.itf};
     const bool tight = fl & F_TIGHT, no_nu = fl & F_NO_NU, no_phot = fl & F_NO_PHOT, ktau = fl & F_KTAU;
     const double k = C.k, k2 = C.k2, adotoa = P.adotoa, a = P.a, opacity = P.opacity, dopacity = P.dopacity;
     const double grhob_t = P.grhob_t, grhoc_t = P.grhoc_t, grhor_t = P.grhor_t, grhog_t = P.grhog_t;
@@ -616,7 +622,7 @@ __device__ void derivs_output(const double (&in)[NV], const MCtl& C, double tau,
     const double sigma = P.sigma, dgrho = P.dgrho, dgq = P.dgq, dz = P.dz;
     double E2v = 0, E3v = 0, Ed2 = 0, Ed3 = 0, octgdot = 0, pigdot = P.pigdot_t, qgdot = R.qgdot, qrdot = R.qrdot;
     double pirdot = ktau ? R.pirdot_k : O.rN2;
-    if (!(tight || no_phot)) { E2v = P.E2; E3v = in[L::SE + 1]; Ed2 = O.rE2; Ed3 = O.rE3; pigdot = O.rJ2; octgdot = O.rJ3; }
+    if (!(tight || no_phot)) { E2v = P.E2; Ed2 = O.rE2; Ed3 = O.rE3; pigdot = O.rJ2; octgdot = O.rJ3; }
     if (no_nu) { pirdot = 0; qrdot = -4 * dz / 3; }
     if (no_phot) { pigdot = 0; octgdot = 0; qgdot = -4 * dz / 3; }
     else if (tight) {
@@ -626,7 +632,7 @@ __device__ void derivs_output(const double (&in)[NV], const MCtl& C, double tau,
         octgdot = 0;
     }
     (void)E3v;
-    const double grhov_t = M.grhov * (a * a);
+    const double grhov_t = C.grhov * (a * a);
     const double grho_matter = grhob_t + grhoc_t;
     const double grho = grho_matter + grhor_t + grhog_t + grhov_t;
     const double gpres = (grhor_t + grhog_t) * (1.0 / 3.0) - grhov_t;
@@ -684,7 +690,8 @@ template <class L>
 __device__ void run_class(const DModel* __restrict__ models, const DModeItem* __restrict__ items, int n_items, unsigned int* counter,
                           int* error_flag, const Store& S, int debug_single) {
     MCtl C;
-    C.phase = PH_FETCH; C.ymod = 0; C.M = models; C.flags = 0; C.k = 1; C.kinv = 1; C.k2inv = 1; C.k2 = 1; C.tau = 1; C.h = 0; C.ymax = 0;
+    C.phase = PH_FETCH; C.ymod = 0; C.M = models; C.flags = 0;
+    C.grhob = C.grhoc = C.grhornomass = C.grhog = C.grhov = C.g_over_b = C.b_over_g = 1; C.k = 1; C.kinv = 1; C.k2inv = 1; C.k2 = 1; C.tau = 1; C.h = 0; C.ymax = 0;
     C.lmaxg = L::MAXLJ; C.lmaxgpol = L::MAXLE; C.lmaxnr = L::MAXLN; C.poltruncfac = 1; C.s = 0; C.out_kind = 0;
     {   // a clean slate: whatever the previous class left in this thread's vectors must not reach the selects below as NaN
         double zero[8];
@@ -692,7 +699,7 @@ __device__ void run_class(const DModel* __restrict__ models, const DModeItem* __
         for (int i = 0; i < 8; i++) zero[i] = 0;
 #pragma unroll
         for (int v = VY; v <= VYT; v++)
-#pragma unroll
+#pragma unroll 1
             for (int b = 0; b < NB; b++) store_vec_block(S, v, b, zero);
         tmem::wait_st();
     }
@@ -703,13 +710,16 @@ __device__ void run_class(const DModel* __restrict__ models, const DModeItem* __
         int out_mode = OUT_NONE;
         double tev;
         if (t == 0) {
-            if (C.phase == PH_FETCH || C.phase == PH_NEXT_GOAL || C.phase == PH_PLAN)
-                advance_schedule_mpl<L>(models, items, n_items, counter, error_flag, C, S, debug_single);
+            if (C.phase == PH_FETCH || C.phase == PH_NEXT_GOAL || C.phase == PH_PLAN) {
+                MCtl T = C;   // the out-of-line schedule works on a copy in thread-local memory; the loop's own copy stays in registers
+                advance_schedule_mpl<L>(models, items, n_items, counter, error_flag, T, S, debug_single);
+                C = T;
+            }
             __syncwarp();
             if (__any_sync(FULL, C.ymod != 0)) {   // patches of the state the schedule asked for, applied warp-wide
                 const int ym = C.ymod;
                 double ymax = 0;
-#pragma unroll
+#pragma unroll 1
                 for (int b = 0; b < NB; b++) {
                     double y[8];
                     tmem::ld8(S.col(VY, b), y);
@@ -753,20 +763,14 @@ __device__ void run_class(const DModel* __restrict__ models, const DModeItem* __
         double in[NV];
         const double h = C.h;
         __syncwarp();   // the warp is converged again after the per-lane schedule / step control: Tensor-Memory accesses are warp-collective
-        switch (t) {
-            case 0: stage_input<0>(S, h, in); break;
-            case 1: stage_input<1>(S, h, in); break;
-            case 2: stage_input<2>(S, h, in); break;
-            case 3: stage_input<3>(S, h, in); break;
-            case 4: stage_input<4>(S, h, in); break;
-            case 5: stage_input<5>(S, h, in); break;
-            default: stage_input<6>(S, h, in); break;
-        }
+        stage_input(S, t, h, in);
         // ---- derivs ----
         const int fl = C.flags;
         Rows R;
-        Pre P;
-        derivs_preamble<L>(in, C, tev, fl, active, R, P);
+        {
+            Pre P;   // (the output branch recomputes it: keeping its 27 values alive through the rows costs more than that)
+            derivs_preamble<L>(in, C, tev, fl, active, R, P);
+        }
         RowOut O;
         __syncwarp();
         // rows, block by block, straight to their destination: k1 (first derivative), k_{t+1} (stages), nothing (outputs)
@@ -801,7 +805,11 @@ __device__ void run_class(const DModel* __restrict__ models, const DModeItem* __
                 C.nderivs++;
                 if (first_deriv) { C.s = 1; C.neq_evals += C.neq; }
                 else {
-                    derivs_output<L>(in, C, tev, fl, R, P, O, out_mode);
+                    OutArgs A;
+                    { Rows R2; derivs_preamble<L>(in, C, tev, fl, false, R2, A.P); }
+                    A.M = C.M; A.k = C.k; A.k2 = C.k2; A.grhov = C.grhov; A.tau = tev; A.q_ix = C.q_ix; A.j = C.j; A.itf = C.itf; A.fl = fl;
+                    A.out_mode = out_mode; A.src_out = nullptr; A.R = R; A.O = O;
+                    derivs_output(A);
                     if (out_mode == OUT_TR) C.itf++;
                     C.stage = C.next_stage;
                     C.phase = PH_NEXT_GOAL;
@@ -813,8 +821,8 @@ __device__ void run_class(const DModel* __restrict__ models, const DModeItem* __
             double temp = 0, ymax = 0;
             bool accept = false;
             __syncwarp();
-            // first pass: the error norm
-#pragma unroll
+            // first pass: the error norm (rolled over the blocks: nothing here needs compile-time element numbers)
+#pragma unroll 1
             for (int b = 0; b < NB; b++) {
                 double y[8], k1[8], k7[8], k3[8], k4[8];
                 tmem::Raw8 qy, q1, q7, q3, q4;
@@ -830,16 +838,18 @@ __device__ void run_class(const DModel* __restrict__ models, const DModeItem* __
                     e = fma(m_dp_a[0][3], k4[i], e);
                     e = fma(m_dp_a[0][4], S.s(VK5, 8 * b + i), e);
                     e = fma(m_dp_a[0][5], S.s(VK6, 8 * b + i), e);
+                    // |e| / max(1, |y|), RungeKuttaDP45.f90:341: no division where |y| <= 1 (almost everywhere); the quotient of the
+                    // few large elements (delta_c, delta_b ...) is taken out of line so the 48 unrolled rows stay short
                     e = fabs(e);
                     const double ay = fabs(y[i]);
-                    if (ay > 1.0) e = e / ay;   // e / max(1, |y|), RungeKuttaDP45.f90:341
+                    if (ay > 1.0) e = div_out_of_line(e, ay);
                     temp = fmax(temp, e);
                 }
             }
             const double est = temp * C.css;
             accept = stepping && !(est > C.tol1);
             // second pass: y <- trial state, k1 <- k7 for the lanes that accept
-#pragma unroll
+#pragma unroll 1
             for (int b = 0; b < NB; b++) {
                 double y[8], k1[8], k7[8];
                 tmem::Raw8 qy, q1, q7;
@@ -883,7 +893,9 @@ __device__ void run_class(const DModel* __restrict__ models, const DModeItem* __
                         C.xend_reached = 1;
                         C.first_derivative_valid = 1;
                         if (C.seg_switch) {
-                            apply_switch_mpl(C);
+                            MCtl T = C;
+                            apply_switch_mpl(T);
+                            C = T;
                             C.phase = PH_PLAN;
                         } else if (C.out_kind != OUT_NONE) {
                             C.phase = PH_OUTPUT;
@@ -911,7 +923,9 @@ __global__ void cb_debug_derivs_mpl_kernel(const DModel* __restrict__ model, dou
                                            const double* __restrict__ y, int n, double* yprime, double* sources) {
     if (threadIdx.x != 0) return;
     MCtl C;
-    C.M = model; C.q = q; C.k = q; C.k2 = q * q; C.kinv = 1.0 / q; C.k2inv = 1.0 / C.k2;
+    C.M = model; C.grhob = model->grhob; C.grhoc = model->grhoc; C.grhornomass = model->grhornomass; C.grhog = model->grhog;
+    C.grhov = model->grhov; C.g_over_b = model->grhog / model->grhob; C.b_over_g = 0.75 / C.g_over_b;
+    C.q = q; C.k = q; C.k2 = q * q; C.kinv = 1.0 / q; C.k2inv = 1.0 / C.k2;
     C.lmaxg = lmaxg; C.lmaxgpol = lmaxgpol; C.lmaxnr = lmaxnr; C.poltruncfac = (double)lmaxgpol / m_imax(1, lmaxgpol - 2);
     C.flags = fl; C.pig = 0; C.pigdot = 0; C.q_ix = 0; C.j = 2; C.itf = 1;
     const bool tight = fl & F_TIGHT, no_nu = fl & F_NO_NU, no_phot = fl & F_NO_PHOT, ktau = fl & F_KTAU;
@@ -954,7 +968,10 @@ __global__ void cb_debug_derivs_mpl_kernel(const DModel* __restrict__ model, dou
     }
     RowOut O;
     O.rJ2 = r[6]; O.rJ3 = r[7]; O.rE2 = r[L::SE]; O.rE3 = r[L::SE + 1]; O.rN2 = r[L::SN + 2];
-    derivs_output<L>(in, C, tau, fl, R, P, O, OUT_SRC, sources);
+    OutArgs A;
+    A.M = C.M; A.k = C.k; A.k2 = C.k2; A.grhov = C.grhov; A.tau = tau; A.q_ix = 0; A.j = 2; A.itf = 1; A.fl = fl;
+    A.out_mode = OUT_SRC; A.src_out = sources; A.R = R; A.P = P; A.O = O;
+    derivs_output(A);
 #pragma unroll
     for (int i = 0; i < NV; i++) {
         int j = -1;

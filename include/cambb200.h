@@ -242,6 +242,10 @@ long long cb_launch_count(const cb_ctx* ctx);
  * for a single cosmology) or 0 = chosen from the number of modes in the call (default).
  * "lanes_class0" ... "lanes_class4": the same per slab-size class of cb_evolve (0 = follow lanes_per_mode; experiments only,
  * 8 everywhere is the measured optimum).
+ * "use_reg_kernel": which evolve kernel launches of massless-neutrino LCDM models take: 1 (default) the register-resident
+ * lane-group kernel (evolve_reg.cu) for every mode that fits one of its static layouts, 0 the general shared-memory kernel
+ * (evolve.cu) only, 3 the mode-per-lane Tensor-Memory kernel (evolve_mpl.cu) for the 48-element classes.  Other models
+ * always take the general kernel.
  * "async_model_upload" = 1: cb_model_create queues its host->device copies and returns; the caller keeps the cb_model arrays
  * alive and unchanged until the next cb_evolve / cb_project / cb_cl* call on the context returns (a Fortran host's
  * allocatables outlive cmbmain anyway).  Default 0: the arrays may be freed as soon as cb_model_create returns. */

@@ -10,7 +10,7 @@ ix = {}
 for i, h in enumerate(hdr):
     ix.setdefault(h, i)
 S, I = ix['# Samples'], ix['Instructions Executed']
-src = open("camb_b200/csrc/cuda/evolve_reg.cu").read().splitlines()
+src = open(sys.argv[3] if len(sys.argv) > 3 else "camb_b200/csrc/cuda/evolve_reg.cu").read().splitlines()
 # region boundaries from the function starts of evolve_reg.cu
 marks = []
 for n, line in enumerate(src, 1):

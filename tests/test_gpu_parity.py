@@ -446,3 +446,21 @@ def test_tensor_memory_vector_storage_selftest(ctx):
     bad, cyc_ld, cyc_st = ctx.tmem_probe()
     print("TMEM probe: mismatches", bad, "cycles per 8-double load", cyc_ld, "store", cyc_st)
     assert bad == 0
+
+
+@pytest.mark.parametrize("path", [0, 1, 3])
+def test_evolve_kernel_variants_agree(ctx, path):
+    """The three evolve kernels of lean launches (general shared-memory kernel, register-resident lane groups, mode-per-lane
+    with the stage vectors in Tensor Memory) against the oracle: C_l to the north-star tolerance, identical step statistics."""
+    hs = host_state("planck_massless_lensing", CASES["planck_massless_lensing"])
+    ctx.set_option("use_reg_kernel", path)
+    try:
+        g = run_gpu(ctx, hs)
+    finally:
+        ctx.set_option("use_reg_kernel", 1)
+    icl_o, aux = O.cls_from_params(hs, nthreads=8)
+    errs = cl_err(g["icl"], icl_o)
+    same = (g["stats"][:, 0] == aux["stats"][:, 0]).mean()
+    print("evolve path", path, "C_l errors", errs, "modes with identical derivs counts", same)
+    assert max(errs) < CL_RTOL, errs
+    assert same > 0.98
