@@ -67,7 +67,7 @@ double cb_fp64_peak_measure(int n_sm, cudaStream_t st, int reps);
 #define CB_TENSOR_CLASS 5
 #define CB_REG_CLASS0 6
 static const size_t kClassSlabLimit[5] = {4714, 5683, 7136, 9557, ~size_t(0)};
-size_t cb_evolve_slab_bytes(int nv, int maxl);   // evolve.cu
+size_t cb_evolve_slab_bytes(int nv, int maxl, int lean);   // evolve.cu
 
 struct cb_dmodel {
     DModel h;                      // host copy with device pointers
@@ -89,8 +89,10 @@ struct cb_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
     std::string err;
-    DBessel bess{};
-    std::vector<void*> bess_owned;
+    DBessel bess{};                // the table in use (a copy of one cache entry)
+    struct BessEntry { unsigned long long key; DBessel B; std::vector<void*> owned; long long stamp; };
+    std::vector<BessEntry> bess_cache;   // resident tables, keyed by content: a batch whose sets have different l samplings
+    long long bess_clock = 0;            // switches between them without re-uploading (26 MB each; evicted oldest-first)
     bool have_bessel = false;
     double ms[4] = {0, 0, 0, 0};
     long long launches = 0;
@@ -239,7 +241,7 @@ void cb_destroy(cb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (void* p : ctx->bess_owned) cudaFree(p);
+    for (auto& e : ctx->bess_cache) for (void* p : e.owned) cudaFree(p);
     for (int i = 0; i < 4; i++) { cudaEventDestroy(ctx->stage_ev[i][0]); cudaEventDestroy(ctx->stage_ev[i][1]); }
     if (ctx->h_models) cudaFreeHost(ctx->h_models);
     if (ctx->h_items) cudaFreeHost(ctx->h_items);
@@ -270,23 +272,51 @@ void cb_destroy(cb_ctx* ctx) {
 
 const char* cb_last_error(const cb_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 
+// Content key of a Bessel table: sizes, the whole l list, the region bounds, the x grid ends and a stride sample of the
+// spline coefficients (the table is a pure function of (l list, x grid), bessels.f90:140-349).
+static unsigned long long bessel_key(const cb_bessel* b) {
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&h](const void* p, size_t n) { const unsigned char* c = (const unsigned char*)p; for (size_t i = 0; i < n; i++) { h ^= c[i]; h *= 1099511628211ull; } };
+    const int n_l_all = b->n_l_all > 0 ? b->n_l_all : b->n_l;
+    mix(&b->n_l, sizeof(int)); mix(&n_l_all, sizeof(int)); mix(&b->nx, sizeof(int)); mix(&b->n_regions, sizeof(int));
+    mix(b->l, sizeof(int) * (size_t)n_l_all);
+    mix(b->regions, sizeof(cb_range) * (size_t)b->n_regions);
+    mix(b->x, sizeof(double)); mix(b->x + b->nx - 1, sizeof(double));
+    const size_t tot = (size_t)4 * (b->nx - 1) * b->n_l, step = tot / 509 + 1;
+    for (size_t i = 0; i < tot; i += step) mix(b->horner + i, sizeof(double));
+    return h;
+}
+
 int cb_set_bessel(cb_ctx* ctx, const cb_bessel* b) {
     if (!ctx) return CB_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
-    for (void* p : ctx->bess_owned) dev_free(ctx, p);
-    ctx->bess_owned.clear();
-    DBessel& B = ctx->bess;
+    if (b->n_regions > 8) { ctx->err = "too many Bessel x regions"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    const unsigned long long key = bessel_key(b);
+    for (auto& e : ctx->bess_cache)
+        if (e.key == key) { e.stamp = ++ctx->bess_clock; ctx->bess = e.B; ctx->have_bessel = true; return 0; }
+    if (ctx->bess_cache.size() >= 8) {   // evict the least recently used table (no call is in flight: entry points are blocking)
+        size_t old = 0;
+        for (size_t i = 1; i < ctx->bess_cache.size(); i++) if (ctx->bess_cache[i].stamp < ctx->bess_cache[old].stamp) old = i;
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (void* p : ctx->bess_cache[old].owned) dev_free(ctx, p);
+        ctx->bess_cache.erase(ctx->bess_cache.begin() + old);
+    }
+    ctx->bess_cache.emplace_back();
+    cb_ctx::BessEntry& E = ctx->bess_cache.back();
+    E.key = key; E.stamp = ++ctx->bess_clock;
+    DBessel& B = E.B;
     B.n_l = b->n_l; B.nx = b->nx; B.n_regions = b->n_regions;
     B.n_l_all = b->n_l_all > 0 ? b->n_l_all : b->n_l;
-    if (b->n_regions > 8) { ctx->err = "too many Bessel x regions"; return CB_ERR_UNSUPPORTED_PARAMS; }
     for (int i = 0; i < b->n_regions; i++) B.regions[i] = b->regions[i];
     B.xmax = b->x[b->nx - 1];
     int* dl; double *dx, *dh;
-    if (int e = upload(ctx, b->l, (size_t)B.n_l_all, &dl, &ctx->bess_owned)) return e;
-    if (int e = upload(ctx, b->x, (size_t)b->nx, &dx, &ctx->bess_owned)) return e;
-    if (int e = upload(ctx, b->horner, (size_t)4 * (b->nx - 1) * b->n_l, &dh, &ctx->bess_owned)) return e;
+    int e = upload(ctx, b->l, (size_t)B.n_l_all, &dl, &E.owned);
+    if (!e) e = upload(ctx, b->x, (size_t)b->nx, &dx, &E.owned);
+    if (!e) e = upload(ctx, b->horner, (size_t)4 * (b->nx - 1) * b->n_l, &dh, &E.owned);
+    if (e) { for (void* p : E.owned) dev_free(ctx, p); ctx->bess_cache.pop_back(); return e; }
     B.l = dl; B.x = dx; B.horner = dh;
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->bess = B;
     ctx->have_bessel = true;
     return 0;
 }
@@ -489,7 +519,7 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
         else if (rc >= 0) { cls_items[CB_REG_CLASS0 + rc].push_back(it); continue; }
         else
             for (;; c++) {
-                const size_t grown = cb_evolve_slab_bytes(std::max(std::max(cls_nv[c], it.nvar), 32), std::max(cls_maxl[c], ml));
+                const size_t grown = cb_evolve_slab_bytes(std::max(std::max(cls_nv[c], it.nvar), 32), std::max(cls_maxl[c], ml), lean);
                 if (grown <= kClassSlabLimit[c]) break;
             }
         cls_nv[c] = std::max(cls_nv[c], it.nvar);

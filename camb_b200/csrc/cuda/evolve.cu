@@ -28,6 +28,15 @@
 #include "thermo.cuh"
 
 #define FULL 0xffffffffu
+// Values evaluated once per trial step at each of the six stage times (attempt_start), per mode, in shared memory:
+// [0..4] cs2b, opacity, a, dopacity, 1/tau; the full variant adds what depends on a alone in the massive-neutrino /
+// dark-energy code of derivs -- [5] grhov_t, [6] w_de, [7] rhonu, [8] pnu of the (single) massive eigenstate,
+// [9 + iq] sqrt(1 + (a m / q_iq)^2) and [14 + iq] its reciprocal v for the first five momenta -- so that the pow / exp of
+// the dark-energy density, the polynomial fits of rho_nu and the square roots and divisions per momentum are not
+// repeated by every lane at every stage.  Models outside that pattern (several eigenstates, nqmax > 5) evaluate in place.
+#define TH_LEAN 5
+#define TH_FULL 20
+#define TH_PRE_NQ 5
 // Cold per-mode / per-segment control code (mode fetch, layout switches, schedule): kept out of line so the hot
 // stage loop around `derivs` stays small in the instruction cache and does not carry their registers.
 #ifdef CB_COLD_NOINLINE
@@ -69,6 +78,7 @@ struct MHot {
     int nwin;
     int nthermo, de_is_cc, de_model, de_nperturb, Num_Nu_massive, Nu_mass_eigenstates, nqmax, n_src;
     int DoLateRadTruncation, AccuracyTarget, WantTransfer, transfer_high_precision, WantCls, WantLateTime, n_tau, num_transfer_redshifts;
+    int th_pre;   // the per-stage values of TH_FULL cover this model (at most one massive eigenstate, nqmax <= TH_PRE_NQ)
 };
 
 __device__ inline void fill_hot(MHot& H, const DModel& M) {
@@ -91,6 +101,7 @@ __device__ inline void fill_hot(MHot& H, const DModel& M) {
     H.LinearSrc = M.LinearSrc; H.TransferData = M.TransferData; H.n_k = M.n_k;
     H.nwin = M.num_redshiftwindows; H.windows = M.num_redshiftwindows > 0 ? M.windows : nullptr; H.terms = M.SourceTerms;
     H.tau_start_redshiftwindows = M.tau_start_redshiftwindows;
+    H.th_pre = (M.Num_Nu_massive == 0 || (M.Nu_mass_eigenstates == 1 && M.nqmax <= TH_PRE_NQ)) ? 1 : 0;
 }
 
 __host__ __device__ inline int d_nint(double x) { return (int)llround(x); }
@@ -337,8 +348,10 @@ __device__ __forceinline__ void derivs(const MHot& M_, EVs& E, const double* __r
     // one reciprocal instead of four divisions (and 1/k, 1/k^2 once per mode): differs from the reference's
     // a/b by at most an ulp per quantity, far inside the 1e-5 parity budget
     const double grhob_t = M.grhob * ainv, grhoc_t = M.grhoc * ainv, grhor_t = M.grhornomass * a2inv, grhog_t = M.grhog * a2inv;
+    const bool pre = !LEAN && th != nullptr && M.th_pre;   // the a-only quantities were evaluated with the stage time (attempt_start)
     double grhov_t, w_de;
     if (de_is_cc) { grhov_t = M.grhov * a2; w_de = -1; }
+    else if (pre) { grhov_t = th[5]; w_de = th[6]; }
     else de_background(M, a, grhov_t, w_de);
     double dgrho_matter = grhob_t * clxb + grhoc_t * clxc;
     double dgq = grhob_t * vb;
@@ -348,7 +361,8 @@ __device__ __forceinline__ void derivs(const MHot& M_, EVs& E, const double* __r
     for (int nu_i = 0; nu_i < n_eig; nu_i++) {  // MassiveNuVars, equations.f90:1358-1401
         double grhormass_t = M.grhormass[nu_i] * a2inv, rhonu, pnu, clxnu, qnu;
         double mass = M.nu_masses[nu_i];
-        nu_rho_P(a * mass, rhonu, pnu);
+        if (pre) { rhonu = th[7]; pnu = th[8]; }
+        else nu_rho_P(a * mass, rhonu, pnu);
         if (E.MassiveNuApprox[nu_i]) {
             clxnu = AY(E.nu_ix[nu_i]);
             qnu = AY(E.nu_ix[nu_i] + 2);
@@ -356,17 +370,21 @@ __device__ __forceinline__ void derivs(const MHot& M_, EVs& E, const double* __r
             double drhonu = 0, fnu = 0, am = a * mass;
             int ind = E.nu_ix[nu_i];
             for (int iq = 1; iq <= E.nq[nu_i]; iq++) {
-                double aq = am / M.nu_q[iq - 1];
-                drhonu = drhonu + M.nu_int_kernel[iq - 1] * AY(ind) * sqrt(1.0 + aq * aq);
+                double sq;
+                if (pre) sq = th[9 + iq - 1];
+                else { double aq = am / M.nu_q[iq - 1]; sq = sqrt(1.0 + aq * aq); }
+                drhonu = drhonu + M.nu_int_kernel[iq - 1] * AY(ind) * sq;
                 fnu = fnu + M.nu_int_kernel[iq - 1] * AY(ind + 1);
                 ind = ind + E.lmaxnu_tau[nu_i] + 1;
             }
             ind = E.nu_pert_ix;
             for (int iq = E.nq[nu_i] + 1; iq <= M.nqmax; iq++) {
-                double aq = am / M.nu_q[iq - 1];
+                double sq;
+                if (pre) sq = th[9 + iq - 1];
+                else { double aq = am / M.nu_q[iq - 1]; sq = sqrt(1.0 + aq * aq); }
                 double pert_scale = (mass / M.nu_q[iq - 1]) * (mass / M.nu_q[iq - 1]) / 2;
                 double tmp = M.nu_int_kernel[iq - 1] * (AY(E.r_ix) + pert_scale * AY(ind));
-                drhonu = drhonu + tmp * sqrt(1.0 + aq * aq);
+                drhonu = drhonu + tmp * sq;
                 fnu = fnu + M.nu_int_kernel[iq - 1] * (AY(E.r_ix + 1) + pert_scale * AY(ind + 1));
             }
             qnu = fnu / rhonu;
@@ -544,8 +562,9 @@ __device__ __forceinline__ void derivs(const MHot& M_, EVs& E, const double* __r
             for (int t = lane; t < tot; t += G) {  // momentum-major blocks of l = 0..lt
                 const int iq = t / (lt + 1), l = t - iq * (lt + 1);
                 const int ind = base + t;
-                const double aq = a * M.nu_masses[nu_i] / M.nu_q[iq];
-                const double v = 1.0 / sqrt(1.0 + aq * aq);
+                double v;
+                if (pre) v = th[9 + TH_PRE_NQ + iq];
+                else { const double aq = a * M.nu_masses[nu_i] / M.nu_q[iq]; v = 1.0 / sqrt(1.0 + aq * aq); }
                 double r;
                 if (l == 0) r = -k * (4.0 / 3.0 * z + v * AY(ind + 1));
                 else if (l == 1) r = v * (denlk[1] * AY(ind - 1) - denlk2[1] * AY(ind + 1));
@@ -748,7 +767,6 @@ struct Ctl {
     double tau, goal, seg_end, next_switch, tol1;
     double t_tight, t_ktau, t_massless, t_nonrel, t_massive, t_no_nu;   // switch times of the current plan
     double h, trial_x, css, hmin;          // the attempt in flight
-    double th[6][5];                       // thermo values (cs2b, opacity, a, dopacity, 1/tau) at the six stage times
     long long steps, attempts, neq_evals, nderivs;
     int xend_reached, first_derivative_valid, successive_failures, ind;
     int phase, stage, next_stage, out_kind, j, itf, seg_switch;
@@ -1130,8 +1148,9 @@ __constant__ double c_dp_c[7] = {0, 1.0 / 5.0, 3.0 / 10.0, 4.0 / 5.0, 8.0 / 9.0,
 // every lane of the group from the shared control block; lane 0 stores the result.  Lanes 0..5 then
 // look up the thermodynamic tables at the six stage times, so the table latency is paid once per
 // step and the log/index arithmetic is not repeated by every lane at every stage.
-template <int G>
-__device__ __forceinline__ bool attempt_start(const MHot& H, const EVs& E, Ctl& C, const double* y, int lane, unsigned gm, int* error_flag) {
+template <int G, bool LEAN>
+__device__ __forceinline__ bool attempt_start(const MHot& H, const EVs& E, Ctl& C, const double* y, int lane, unsigned gm, int* error_flag,
+                                              double* thbuf) {
     const int n = E.neq;
     const double eps = 2.220446049250313e-16, tiny = 2.2250738585072014e-308;
     const double x = C.tau, xend = C.seg_end, tol = C.tol1;
@@ -1174,8 +1193,24 @@ __device__ __forceinline__ bool attempt_start(const MHot& H, const EVs& E, Ctl& 
         const double ts = x + c_dp_c[st + 1] * h;
         double a, cs2, opac, dopac = 0;
         thermo_values(H, ts, a, cs2, opac, dopac, E.TightCoupling != 0);
-        double* t = C.th[st];
+        double* t = thbuf + (LEAN ? TH_LEAN : TH_FULL) * st;
         t[0] = cs2; t[1] = opac; t[2] = a; t[3] = dopac; t[4] = 1.0 / ts;
+        if (!LEAN && H.th_pre) {
+            double grhov_t = 0, w_de = -1;
+            if (!H.de_is_cc) de_background(H, a, grhov_t, w_de);
+            t[5] = grhov_t; t[6] = w_de;
+            if (H.Num_Nu_massive > 0) {
+                const double am = a * H.nu_masses[0];
+                double rhonu, pnu;
+                nu_rho_P(am, rhonu, pnu);
+                t[7] = rhonu; t[8] = pnu;
+                for (int iq = 0; iq < H.nqmax; iq++) {
+                    const double aq = am / H.nu_q[iq], sq = sqrt(1.0 + aq * aq);
+                    t[9 + iq] = sq;
+                    t[9 + TH_PRE_NQ + iq] = 1.0 / sq;
+                }
+            }
+        }
     }
     return true;
 }
@@ -1191,7 +1226,10 @@ __device__ __forceinline__ void attempt_finish(const DModel& M, EVs& E, Ctl& C, 
         double e = c_dp_a[0][0] * v[nv + i];
 #pragma unroll
         for (int j = 1; j < 6; j++) e = fma(c_dp_a[0][j], v[(j + 1) * nv + i], e);
-        temp = fmax(temp, fabs(e) / fmax(1.0, fabs(y[i])));
+        e = fabs(e);
+        const double ay = fabs(y[i]);
+        if (ay > 1.0) e = e / ay;   // e / max(1, |y|), RungeKuttaDP45.f90:341: most elements are below one (and many e are exactly zero, the
+        temp = fmax(temp, e);       // slow path of the division routine): no division there
     }
     temp = group_max<G>(temp, gm);
     const double css = C.css, est = temp * css, xend = C.seg_end, trial_x = C.trial_x;
@@ -1271,6 +1309,7 @@ cb_evolve_kernel(const DModel* __restrict__ models, const DModeItem* __restrict_
     double* polfack = denlk2 + (maxl + 1);
     double* vec = polfack + (maxl + 1);
     const Vecs V(vec, nv);
+    double* const thbuf = vec + (size_t)NVEC * nv;   // [6][TH_LEAN | TH_FULL]
     if (lane == 0) C.phase = PH_FETCH;
     __syncwarp(gm);
     // t is warp-uniform: 0 = schedule / single evaluations (first derivative of a segment, source or
@@ -1304,7 +1343,7 @@ cb_evolve_kernel(const DModel* __restrict__ models, const DModeItem* __restrict_
         } else {
             active = C.phase == PH_STEP;
             if (active && t == 1) {
-                active = attempt_start<G>(H, E, C, V.y, lane, gm, error_flag);
+                active = attempt_start<G, LEAN>(H, E, C, V.y, lane, gm, error_flag, thbuf);
                 __syncwarp(gm);
                 if (!active && lane == 0) C.phase = PH_FETCH;   // step-size underflow: abandon the mode (error flag is set)
             }
@@ -1343,7 +1382,7 @@ cb_evolve_kernel(const DModel* __restrict__ models, const DModeItem* __restrict_
                 in = yt;
                 out = t == 6 ? V.k2 : vec + (size_t)(t + 1) * nv;
                 tev = C.tau + c_dp_c[t] * h;
-                th = C.th[t - 1];
+                th = thbuf + (LEAN ? TH_LEAN : TH_FULL) * (t - 1);
             }
         }
         if (active) {
@@ -1437,10 +1476,11 @@ cudaError_t cb_debug_derivs_launch(const DModel* d_model, double q, double tau, 
 }
 
 // ---------------- host-side helpers used by cabi.cu ----------------
-size_t cb_evolve_slab_bytes(int nv, int maxl) {
+size_t cb_evolve_slab_bytes(int nv, int maxl, int lean) {
     const size_t ctl_bytes = (sizeof(Ctl) + 15) & ~size_t(15), hot_bytes = (sizeof(MHot) + 15) & ~size_t(15),
                  ev_bytes = (sizeof(EVs) + 15) & ~size_t(15);
-    size_t b = ctl_bytes + hot_bytes + ev_bytes + sizeof(double) * (3 * (size_t)(maxl + 1) + NVEC * (size_t)nv);
+    size_t b = ctl_bytes + hot_bytes + ev_bytes +
+               sizeof(double) * (3 * (size_t)(maxl + 1) + NVEC * (size_t)nv + 6 * (size_t)(lean ? TH_LEAN : TH_FULL));
     b = (b + 127) & ~size_t(127);
     return b + 64;   // stride = 64 (mod 128)
 }
@@ -1462,7 +1502,7 @@ template <int G, bool LEAN>
 static cudaError_t launch_g(const DModel* d_models, const DModeItem* d_items, int n_items, int nv, int maxl, unsigned int* d_counter,
                             int* d_error, int n_sm, cudaStream_t stream, int* grid_out, int block_cap) {
     constexpr int MPW = 32 / G;
-    const size_t slab = cb_evolve_slab_bytes(nv, maxl);
+    const size_t slab = cb_evolve_slab_bytes(nv, maxl, LEAN ? 1 : 0);
     const size_t smem = slab * MPW * WPB(G);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(cb_evolve_kernel<G, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -304,9 +304,12 @@ __device__ int dp45(const DModel& M, const TEv& E, const double* dk, int dks, do
         s.nderivs += 6; s.neq_evals += 6 * (long long)n; s.attempts++;
         temp = 0;
         for (int i = lane; i < n; i += 32) {
-            const double e = (71.0 / 57600.0) * k1[i] + (-71.0 / 16695.0) * k3[i] + (71.0 / 1920.0) * k4[i] + (-17253.0 / 339200.0) * k5[i] +
+            double e = (71.0 / 57600.0) * k1[i] + (-71.0 / 16695.0) * k3[i] + (71.0 / 1920.0) * k4[i] + (-17253.0 / 339200.0) * k5[i] +
                              (22.0 / 525.0) * k6[i] + (-1.0 / 40.0) * k7[i];
-            temp = fmax(temp, fabs(e) / fmax(1.0, fabs(y[i])));
+            e = fabs(e);
+            const double ay = fabs(y[i]);
+            if (ay > 1.0) e = e / ay;   // e / max(1, |y|): no division (and no zero-numerator slow path) where |y| <= 1
+            temp = fmax(temp, e);
         }
         temp = warp_max(temp);
         s.estimated_error = temp * css;

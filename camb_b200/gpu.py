@@ -79,6 +79,16 @@ def _dp(a):
     return a.ctypes.data_as(c_double_p)
 
 
+def group_by_l_sampling(hss):
+    """Index groups of a batch by identical l sampling (lSamples_init shifts the samples with the acoustic scale,
+    results.f90:1517-1520, so a few sets of a wide parameter box differ from the rest).  Loops B and C run once per group
+    against that group's own Bessel table: every set is projected and integrated at ITS l samples, as the reference would."""
+    groups = {}
+    for i, hs in enumerate(hss):
+        groups.setdefault(tuple(np.asarray(hs.ls).tolist()), []).append(i)
+    return list(groups.values())
+
+
 class GpuContext:
     """One per process and device (cmbmain.f90:7-8: the reference is not re-entrant either)."""
 
@@ -98,11 +108,10 @@ class GpuContext:
             raise CAMBError(self._lib.cb_last_error(self._h).decode(), e)
 
     def set_bessel(self, hs):
+        """Select the Bessel table of this host state's l sampling (the library keeps the tables it has seen resident and
+        recognises them by content, so switching between the l samplings of a batch costs no upload)."""
         b = hs.bessel()
-        key = (b.n_l, b.nx, tuple(hs.ls.tolist()))
-        if key != self._bessel_key:
-            self._check(self._lib.cb_set_bessel(self._h, C.byref(b)))
-            self._bessel_key = key
+        self._check(self._lib.cb_set_bessel(self._h, C.byref(b)))
         self.n_l = b.n_l
 
     def create_model(self, hs):

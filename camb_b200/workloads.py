@@ -7,7 +7,7 @@ from .host import default_params
 
 
 def planck2018_params(lmax=2500, lensing=True, massless=True, k_eta_max=None, accuracy_boost=1.0,
-                      de="lcdm", w=-1.0, wa=0.0, want_transfer=False):
+                      de="lcdm", w=-1.0, wa=0.0, want_transfer=False, lensed_to_lmax=False):
     """inifiles/planck_2018.ini:38-110 cosmology + recombination/reionization settings.
     `massless=True` is BASELINE.json config 2's "massless neutrinos" override
     (omnuh2=0, massive_neutrinos=0, massless_neutrinos=3.046)."""
@@ -48,7 +48,11 @@ def planck2018_params(lmax=2500, lensing=True, massless=True, k_eta_max=None, ac
     p.w, p.wa = (w, wa) if de != "lcdm" else (-1.0, 0.0)
     p.DoLensing = 1 if lensing else 0
     p.Max_l = int(lmax)
-    p.Max_eta_k = float(k_eta_max) if k_eta_max else 2.5 * lmax
+    if lensed_to_lmax and lensing:
+        # CAMBparams.set_for_lmax (camb/model.py:1053-1058): the scalar spectra are computed to lmax + lens_output_margin so that
+        # the LENSED output reaches lmax (the convolution loses the margin, lensing.f90:230-247)
+        p.Max_l = int(lmax) + int(p.lens_output_margin)
+    p.Max_eta_k = float(k_eta_max) if k_eta_max else 2.5 * p.Max_l
     p.Accuracy.AccuracyBoost = float(accuracy_boost)
     p.WantTransfer = 1 if want_transfer else 0
     return p
@@ -79,7 +83,7 @@ def params_ini_config1():
     return p
 
 
-def synthetic_lcdm_batch(n, seed=20261017, lmax=2500, lensing=True, massless=True, extended=False):
+def synthetic_lcdm_batch(n, seed=20261017, lmax=2500, lensing=True, massless=True, extended=False, lensed_to_lmax=False):
     """Synthetic parameter sets (SURVEY.md 8(d) config 5 box; the reference defines no
     distribution).  `extended` adds mnu and w0wa (PPF)."""
     rng = np.random.default_rng(seed)
@@ -96,7 +100,7 @@ def synthetic_lcdm_batch(n, seed=20261017, lmax=2500, lensing=True, massless=Tru
         wa = rng.uniform(-0.5, 0.5)
         if w0 + wa >= 0:
             wa = -w0 - 0.05
-        p = planck2018_params(lmax=lmax, lensing=lensing, massless=massless and not extended)
+        p = planck2018_params(lmax=lmax, lensing=lensing, massless=massless and not extended, lensed_to_lmax=lensed_to_lmax)
         p.ombh2, p.omch2, p.H0, p.optical_depth, p.ns = ombh2, omch2, H0, tau, ns
         p.As = np.exp(lnAs) * 1e-10
         if extended:

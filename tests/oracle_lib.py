@@ -97,11 +97,12 @@ def spline_k(q_src, src):
     return dd
 
 
-def project(hs, q_src, src, dd, nthreads=1, q_slice=None):
+def project(hs, q_src, src, dd, nthreads=1, q_slice=None, bessel_owner=None):
     """Delta_p_l_k with shape (n_q, n_l, n_src) (C order == Fortran (src, l, q)); `q_slice` = (lo, hi)
-    restricts loop B to a slice of the integration grid (q-sharding)."""
+    restricts loop B to a slice of the integration grid (q-sharding); `bessel_owner`: the host state whose Bessel table
+    and l sampling the projection uses (a batch projected against one table)."""
     lib = load()
-    b = hs.bessel()
+    b = (bessel_owner or hs).bessel()
     q_src = np.ascontiguousarray(q_src)
     qi = np.ascontiguousarray(hs.q_int if q_slice is None else hs.q_int[q_slice[0]:q_slice[1]])
     out = np.zeros((len(qi), b.n_l, hs.model.n_src))
@@ -110,10 +111,10 @@ def project(hs, q_src, src, dd, nthreads=1, q_slice=None):
     return out
 
 
-def cl(hs, delta, pows=None, q_slice=None):
+def cl(hs, delta, pows=None, q_slice=None, bessel_owner=None):
     """iCl with shape (n_l, n_cl); with `q_slice` the partial sum over that slice of the integration grid."""
     lib = load()
-    b = hs.bessel()
+    b = (bessel_owner or hs).bessel()
     sl = slice(None) if q_slice is None else slice(q_slice[0], q_slice[1])
     qi = np.ascontiguousarray(hs.q_int[sl])
     dq = np.ascontiguousarray(hs.dq_int[sl])

@@ -464,3 +464,49 @@ def test_evolve_kernel_variants_agree(ctx, path):
     print("evolve path", path, "C_l errors", errs, "modes with identical derivs counts", same)
     assert max(errs) < CL_RTOL, errs
     assert same > 0.98
+
+
+def test_config5_mnu_w0wa_ragged_batch_parity(ctx):
+    """BASELINE.json configs[4] as specified: synthetic LCDM + mnu + w0wa (PPF) parameter sets at lmax 2500,
+    no lensing, evolved as ONE ragged batch; loops B and C per group of identical l sampling.  Every set against the oracle."""
+    from camb_b200.gpu import group_by_l_sampling
+    ps = synthetic_lcdm_batch(8, seed=20261017, lmax=2500, lensing=False, extended=True)
+    hss = [HostState(p) for p in ps]
+    assert all(hs.model.Num_Nu_massive == 1 and not hs.model.de_is_cosmological_constant and hs.ls[-1] == 2500 for hs in hss)
+    dms = [ctx.create_model(hs) for hs in hss]
+    icl = [None] * len(hss)
+    try:
+        ctx.evolve(hss, dms, want_sources=False, want_stats=False)
+        for g in group_by_l_sampling(hss):
+            ctx.set_bessel(hss[g[0]])
+            ctx.project([hss[i] for i in g], [dms[i] for i in g], want_delta=False)
+            for i, x in zip(g, ctx.cl([hss[i] for i in g], [dms[i] for i in g])):
+                icl[i] = x
+    finally:
+        for dm in dms:
+            ctx.destroy_model(dm)
+    worst = 0.0
+    for hs, a in zip(hss, icl):
+        icl_o, _ = O.cls_from_params(hs, nthreads=8)
+        worst = max(worst, max(cl_err(a, icl_o)))
+    print("config 5 batch (8 sets, mnu + w0wa PPF, lmax 2500): worst C_l error", worst)
+    assert worst < CL_RTOL
+
+
+def test_planck_transfer_high_precision_parity(ctx):
+    """planck_2018.ini's transfer settings on its own cosmology: one massive neutrino, matter transfer with
+    transfer_high_precision = T (tolerance / 100, lmaxnr ramp to 45, lmaxnu 25: equations.f90:979-995, cmbmain.f90:1021)."""
+    def build():
+        p = planck2018_params(lmax=2500, lensing=True, massless=False, want_transfer=True)
+        p.transfer_high_precision = 1
+        p.transfer_kmax = 5.0
+        return p
+    hs = host_state("planck_massive_transfer_hp", build)
+    g = run_gpu(ctx, hs)
+    icl_o, aux = O.cls_from_params(hs, nthreads=8)
+    errs = cl_err(g["icl"], icl_o)
+    print("planck_2018 + transfer_high_precision C_l errors", errs, "n_k", len(hs.source_q()))
+    assert max(errs) < CL_RTOL, errs
+    tr, tr_o = g["transfer"], aux["transfer"]
+    for c in range(13):
+        assert np.abs(tr[:, :, c] - tr_o[:, :, c]).max() <= 2e-5 * np.abs(tr_o[:, :, c]).max(), c
