@@ -42,9 +42,9 @@ cudaError_t cb_evolve_tensor_launch(const DModel*, const DModeItem*, int n_items
                                     cudaStream_t, int* grid_out);
 // project.cu
 void cb_spline_k_launch(const DModel*, int, int, double* const*, cudaStream_t);
-size_t cb_los_smem(int, int);
-cudaError_t cb_los_set_smem(size_t);
-void cb_los_launch(const DModel*, int, const DBessel&, int, int, size_t, cudaStream_t);
+size_t cb_los_smem(int, int, int);
+cudaError_t cb_los_launch(const DModel*, int, const DBessel&, int, int, size_t, int, cudaStream_t);
+void cb_bessel_transpose_launch(const double*, double*, int, int, int, cudaStream_t);
 cudaError_t cb_los_win_launch(const DModel*, int, const DBessel&, int, int, cudaStream_t);
 void cb_cl_launch(const DModel*, int, const DBessel&, cudaStream_t);
 void cb_cl_array_launch(const DModel*, int, const DBessel&, double* const*, cudaStream_t);
@@ -111,6 +111,7 @@ struct cb_ctx {
     // 48-element classes, register kernel for the deep low-k hierarchies (equal throughput at >= 192 sets per call,
     // slower below: DESIGN.md section 4.1)
     int use_reg_kernel = 1;
+    int los_kernel = 1;            // 1: lanes on the multipoles (transposed table, coalesced rows); 0: the gather kernel
     cudaEvent_t stage_ev[4][2] = {};     // per-stage kernel brackets of the last calls (evolve, spline-k, LOS, C_l)
     DModel* h_models = nullptr;   size_t cap_h_models = 0;   // page-locked staging
     DModeItem* h_items = nullptr; size_t cap_h_items = 0;
@@ -223,6 +224,11 @@ int cb_create(int device, cb_ctx** out) {
     cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming);
     if (const char* e = getenv("CAMB_B200_LANES")) ctx->lanes_per_mode = atoi(e);
     if (const char* e = getenv("CAMB_B200_REG")) ctx->use_reg_kernel = atoi(e);
+    if (const char* e = getenv("CAMB_B200_LOS")) ctx->los_kernel = atoi(e);
+    if (const char* e = getenv("CAMB_B200_CLASS_LANES")) {   // tuning runs: lane width per slab-size class, e.g. "8,8,16,32,32"
+        int i = 0;
+        for (const char* p = e; *p && i < CB_TENSOR_CLASS; i++) { ctx->class_lanes[i] = atoi(p); while (*p && *p != ',') p++; if (*p == ',') p++; }
+    }
     {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -315,6 +321,20 @@ int cb_set_bessel(cb_ctx* ctx, const cb_bessel* b) {
     if (!e) e = upload(ctx, b->horner, (size_t)4 * (b->nx - 1) * b->n_l, &dh, &E.owned);
     if (e) { for (void* p : E.owned) dev_free(ctx, p); ctx->bess_cache.pop_back(); return e; }
     B.l = dl; B.x = dx; B.horner = dh;
+    {   // the transposed copy for the line-of-sight kernel (rows of all l at one x interval, padded to whole 128-byte lines)
+        B.n_l_pad = (b->n_l + 3) & ~3;
+        double* dht = nullptr;
+        const size_t nt = (size_t)4 * (b->nx - 1) * B.n_l_pad;
+        if (dev_alloc(ctx, (void**)&dht, sizeof(double) * nt) != cudaSuccess) {
+            for (void* p : E.owned) dev_free(ctx, p);
+            ctx->bess_cache.pop_back();
+            ctx->err = "out of device memory for the transposed Bessel table";
+            return CB_ERR_CUDA;
+        }
+        E.owned.push_back(dht);
+        cb_bessel_transpose_launch(dh, dht, b->nx - 1, b->n_l, B.n_l_pad, ctx->stream);
+        B.horner_t = dht;
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->bess = B;
     ctx->have_bessel = true;
@@ -581,6 +601,16 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
 #endif
         // the scratch EvolutionVars of a layout switch aliases two stage vectors (evolve.cu)
         const int nv = std::max(cls_nv[c], 32);
+        // Lane width of a general-kernel class (measured on the massive-neutrino batches, profiles/r02z_lanes.log): a class with
+        // few modes for the machine, or one whose slab leaves room for a single eight-mode block per SM, runs a mode per warp
+        // (the elements of a deep hierarchy spread over 32 lanes, 5 two-mode blocks per SM instead of one eight-mode block)
+        int lanes_c = ctx->class_lanes[c] ? ctx->class_lanes[c] : lanes;
+        if (!ctx->class_lanes[c] && ctx->lanes_per_mode == 0 && c < CB_TENSOR_CLASS &&
+            (n_c < 24 * ctx->n_sm || cb_evolve_slab_bytes(nv, cls_maxl[c], lean) > 16384))
+            lanes_c = 32;
+        if (getenv("CAMB_B200_VERBOSE"))
+            fprintf(stderr, "cb_evolve: class %d: %d modes, nv %d, maxl %d, slab %zu bytes\n", c, n_c, nv, cls_maxl[c],
+                    c < CB_TENSOR_CLASS ? cb_evolve_slab_bytes(nv, cls_maxl[c], lean) : (size_t)0);
         CK(cudaStreamWaitEvent(ctx->class_stream[c], ctx->fork, 0));
         cudaError_t le = c == CB_MPL_CLASS_A
                              ? cb_evolve_mpl_launch(ctx->d_models, ctx->d_items + cls_off[CB_MPL_CLASS_A], (int)cls_items[CB_MPL_CLASS_A].size(),
@@ -593,7 +623,7 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
                          : c == CB_TENSOR_CLASS
                              ? cb_evolve_tensor_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, cls_nv[c], cls_maxl[c], ctx->d_counter + c,
                                                        ctx->d_error, ctx->n_sm, ctx->class_stream[c], &ctx->last_grid[c])
-                             : cb_evolve_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, nv, cls_maxl[c], ctx->class_lanes[c] ? ctx->class_lanes[c] : lanes, lean, ctx->d_counter + c,
+                             : cb_evolve_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, nv, cls_maxl[c], lanes_c, lean, ctx->d_counter + c,
                                                 ctx->d_error, ctx->n_sm, ctx->class_stream[c], &ctx->last_grid[c], caps[c]);
         if (le != cudaSuccess) { ctx->err = std::string("evolve launch: ") + cudaGetErrorString(le); return CB_ERR_CUDA; }
         ctx->launches++;
@@ -698,7 +728,7 @@ int cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q, 
     CK(cudaEventRecord(ctx->stage_ev[1][1], ctx->stream));
     bool any_windows = false;
     for (int m = 0; m < n_models; m++) any_windows = any_windows || dm[m]->h.num_redshiftwindows > 0;
-    const size_t smem = cb_los_smem(max_nsrc, max_ntau);
+    const size_t smem = cb_los_smem(max_nsrc, max_ntau, n_l);
     CK(cudaEventRecord(ctx->stage_ev[2][0], ctx->stream));
     if (any_windows || smem > 227 * 1024 || n_l > 192 /* LOS_MAX_L */) {
         // source windows (or a time grid too long to stage the sources): the general kernel
@@ -707,8 +737,8 @@ int cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q, 
         cudaError_t le = cb_los_win_launch(ctx->d_models, n_models, ctx->bess, max_nq, max_ntau, ctx->stream);
         if (le != cudaSuccess) { ctx->err = std::string("LOS (windows): ") + cudaGetErrorString(le); return le == cudaErrorInvalidValue ? CB_ERR_UNSUPPORTED_PARAMS : CB_ERR_CUDA; }
     } else {
-        CK(cb_los_set_smem(smem));
-        cb_los_launch(ctx->d_models, n_models, ctx->bess, max_nq, max_ntau, smem, ctx->stream);
+        cudaError_t le = cb_los_launch(ctx->d_models, n_models, ctx->bess, max_nq, max_ntau, smem, ctx->los_kernel, ctx->stream);
+        if (le != cudaSuccess) { ctx->err = std::string("LOS: ") + cudaGetErrorString(le); return CB_ERR_CUDA; }
     }
     ctx->launches++;
     CK(cudaGetLastError());
@@ -963,6 +993,7 @@ int cb_set_option(cb_ctx* ctx, const char* name, double value) {
     }
     if (!strcmp(name, "async_model_upload")) { ctx->async_model_upload = value != 0; return 0; }
     if (!strcmp(name, "use_reg_kernel")) { ctx->use_reg_kernel = (int)value; return 0; }
+    if (!strcmp(name, "los_kernel")) { ctx->los_kernel = (int)value; return 0; }
     ctx->err = std::string("unknown option ") + name;
     return CB_ERR_UNSUPPORTED_PARAMS;
 }

@@ -96,6 +96,8 @@ struct DBessel {
     const int* l;
     const double* x;
     const double* horner;  // (4, nx-1, n_l)
+    const double* horner_t;   // (4, n_l_pad, nx-1): the same records, all l of one x interval contiguous (cb_los_kernel)
+    int n_l_pad;
     cb_range regions[8];
     double xmax;
 };

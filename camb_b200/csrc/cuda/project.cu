@@ -94,9 +94,11 @@ __global__ void cb_spline_k_kernel(const DModel* __restrict__ models, int n_mode
     for (int i = n_k - 2; i >= 0; i--) d2[i] = d2[i] * d2[i + 1] + u[i];
 }
 
+// The first mapping of loop B (kept for A/B runs, option "los_kernel" = 0): a warp owns one l, its lanes stride the time
+// steps, so the 32 lanes of a load hit 32 different sectors of one l-column of the table (one 32-byte gather each).
 // grid = (max n_q, n_models); dynamic smem: Source_q[n_src*n_tau] + left_weight[n_tau] + dtau[n_tau] + bes_index[n_tau]
 __global__ void __launch_bounds__(LOS_THREADS, LOS_MIN_BLOCKS)
-cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
+cb_los_gather_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
     const DModel& M = models[blockIdx.y];
     const int iq = blockIdx.x;
     if (iq >= M.n_q) return;
@@ -254,6 +256,204 @@ cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
             if (nsrc > 2) o[2] = s2;
         }
     }
+}
+
+// Loop B with the lanes on the MULTIPOLES.  The Bessel table is kept a second time transposed on the device,
+// horner_t(4, n_l_pad, nx-1): at one x interval the records of all l are contiguous (92 x 32 B for the default sampling).
+// A warp takes one time step n at a time -- x = q (tau0 - tau_n), i.e. the table row and the interpolation weight are the
+// same for every l -- and its lanes load the row with fully coalesced 256-bit loads (eight whole 128-byte lines per
+// instruction instead of 32 scattered sectors), each lane accumulating the three sources of ITS l's (NSLOT l per lane) in
+// registers: no shuffle reduction per (q, l) at all.  The eight warps of the CTA deal the time steps round-robin; their
+// partial sums are added in warp order through shared memory, so the result is deterministic.  Every term is the same
+// product as in the reference (J_l dtau, then Source J_l: cmbmain.f90:1720-1737); only the order of the sum over time
+// steps differs (warp-strided instead of sequential).
+// grid = (max n_q, n_models); dynamic smem: as cb_los_gather_kernel, the reduction buffer aliases the per-step arrays.
+template <int NSLOT>
+__global__ void __launch_bounds__(LOS_THREADS, 3)
+cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
+    const DModel& M = models[blockIdx.y];
+    const int iq = blockIdx.x;
+    if (iq >= M.n_q) return;
+    extern __shared__ __align__(16) double sm[];
+    const int ntime = M.n_tau, nsrc = M.n_src, n_k = M.n_k, n_l = B.n_l;
+    double* Source_q = sm;                       // [nsrc][ntime]
+    double* left_weight = Source_q + (size_t)nsrc * max_n_tau;
+    double* dtau_s = left_weight + max_n_tau;
+    int* bes_index = reinterpret_cast<int*>(dtau_s + max_n_tau);
+    double* red = left_weight;                   // [nwarp][NSLOT * 32][3] after the main loop (cb_los_smem sizes for both)
+    __shared__ int s_firstfail, s_nlo, s_nhi;
+    __shared__ cb_range s_tau_regions[8];
+    __shared__ double s_xlim[LOS_MAX_L], s_xlmax1[LOS_MAX_L], s_qmax_int[LOS_MAX_L], s_limfac[LOS_MAX_L];
+    __shared__ int s_n1[LOS_MAX_L], s_n2[LOS_MAX_L];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = LOS_THREADS / 32;
+    const double q = M.q_int[iq], tau0 = M.tau0;
+    const double* TimePoints = M.tau;
+    if (tid == 0) { s_firstfail = ntime + 1; s_nlo = 0x7fffffff; s_nhi = 0; }
+    if (tid < M.n_tau_regions) s_tau_regions[tid] = M.tau_regions[tid];
+    {
+        const double BessIntBoost = M.AccuracyBoost * M.BessIntBoost;
+        for (int j = tid; j < n_l; j += LOS_THREADS) {
+            const int l = B.l[j];
+            s_xlim[j] = fmax(0.0, l - 4.2 * pow((double)l, 1.0 / 3.0));
+            s_xlmax1[j] = 80 * l * BessIntBoost;
+            s_qmax_int[j] = (l > 850 ? l : 850) * 3 * BessIntBoost / tau0 * 1.2;
+            s_limfac[j] = l > 400 * pow(M.AccuracyBoost * M.LimberBoost, 0.5) ? sqrt(3.1415926535897932384626433832795 / 2 / (l + 0.5)) : -1.0;
+        }
+    }
+    __syncthreads();
+    // ---- InterpolateSources, cmbmain.f90:1351-1480 ----
+    const bool tensors = M.is_tensor != 0;   // cmbmain.f90:1391-1403
+    const bool ignore_etak = !tensors && M.WantLateTime != 0;
+    const double max_etak = ignore_etak ? 0.0 : (tensors ? M.max_etak_tensor : M.max_etak_scalar);
+    const double* qs = M.q_src;
+    int klo;
+    if (q <= qs[0]) klo = 1;
+    else if (q >= qs[n_k - 1]) klo = n_k - 1;
+    else {
+        int lo = 1, hi = n_k;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) / 2;
+            if (q >= qs[mid - 1]) lo = mid; else hi = mid;
+        }
+        klo = lo;
+    }
+    const int khi = klo + 1;
+    const double ho = qs[khi - 1] - qs[klo - 1];
+    const double a0 = (qs[khi - 1] - q) / ho, b0 = (q - qs[klo - 1]) / ho, ho2o6 = ho * ho / 6.0;
+    const double a03 = a0 * a0 * a0 - a0, b03 = b0 * b0 * b0 - b0;
+    for (int i = 2 + tid; i <= ntime; i += LOS_THREADS) {
+        const double tau = TimePoints[i - 1];
+        const bool pass = (ignore_etak || q * tau < max_etak) && (q * (tau0 - tau) > 1.e-8);
+        if (!pass) atomicMin(&s_firstfail, i);
+    }
+    __syncthreads();
+    const int SourceSteps = max(2, s_firstfail - 1);
+    for (int i = 1 + tid; i <= ntime; i += LOS_THREADS) {
+        const bool live = (i >= 2 && i < s_firstfail);
+        for (int j = 0; j < nsrc; j++) {
+            double v = 0.0;
+            if (live) {
+                const size_t off = (size_t)n_k * (j + (size_t)nsrc * (i - 1));
+                const double* S = M.LinearSrc + off;
+                const double* D = M.ddSrc + off;
+                v = a0 * S[klo - 1] + b0 * S[khi - 1] + (a03 * D[klo - 1] + b03 * D[khi - 1]) * ho2o6;
+            }
+            Source_q[(size_t)j * max_n_tau + (i - 1)] = v;
+        }
+        dtau_s[i - 1] = M.dtau[i - 1];
+        // ---- DoFlatIntegration preamble, cmbmain.f90:1680-1692 ----
+        if (i <= SourceSteps) {
+            const double xf = fabs(q * (tau0 - TimePoints[i - 1]));
+            int bes_ix = ranges_index_of_ordered(B.regions, B.n_regions, B.nx, B.xmax, xf);
+            if (bes_ix >= B.nx) bes_ix = B.nx - 1;
+            const double x_hi = B.x[bes_ix], dx = x_hi - B.x[bes_ix - 1];
+            left_weight[i - 1] = (x_hi - xf) / dx;
+            bes_index[i - 1] = bes_ix;
+        }
+    }
+    // ---- DoSourceIntegration: llmax (flat), cmbmain.f90:1516-1521 ----
+    int llmax = (int)llround(q * tau0);
+    if (llmax < 15) llmax = 17;
+    else llmax = (int)llround(q * (tau0 + 6.0 * 3.1415926535897932384626433832795 / q));
+    // time-step window [n1, n2] of every l (cmbmain.f90:1702-1716), one thread per l; n1 < 0: this l takes no part at this q
+    for (int j = 1 + tid; j <= n_l; j += LOS_THREADS) {
+        int n1 = -1, n2 = 0;
+        if (B.l[j - 1] <= llmax) {
+            const double tmin = fmax(TimePoints[1], tau0 - s_xlmax1[j - 1] / q);
+            const double tmax = tau0 - s_xlim[j - 1] / q;
+            if (!(tmax < TimePoints[1])) {
+                n1 = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, tmin);
+                n2 = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, tmax);
+                if (n2 > SourceSteps) n2 = SourceSteps;
+                const bool DoInt = nsrc <= 2 || tensors || q < s_qmax_int[j - 1];
+                if (DoInt && n1 <= n2) { atomicMin(&s_nlo, n1); atomicMax(&s_nhi, n2); }
+            }
+        }
+        s_n1[j - 1] = n1; s_n2[j - 1] = n2;
+    }
+    __syncthreads();
+    // this lane's l's: slot s holds l index 32 s + lane; an empty window for the l's that do not integrate at this q
+    int n1s[NSLOT], n2s[NSLOT];
+    double acc[NSLOT][3];
+#pragma unroll
+    for (int s = 0; s < NSLOT; s++) {
+        const int j = 32 * s + lane;
+        n1s[s] = 1; n2s[s] = 0;
+        if (j < n_l && s_n1[j] >= 0 && (nsrc <= 2 || tensors || q < s_qmax_int[j])) { n1s[s] = s_n1[j]; n2s[s] = s_n2[j]; }
+        acc[s][0] = 0; acc[s][1] = 0; acc[s][2] = 0;
+    }
+    {
+        const double* Ht = B.horner_t + 4 * (size_t)lane;
+        const size_t row = (size_t)4 * B.n_l_pad;
+        const int nlo = s_nlo, nhi = s_nhi;   // nlo > nhi: no l integrates at this q
+        const bool three = nsrc > 2;
+#pragma unroll 2
+        for (int n = nlo <= nhi ? nlo + warp : nhi + 1; n <= nhi; n += nwarp) {
+            const double a2 = left_weight[n - 1], dt = dtau_s[n - 1];
+            const double S0 = Source_q[n - 1], S1 = Source_q[max_n_tau + n - 1];
+            const double S2 = three ? Source_q[2 * (size_t)max_n_tau + n - 1] : 0.0;
+            const double* R = Ht + row * (size_t)(bes_index[n - 1] - 1);
+#pragma unroll
+            for (int s = 0; s < NSLOT; s++) {
+                if (n >= n1s[s] && n <= n2s[s]) {
+                    double c0, c1, c2, c3;
+                    ld_horner(R + 128 * s, c0, c1, c2, c3);
+                    double J_l = c0 + a2 * (c1 + a2 * (c2 + a2 * c3));
+                    J_l = J_l * dt;
+                    acc[s][0] = acc[s][0] + S0 * J_l;
+                    acc[s][1] = acc[s][1] + S1 * J_l;
+                    if (three) acc[s][2] = acc[s][2] + S2 * J_l;
+                }
+            }
+        }
+    }
+    __syncthreads();   // every warp is done with the per-step arrays: the reduction buffer takes their place
+#pragma unroll
+    for (int s = 0; s < NSLOT; s++) {
+        double* r = red + 3 * ((size_t)warp * (NSLOT * 32) + 32 * s + lane);
+        r[0] = acc[s][0]; r[1] = acc[s][1]; r[2] = acc[s][2];
+    }
+    __syncthreads();
+    double* Dout = M.Delta + (size_t)nsrc * n_l * iq;
+    for (int j = 1 + tid; j <= n_l; j += LOS_THREADS) {
+        const int l = B.l[j - 1];
+        double s0 = 0, s1 = 0, s2 = 0;
+        if (s_n1[j - 1] >= 0) {
+            const bool DoInt = nsrc <= 2 || tensors || q < s_qmax_int[j - 1];
+            if (DoInt) {
+                for (int w = 0; w < nwarp; w++) {   // warp order: deterministic
+                    const double* r = red + 3 * ((size_t)w * (NSLOT * 32) + (j - 1));
+                    s0 = s0 + r[0]; s1 = s1 + r[1]; s2 = s2 + r[2];
+                }
+            }
+            if (nsrc > 2 && !tensors) {  // UseLimber, cmbmain.f90:1619-1636, 1821-1832 (scalars only)
+                const double limfac = s_limfac[j - 1];
+                if (!DoInt || limfac > 0) {
+                    double xf = tau0 - (l + 0.5) / q;
+                    if (xf < M.tau_highest && xf > M.tau_lowest) {
+                        const int n = ranges_index_of(s_tau_regions, M.n_tau_regions, ntime, M.tau_highest, xf);
+                        xf = (xf - TimePoints[n - 1]) / (TimePoints[n] - TimePoints[n - 1]);
+                        s2 = (Source_q[2 * (size_t)max_n_tau + n - 1] * (1 - xf) + xf * Source_q[2 * (size_t)max_n_tau + n]) *
+                             (limfac > 0 ? limfac : sqrt(3.1415926535897932384626433832795 / 2 / (l + 0.5))) / q;
+                    } else s2 = 0;
+                }
+            }
+        }
+        double* o = Dout + (size_t)nsrc * (j - 1);
+        o[0] = s0; o[1] = s1;
+        if (nsrc > 2) o[2] = s2;
+    }
+}
+
+// (4, nx-1, n_l) -> (4, n_l_pad, nx-1): one thread per record
+__global__ void cb_bessel_transpose_kernel(const double* __restrict__ H, double* __restrict__ Ht, int nxm1, int n_l, int n_l_pad) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)nxm1 * n_l_pad) return;
+    const int j = (int)(t % n_l_pad);
+    const size_t ix = t / n_l_pad;
+    double4 v = make_double4(0, 0, 0, 0);
+    if (j < n_l) v = *reinterpret_cast<const double4*>(H + 4 * ((size_t)(nxm1) * j + ix));
+    *reinterpret_cast<double4*>(Ht + 4 * t) = v;
 }
 
 // Scalar models with source windows (config 4): the same loop B for any number of sources.  Window runs have far more time
@@ -683,17 +883,38 @@ void cb_spline_k_launch(const DModel* d_models, int n_models, int max_cols, doub
     cb_spline_k_kernel<<<grid, 128, 0, st>>>(d_models, n_models, d_scratch);
 }
 
-size_t cb_los_smem(int max_nsrc, int max_n_tau) {
-    return sizeof(double) * ((size_t)max_nsrc * max_n_tau + 2 * (size_t)max_n_tau) + sizeof(int) * (size_t)max_n_tau + 16;
+size_t cb_los_smem(int max_nsrc, int max_n_tau, int n_l) {
+    const size_t steps = sizeof(double) * 2 * (size_t)max_n_tau + sizeof(int) * (size_t)max_n_tau + 16;   // left_weight, dtau, bes_index
+    int nslot = (n_l + 31) / 32;
+    if (nslot > 4) nslot = 6;                                                                             // the instantiated slot counts: 1, 2, 3, 4, 6
+    const size_t red = sizeof(double) * 3 * (LOS_THREADS / 32) * 32 * (size_t)nslot;                      // the reduction buffer aliases them
+    return sizeof(double) * (size_t)max_nsrc * max_n_tau + (steps > red ? steps : red);
 }
 
-cudaError_t cb_los_set_smem(size_t smem) {
-    return cudaFuncSetAttribute(cb_los_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+void cb_bessel_transpose_launch(const double* d_h, double* d_ht, int nxm1, int n_l, int n_l_pad, cudaStream_t st) {
+    const size_t tot = (size_t)nxm1 * n_l_pad;
+    cb_bessel_transpose_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_h, d_ht, nxm1, n_l, n_l_pad);
 }
 
-void cb_los_launch(const DModel* d_models, int n_models, const DBessel& B, int max_n_q, int max_n_tau, size_t smem, cudaStream_t st) {
+// which = 1: lanes on the multipoles (coalesced rows of the transposed table); 0: the gather kernel
+cudaError_t cb_los_launch(const DModel* d_models, int n_models, const DBessel& B, int max_n_q, int max_n_tau, size_t smem, int which,
+                          cudaStream_t st) {
     dim3 grid(max_n_q, n_models);
-    cb_los_kernel<<<grid, LOS_THREADS, smem, st>>>(d_models, B, max_n_tau);
+    const int nslot = (B.n_l + 31) / 32;
+#define CB_LOS_GO(K)                                                                                          \
+    do {                                                                                                      \
+        cudaError_t e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        if (e != cudaSuccess) return e;                                                                       \
+        K<<<grid, LOS_THREADS, smem, st>>>(d_models, B, max_n_tau);                                           \
+    } while (0)
+    if (which == 0 || !B.horner_t) CB_LOS_GO(cb_los_gather_kernel);
+    else if (nslot <= 1) CB_LOS_GO(cb_los_kernel<1>);
+    else if (nslot == 2) CB_LOS_GO(cb_los_kernel<2>);
+    else if (nslot == 3) CB_LOS_GO(cb_los_kernel<3>);
+    else if (nslot == 4) CB_LOS_GO(cb_los_kernel<4>);
+    else CB_LOS_GO(cb_los_kernel<6>);
+#undef CB_LOS_GO
+    return cudaGetLastError();
 }
 
 size_t cb_los_win_smem(int max_n_tau) { return (sizeof(double) + sizeof(int)) * (size_t)max_n_tau + 16; }

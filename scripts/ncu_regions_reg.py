@@ -16,7 +16,8 @@ marks = []
 for n, line in enumerate(src, 1):
     m = re.match(r"(?:__device__|__global__|template|static|cudaError_t).*?\b(\w+)\(", line)
     if line.startswith("__device__") or line.startswith("__global__"):
-        marks.append((n, re.search(r"(\w+)\(", line).group(1)))
+        mm = re.search(r"(\w+)\(", line)
+        if mm: marks.append((n, mm.group(1)))
     elif "// ---- the uniform sweep" in line: marks.append((n, "derivs_reg: sweep"))
     elif "// ---- rows with metric" in line: marks.append((n, "derivs_reg: special rows"))
     elif "// ---- output branch" in line: marks.append((n, "derivs_reg: output branch"))
