@@ -43,7 +43,7 @@ build/cuda/%.o: camb_b200/csrc/cuda/%.cu $(CUDA_HDR)
 	$(NVCC) $(NVFLAGS) -c -o $@ $< 2> build/cuda/$*.ptxas.log || (cat build/cuda/$*.ptxas.log; exit 1)
 
 camb_b200/libcambb200.so: $(CUDA_OBJ)
-	$(NVCC) $(ARCH) -shared -o $@ $(CUDA_OBJ) -lcudart
+	$(NVCC) $(ARCH) -shared -o $@ $(CUDA_OBJ) -lcudart -ldl
 	@cat build/cuda/*.ptxas.log > camb_b200/csrc/cuda/ptxas.log
 
 clean:

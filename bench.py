@@ -221,7 +221,7 @@ def los_gather_evals(hs):
     return total
 
 
-def model_h2d_bytes(hs):
+def model_h2d_bytes(hs, thermo_on_device=False):
     m = hs.model
     return 8 * (m.nthermo * (16 + 7) + 2 * m.n_tau) + 8 * max(0, m.num_transfer_redshifts)
 
@@ -268,6 +268,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the one-cosmology latency measurement")
+    ap.add_argument("--host-thermo-tables", action="store_true",
+                    help="e2e leg: upload the host-packed thermo tables (3.3 MB per set) instead of deriving them on the device")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.warmup < 3:
@@ -371,7 +373,8 @@ def main():
 
     # ---- e2e: host buffers -> C-ABI -> host results, copies inside the timed region.  What the drop-in API hands back
     # is read back every step: iCl AND Delta_p_l_k (results.py:541 reads it from the host), plus the lensed C_l.
-    h2d = sum(model_h2d_bytes(hs) for hs in hss) + sum(8 * (3 * len(hs.q_int) + len(hs.source_q())) for hs in hss)
+    tod = not args.host_thermo_tables    # e2e: the thermo derivative tables and Horner records are derived on the device (8(f) rank 1)
+    h2d = sum(model_h2d_bytes(hs, tod) for hs in hss) + sum(8 * (3 * len(hs.q_int) + len(hs.source_q())) for hs in hss)
     d2h = sum(8 * len(hs.ls) * (6 if hs.n_src > 2 else 3) for hs in hss)
     d2h += sum(8 * hs.n_src * len(hs.ls) * len(hs.q_int) for hs in hss)
     if lensing:
@@ -382,7 +385,7 @@ def main():
         ctx.pin_array(a)
 
     def e2e_step():
-        d = [ctx.create_model(hs) for hs in hss]
+        d = [ctx.create_model(hs, thermo_on_device=tod) for hs in hss]
         ctx.evolve(hss, d, want_sources=False, want_stats=False)
         out = project_cl_lens(d, dict(spline_k=0.0, los=0.0, cl=0.0, lens=0.0), delta_out=delta_host)
         for x in d:
@@ -438,7 +441,8 @@ def main():
             # BASELINE.json's second metric: Boltzmann k-modes/s of stages 1-2 alone (this rank's evolve stage, CUDA events)
             "k_modes_per_sec_evolve_stage": world * n_modes / (t_ev / args.steps * 1e-3),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "returns": "iCl, Delta_p_l_k" + (", lensed C_l" if lensing else "")},
+                    "returns": "iCl, Delta_p_l_k" + (", lensed C_l" if lensing else ""),
+                    "thermo_tables": "derived on the device from five base arrays" if tod else "host-packed, uploaded"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "kernel": "cb_evolve_reg_kernel (three static layouts)" if lean else "cb_evolve_kernel",

@@ -160,6 +160,7 @@ class cb_model(C.Structure):
         ("Want_CMB_lensing", C.c_int),
         ("max_bessels_l_index", C.c_int),
         ("Limber_l_min", C.c_int * (3 + CB_MAX_WINDOWS)),
+        ("scale_factor", c_double_p),
     ]
 
 

@@ -45,6 +45,23 @@ void cb_spline_k_launch(const DModel*, int, int, double* const*, cudaStream_t);
 size_t cb_los_smem(int, int, int);
 cudaError_t cb_los_launch(const DModel*, int, const DBessel&, int, int, size_t, int, cudaStream_t);
 void cb_bessel_transpose_launch(const double*, double*, int, int, int, cudaStream_t);
+// collective.cu (NCCL bound at run time)
+bool cb_nccl_unique_id(char* id128, std::string* err);
+bool cb_nccl_init(void** comm, int nranks, int rank, const char* id128, std::string* err);
+void cb_nccl_destroy(void* comm);
+bool cb_nccl_gather_rows(void* comm, int nranks, double* d_src, int n_k, int ncol, const int* d_idx, int n_act, int n_pack, const int* d_owner,
+                         const int* d_pos, double* d_packed, double* d_gathered, cudaStream_t st, std::string* err);
+bool cb_nccl_allreduce_sum(void* comm, double* d_buf, size_t n, cudaStream_t st, std::string* err);
+struct ThermoPackArgs {   // thermo_pack.cu
+    int n;
+    double dlntau;
+    const double *cs2, *dotmu, *emmu, *adot, *sf;
+    double *ddotmu, *dddotmu, *ddddotmu, *demmu, *dadot, *dcs2, *g, *horner;
+};
+cudaError_t cb_thermo_pack_launch(const ThermoPackArgs* d_args, int n_models, int max_n, cudaStream_t st);
+cudaError_t cb_bessel_build_launch(const double* d_x, int nx, const int* d_l, int n_l, int n_l_pad, const cb_range* d_regions, int n_regions,
+                                   double* d_work, double* d_dend, int* d_min_ix, double* d_h, double* d_ht, cudaStream_t st);   // bessel_table.cu
+cudaError_t cb_nonlinear_sources_launch(const DModel* d_model, int n_k, const double* d_ratio, int n_z, double min_kh, cudaStream_t st);
 cudaError_t cb_los_win_launch(const DModel*, int, const DBessel&, int, int, cudaStream_t);
 void cb_cl_launch(const DModel*, int, const DBessel&, cudaStream_t);
 void cb_cl_array_launch(const DModel*, int, const DBessel&, double* const*, cudaStream_t);
@@ -82,6 +99,11 @@ struct cb_dmodel {
     long long* d_stats = nullptr;
     size_t cap_src = 0, cap_k = 0, cap_q = 0, cap_delta = 0, cap_tr = 0, cap_icl = 0, cap_stats = 0;
     int n_cl = 3;
+    // thermo tables derived on the device (cb_model.thermo_horner == NULL): packed by the next cb_evolve together with the
+    // other models of its batch, one launch for all of them
+    bool needs_thermo_pack = false;
+    ThermoPackArgs pack_args{};
+    std::vector<void*> pack_tmp;   // work arrays of the packing, released after it
 };
 
 struct cb_ctx {
@@ -111,6 +133,7 @@ struct cb_ctx {
     // 48-element classes, register kernel for the deep low-k hierarchies (equal throughput at >= 192 sets per call,
     // slower below: DESIGN.md section 4.1)
     int use_reg_kernel = 1;
+    void* comm = nullptr; int comm_ranks = 1, comm_rank = 0;   // NCCL communicator of a k-sharded run (cb_comm_init)
     int los_kernel = 1;            // 1: lanes on the multipoles (transposed table, coalesced rows); 0: the gather kernel
     cudaEvent_t stage_ev[4][2] = {};     // per-stage kernel brackets of the last calls (evolve, spline-k, LOS, C_l)
     DModel* h_models = nullptr;   size_t cap_h_models = 0;   // page-locked staging
@@ -247,6 +270,7 @@ void cb_destroy(cb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) cb_nccl_destroy(ctx->comm);
     for (auto& e : ctx->bess_cache) for (void* p : e.owned) cudaFree(p);
     for (int i = 0; i < 4; i++) { cudaEventDestroy(ctx->stage_ev[i][0]); cudaEventDestroy(ctx->stage_ev[i][1]); }
     if (ctx->h_models) cudaFreeHost(ctx->h_models);
@@ -280,7 +304,7 @@ const char* cb_last_error(const cb_ctx* ctx) { return ctx ? ctx->err.c_str() : "
 
 // Content key of a Bessel table: sizes, the whole l list, the region bounds, the x grid ends and a stride sample of the
 // spline coefficients (the table is a pure function of (l list, x grid), bessels.f90:140-349).
-static unsigned long long bessel_key(const cb_bessel* b) {
+static unsigned long long bessel_key(const cb_bessel* b, bool with_table = true) {
     unsigned long long h = 1469598103934665603ull;
     auto mix = [&h](const void* p, size_t n) { const unsigned char* c = (const unsigned char*)p; for (size_t i = 0; i < n; i++) { h ^= c[i]; h *= 1099511628211ull; } };
     const int n_l_all = b->n_l_all > 0 ? b->n_l_all : b->n_l;
@@ -288,6 +312,12 @@ static unsigned long long bessel_key(const cb_bessel* b) {
     mix(b->l, sizeof(int) * (size_t)n_l_all);
     mix(b->regions, sizeof(cb_range) * (size_t)b->n_regions);
     mix(b->x, sizeof(double)); mix(b->x + b->nx - 1, sizeof(double));
+    if (!with_table) {   // a table generated on the device is a pure function of what has been mixed in so far
+        const unsigned long long tag = 0x6275696c74ull;
+        mix(&tag, sizeof(tag));
+        mix(b->x, sizeof(double) * (size_t)b->nx);
+        return h;
+    }
     const size_t tot = (size_t)4 * (b->nx - 1) * b->n_l, step = tot / 509 + 1;
     for (size_t i = 0; i < tot; i += step) mix(b->horner + i, sizeof(double));
     return h;
@@ -341,6 +371,70 @@ int cb_set_bessel(cb_ctx* ctx, const cb_bessel* b) {
     return 0;
 }
 
+// GenerateBessels on the device (bessels.f90:140-228; bessel_table.cu): b->horner is not read.  The table becomes the one
+// in use, exactly as after cb_set_bessel; horner_out (may be NULL) receives bessel_horner(4, nx-1, n_l) for the host.
+int cb_build_bessel(cb_ctx* ctx, const cb_bessel* b, double* horner_out) {
+    if (!ctx) return CB_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    if (b->n_regions > 8) { ctx->err = "too many Bessel x regions"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    if (b->n_l < 1 || b->nx < 3) { ctx->err = "cb_build_bessel: empty table"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    if (b->x[b->nx - 1] < b->l[b->n_l - 1] + 1) { ctx->err = "cb_build_bessel: x grid ends below the largest l"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    const unsigned long long key = bessel_key(b, false);
+    const size_t n_tab = (size_t)4 * (b->nx - 1) * b->n_l;
+    for (auto& e : ctx->bess_cache)
+        if (e.key == key) {
+            e.stamp = ++ctx->bess_clock; ctx->bess = e.B; ctx->have_bessel = true;
+            if (horner_out) {
+                CK(cudaMemcpyAsync(horner_out, e.B.horner, sizeof(double) * n_tab, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+            }
+            return 0;
+        }
+    if (ctx->bess_cache.size() >= 8) {
+        size_t old = 0;
+        for (size_t i = 1; i < ctx->bess_cache.size(); i++) if (ctx->bess_cache[i].stamp < ctx->bess_cache[old].stamp) old = i;
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (void* p : ctx->bess_cache[old].owned) dev_free(ctx, p);
+        ctx->bess_cache.erase(ctx->bess_cache.begin() + old);
+    }
+    ctx->bess_cache.emplace_back();
+    cb_ctx::BessEntry& E = ctx->bess_cache.back();
+    E.key = key; E.stamp = ++ctx->bess_clock;
+    DBessel& B = E.B;
+    B.n_l = b->n_l; B.nx = b->nx; B.n_regions = b->n_regions;
+    B.n_l_all = b->n_l_all > 0 ? b->n_l_all : b->n_l;
+    B.n_l_pad = (b->n_l + 3) & ~3;
+    for (int i = 0; i < b->n_regions; i++) B.regions[i] = b->regions[i];
+    B.xmax = b->x[b->nx - 1];
+    int* dl = nullptr; double *dx = nullptr, *dh = nullptr, *dht = nullptr, *dwork = nullptr, *ddend = nullptr; int* dmin = nullptr; cb_range* dreg = nullptr;
+    std::vector<void*> tmp;   // work buffers, released after the build
+    int e = upload(ctx, b->l, (size_t)B.n_l_all, &dl, &E.owned);
+    if (!e) e = upload(ctx, b->x, (size_t)b->nx, &dx, &E.owned);
+    if (!e) e = upload(ctx, b->regions, (size_t)b->n_regions, &dreg, &tmp);
+    auto alloc = [&](void** p, size_t bytes, std::vector<void*>* own) {
+        if (e) return;
+        if (dev_alloc(ctx, p, bytes) != cudaSuccess) { ctx->err = "out of device memory building the Bessel table"; e = CB_ERR_CUDA; return; }
+        own->push_back(*p);
+    };
+    alloc((void**)&dh, sizeof(double) * n_tab, &E.owned);
+    alloc((void**)&dht, sizeof(double) * 4 * (size_t)(b->nx - 1) * B.n_l_pad, &E.owned);
+    alloc((void**)&dwork, sizeof(double) * 3 * (size_t)b->nx * b->n_l, &tmp);
+    alloc((void**)&ddend, sizeof(double) * (size_t)b->n_l, &tmp);
+    alloc((void**)&dmin, sizeof(int) * (size_t)b->n_l, &tmp);
+    if (!e && cb_bessel_build_launch(dx, b->nx, dl, b->n_l, B.n_l_pad, dreg, b->n_regions, dwork, ddend, dmin, dh, dht, ctx->stream) != cudaSuccess) {
+        ctx->err = "cb_build_bessel: launch failed"; e = CB_ERR_CUDA;
+    }
+    ctx->launches += 3;
+    for (void* p : tmp) dev_free(ctx, p);
+    if (e) { for (void* p : E.owned) dev_free(ctx, p); ctx->bess_cache.pop_back(); return e; }
+    B.l = dl; B.x = dx; B.horner = dh; B.horner_t = dht;
+    if (horner_out) CK(cudaMemcpyAsync(horner_out, dh, sizeof(double) * n_tab, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->bess = B;
+    ctx->have_bessel = true;
+    return 0;
+}
+
 int cb_model_create(cb_ctx* ctx, const cb_model* m, cb_dmodel** out) {
     *out = nullptr;
     if (!ctx) return CB_ERR_NO_DEVICE;
@@ -358,7 +452,7 @@ int cb_model_create(cb_ctx* ctx, const cb_model* m, cb_dmodel** out) {
     const bool is_tensor = !m->WantScalars && m->WantTensors;
     if (m->WantScalars && m->WantTensors) { ctx->err = "cmbmain cannot generate tensors and scalars in one pass (cmbmain.f90:142)"; return CB_ERR_UNSUPPORTED_PARAMS; }
     if (!m->WantScalars && !is_tensor) { ctx->err = "vector modes are not supported"; return CB_ERR_UNSUPPORTED_PARAMS; }
-    if (is_tensor && (m->n_src != 3 || !m->adot || !m->dadot)) { ctx->err = "tensor models need n_src = 3 and the adot/dadot tables"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    if (is_tensor && (m->n_src != 3 || !m->adot || (m->thermo_horner && !m->dadot))) { ctx->err = "tensor models need n_src = 3 and the adot/dadot tables"; return CB_ERR_UNSUPPORTED_PARAMS; }
     cb_dmodel* dm = new cb_dmodel();
     DModel& D = dm->h;
     memset(&D, 0, sizeof(D));
@@ -397,12 +491,39 @@ int cb_model_create(cb_ctx* ctx, const cb_model* m, cb_dmodel** out) {
     double* p;
     size_t nt = (size_t)m->nthermo;
 #define UP(field, src, n) do { if ((e = upload(ctx, (src), (n), &p, &dm->owned))) { cb_model_destroy(ctx, dm); return e; } D.field = p; } while (0)
-    UP(thermo_horner, m->thermo_horner, nt * 16);
-    UP(cs2, m->cs2, nt); UP(dotmu, m->dotmu, nt); UP(ddotmu, m->ddotmu, nt); UP(dddotmu, m->dddotmu, nt);
-    UP(ddddotmu, m->ddddotmu, nt); UP(emmu, m->emmu, nt); UP(demmu, m->demmu, nt);
+    if (m->thermo_horner) {
+        UP(thermo_horner, m->thermo_horner, nt * 16);
+        UP(cs2, m->cs2, nt); UP(dotmu, m->dotmu, nt); UP(ddotmu, m->ddotmu, nt); UP(dddotmu, m->dddotmu, nt);
+        UP(ddddotmu, m->ddddotmu, nt); UP(emmu, m->emmu, nt); UP(demmu, m->demmu, nt);
+        if (is_tensor) { UP(adot, m->adot, nt); UP(dadot, m->dadot, nt); }
+    } else {
+        // results.f90:2430-2494 on the device: five base arrays up, the derivative tables and the Horner records are
+        // computed by thermo_pack.cu before the first kernel that reads them
+        if (!m->cs2 || !m->dotmu || !m->emmu || !m->adot || !m->scale_factor || nt < 4) {
+            cb_model_destroy(ctx, dm);
+            ctx->err = "thermo_horner is NULL: cs2, dotmu, emmu, adot and scale_factor are needed to build the tables on the device";
+            return CB_ERR_UNSUPPORTED_PARAMS;
+        }
+        UP(cs2, m->cs2, nt); UP(dotmu, m->dotmu, nt); UP(emmu, m->emmu, nt); UP(adot, m->adot, nt);
+        ThermoPackArgs& A = dm->pack_args;
+        A.n = (int)nt; A.dlntau = m->dlntau;
+        A.cs2 = D.cs2; A.dotmu = D.dotmu; A.emmu = D.emmu; A.adot = D.adot;
+        if ((e = upload(ctx, m->scale_factor, nt, &p, &dm->pack_tmp))) { cb_model_destroy(ctx, dm); return e; }
+        A.sf = p;
+        auto dalloc = [&](double** q, size_t n, std::vector<void*>* own) {
+            if (e) return;
+            if (dev_alloc(ctx, (void**)q, sizeof(double) * n) != cudaSuccess) { ctx->err = "out of device memory for the thermo tables"; e = CB_ERR_CUDA; return; }
+            own->push_back(*q);
+        };
+        dalloc(&A.ddotmu, nt, &dm->owned); dalloc(&A.dddotmu, nt, &dm->owned); dalloc(&A.ddddotmu, nt, &dm->owned);
+        dalloc(&A.demmu, nt, &dm->owned); dalloc(&A.dadot, nt, &dm->owned); dalloc(&A.horner, nt * 16, &dm->owned);
+        dalloc(&A.dcs2, nt, &dm->pack_tmp); dalloc(&A.g, nt * 4, &dm->pack_tmp);
+        if (e) { cb_model_destroy(ctx, dm); return e; }
+        D.thermo_horner = A.horner; D.ddotmu = A.ddotmu; D.dddotmu = A.dddotmu; D.ddddotmu = A.ddddotmu; D.demmu = A.demmu; D.dadot = A.dadot;
+        dm->needs_thermo_pack = true;
+    }
     UP(tau, m->tau, (size_t)m->n_tau); UP(dtau, m->dtau, (size_t)m->n_tau);
     if (D.num_transfer_redshifts > 0) UP(transfer_times, m->transfer_times, (size_t)D.num_transfer_redshifts);
-    if (is_tensor) { UP(adot, m->adot, nt); UP(dadot, m->dadot, nt); }
 #undef UP
     D.num_redshiftwindows = nwin; D.num_extra_redshiftwindows = nwin > 0 ? m->num_extra_redshiftwindows : 0;
     D.SourceTerms = m->SourceTerms; D.tau_start_redshiftwindows = m->tau_start_redshiftwindows; D.qmax = m->qmax;
@@ -429,6 +550,7 @@ void cb_model_destroy(cb_ctx* ctx, cb_dmodel* dm) {
     if (ctx) cudaSetDevice(ctx->device);
     if (!ctx) { delete dm; return; }
     for (void* p : dm->owned) dev_free(ctx, p);
+    for (void* p : dm->pack_tmp) dev_free(ctx, p);
     void* bufs[] = {dm->d_q_src, dm->d_src, dm->d_dd, dm->d_scratch, dm->d_delta, dm->d_icl, dm->d_q_int, dm->d_dq_int,
                     dm->d_pows, dm->d_transfer, dm->d_stats, dm->d_icl_array, dm->d_limb, dm->d_lpow, dm->d_icl_w};
     for (void* p : bufs) dev_free(ctx, p);
@@ -449,10 +571,37 @@ static int push_models(cb_ctx* ctx, int n_models, cb_dmodel* const* dm) {
     return 0;
 }
 
+}  // extern "C"
+
+// The models of this call whose thermo tables are still to be derived (cb_model.thermo_horner == NULL): one launch for all.
+static int pack_thermo_tables(cb_ctx* ctx, int n_models, cb_dmodel* const* dm) {
+    std::vector<ThermoPackArgs> args;
+    int max_n = 0;
+    for (int m = 0; m < n_models; m++)
+        if (dm[m]->needs_thermo_pack) { args.push_back(dm[m]->pack_args); max_n = std::max(max_n, dm[m]->pack_args.n); }
+    if (args.empty()) return 0;
+    ThermoPackArgs* d_args = nullptr;
+    CK(dev_alloc(ctx, (void**)&d_args, sizeof(ThermoPackArgs) * args.size()));
+    CK(cudaMemcpyAsync(d_args, args.data(), sizeof(ThermoPackArgs) * args.size(), cudaMemcpyHostToDevice, ctx->stream));   // pageable: staged before return
+    CK(cb_thermo_pack_launch(d_args, (int)args.size(), max_n, ctx->stream));
+    ctx->launches += 2;
+    dev_free(ctx, d_args);
+    for (int m = 0; m < n_models; m++)
+        if (dm[m]->needs_thermo_pack) {
+            for (void* p : dm[m]->pack_tmp) dev_free(ctx, p);
+            dm[m]->pack_tmp.clear();
+            dm[m]->needs_thermo_pack = false;
+        }
+    return 0;
+}
+
+extern "C" {
+
 int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* modes, double* const* LinearSrc,
               float* const* TransferData, long long* const* stats) {
     if (!ctx) return CB_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
+    if (int e = pack_thermo_tables(ctx, n_models, dm)) return e;
     std::vector<DModeItem> cls_items[CB_N_CLASSES], all_items;
     int lean = 1;   // every model massless-nu LCDM: the kernel variants without massive-nu / dark-energy code
     for (int m = 0; m < n_models; m++) if (dm[m]->h.Num_Nu_massive != 0 || !dm[m]->h.de_is_cc || dm[m]->h.num_redshiftwindows > 0 || dm[m]->h.is_tensor) lean = 0;
@@ -651,6 +800,32 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
     }
 #endif
     if (herr) { ctx->err = "RungeKuttaDP45 error: step size underflow in the device integrator"; return herr; }
+    return 0;
+}
+
+// MakeNonlinearSources (cmbmain.f90:1190-1247) on the device-resident sources of the last cb_evolve, in place.
+// nonlin_ratio: CAMB_PK%nonlin_ratio(n_k, n_z), wavenumber fastest, n_z = num_transfer_redshifts of the model.
+int cb_make_nonlinear_sources(cb_ctx* ctx, cb_dmodel* dm, int n_k, int n_z, const double* nonlin_ratio, double Min_kh_nonlinear) {
+    if (!ctx || !dm) return CB_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    DModel& D = dm->h;
+    if (!dm->d_src || n_k != D.n_k) { ctx->err = "cb_make_nonlinear_sources: call cb_evolve on this model first"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    if (D.is_tensor || n_z < 2 || n_z != D.num_transfer_redshifts || !D.transfer_times) {
+        ctx->err = "cb_make_nonlinear_sources: the model has no transfer output times to interpolate the ratios over";
+        return CB_ERR_UNSUPPORTED_PARAMS;
+    }
+    if (D.n_src < 3) return 0;   // nothing to scale (cmbmain.f90:1240 scales sources 3..)
+    double* d_ratio = nullptr;
+    DModel* d_model = nullptr;
+    CK(dev_alloc(ctx, (void**)&d_ratio, sizeof(double) * (size_t)n_k * n_z));
+    CK(dev_alloc(ctx, (void**)&d_model, sizeof(DModel)));
+    CK(cudaMemcpyAsync(d_ratio, nonlin_ratio, sizeof(double) * (size_t)n_k * n_z, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_model, &D, sizeof(DModel), cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t le = cb_nonlinear_sources_launch(d_model, n_k, d_ratio, n_z, Min_kh_nonlinear, ctx->stream);
+    ctx->launches++;
+    dev_free(ctx, d_ratio); dev_free(ctx, d_model);
+    if (le != cudaSuccess) { ctx->err = std::string("cb_make_nonlinear_sources: ") + cudaGetErrorString(le); return CB_ERR_CUDA; }
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -1041,6 +1216,71 @@ void cb_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
+// ---- one cosmology sharded over the GPUs of a box: the two exchange steps, stream-ordered (collective.cu) ----
+int cb_comm_unique_id(cb_ctx* ctx, char* id128) {
+    if (!ctx) return CB_ERR_NO_DEVICE;
+    if (!cb_nccl_unique_id(id128, &ctx->err)) return CB_ERR_CUDA;
+    return 0;
+}
+
+int cb_comm_init(cb_ctx* ctx, int nranks, int rank, const char* id128) {
+    if (!ctx) return CB_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    if (nranks < 1 || rank < 0 || rank >= nranks) { ctx->err = "cb_comm_init: bad rank"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    if (ctx->comm) { cb_nccl_destroy(ctx->comm); ctx->comm = nullptr; }
+    if (!cb_nccl_init(&ctx->comm, nranks, rank, id128, &ctx->err)) return CB_ERR_CUDA;
+    ctx->comm_ranks = nranks; ctx->comm_rank = rank;
+    return 0;
+}
+
+// owner[k] (0 .. nranks-1): the rank whose cb_evolve call had mode k in cb_modes.active.  Returns with the exchange
+// queued on the library's stream (no host synchronisation): the next entry point is ordered after it.
+int cb_gather_sources(cb_ctx* ctx, cb_dmodel* dm, int n_k, const int* owner) {
+    if (!ctx || !dm) return CB_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->comm) { ctx->err = "cb_gather_sources: no communicator (cb_comm_init)"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    const DModel& D = dm->h;
+    if (n_k != D.n_k || !dm->d_src) { ctx->err = "cb_gather_sources: call cb_evolve on this model first"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    const int R = ctx->comm_ranks, me = ctx->comm_rank, ncol = D.n_src * D.n_tau;
+    std::vector<int> cnt(R, 0), pos(n_k), idx;
+    for (int k = 0; k < n_k; k++) {
+        if (owner[k] < 0 || owner[k] >= R) { ctx->err = "cb_gather_sources: owner out of range"; return CB_ERR_UNSUPPORTED_PARAMS; }
+        pos[k] = cnt[owner[k]]++;
+        if (owner[k] == me) idx.push_back(k);
+    }
+    int n_pack = 1;
+    for (int r = 0; r < R; r++) n_pack = std::max(n_pack, cnt[r]);
+    // small index arrays: pageable cudaMemcpyAsync stages them before returning
+    int *d_owner = nullptr, *d_pos = nullptr, *d_idx = nullptr;
+    double *d_packed = nullptr, *d_gathered = nullptr;
+    CK(dev_alloc(ctx, (void**)&d_owner, sizeof(int) * n_k));
+    CK(dev_alloc(ctx, (void**)&d_pos, sizeof(int) * n_k));
+    CK(dev_alloc(ctx, (void**)&d_idx, sizeof(int) * std::max<size_t>(idx.size(), 1)));
+    CK(dev_alloc(ctx, (void**)&d_packed, sizeof(double) * (size_t)n_pack * ncol));
+    CK(dev_alloc(ctx, (void**)&d_gathered, sizeof(double) * (size_t)R * n_pack * ncol));
+    CK(cudaMemcpyAsync(d_owner, owner, sizeof(int) * n_k, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_pos, pos.data(), sizeof(int) * n_k, cudaMemcpyHostToDevice, ctx->stream));
+    if (!idx.empty()) CK(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice, ctx->stream));
+    const bool ok = cb_nccl_gather_rows(ctx->comm, R, dm->d_src, n_k, ncol, d_idx, (int)idx.size(), n_pack, d_owner, d_pos, d_packed, d_gathered,
+                                        ctx->stream, &ctx->err);
+    ctx->launches += 2;
+    dev_free(ctx, d_owner); dev_free(ctx, d_pos); dev_free(ctx, d_idx); dev_free(ctx, d_packed); dev_free(ctx, d_gathered);
+    return ok ? 0 : CB_ERR_CUDA;
+}
+
+// Sum of the partial iCl (this rank's slice of the integration wavenumbers) over the ranks; iCl (may be NULL) receives it.
+int cb_allreduce_cl(cb_ctx* ctx, cb_dmodel* dm, double* iCl) {
+    if (!ctx || !dm) return CB_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->comm) { ctx->err = "cb_allreduce_cl: no communicator (cb_comm_init)"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    if (!dm->d_icl) { ctx->err = "cb_allreduce_cl: call cb_cl on this model first"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    const size_t n = (size_t)ctx->bess.n_l * dm->n_cl;
+    if (!cb_nccl_allreduce_sum(ctx->comm, dm->d_icl, n, ctx->stream, &ctx->err)) return CB_ERR_CUDA;
+    if (iCl) CK(cudaMemcpyAsync(iCl, dm->d_icl, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int cb_device_buffer(cb_ctx* ctx, cb_dmodel* dm, int which, void** ptr, size_t* bytes) {
     if (!ctx || !dm) return CB_ERR_NO_DEVICE;
     const DModel& D = dm->h;
@@ -1063,6 +1303,7 @@ int cb_debug_derivs(cb_ctx* ctx, cb_dmodel* dm, double q, double tau, const int*
     CK(cudaSetDevice(ctx->device));
     const DModel& D = dm->h;
     if (D.is_tensor) { ctx->err = "cb_debug_derivs: scalar models only"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    if (int e = pack_thermo_tables(ctx, 1, &dm)) return e;
     if (lean && (D.Num_Nu_massive != 0 || !D.de_is_cc || D.num_redshiftwindows > 0)) {
         ctx->err = "cb_debug_derivs: the lean variant is for massless-neutrino LCDM models";
         return CB_ERR_UNSUPPORTED_PARAMS;

@@ -456,6 +456,77 @@ __global__ void cb_bessel_transpose_kernel(const double* __restrict__ H, double*
     *reinterpret_cast<double4*>(Ht + 4 * t) = v;
 }
 
+// MakeNonlinearSources, cmbmain.f90:1190-1247, on the device-resident LinearSrc (in place: the reference's ScaledSrc): one CTA
+// per source wavenumber; thread 0 solves the natural spline of that wavenumber's non-linear ratios over the transfer
+// output times (n_z <= a few hundred), then the threads scale sources 3..n_src of the time steps in parallel.  The host's
+// halofit hands over nonlin_ratio(n_k, n_z) only: the sources never make the D2H / H2D round trip of cb_set_sources.
+// dynamic smem: 3 n_z doubles
+__global__ void cb_nonlinear_sources_kernel(const DModel* __restrict__ model, const double* __restrict__ ratio, int n_z, double min_kh) {
+    extern __shared__ __align__(16) double sm[];
+    const DModel& M = *model;
+    const int ik = blockIdx.x, n_k = M.n_k, n_src = M.n_src, n_tau = M.n_tau;
+    double* scaling = sm;
+    double* dd = scaling + n_z;
+    double* u = dd + n_z;
+    const double* tt = M.transfer_times;
+    __shared__ int s_skip, s_first;
+    if (threadIdx.x == 0) {
+        int skip = !(M.q_src[ik] / (M.H0 / 100) > min_kh);
+        if (!skip) {
+            int all_one = 1;
+            for (int z = 0; z < n_z; z++) {
+                scaling[z] = ratio[ik + (size_t)n_k * z];
+                if (!(fabs(scaling[z] - 1) < 5e-4)) all_one = 0;
+            }
+            skip = all_one;
+        }
+        if (!skip) {   // forutils spline, natural at both ends (Interpolation.f90:919-964)
+            double d1r = (scaling[1] - scaling[0]) / (tt[1] - tt[0]), d1l;
+            dd[0] = 0; u[0] = 0;
+            for (int i = 1; i < n_z - 1; i++) {
+                d1l = d1r;
+                d1r = (scaling[i + 1] - scaling[i]) / (tt[i + 1] - tt[i]);
+                const double xxdiv = 1.0 / (tt[i + 1] - tt[i - 1]);
+                const double sig = (tt[i] - tt[i - 1]) * xxdiv;
+                const double xp = 1.0 / (sig * dd[i - 1] + 2.0);
+                dd[i] = (sig - 1.0) * xp;
+                u[i] = (6.0 * (d1r - d1l) * xxdiv - sig * u[i - 1]) * xp;
+            }
+            dd[n_z - 1] = 0.0;
+            for (int i = n_z - 2; i >= 0; i--) dd[i] = dd[i] * dd[i + 1] + u[i];
+            int first_step = 1;
+            while (M.tau[first_step - 1] < tt[0]) first_step++;
+            s_first = first_step;
+        }
+        s_skip = skip;
+    }
+    __syncthreads();
+    if (s_skip) return;
+    for (int i = s_first + threadIdx.x; i <= n_tau - 1; i += blockDim.x) {
+        const double tau = M.tau[i - 1];
+        int lo = 0, hi = n_z - 1;               // the interval the reference's running (tf_lo, tf_hi) pair stands on:
+        while (hi - lo > 1) {                   // the first tf_hi with tau <= transfer_times(tf_hi)
+            const int mid = (lo + hi) >> 1;
+            if (tau > tt[mid]) lo = mid; else hi = mid;
+        }
+        if (!(tau > tt[0])) { lo = 0; hi = 1; }
+        const double ho = tt[hi] - tt[lo];
+        const double a0 = (tt[hi] - tau) / ho, b0 = 1 - a0;
+        const double ascale = a0 * scaling[lo] + b0 * scaling[hi] + ((a0 * a0 * a0 - a0) * dd[lo] + (b0 * b0 * b0 - b0) * dd[hi]) * (ho * ho) / 6;
+        for (int s = 3; s <= n_src; s++) {
+            double* v = M.LinearSrc + ik + (size_t)n_k * ((s - 1) + (size_t)n_src * (i - 1));
+            *v = *v * ascale;
+        }
+    }
+}
+
+cudaError_t cb_nonlinear_sources_launch(const DModel* d_model, int n_k, const double* d_ratio, int n_z, double min_kh, cudaStream_t st) {
+    const size_t smem = sizeof(double) * 3 * (size_t)n_z;
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;
+    cb_nonlinear_sources_kernel<<<n_k, 128, smem, st>>>(d_model, d_ratio, n_z, min_kh);
+    return cudaGetLastError();
+}
+
 // Scalar models with source windows (config 4): the same loop B for any number of sources.  Window runs have far more time
 // steps (up to ~1e4 without the Limber switch) and sources than fit shared memory, so only the per-q Bessel index and weight
 // are staged; Source_q(n, s) is evaluated from the k-spline where it is used.  Not the benchmark path: clarity over speed.

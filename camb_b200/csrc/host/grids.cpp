@@ -477,7 +477,7 @@ void HostState::fill_model(cb_model& m) const {
     m.transfer_times = transfer_times.data();
     m.max_etak_scalar = max_etak_scalar; m.max_etak_tensor = max_etak_tensor; m.qmin = qmin; m.qmax = qmax;
     m.WantLateTime = WantLateTime; m.n_src = n_src;
-    m.adot = th.adot.data(); m.dadot = th.dadot.data();
+    m.adot = th.adot.data(); m.dadot = th.dadot.data(); m.scale_factor = th.ScaleFactor.data();
     for (int i = 0; i < 5; i++) m.InitialConditionVector[i] = CP.InitialConditionVector[i];
     m.num_redshiftwindows = num_redshiftwindows; m.num_extra_redshiftwindows = num_extra_redshiftwindows;
     m.windows = windows_c.empty() ? nullptr : windows_c.data();

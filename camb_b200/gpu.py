@@ -18,12 +18,13 @@ _lib = None
 c_ll_p = C.POINTER(C.c_longlong)
 c_void_pp = C.POINTER(C.c_void_p)
 
-SYMBOLS = ["cb_create", "cb_destroy", "cb_last_error", "cb_device_count", "cb_set_bessel", "cb_model_create",
-           "cb_model_destroy", "cb_evolve", "cb_set_sources", "cb_project", "cb_cl", "cb_last_timings",
+SYMBOLS = ["cb_create", "cb_destroy", "cb_last_error", "cb_device_count", "cb_set_bessel", "cb_build_bessel", "cb_model_create",
+           "cb_model_destroy", "cb_evolve", "cb_set_sources", "cb_make_nonlinear_sources", "cb_project", "cb_cl", "cb_last_timings",
            "cb_launch_count", "cb_abi_sizeof", "cb_timer_start", "cb_timer_stop", "cb_fp64_peak",
            "cb_host_alloc", "cb_host_free", "cb_device_buffer", "cb_set_option", "cb_host_register",
            "cb_host_unregister", "cb_cl_array", "cb_cl_windows", "cb_lens_contrib",
-           "cb_last_lens_timing", "cb_debug_derivs", "cb_tmem_probe"]
+           "cb_last_lens_timing", "cb_debug_derivs", "cb_tmem_probe", "cb_comm_unique_id", "cb_comm_init",
+           "cb_gather_sources", "cb_allreduce_cl"]
 
 
 def load_gpu_lib():
@@ -40,11 +41,13 @@ def load_gpu_lib():
         lib.cb_last_error.restype = C.c_char_p
         lib.cb_last_error.argtypes = [C.c_void_p]
         lib.cb_set_bessel.argtypes = [C.c_void_p, C.POINTER(cb_bessel)]
+        lib.cb_build_bessel.argtypes = [C.c_void_p, C.POINTER(cb_bessel), c_double_p]
         lib.cb_model_create.argtypes = [C.c_void_p, C.POINTER(cb_model), c_void_pp]
         lib.cb_model_destroy.argtypes = [C.c_void_p, C.c_void_p]
         lib.cb_evolve.argtypes = [C.c_void_p, C.c_int, c_void_pp, C.POINTER(cb_modes), C.POINTER(c_double_p),
                                   C.POINTER(c_float_p), C.POINTER(c_ll_p)]
         lib.cb_set_sources.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_double_p, c_double_p]
+        lib.cb_make_nonlinear_sources.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_double]
         lib.cb_project.argtypes = [C.c_void_p, C.c_int, c_void_pp, c_int_p, C.POINTER(c_double_p),
                                    C.POINTER(c_double_p), C.POINTER(c_double_p)]
         lib.cb_cl.argtypes = [C.c_void_p, C.c_int, c_void_pp, C.c_int, C.POINTER(c_double_p), C.POINTER(c_double_p)]
@@ -69,6 +72,10 @@ def load_gpu_lib():
         lib.cb_debug_derivs.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, c_int_p, c_double_p, C.c_int, C.c_int,
                                         C.c_int, c_double_p, c_double_p]
         lib.cb_tmem_probe.argtypes = [C.c_void_p, C.c_int, c_int_p, C.POINTER(C.c_longlong)]
+        lib.cb_comm_unique_id.argtypes = [C.c_void_p, C.c_char_p]
+        lib.cb_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+        lib.cb_gather_sources.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_int_p]
+        lib.cb_allreduce_cl.argtypes = [C.c_void_p, C.c_void_p, c_double_p]
         lib.cb_abi_sizeof.restype = C.c_size_t
         lib.cb_abi_sizeof.argtypes = [C.c_int]
         _lib = lib
@@ -114,9 +121,26 @@ class GpuContext:
         self._check(self._lib.cb_set_bessel(self._h, C.byref(b)))
         self.n_l = b.n_l
 
-    def create_model(self, hs):
+    def build_bessel(self, hs, want_table=False):
+        """GenerateBessels on the device (bessels.f90:140-228): only the l list and the x grid of this host state cross PCIe.
+        Returns bessel_horner(4, nx-1, n_l) as an array of shape (n_l, nx-1, 4) when want_table."""
+        b = hs.bessel()
+        out = np.zeros((b.n_l, b.nx - 1, 4)) if want_table else None
+        self._check(self._lib.cb_build_bessel(self._h, C.byref(b), _dp(out) if want_table else None))
+        self.n_l = b.n_l
+        return out
+
+    def create_model(self, hs, thermo_on_device=False):
+        """cb_model_create.  thermo_on_device: pass only the five base thermo arrays (cs2, dotmu, emmu, adot, a/tau) and let the
+        library derive the derivative tables and Horner records (results.f90:2430-2494) on the device."""
         dm = C.c_void_p()
-        self._check(self._lib.cb_model_create(self._h, C.byref(hs.model), C.byref(dm)))
+        m = hs.model
+        if thermo_on_device:
+            m = type(hs.model)()
+            C.memmove(C.byref(m), C.byref(hs.model), C.sizeof(m))
+            null = C.POINTER(C.c_double)()
+            m.thermo_horner = m.ddotmu = m.dddotmu = m.ddddotmu = m.demmu = m.dadot = null
+        self._check(self._lib.cb_model_create(self._h, C.byref(m), C.byref(dm)))
         return dm
 
     def debug_derivs(self, dm, q, tau, y, flags=(0, 0, 0, 0), lanes=32, lean=False):
@@ -180,6 +204,11 @@ class GpuContext:
                 st.append(None)
         self._check(self._lib.cb_evolve(self._h, n, dm_arr, md_arr, src_p, tr_p, st_p))
         return src, tr, st
+
+    def make_nonlinear_sources(self, dm, ratio, min_kh=0.005):
+        """MakeNonlinearSources on the device-resident sources of the last evolve; ratio: (n_z, n_k) = nonlin_ratio(ik, iz)."""
+        ratio = np.ascontiguousarray(ratio, dtype=np.float64)
+        self._check(self._lib.cb_make_nonlinear_sources(self._h, dm, ratio.shape[1], ratio.shape[0], _dp(ratio), float(min_kh)))
 
     def set_sources(self, dm, q_src, src):
         q_src = np.ascontiguousarray(q_src)
@@ -280,7 +309,7 @@ class GpuContext:
         m = hs.model
         n = m.nthermo
         for ptr, cnt in [(m.thermo_horner, 16 * n), (m.cs2, n), (m.dotmu, n), (m.ddotmu, n), (m.dddotmu, n), (m.ddddotmu, n),
-                         (m.emmu, n), (m.demmu, n), (m.tau, m.n_tau), (m.dtau, m.n_tau)]:
+                         (m.emmu, n), (m.demmu, n), (m.adot, n), (m.scale_factor, n), (m.tau, m.n_tau), (m.dtau, m.n_tau)]:
             addr = C.cast(ptr, C.c_void_p).value
             if addr:
                 self._lib.cb_host_register(addr, 8 * cnt)   # best effort: an unpinned table is still copied correctly
@@ -304,6 +333,26 @@ class GpuContext:
         t = C.c_double()
         self._check(self._lib.cb_fp64_peak(self._h, C.byref(t)))
         return t.value
+
+    def comm_unique_id(self):
+        """128-byte NCCL unique id (rank 0); distribute it and call comm_init on every rank."""
+        buf = C.create_string_buffer(128)
+        self._check(self._lib.cb_comm_unique_id(self._h, buf))
+        return buf.raw
+
+    def comm_init(self, nranks, rank, uid):
+        self._check(self._lib.cb_comm_init(self._h, int(nranks), int(rank), C.create_string_buffer(bytes(uid), 128)))
+
+    def gather_sources(self, dm, owner):
+        """One all-gather of the evolved rows of LinearSrc along k (owner[k] = rank that evolved mode k); stream-ordered."""
+        owner = np.ascontiguousarray(owner, dtype=np.int32)
+        self._check(self._lib.cb_gather_sources(self._h, dm, len(owner), owner.ctypes.data_as(c_int_p)))
+
+    def allreduce_cl(self, dm, n_l, n_cl):
+        """Sum of the partial iCl over the ranks; returns (n_l, n_cl)."""
+        out = np.zeros((n_cl, n_l))
+        self._check(self._lib.cb_allreduce_cl(self._h, dm, _dp(out)))
+        return out.T.copy()
 
     def device_buffer(self, dm, which):
         """(device pointer, bytes) of a result buffer: 0 LinearSrc, 1 Delta_p_l_k, 2 iCl, 3 TransferData."""

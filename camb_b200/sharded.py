@@ -52,10 +52,20 @@ def partition_q(q_int, ls, tau0, world):
 class GpuBackend:
     """The product path: libcambb200.so through camb_b200.gpu.GpuContext; arrays stay on the device."""
 
-    def __init__(self, ctx):
+    def __init__(self, ctx, rank=0, world=1, native_collectives=False):
+        """native_collectives: the two exchange steps are issued by the library itself (cb_gather_sources: one ncclAllGather
+        of the evolved rows; cb_allreduce_cl), stream-ordered behind its kernels, instead of torch.distributed calls on
+        views of its buffers with a host synchronisation on either side.  The NCCL unique id travels through the
+        torch.distributed store."""
         import torch
         self.torch = torch
         self.ctx = ctx
+        self.native = bool(native_collectives) and world > 1
+        if self.native:
+            import torch.distributed as dist
+            box = [ctx.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            ctx.comm_init(world, rank, box[0])
 
     def _view(self, dm, which, dtype):
         """torch view (no copy) of one of the library's device buffers."""
@@ -113,6 +123,19 @@ class ShardedBoltzmann:
         idx = partition_modes(hs.source_q(), self.world)[self.rank]
         lo, hi = partition_q(hs.q_int, hs.ls, hs.model.tau0, self.world)[self.rank]
         dm = self.b.begin(hs)
+        if getattr(self.b, "native", False):          # collectives issued by the library on its own stream (collective.cu)
+            try:
+                parts = partition_modes(hs.source_q(), self.world)
+                owner = np.empty(len(hs.source_q()), dtype=np.int32)
+                for r, ix in enumerate(parts):
+                    owner[ix] = r
+                self.b.ctx.evolve([hs], [dm], want_sources=False, want_stats=False, active=[idx])
+                self.b.ctx.gather_sources(dm, owner)                       # one all-gather of the evolved rows, queued
+                self.b.ctx.project([hs], [dm], want_delta=False, q_slices=[(lo, hi)])
+                self.b.ctx.cl([hs], [dm], [pows[lo:hi]])
+                return self.b.ctx.allreduce_cl(dm, len(hs.ls), n_cl)
+            finally:
+                self.b.end(dm)
         try:
             src = self.b.evolve(hs, dm, idx)          # full-size LinearSrc, zero outside this rank's modes
             self.b.sync()

@@ -112,6 +112,11 @@ typedef struct cb_model {
     int    Want_CMB_lensing;
     int    max_bessels_l_index;    /* l samples above this index are Limber-only; 0 = all of them are integrated */
     int    Limber_l_min[3 + CB_MAX_WINDOWS];   /* 1-based by source (slots 0..1 unused, slot 2 = phi); 0 = never Limber */
+    /* ---- thermo tables derived on the device (the derivative tables and the Horner packing of
+     *      ThermoData%Init, results.f90:2430-2494).  thermo_horner == NULL asks the library to compute ddotmu, dddotmu,
+     *      ddddotmu, demmu, dadot and the sixteen Horner coefficients of every interval from cs2, dotmu, emmu, adot and
+     *      scale_factor: five [nthermo] arrays (0.7 MB) cross PCIe instead of 3.3 MB per cosmology ---- */
+    const double* scale_factor;    /* [nthermo] ThermoData%ScaleFactor as results.f90:2441 leaves it (a / tau); may be NULL otherwise */
 } cb_model;
 
 /* Per-call mode list for loop A / A'.  The two per-k host look-ups that the
@@ -155,6 +160,10 @@ int  cb_device_count(void);
 
 /* Upload (once; cosmology independent, cached across calls like bessels.f90:83-103). */
 int  cb_set_bessel(cb_ctx* ctx, const cb_bessel* b);
+/* GenerateBessels on the device (bessels.f90:140-228): the table is built from b->l, b->x and b->regions (b->horner is not
+ * read, may be NULL) and becomes the table in use, as after cb_set_bessel -- the 26 MB ... 4.6 GB array never crosses PCIe.
+ * horner_out (may be NULL): bessel_horner(4, nx-1, n_l) for a host that wants it (ExtendBessels, tests). */
+int  cb_build_bessel(cb_ctx* ctx, const cb_bessel* b, double* horner_out);
 
 /* Upload one cosmology's boundary data.  The cb_model and the arrays it points to
  * may be freed after the call. */
@@ -174,6 +183,10 @@ int  cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* 
 /* Replace the device-resident sources (e.g. after the host's non-linear scaling,
  * cmbmain.f90:1190-1247) -- optional. ScaledSrc has LinearSrc's shape. */
 int  cb_set_sources(cb_ctx* ctx, cb_dmodel* dm, int n_k, const double* q, const double* ScaledSrc);
+/* MakeNonlinearSources (cmbmain.f90:1190-1247) on the device: the sources of the last cb_evolve are scaled in place by the
+ * host's non-linear ratios, nonlin_ratio = CAMB_PK%nonlin_ratio(n_k, n_z) (wavenumber fastest; n_z = the model's
+ * num_transfer_redshifts), interpolated in conformal time over the model's transfer_times.  Only the ratios cross PCIe. */
+int  cb_make_nonlinear_sources(cb_ctx* ctx, cb_dmodel* dm, int n_k, int n_z, const double* nonlin_ratio, double Min_kh_nonlinear);
 
 /* Spline-in-k + loop B.  q_int/dq: ThisCT%q%points/dpoints [n_q].
  *   Delta_p_l_k[i]  double (n_src, n_l, n_q)  source fastest (results.f90:3118-3119); may be NULL. */
@@ -265,6 +278,17 @@ int   cb_host_register(void* p, size_t bytes);     /* page-lock an existing host
 void  cb_host_unregister(void* p);
 /* Raw device pointers of a model's result buffers, for the caller's collectives
  * (torch.distributed / NCCL all-reduce of k-sharded LinearSrc and partial iCl). */
+/* ---- ONE cosmology sharded over the GPUs of a box: the two exchange steps, issued by the library on its
+ *      own stream through NCCL (bound at run time; single-GPU users never load it).  Rank 0 obtains a unique id, the
+ *      host program distributes its 128 bytes (MPI_Bcast in CAMB's MPI builds), every rank calls cb_comm_init.
+ *   cb_gather_sources: after cb_evolve with cb_modes.active = this rank's modes; owner[k] = rank that evolved mode k.  One
+ *                      all-gather of the evolved rows; queued, not waited for.
+ *   cb_allreduce_cl:   after cb_cl over this rank's q slice; one all-reduce(sum) of iCl(n_l, 3|6), copied to iCl if given. ---- */
+int  cb_comm_unique_id(cb_ctx* ctx, char* id128);
+int  cb_comm_init(cb_ctx* ctx, int nranks, int rank, const char* id128);
+int  cb_gather_sources(cb_ctx* ctx, cb_dmodel* dm, int n_k, const int* owner);
+int  cb_allreduce_cl(cb_ctx* ctx, cb_dmodel* dm, double* iCl);
+
 enum { CB_BUF_LINEARSRC = 0, CB_BUF_DELTA = 1, CB_BUF_ICL = 2, CB_BUF_TRANSFER = 3 };
 int  cb_device_buffer(cb_ctx* ctx, cb_dmodel* dm, int which, void** ptr, size_t* bytes);
 /* Test hook: ONE evaluation of the device `derivs` (equations.f90:2273-2949) with its source output branch (:2775-2947)

@@ -24,6 +24,8 @@ module GpuBoltzmann
     include 'gpu_boltzmann_types.inc'
 
     logical, public :: use_gpu_boltzmann = .true.      ! ini key / CAMBparams flag in a full integration
+    logical, public :: build_bessel_on_device = .true.  ! skip GenerateBessels on the host: cb_build_bessel (bessels.f90:140-228 on the device)
+    logical, public :: thermo_tables_on_device = .true. ! leave results.f90:2430-2494 (derivative tables, Horner packing) to the device
     type(c_ptr), save :: ctx = c_null_ptr              ! one context per process (cmbmain is not re-entrant, cmbmain.f90:7-8)
     type(c_ptr), save :: dm = c_null_ptr               ! device copy of the current CAMBdata
     ! per-call arrays the cb_model / cb_modes structs point to (kept alive until the calls return)
@@ -47,6 +49,9 @@ module GpuBoltzmann
         integer(c_int) function cb_set_bessel(ctx, b) bind(C, name='cb_set_bessel')
             import; type(c_ptr), value :: ctx; type(cb_bessel), intent(in) :: b
         end function
+        integer(c_int) function cb_build_bessel(ctx, b, horner_out) bind(C, name='cb_build_bessel')   ! GenerateBessels on the device
+            import; type(c_ptr), value :: ctx; type(cb_bessel), intent(in) :: b; type(c_ptr), value :: horner_out
+        end function
         integer(c_int) function cb_model_create(ctx, m, dm) bind(C, name='cb_model_create')
             import; type(c_ptr), value :: ctx; type(cb_model), intent(in) :: m; type(c_ptr) :: dm
         end function
@@ -60,6 +65,23 @@ module GpuBoltzmann
         end function
         integer(c_int) function cb_set_sources(ctx, dm, n_k, q, ScaledSrc) bind(C, name='cb_set_sources')
             import; type(c_ptr), value :: ctx, dm; integer(c_int), value :: n_k; type(c_ptr), value :: q, ScaledSrc
+        end function
+        integer(c_int) function cb_make_nonlinear_sources(ctx, dm, n_k, n_z, nonlin_ratio, Min_kh_nonlinear) &
+                bind(C, name='cb_make_nonlinear_sources')                                            ! MakeNonlinearSources on the device
+            import; type(c_ptr), value :: ctx, dm; integer(c_int), value :: n_k, n_z; type(c_ptr), value :: nonlin_ratio
+            real(c_double), value :: Min_kh_nonlinear
+        end function
+        integer(c_int) function cb_comm_unique_id(ctx, id128) bind(C, name='cb_comm_unique_id')     ! MPI builds: one cosmology over
+            import; type(c_ptr), value :: ctx; character(kind=c_char), intent(out) :: id128(128)     ! the GPUs of a box (k-sharding)
+        end function
+        integer(c_int) function cb_comm_init(ctx, nranks, rank, id128) bind(C, name='cb_comm_init')
+            import; type(c_ptr), value :: ctx; integer(c_int), value :: nranks, rank; character(kind=c_char), intent(in) :: id128(128)
+        end function
+        integer(c_int) function cb_gather_sources(ctx, dm, n_k, owner) bind(C, name='cb_gather_sources')
+            import; type(c_ptr), value :: ctx, dm; integer(c_int), value :: n_k; integer(c_int), intent(in) :: owner(*)
+        end function
+        integer(c_int) function cb_allreduce_cl(ctx, dm, iCl) bind(C, name='cb_allreduce_cl')
+            import; type(c_ptr), value :: ctx, dm, iCl
         end function
         integer(c_int) function cb_project(ctx, n_models, dm, n_q, q_int, dq, Delta) bind(C, name='cb_project')
             import; type(c_ptr), value :: ctx; integer(c_int), value :: n_models
@@ -211,10 +233,14 @@ contains
         gm%nthermo = State%ThermoData%nthermo; gm%tauminn = State%ThermoData%tauminn; gm%dlntau = State%ThermoData%dlntau
         gm%tight_tau = State%ThermoData%tight_tau; gm%matter_verydom_tau = State%ThermoData%matter_verydom_tau
         gm%thermo_horner = c_loc(State%ThermoData%thermo_horner); gm%cs2 = c_loc(State%ThermoData%cs2)
+        if (thermo_tables_on_device) gm%thermo_horner = c_null_ptr   ! the library derives the tables from cs2, dotmu, emmu, adot, ScaleFactor
         gm%dotmu = c_loc(State%ThermoData%dotmu); gm%ddotmu = c_loc(State%ThermoData%ddotmu)
         gm%dddotmu = c_loc(State%ThermoData%dddotmu); gm%ddddotmu = c_loc(State%ThermoData%ddddotmu)
         gm%emmu = c_loc(State%ThermoData%emmu); gm%demmu = c_loc(State%ThermoData%demmu)
         gm%adot = c_loc(State%ThermoData%adot); gm%dadot = c_loc(State%ThermoData%dadot)               ! tensor pass only
+        ! a / tau (results.f90:2441): read only when thermo_horner is c_null_ptr, i.e. when ThermoData%Init skips its packing loops
+        ! (results.f90:2430-2494) and leaves the derivative tables and Horner coefficients to the device
+        gm%scale_factor = c_loc(State%ThermoData%ScaleFactor)
         ! TimeSteps (TRanges, RangeUtils.f90:13-47)
         gm%n_tau = TimeSteps%npoints; gm%tau = c_loc(TimeSteps%points); gm%dtau = c_loc(TimeSteps%dpoints)
         if (allocated(tau_regions)) deallocate(tau_regions)
@@ -340,6 +366,21 @@ contains
     end subroutine
 
     ! ---- InitSourceInterpolation + loop B (cmbmain.f90:262-291) ----
+    ! ---- MakeNonlinearSources (cmbmain.f90:1190-1247) on the device: Transfer_CacheNonLinRatios stays on the host (halofit is
+    !      CP%NonLinearModel's business), only CAMB_PK%nonlin_ratio(n_k, n_z) goes down; the sources stay where they are.
+    !      Called from cmbmain in place of `call MakeNonlinearSources` when use_gpu_boltzmann; GpuSourceToTransfers is then
+    !      called with sources_rescaled = .false. ----
+    subroutine GpuMakeNonlinearSources(State, Evolve_q)
+        use NonLinear
+        type(CAMBdata), intent(inout), target :: State
+        type(TRanges), intent(in) :: Evolve_q
+        if (allocated(State%CAMB_PK)) deallocate(State%CAMB_PK)
+        call Transfer_CacheNonLinRatios(State)
+        if (global_error_flag /= 0) return
+        call Check(cb_make_nonlinear_sources(ctx, dm, Evolve_q%npoints, State%num_transfer_redshifts, &
+            c_loc(State%CAMB_PK%nonlin_ratio), State%CP%NonLinearModel%Min_kh_nonlinear), 'cb_make_nonlinear_sources')
+    end subroutine
+
     subroutine GpuSourceToTransfers(State, ThisCT, Evolve_q, ScaledSrc, sources_rescaled, BessRanges, bessel_horner)
         type(CAMBdata), intent(inout), target :: State
         type(ClTransferData), intent(inout), target :: ThisCT
@@ -359,7 +400,14 @@ contains
         end do
         gb%n_l = ThisCT%max_index_nonlimber; gb%l = c_loc(ThisCT%ls%l); gb%nx = BessRanges%npoints; gb%x = c_loc(BessRanges%points)
         gb%n_regions = BessRanges%count; gb%regions = c_loc(bess_regions); gb%horner = c_loc(bessel_horner); gb%n_l_all = ThisCT%ls%nl
-        call Check(cb_set_bessel(ctx, gb), 'cb_set_bessel')      ! the library re-uploads only when the table changed
+        if (build_bessel_on_device) then
+            ! GenerateBessels skipped on the host (bessels.f90:140-228): the table is generated on the device from the l list and
+            ! the x grid; bessel_horner is not read
+            gb%horner = c_null_ptr
+            call Check(cb_build_bessel(ctx, gb, c_null_ptr), 'cb_build_bessel')
+        else
+            call Check(cb_set_bessel(ctx, gb), 'cb_set_bessel')  ! the library re-uploads only when the table changed
+        end if
         dms(1) = dm; nq(1) = ThisCT%q%npoints; qs(1) = c_loc(ThisCT%q%points); dqs(1) = c_loc(ThisCT%q%dpoints)
         deltas(1) = c_loc(ThisCT%Delta_p_l_k)                    ! (n_src, max_index_nonlimber, n_q), results.f90:3118-3119
         call Check(cb_project(ctx, 1, dms, nq, qs, dqs, deltas), 'cb_project')

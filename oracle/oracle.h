@@ -18,6 +18,9 @@ int oracle_evolve(const cb_model* M, const cb_modes* modes, double* LinearSrc, f
                   int nthreads);
 
 /* InitSourceInterpolation: natural-spline second derivatives along k for every (src, tau). */
+/* cmbmain.f90:1190-1247 MakeNonlinearSources (in place) */
+int oracle_make_nonlinear_sources(const cb_model* M, int n_k, const double* q_src, double* Src, int n_z, const double* nonlin_ratio,
+                                  double Min_kh_nonlinear);
 int oracle_spline_k(int n_k, int n_src, int n_tau, const double* q_src, const double* ScaledSrc, double* ddScaledSrc);
 
 /* loop B: Delta_p_l_k (n_src, n_l, n_q), source fastest. */

@@ -48,6 +48,46 @@ int oracle_spline_k(int n_k, int n_src, int n_tau, const double* q_src, const do
     return 0;
 }
 
+/* MakeNonlinearSources, cmbmain.f90:1190-1247: the lensing potential and the later sources (3..n_src) of every wavenumber above
+ * Min_kh_nonlinear are multiplied by the non-linear ratio of that wavenumber, interpolated in conformal time with a natural
+ * cubic spline over the transfer output times.  Src is LinearSrc(n_k, n_src, n_tau), scaled in place (the reference scales
+ * a copy, ScaledSrc).  nonlin_ratio is CAMB_PK%nonlin_ratio(n_k, n_z), wavenumber fastest. */
+int oracle_make_nonlinear_sources(const cb_model* M, int n_k, const double* q_src, double* Src, int n_z, const double* nonlin_ratio,
+                                  double Min_kh_nonlinear) {
+    const int n_src = M->n_src, n_tau = M->n_tau;
+    const double* tt = M->transfer_times;
+    if (n_z < 2 || n_z != M->num_transfer_redshifts || !tt) return 5;
+    int first_step = 1;
+    while (M->tau[first_step - 1] < tt[0]) first_step++;
+    double* scaling = (double*)malloc(sizeof(double) * 3 * n_z);
+    double *dd = scaling + n_z, *u = dd + n_z;
+    for (int ik = 1; ik <= n_k; ik++) {
+        if (!(q_src[ik - 1] / (M->H0 / 100) > Min_kh_nonlinear)) continue;
+        int all_one = 1;
+        for (int z = 0; z < n_z; z++) {
+            scaling[z] = nonlin_ratio[(ik - 1) + (size_t)n_k * z];
+            if (!(fabs(scaling[z] - 1) < 5e-4)) all_one = 0;
+        }
+        if (all_one) continue;
+        spline_natural(tt, scaling, n_z, dd, u);
+        int tf_lo = 1, tf_hi = 2;
+        for (int i = first_step; i <= n_tau - 1; i++) {
+            const double tau = M->tau[i - 1];
+            while (tf_hi < n_z && tau > tt[tf_hi - 1]) { tf_lo++; tf_hi++; }   /* (the reference relies on transfer_times(n_z) = tau0) */
+            const double ho = tt[tf_hi - 1] - tt[tf_lo - 1];
+            const double a0 = (tt[tf_hi - 1] - tau) / ho, b0 = 1 - a0;
+            const double ascale = a0 * scaling[tf_lo - 1] + b0 * scaling[tf_hi - 1] +
+                                  ((a0 * a0 * a0 - a0) * dd[tf_lo - 1] + (b0 * b0 * b0 - b0) * dd[tf_hi - 1]) * (ho * ho) / 6;
+            for (int s = 3; s <= n_src; s++) {
+                double* v = Src + (ik - 1) + (size_t)n_k * ((s - 1) + (size_t)n_src * (i - 1));
+                *v = *v * ascale;
+            }
+        }
+    }
+    free(scaling);
+    return 0;
+}
+
 /* TRanges_IndexOf, 1-based result */
 static int ranges_index_of(const cb_range* R, int count, int npoints, double highest, double tau) {
     for (int i = 0; i < count; i++) {

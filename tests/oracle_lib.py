@@ -51,6 +51,7 @@ def load():
         lib = C.CDLL(path)
         lib.oracle_evolve.argtypes = [C.POINTER(cb_model), C.POINTER(cb_modes), c_double_p, c_float_p, c_ll_p, C.c_int]
         lib.oracle_spline_k.argtypes = [C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]
+        lib.oracle_make_nonlinear_sources.argtypes = [C.POINTER(cb_model), C.c_int, c_double_p, c_double_p, C.c_int, c_double_p, C.c_double]
         lib.oracle_project.argtypes = [C.POINTER(cb_model), C.POINTER(cb_bessel), C.c_int, c_double_p, c_double_p,
                                        c_double_p, C.c_int, c_double_p, c_double_p, C.c_int]
         lib.oracle_cl.argtypes = [C.POINTER(cb_model), C.POINTER(cb_bessel), C.c_int, c_double_p, c_double_p,
@@ -86,6 +87,18 @@ def evolve(hs, transfer_only=False, nthreads=1, modes=None, active=None):
     if e:
         raise RuntimeError(f"oracle_evolve error {e}")
     return src, tr, stats
+
+
+def make_nonlinear_sources(hs, q_src, src, ratio, min_kh=0.005):
+    """MakeNonlinearSources (cmbmain.f90:1190-1247) on a copy of src (n_tau, n_src, n_k); ratio: (n_z, n_k) = nonlin_ratio(ik, iz)."""
+    lib = load()
+    out = np.array(src, dtype=np.float64, order="C", copy=True)
+    ratio = np.ascontiguousarray(ratio, dtype=np.float64)
+    q_src = np.ascontiguousarray(q_src)
+    e = lib.oracle_make_nonlinear_sources(C.byref(hs.model), len(q_src), _dp(q_src), _dp(out), ratio.shape[0], _dp(ratio), float(min_kh))
+    if e:
+        raise RuntimeError(f"oracle_make_nonlinear_sources error {e}")
+    return out
 
 
 def spline_k(q_src, src):

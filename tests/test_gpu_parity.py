@@ -510,3 +510,104 @@ def test_planck_transfer_high_precision_parity(ctx):
     tr, tr_o = g["transfer"], aux["transfer"]
     for c in range(13):
         assert np.abs(tr[:, :, c] - tr_o[:, :, c]).max() <= 2e-5 * np.abs(tr_o[:, :, c]).max(), c
+
+
+def test_bessel_table_built_on_device(ctx):
+    """cb_build_bessel (GenerateBessels on the device, bessels.f90:140-228) against the host table of the same l list and
+    x grid: the zeroed small-x part interval for interval, every Horner coefficient to 1e-11 of the l's peak; loop B on the
+    device-built table reproduces loop B on the uploaded one."""
+    hs = host_state("planck_massless_lensing", CASES["planck_massless_lensing"])
+    b = hs.bessel()
+    host_tab = np.ctypeslib.as_array(b.horner, shape=(b.n_l, b.nx - 1, 4)).copy()
+    ctx.set_bessel(hs)
+    dm = ctx.create_model(hs)
+    try:
+        ctx.evolve([hs], [dm], want_sources=False, want_stats=False)
+        delta_up = ctx.project([hs], [dm])[0]
+        dev_tab = ctx.build_bessel(hs, want_table=True)
+        delta_dev = ctx.project([hs], [dm])[0]
+    finally:
+        ctx.destroy_model(dm)
+        ctx.set_bessel(hs)
+    # The table of an l starts at the knot below xlim = l - 4.2 l^(1/3) - 1 (bessels.f90:201-206).  For a perfect cube (l = 27:
+    # xlim = 13.4, on a knot of the 0.2 grid) the last bit of pow(l, 1/3) decides between two neighbouring knots, on the host,
+    # on the device and in the reference alike; j_l is ~1e-6 of its peak there.  So: the first tabulated interval may differ by
+    # one, the intervals just after it are held to the reference's own accuracy contract (7e-6 of the peak, bessels.f90:363-369),
+    # everything else to rounding.
+    zh, zd = (host_tab == 0).all(axis=2), (dev_tab == 0).all(axis=2)
+    first_h, first_d = np.argmax(~zh, axis=1), np.argmax(~zd, axis=1)
+    assert np.abs(first_h - first_d).max() <= 1 and (first_h != first_d).sum() <= 2
+    peak = np.abs(host_tab[:, :, 0]).max(axis=1)[:, None, None]
+    err = np.abs(dev_tab - host_tab) / peak
+    edge = np.zeros(err.shape[:2], dtype=bool)
+    for j in np.nonzero(first_h != first_d)[0]:
+        edge[j, min(first_h[j], first_d[j]):max(first_h[j], first_d[j]) + 20] = True   # the spline carries the difference a few knots on
+    assert err[edge].max(initial=0.0) < 7e-6
+    assert err[~edge].max() < 1e-11
+    for s in range(hs.n_src):
+        pk = np.abs(delta_up[:, :, s]).max(axis=0, keepdims=True)
+        assert (np.abs(delta_dev[:, :, s] - delta_up[:, :, s]) / pk).max() < 1e-9
+
+
+@pytest.mark.parametrize("name", ["planck_massless_lensing", "config1_massive_nu_nolens"])
+def test_thermo_tables_packed_on_device(ctx, name):
+    """cb_model_create with thermo_horner = NULL (the derivative tables and Horner records of results.f90:2430-2494 derived on
+    the device from cs2, dotmu, emmu, adot and a/tau) against the same model with the host-packed tables: the device
+    arithmetic is written without FMA contraction, operation for operation as the host's, so every source value and
+    every C_l must be IDENTICAL, and the per-mode integrator statistics with them."""
+    hs = host_state(name, CASES[name])
+    ref = run_gpu(ctx, hs)
+    ctx.set_bessel(hs)
+    dm = ctx.create_model(hs, thermo_on_device=True)
+    try:
+        src, tr, st = ctx.evolve([hs], [dm])
+        ctx.project([hs], [dm])
+        icl = ctx.cl([hs], [dm])[0]
+    finally:
+        ctx.destroy_model(dm)
+    assert np.array_equal(st[0], ref["stats"])
+    assert np.array_equal(src[0], ref["src"])
+    assert np.array_equal(icl, ref["icl"])
+
+
+def test_tensor_thermo_tables_packed_on_device(ctx):
+    """The tensor pass reads adot / dadot (Thermo_expansion_values, results.f90:1882-1906): dadot derived on the device too."""
+    hs = host_state("tensor_massless", lambda: tensor_params(massless=True))
+    ref = run_gpu(ctx, hs)
+    ctx.set_bessel(hs)
+    dm = ctx.create_model(hs, thermo_on_device=True)
+    try:
+        src, _, _ = ctx.evolve([hs], [dm])
+    finally:
+        ctx.destroy_model(dm)
+    assert np.array_equal(src[0], ref["src"])
+
+
+def test_nonlinear_source_scaling_parity(ctx):
+    """cb_make_nonlinear_sources (MakeNonlinearSources, cmbmain.f90:1190-1247, on the device-resident sources) against the
+    oracle on the same ratios: the scaled sources to rounding, and the lensing-potential C_l that follow from them."""
+    from test_oracle_nonlinear_sources import nl_params, synthetic_ratio
+    hs = host_state("nl_sources", nl_params)
+    q = np.asarray(hs.source_q())
+    _, ratio = synthetic_ratio(hs, q)
+    ctx.set_bessel(hs)
+    dm = ctx.create_model(hs)
+    try:
+        src_lin = ctx.evolve([hs], [dm])[0][0]
+        ctx.make_nonlinear_sources(dm, ratio)
+        delta = ctx.project([hs], [dm])[0]
+        icl = ctx.cl([hs], [dm])[0]
+        # the same through the round trip the device call replaces: scale on the host, cb_set_sources
+        src_o = O.make_nonlinear_sources(hs, q, src_lin, ratio)
+        ctx.set_sources(dm, q, src_o)
+        delta_rt = ctx.project([hs], [dm])[0]
+        icl_rt = ctx.cl([hs], [dm])[0]
+    finally:
+        ctx.destroy_model(dm)
+    nz = src_lin[:, 2, :] != 0
+    assert np.abs(src_o[:, 2, :][nz] / src_lin[:, 2, :][nz] - 1).max() > 0.1   # the scaling is not a no-op
+    for s in range(3):
+        pk = np.abs(delta_rt[:, :, s]).max(axis=0, keepdims=True)
+        assert (np.abs(delta[:, :, s] - delta_rt[:, :, s]) / pk).max() < 1e-12
+    assert max(cl_err(icl, icl_rt)) < 1e-12
+    assert np.array_equal(icl[:, :3], icl_rt[:, :3]) or max(cl_err(icl, icl_rt)[:3]) < 1e-13   # T, E untouched

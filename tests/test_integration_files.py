@@ -52,5 +52,5 @@ def test_cmbmain_patch_applies_to_the_reference(tmp_path):
     r = subprocess.run(["patch", "-p1", "--dry-run", "-i", os.path.join(INT, "cmbmain.patch")], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     txt = open(os.path.join(INT, "cmbmain.patch")).read()
-    for call in ("GpuCalcSources", "GpuTransferOut", "GpuSourceToTransfers", "GpuCalcScalCls", "GpuCalcTensCls", "use GpuBoltzmann"):
+    for call in ("GpuCalcSources", "GpuTransferOut", "GpuSourceToTransfers", "GpuCalcScalCls", "GpuCalcTensCls", "GpuMakeNonlinearSources", "use GpuBoltzmann"):
         assert call in txt, call
