@@ -4,7 +4,7 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       := $(shell test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)
 CC        := $(shell test -x /usr/bin/gcc && echo /usr/bin/gcc || echo gcc)
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -Xptxas -v
+NVFLAGS   := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -Xcompiler -fopenmp -Xptxas -v
 CXXFLAGS  := -O2 -std=c++17 -fPIC -fopenmp -Wall -Wno-unused-variable -Wno-unused-but-set-variable
 # the oracle is compiled without FMA contraction so it is an independent arithmetic path
 CFLAGS    := -O2 -std=c11 -fPIC -fopenmp -ffp-contract=off -Wall -Wno-unused-variable -Wno-unused-but-set-variable
@@ -43,7 +43,7 @@ build/cuda/%.o: camb_b200/csrc/cuda/%.cu $(CUDA_HDR)
 	$(NVCC) $(NVFLAGS) -c -o $@ $< 2> build/cuda/$*.ptxas.log || (cat build/cuda/$*.ptxas.log; exit 1)
 
 camb_b200/libcambb200.so: $(CUDA_OBJ)
-	$(NVCC) $(ARCH) -shared -o $@ $(CUDA_OBJ) -lcudart -ldl
+	$(NVCC) $(ARCH) -shared -o $@ $(CUDA_OBJ) -lcudart -ldl -lgomp
 	@cat build/cuda/*.ptxas.log > camb_b200/csrc/cuda/ptxas.log
 
 clean:

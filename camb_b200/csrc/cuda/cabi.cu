@@ -133,6 +133,13 @@ struct cb_ctx {
     // 48-element classes, register kernel for the deep low-k hierarchies (equal throughput at >= 192 sets per call,
     // slower below: DESIGN.md section 4.1)
     int use_reg_kernel = 1;
+    // asynchronous result copies (option "async_outputs"): Delta_p_l_k goes to the host on its own stream, behind the
+    // kernel that produced it, while the next kernels run; cb_wait_outputs is the point where the host may read it
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_los_done = nullptr, ev_copy_done = nullptr;
+    bool async_outputs = false, copies_pending = false;
+    struct DeferredCopy { void* dst; const void* src; size_t bytes; };
+    std::vector<DeferredCopy> deferred;   // queued by cb_project, issued by the next cb_evolve / cb_wait_outputs (see flush_outputs)
     void* comm = nullptr; int comm_ranks = 1, comm_rank = 0;   // NCCL communicator of a k-sharded run (cb_comm_init)
     int los_kernel = 1;            // 1: lanes on the multipoles (transposed table, coalesced rows); 0: the gather kernel
     cudaEvent_t stage_ev[4][2] = {};     // per-stage kernel brackets of the last calls (evolve, spline-k, LOS, C_l)
@@ -217,6 +224,20 @@ static int stage_upload(cb_ctx* ctx, const std::vector<StagePiece>& pieces) {
     return 0;
 }
 
+// "async_outputs": the big result copies are handed to the copy engine when the NEXT batch's evolve kernels are about to
+// start (or when the host asks for them), not right behind the kernel that produced them -- issued there, the small
+// device->host copies of cb_cl / cb_lens_contrib would queue behind them on the same engine.
+static int flush_outputs(cb_ctx* ctx) {
+    if (ctx->deferred.empty()) return 0;
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_los_done, 0));
+    for (const cb_ctx::DeferredCopy& c : ctx->deferred)
+        CK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    ctx->deferred.clear();
+    CK(cudaEventRecord(ctx->ev_copy_done, ctx->copy_stream));
+    ctx->copies_pending = true;
+    return 0;
+}
+
 extern "C" {
 
 int cb_device_count(void) {
@@ -245,6 +266,9 @@ int cb_create(int device, cb_ctx** out) {
         cudaEventCreateWithFlags(&ctx->class_done[c], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_los_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_copy_done, cudaEventDisableTiming);
     if (const char* e = getenv("CAMB_B200_LANES")) ctx->lanes_per_mode = atoi(e);
     if (const char* e = getenv("CAMB_B200_REG")) ctx->use_reg_kernel = atoi(e);
     if (const char* e = getenv("CAMB_B200_LOS")) ctx->los_kernel = atoi(e);
@@ -270,6 +294,9 @@ void cb_destroy(cb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->ev_los_done) cudaEventDestroy(ctx->ev_los_done);
+    if (ctx->ev_copy_done) cudaEventDestroy(ctx->ev_copy_done);
     if (ctx->comm) cb_nccl_destroy(ctx->comm);
     for (auto& e : ctx->bess_cache) for (void* p : e.owned) cudaFree(p);
     for (int i = 0; i < 4; i++) { cudaEventDestroy(ctx->stage_ev[i][0]); cudaEventDestroy(ctx->stage_ev[i][1]); }
@@ -549,6 +576,8 @@ void cb_model_destroy(cb_ctx* ctx, cb_dmodel* dm) {
     if (!dm) return;
     if (ctx) cudaSetDevice(ctx->device);
     if (!ctx) { delete dm; return; }
+    flush_outputs(ctx);
+    if (ctx->copies_pending) { cudaEventSynchronize(ctx->ev_copy_done); ctx->copies_pending = false; }   // a result copy may still read this model's buffers
     for (void* p : dm->owned) dev_free(ctx, p);
     for (void* p : dm->pack_tmp) dev_free(ctx, p);
     void* bufs[] = {dm->d_q_src, dm->d_src, dm->d_dd, dm->d_scratch, dm->d_delta, dm->d_icl, dm->d_q_int, dm->d_dq_int,
@@ -601,12 +630,14 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
               float* const* TransferData, long long* const* stats) {
     if (!ctx) return CB_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
+    if (int e = flush_outputs(ctx)) return e;   // the previous batch's results travel to the host under this batch's kernels
     if (int e = pack_thermo_tables(ctx, n_models, dm)) return e;
     std::vector<DModeItem> cls_items[CB_N_CLASSES], all_items;
     int lean = 1;   // every model massless-nu LCDM: the kernel variants without massive-nu / dark-energy code
     for (int m = 0; m < n_models; m++) if (dm[m]->h.Num_Nu_massive != 0 || !dm[m]->h.de_is_cc || dm[m]->h.num_redshiftwindows > 0 || dm[m]->h.is_tensor) lean = 0;
     int cls_nv[CB_N_CLASSES] = {}, cls_maxl[CB_N_CLASSES] = {};
     std::vector<StagePiece> pieces;
+    std::vector<size_t> item_off((size_t)n_models + 1, 0);
     {
         size_t tot = 0;
         for (int m = 0; m < n_models; m++) tot += (size_t)std::max(modes[m].n_k, 0);
@@ -648,7 +679,11 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
         D.stats = d->d_stats;
         // k-sharding (cb_modes.active): this call evolves a subset; rows of the other modes stay zero
         const bool subset = md.n_active > 0 && md.active;
-        const int n_act = subset ? md.n_active : n_k;
+        const int n_act = md.n_active < 0 ? 0 : (subset ? md.n_active : n_k);   // n_active < 0: a rank with an empty share evolves nothing
+        if (md.n_active < 0) {
+            CK(cudaMemsetAsync(d->d_stats, 0, sizeof(long long) * 4 * (size_t)n_k, ctx->stream));
+            if (nz > 0) CK(cudaMemsetAsync(d->d_transfer, 0, sizeof(float) * (size_t)13 * n_k * nz, ctx->stream));
+        }
         if (subset) {
             CK(cudaMemsetAsync(d->d_stats, 0, sizeof(long long) * 4 * (size_t)n_k, ctx->stream));
             if (nz > 0) CK(cudaMemsetAsync(d->d_transfer, 0, sizeof(float) * (size_t)13 * n_k * nz, ctx->stream));
@@ -656,7 +691,22 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
         for (int a = 0; a < n_act; a++) {
             const int i = subset ? md.active[a] : a;
             if (i < 0 || i >= n_k) { ctx->err = "cb_evolve: cb_modes.active index out of range"; return CB_ERR_UNSUPPORTED_PARAMS; }
-            DModeItem it;
+        }
+        item_off[m + 1] = item_off[m] + (size_t)n_act;
+    }
+    // The work items (GetNumEqns per mode, equations.f90:860-1070, on the host: a few hundred ns each, 14 000 of them per
+    // 64 parameter sets) are filled by the host's cores model by model.
+    all_items.resize(item_off[n_models]);
+    int size_err = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(|| : size_err)
+    for (int m = 0; m < n_models; m++) {
+        const cb_modes& md = modes[m];
+        const DModel& D = dm[m]->h;
+        const bool subset = md.n_active > 0 && md.active;
+        const int n_act = (int)(item_off[m + 1] - item_off[m]);
+        for (int a = 0; a < n_act; a++) {
+            const int i = subset ? md.active[a] : a;
+            DModeItem& it = all_items[item_off[m] + a];
             memset(&it, 0, sizeof(it));
             it.model = m; it.q_ix = i; it.transfer_only = md.transfer_only; it.q = md.q[i];
             it.tight_switchoff = md.tight_switchoff[i];
@@ -665,15 +715,22 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
             if (D.is_tensor) cb_tensor_mode_size(D, &it.nvar, &ml);
             else cb_mode_size(D, it.q, it.transfer_only, &it.nvar, &ml, lm3);
             it.lmaxg = lm3[0]; it.lmaxgpol = lm3[1]; it.lmaxnr = lm3[2];
-            if (ml > CBD_MAX_L_EVOLVE) { ctx->err = "Need to increase max_l_evolve"; return CB_ERR_UNSUPPORTED_PARAMS; }
+            if (ml > CBD_MAX_L_EVOLVE) size_err = 1;
             it.transfer_only |= ml << 8;   // deepest multipole rides along until the binning pass below
-            all_items.push_back(it);
         }
     }
+    if (size_err) { ctx->err = "Need to increase max_l_evolve"; return CB_ERR_UNSUPPORTED_PARAMS; }
     // Binning pass, most expensive modes first (largest k: cmbmain.f90:205-206 runs them first too): a mode joins the first
     // class whose slab, grown to hold it, stays inside that class's limit -- so the high-k bulk (45-ish equations, 14
     // multipoles) keeps the smallest slab and the few deep low-k hierarchies land in the larger classes.
-    std::stable_sort(all_items.begin(), all_items.end(), [](const DModeItem& a, const DModeItem& b) { return a.q > b.q; });
+    {   // stable order on a light key array, then one gather of the (large) items
+        std::vector<unsigned> ord(all_items.size());
+        for (size_t i = 0; i < ord.size(); i++) ord[i] = (unsigned)i;
+        std::stable_sort(ord.begin(), ord.end(), [&](unsigned a, unsigned b) { return all_items[a].q > all_items[b].q; });
+        std::vector<DModeItem> sorted(all_items.size());
+        for (size_t i = 0; i < ord.size(); i++) sorted[i] = all_items[ord[i]];
+        all_items.swap(sorted);
+    }
     for (DModeItem& it : all_items) {
         const int ml = it.transfer_only >> 8;
         it.transfer_only &= 0xff;
@@ -774,7 +831,11 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
                                                        ctx->d_error, ctx->n_sm, ctx->class_stream[c], &ctx->last_grid[c])
                              : cb_evolve_launch(ctx->d_models, ctx->d_items + cls_off[c], n_c, nv, cls_maxl[c], lanes_c, lean, ctx->d_counter + c,
                                                 ctx->d_error, ctx->n_sm, ctx->class_stream[c], &ctx->last_grid[c], caps[c]);
-        if (le != cudaSuccess) { ctx->err = std::string("evolve launch: ") + cudaGetErrorString(le); return CB_ERR_CUDA; }
+        if (le != cudaSuccess) {
+            for (int j = 0; j < CB_N_CLASSES; j++) cudaStreamSynchronize(ctx->class_stream[j]);   // classes already launched finish first
+            ctx->err = std::string("evolve launch: ") + cudaGetErrorString(le);
+            return CB_ERR_CUDA;
+        }
         ctx->launches++;
         CK(cudaEventRecord(ctx->class_done[c], ctx->class_stream[c]));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->class_done[c], 0));
@@ -857,6 +918,11 @@ int cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q, 
     if (!ctx) return CB_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
     if (!ctx->have_bessel) { ctx->err = "cb_set_bessel must be called before cb_project"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    // a Delta buffer may be rewritten below: the copies of an earlier call on these models go first
+    for (int m = 0; m < n_models && !ctx->deferred.empty(); m++)
+        for (const cb_ctx::DeferredCopy& c : ctx->deferred)
+            if (c.src == dm[m]->d_delta) { if (int e = flush_outputs(ctx)) return e; break; }
+    if (ctx->copies_pending) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done, 0));
     const int n_l = ctx->bess.n_l;
     int max_cols = 0, max_nq = 0, max_ntau = 0, max_nsrc = 0;
     std::vector<double*> scr(n_models);
@@ -905,7 +971,9 @@ int cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q, 
     for (int m = 0; m < n_models; m++) any_windows = any_windows || dm[m]->h.num_redshiftwindows > 0;
     const size_t smem = cb_los_smem(max_nsrc, max_ntau, n_l);
     CK(cudaEventRecord(ctx->stage_ev[2][0], ctx->stream));
-    if (any_windows || smem > 227 * 1024 || n_l > 192 /* LOS_MAX_L */) {
+    if (max_nq == 0) {
+        // an empty slice of the integration grid (a rank with no share of a q-sharded run): nothing to project
+    } else if (any_windows || smem > 227 * 1024 || n_l > 192 /* LOS_MAX_L */) {
         // source windows (or a time grid too long to stage the sources): the general kernel
         for (int m = 0; m < n_models; m++)
             if (dm[m]->h.is_tensor) { ctx->err = "LOS: tensor models cannot share a call with source-window models"; return CB_ERR_UNSUPPORTED_PARAMS; }
@@ -918,10 +986,18 @@ int cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q, 
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->stage_ev[2][1], ctx->stream));
-    for (int m = 0; m < n_models; m++) {
-        const DModel& D = dm[m]->h;
-        if (Delta_p_l_k && Delta_p_l_k[m])
-            CK(cudaMemcpyAsync(Delta_p_l_k[m], dm[m]->d_delta, sizeof(double) * (size_t)D.n_src * n_l * D.n_q, cudaMemcpyDeviceToHost, ctx->stream));
+    {
+        bool any = false;
+        for (int m = 0; m < n_models; m++) any = any || (Delta_p_l_k && Delta_p_l_k[m]);
+        const bool defer = any && ctx->async_outputs;   // queued now, issued by flush_outputs
+        for (int m = 0; m < n_models; m++) {
+            const DModel& D = dm[m]->h;
+            if (!(Delta_p_l_k && Delta_p_l_k[m])) continue;
+            const size_t bytes = sizeof(double) * (size_t)D.n_src * n_l * D.n_q;
+            if (defer) ctx->deferred.push_back({Delta_p_l_k[m], dm[m]->d_delta, bytes});
+            else CK(cudaMemcpyAsync(Delta_p_l_k[m], dm[m]->d_delta, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (defer) CK(cudaEventRecord(ctx->ev_los_done, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -1152,6 +1228,15 @@ int cb_last_timings(const cb_ctx* ctx, double ms[4]) {
 
 long long cb_launch_count(const cb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+// With the option "async_outputs" cb_project returns while Delta_p_l_k is still on its way to the host: this is the point
+// after which the host arrays of every earlier call are complete.
+int cb_wait_outputs(cb_ctx* ctx) {
+    if (!ctx) return CB_ERR_NO_DEVICE;
+    if (int e = flush_outputs(ctx)) return e;
+    if (ctx->copies_pending) { CK(cudaEventSynchronize(ctx->ev_copy_done)); ctx->copies_pending = false; }
+    return 0;
+}
+
 int cb_set_option(cb_ctx* ctx, const char* name, double value) {
     if (!ctx) return CB_ERR_NO_DEVICE;
     if (!strncmp(name, "lanes_class", 11) && name[11] >= '0' && name[11] < '0' + CB_TENSOR_CLASS && !name[12]) {
@@ -1169,6 +1254,12 @@ int cb_set_option(cb_ctx* ctx, const char* name, double value) {
     if (!strcmp(name, "async_model_upload")) { ctx->async_model_upload = value != 0; return 0; }
     if (!strcmp(name, "use_reg_kernel")) { ctx->use_reg_kernel = (int)value; return 0; }
     if (!strcmp(name, "los_kernel")) { ctx->los_kernel = (int)value; return 0; }
+    if (!strcmp(name, "async_outputs")) {
+        flush_outputs(ctx);
+        if (ctx->copies_pending) { cudaEventSynchronize(ctx->ev_copy_done); ctx->copies_pending = false; }
+        ctx->async_outputs = value != 0;
+        return 0;
+    }
     ctx->err = std::string("unknown option ") + name;
     return CB_ERR_UNSUPPORTED_PARAMS;
 }

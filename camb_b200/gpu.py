@@ -24,7 +24,7 @@ SYMBOLS = ["cb_create", "cb_destroy", "cb_last_error", "cb_device_count", "cb_se
            "cb_host_alloc", "cb_host_free", "cb_device_buffer", "cb_set_option", "cb_host_register",
            "cb_host_unregister", "cb_cl_array", "cb_cl_windows", "cb_lens_contrib",
            "cb_last_lens_timing", "cb_debug_derivs", "cb_tmem_probe", "cb_comm_unique_id", "cb_comm_init",
-           "cb_gather_sources", "cb_allreduce_cl"]
+           "cb_gather_sources", "cb_allreduce_cl", "cb_wait_outputs"]
 
 
 def load_gpu_lib():
@@ -60,6 +60,7 @@ def load_gpu_lib():
         lib.cb_launch_count.restype = C.c_longlong
         lib.cb_launch_count.argtypes = [C.c_void_p]
         lib.cb_timer_start.argtypes = [C.c_void_p]
+        lib.cb_wait_outputs.argtypes = [C.c_void_p]
         lib.cb_timer_stop.argtypes = [C.c_void_p, c_double_p]
         lib.cb_fp64_peak.argtypes = [C.c_void_p, c_double_p]
         lib.cb_host_alloc.restype = C.c_void_p
@@ -109,6 +110,7 @@ class GpuContext:
         self._h = h
         self.device = device
         self._bessel_key = None
+        self._registered = []     # host ranges page-locked through this context (unregistered in close())
 
     def _check(self, e):
         if e:
@@ -174,7 +176,7 @@ class GpuContext:
         for i, md in enumerate(mds):
             if active is not None and active[i] is not None:
                 act[i] = np.ascontiguousarray(active[i], dtype=np.int32)
-                md.n_active = len(act[i])
+                md.n_active = len(act[i]) if len(act[i]) else -1   # -1: none of the modes (a rank with an empty share); 0 means all
                 md.active = act[i].ctypes.data_as(c_int_p)
             md_arr[i] = md
         src, tr, st = [], [], []
@@ -312,11 +314,23 @@ class GpuContext:
                          (m.emmu, n), (m.demmu, n), (m.adot, n), (m.scale_factor, n), (m.tau, m.n_tau), (m.dtau, m.n_tau)]:
             addr = C.cast(ptr, C.c_void_p).value
             if addr:
-                self._lib.cb_host_register(addr, 8 * cnt)   # best effort: an unpinned table is still copied correctly
+                if self._lib.cb_host_register(addr, 8 * cnt) == 0:   # best effort: an unpinned table is still copied correctly
+                    self._registered.append(addr)
 
     def pin_array(self, a):
         """Page-lock a numpy array in place (best effort) so its copies are asynchronous DMA; the array must outlive the context use."""
-        self._lib.cb_host_register(a.ctypes.data, a.nbytes)
+        if self._lib.cb_host_register(a.ctypes.data, a.nbytes) == 0:
+            self._registered.append(a.ctypes.data)
+
+    def unpin_all(self):
+        """Undo pin_host_tables / pin_array: call before the owners of the arrays free them (close() does it)."""
+        for addr in self._registered:
+            self._lib.cb_host_unregister(addr)
+        self._registered = []
+
+    def wait_outputs(self):
+        """With set_option("async_outputs", 1): returns when the Delta_p_l_k host arrays of every earlier project call are complete."""
+        self._check(self._lib.cb_wait_outputs(self._h))
 
     def set_option(self, name, value):
         self._check(self._lib.cb_set_option(self._h, name.encode(), float(value)))
@@ -370,6 +384,7 @@ class GpuContext:
 
     def close(self):
         if getattr(self, "_h", None):
+            self.unpin_all()
             self._lib.cb_destroy(self._h)
             self._h = None
 

@@ -7,6 +7,7 @@ committed anchors are the reference's OWN known answers for the path (SURVEY.md 
   * docs/CAMBdemo.ipynb cell outputs: derived parameters for H0=67.5, ombh2=0.022,
     omch2=0.122 (:854), grid sizes 3 sources / 89 l / 3027 k (:945), tensor l samples (:1094).
 Run:  python tests/golden/make_golden.py  (needs /root/reference; the tests do not)."""
+import ast
 import json
 import os
 
@@ -28,7 +29,7 @@ for c in nb["cells"]:
     for o in c.get("outputs", []):
         txt = "".join(o.get("text", []))
         if txt.startswith("Derived parameter dictionary:"):
-            derived = eval(txt.split(":", 1)[1])
+            derived = ast.literal_eval(txt.split(":", 1)[1].strip())   # text of an untrusted notebook: literals only
 out = {
     "source": "cmbant/CAMB v2.0.3: fortran/HighLExtrapTemplate_lenspotentialCls.dat; docs/CAMBdemo.ipynb",
     "template_columns": ["L", "TT", "EE", "BB", "TE", "PP", "TP", "EP"],
