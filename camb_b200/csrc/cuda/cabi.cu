@@ -138,6 +138,12 @@ struct cb_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_los_done = nullptr, ev_copy_done = nullptr;
     bool async_outputs = false, copies_pending = false;
+    // "async_calls": cb_evolve / cb_project return once their work is queued when the call has no host output to fill; the
+    // staging buffers are protected by ev_staged (recorded behind the call's host->device copies), an integrator failure
+    // surfaces at the next blocking call through the page-locked h_error
+    bool async_calls = false, staged_pending = false, error_pending = false;
+    cudaEvent_t ev_staged = nullptr;
+    int* h_error = nullptr;
     struct DeferredCopy { void* dst; const void* src; size_t bytes; };
     std::vector<DeferredCopy> deferred;   // queued by cb_project, issued by the next cb_evolve / cb_wait_outputs (see flush_outputs)
     void* comm = nullptr; int comm_ranks = 1, comm_rank = 0;   // NCCL communicator of a k-sharded run (cb_comm_init)
@@ -227,6 +233,20 @@ static int stage_upload(cb_ctx* ctx, const std::vector<StagePiece>& pieces) {
 // "async_outputs": the big result copies are handed to the copy engine when the NEXT batch's evolve kernels are about to
 // start (or when the host asks for them), not right behind the kernel that produced them -- issued there, the small
 // device->host copies of cb_cl / cb_lens_contrib would queue behind them on the same engine.
+// Entry points that write the staging buffers wait for the previous call's host->device copies (not for its kernels).
+static int begin_call(cb_ctx* ctx) {
+    if (ctx->staged_pending) { CK(cudaEventSynchronize(ctx->ev_staged)); ctx->staged_pending = false; }
+    return 0;
+}
+// After a stream synchronisation: the error flag of an earlier asynchronous cb_evolve has landed in h_error.
+static int deferred_error(cb_ctx* ctx) {
+    if (!ctx->error_pending) return 0;
+    ctx->error_pending = false;
+    const int herr = ctx->h_error ? *ctx->h_error : 0;
+    if (herr) { *ctx->h_error = 0; ctx->err = "RungeKuttaDP45 error: step size underflow in the device integrator (reported by an earlier cb_evolve)"; return herr; }
+    return 0;
+}
+
 static int flush_outputs(cb_ctx* ctx) {
     if (ctx->deferred.empty()) return 0;
     CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_los_done, 0));
@@ -267,6 +287,9 @@ int cb_create(int device, cb_ctx** out) {
     }
     cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_staged, cudaEventDisableTiming);
+    cudaHostAlloc((void**)&ctx->h_error, sizeof(int), cudaHostAllocDefault);
+    if (ctx->h_error) *ctx->h_error = 0;
     cudaEventCreateWithFlags(&ctx->ev_los_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_copy_done, cudaEventDisableTiming);
     if (const char* e = getenv("CAMB_B200_LANES")) ctx->lanes_per_mode = atoi(e);
@@ -295,6 +318,8 @@ void cb_destroy(cb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->ev_staged) cudaEventDestroy(ctx->ev_staged);
+    if (ctx->h_error) cudaFreeHost(ctx->h_error);
     if (ctx->ev_los_done) cudaEventDestroy(ctx->ev_los_done);
     if (ctx->ev_copy_done) cudaEventDestroy(ctx->ev_copy_done);
     if (ctx->comm) cb_nccl_destroy(ctx->comm);
@@ -630,6 +655,7 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
               float* const* TransferData, long long* const* stats) {
     if (!ctx) return CB_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
+    if (int e = begin_call(ctx)) return e;
     if (int e = flush_outputs(ctx)) return e;   // the previous batch's results travel to the host under this batch's kernels
     if (int e = pack_thermo_tables(ctx, n_models, dm)) return e;
     std::vector<DModeItem> cls_items[CB_N_CLASSES], all_items;
@@ -778,9 +804,11 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
     if (const char* tq = getenv("CAMB_B200_TRACE")) { cb_trace_mpl_begin(atoi(tq), 4096); cb_trace_reg_begin(atoi(tq), 4096); }
 #endif
     CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int) * CB_N_CLASSES, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_error, 0, sizeof(int), ctx->stream));
+    if (!ctx->error_pending) CK(cudaMemsetAsync(ctx->d_error, 0, sizeof(int), ctx->stream));   // an unreported failure stays set
     int lanes = ctx->lanes_per_mode;
     if (lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) lanes = n_items >= 16 * ctx->n_sm ? 8 : 32;
+    CK(cudaEventRecord(ctx->ev_staged, ctx->stream));   // every host->device copy of this call is queued before this point
+    ctx->staged_pending = true;
     CK(cudaEventRecord(ctx->stage_ev[0][0], ctx->stream));
     CK(cudaEventRecord(ctx->fork, ctx->stream));
     // Launch order and block caps of the slab classes.  The scheduling experiments of DESIGN.md 4.1 (profiles/r01o, r01p)
@@ -797,7 +825,11 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
     for (int cc = 0; cc < CB_N_CLASSES; cc++) {
         // the register classes go first (deep low-k layout, then the bulk): their modes are the longest serial chains
         static const int kOrder[CB_N_CLASSES] = {CB_MPL_CLASS_A, CB_MPL_CLASS_C, CB_REG_CLASS0 + 1, CB_REG_CLASS0, CB_REG_CLASS0 + 2, 0, 1, 2, 3, 4, CB_TENSOR_CLASS};
-        const int c = order_desc ? CB_N_CLASSES - 1 - cc : kOrder[cc];
+        int c = order_desc ? CB_N_CLASSES - 1 - cc : kOrder[cc];
+#ifdef CB_TUNING_KNOBS
+        if (const char* ro = getenv("CAMB_B200_REG_ORDER"))   // launch order of the three register layouts, e.g. "0,2,1"
+            if (cc >= 2 && cc <= 4 && strlen(ro) >= 5) c = CB_REG_CLASS0 + (ro[2 * (cc - 2)] - '0');
+#endif
         int n_c = (int)cls_items[c].size();
         if (c == CB_MPL_CLASS_C) continue;                                   // launched together with class A
         if (c == CB_MPL_CLASS_A) n_c += (int)cls_items[CB_MPL_CLASS_C].size();
@@ -841,6 +873,14 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
         CK(cudaStreamWaitEvent(ctx->stream, ctx->class_done[c], 0));
     }
     CK(cudaEventRecord(ctx->stage_ev[0][1], ctx->stream));
+    bool host_out = false;
+    for (int m = 0; m < n_models; m++)
+        host_out = host_out || (LinearSrc && LinearSrc[m]) || (TransferData && TransferData[m]) || (stats && stats[m]);
+    if (ctx->async_calls && !host_out && ctx->h_error) {   // nothing for the host to read: queued is done
+        CK(cudaMemcpyAsync(ctx->h_error, ctx->d_error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->error_pending = true;
+        return 0;
+    }
     int herr = 0;
     CK(cudaMemcpyAsync(&herr, ctx->d_error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     for (int m = 0; m < n_models; m++) {
@@ -860,8 +900,9 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
         cb_trace_reg_end(ctx->use_reg_kernel == 1 ? "gpurun_out/trace_reg.bin" : "gpurun_out/trace_reg_unused.bin");
     }
 #endif
-    if (herr) { ctx->err = "RungeKuttaDP45 error: step size underflow in the device integrator"; return herr; }
-    return 0;
+    ctx->staged_pending = false;
+    if (herr) { ctx->error_pending = false; ctx->err = "RungeKuttaDP45 error: step size underflow in the device integrator"; return herr; }
+    return deferred_error(ctx);
 }
 
 // MakeNonlinearSources (cmbmain.f90:1190-1247) on the device-resident sources of the last cb_evolve, in place.
@@ -869,6 +910,7 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
 int cb_make_nonlinear_sources(cb_ctx* ctx, cb_dmodel* dm, int n_k, int n_z, const double* nonlin_ratio, double Min_kh_nonlinear) {
     if (!ctx || !dm) return CB_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
+    if (int e = begin_call(ctx)) return e;
     DModel& D = dm->h;
     if (!dm->d_src || n_k != D.n_k) { ctx->err = "cb_make_nonlinear_sources: call cb_evolve on this model first"; return CB_ERR_UNSUPPORTED_PARAMS; }
     if (D.is_tensor || n_z < 2 || n_z != D.num_transfer_redshifts || !D.transfer_times) {
@@ -887,12 +929,15 @@ int cb_make_nonlinear_sources(cb_ctx* ctx, cb_dmodel* dm, int n_k, int n_z, cons
     dev_free(ctx, d_ratio); dev_free(ctx, d_model);
     if (le != cudaSuccess) { ctx->err = std::string("cb_make_nonlinear_sources: ") + cudaGetErrorString(le); return CB_ERR_CUDA; }
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->staged_pending = false;
+    if (int e = deferred_error(ctx)) return e;
     return 0;
 }
 
 int cb_set_sources(cb_ctx* ctx, cb_dmodel* d, int n_k, const double* q, const double* ScaledSrc) {
     if (!ctx) return CB_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
+    if (int e = begin_call(ctx)) return e;
     DModel& D = d->h;
     size_t ns = (size_t)n_k * D.n_src * D.n_tau;
     if (ns > d->cap_src || !d->d_src) {
@@ -909,6 +954,8 @@ int cb_set_sources(cb_ctx* ctx, cb_dmodel* d, int n_k, const double* q, const do
     CK(cudaMemcpyAsync(d->d_q_src, q, sizeof(double) * n_k, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d->d_src, ScaledSrc, sizeof(double) * ns, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->staged_pending = false;
+    if (int e = deferred_error(ctx)) return e;
     D.n_k = n_k; D.q_src = d->d_q_src; D.LinearSrc = d->d_src; D.ddSrc = d->d_dd;
     return 0;
 }
@@ -918,6 +965,7 @@ int cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q, 
     if (!ctx) return CB_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
     if (!ctx->have_bessel) { ctx->err = "cb_set_bessel must be called before cb_project"; return CB_ERR_UNSUPPORTED_PARAMS; }
+    if (int e = begin_call(ctx)) return e;
     // a Delta buffer may be rewritten below: the copies of an earlier call on these models go first
     for (int m = 0; m < n_models && !ctx->deferred.empty(); m++)
         for (const cb_ctx::DeferredCopy& c : ctx->deferred)
@@ -962,6 +1010,8 @@ int cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q, 
     if (int e = push_models(ctx, n_models, dm)) return e;
     if (int e = ensure(ctx, &ctx->d_scratch_ptrs, &ctx->cap_scr, (size_t)n_models)) return e;
     CK(cudaMemcpyAsync(ctx->d_scratch_ptrs, scr.data(), sizeof(double*) * n_models, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_staged, ctx->stream));
+    ctx->staged_pending = true;
     CK(cudaEventRecord(ctx->stage_ev[1][0], ctx->stream));
     cb_spline_k_launch(ctx->d_models, n_models, max_cols, ctx->d_scratch_ptrs, ctx->stream);
     ctx->launches++;
@@ -998,14 +1048,17 @@ int cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q, 
             else CK(cudaMemcpyAsync(Delta_p_l_k[m], dm[m]->d_delta, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         }
         if (defer) CK(cudaEventRecord(ctx->ev_los_done, ctx->stream));
+        if (ctx->async_calls && (!any || defer)) return 0;   // no host array is filled by this call itself: queued is done
     }
     CK(cudaStreamSynchronize(ctx->stream));
-    return 0;
+    ctx->staged_pending = false;
+    return deferred_error(ctx);
 }
 
 int cb_cl(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, int tensor, const double* const* pows, double* const* iCl) {
     if (!ctx) return CB_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
+    if (int e = begin_call(ctx)) return e;
     const int n_l = ctx->bess.n_l;
     std::vector<StagePiece> pieces;
     {
@@ -1040,6 +1093,8 @@ int cb_cl(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, int tensor, const dou
     }
     if (iCl && off) CK(cudaMemcpyAsync(ctx->h_out, ctx->d_out, sizeof(double) * off, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->staged_pending = false;
+    if (int e = deferred_error(ctx)) return e;
     off = 0;
     for (int m = 0; m < n_models; m++) {
         const size_t n = (size_t)n_l * dm[m]->n_cl;
@@ -1052,6 +1107,7 @@ int cb_cl(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, int tensor, const dou
 int cb_cl_array(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const double* const* pows, double* const* iCl_Array) {
     if (!ctx) return CB_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
+    if (int e = begin_call(ctx)) return e;
     const int n_l = ctx->bess.n_l;
     std::vector<double*> outs(n_models);
     for (int m = 0; m < n_models; m++) {
@@ -1075,6 +1131,8 @@ int cb_cl_array(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const double* c
         if (iCl_Array && iCl_Array[m])
             CK(cudaMemcpyAsync(iCl_Array[m], dm[m]->d_icl_array, sizeof(double) * (size_t)n_l * dm[m]->h.n_src * dm[m]->h.n_src, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->staged_pending = false;
+    if (int e = deferred_error(ctx)) return e;
     return 0;
 }
 
@@ -1082,6 +1140,7 @@ int cb_cl_windows(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const double*
                   double* const* iCl, double* const* iCl_Array) {
     if (!ctx) return CB_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
+    if (int e = begin_call(ctx)) return e;
     const int n_l = ctx->bess.n_l_all;
     std::vector<double*> limb(n_models), lpow(n_models), outs(2 * (size_t)n_models);
     int max_nw = 0;
@@ -1120,12 +1179,15 @@ int cb_cl_windows(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const double*
             CK(cudaMemcpyAsync(iCl_Array[m], dm[m]->d_icl_array, sizeof(double) * (size_t)n_l * n * n, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->staged_pending = false;
+    if (int e = deferred_error(ctx)) return e;
     return 0;
 }
 
 int cb_lens_contrib(cb_ctx* ctx, int n_sets, const cb_lens_plan* P, const double* const* spectra, double* const* lens_contrib) {
     if (!ctx) return CB_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
+    if (int e = begin_call(ctx)) return e;
     if (!P || n_sets <= 0 || !spectra || !lens_contrib) { ctx->err = "cb_lens_contrib: null argument"; return CB_ERR_UNSUPPORTED_PARAMS; }
     if ((P->variant != CB_LENS_APODIZED && P->variant != CB_LENS_FULL) || (P->lmin != 1 && P->lmin != 2) || P->lmax < 4 ||
         P->lmax_lensed < P->lmin || P->lmax_lensed > P->lmax || P->npoints < 2) {
@@ -1202,6 +1264,8 @@ int cb_lens_contrib(cb_ctx* ctx, int n_sets, const cb_lens_plan* P, const double
     release();
     if (ce != cudaSuccess) { ctx->err = std::string("cb_lens_contrib: ") + cudaGetErrorString(ce); return CB_ERR_CUDA; }
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->staged_pending = false;
+    if (int e = deferred_error(ctx)) return e;
     return 0;
 }
 
@@ -1254,6 +1318,11 @@ int cb_set_option(cb_ctx* ctx, const char* name, double value) {
     if (!strcmp(name, "async_model_upload")) { ctx->async_model_upload = value != 0; return 0; }
     if (!strcmp(name, "use_reg_kernel")) { ctx->use_reg_kernel = (int)value; return 0; }
     if (!strcmp(name, "los_kernel")) { ctx->los_kernel = (int)value; return 0; }
+    if (!strcmp(name, "async_calls")) {
+        if (ctx->async_calls && value == 0) { CK(cudaStreamSynchronize(ctx->stream)); ctx->staged_pending = false; if (int e = deferred_error(ctx)) return e; }
+        ctx->async_calls = value != 0;
+        return 0;
+    }
     if (!strcmp(name, "async_outputs")) {
         flush_outputs(ctx);
         if (ctx->copies_pending) { cudaEventSynchronize(ctx->ev_copy_done); ctx->copies_pending = false; }

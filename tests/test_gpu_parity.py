@@ -611,3 +611,49 @@ def test_nonlinear_source_scaling_parity(ctx):
         assert (np.abs(delta[:, :, s] - delta_rt[:, :, s]) / pk).max() < 1e-12
     assert max(cl_err(icl, icl_rt)) < 1e-12
     assert np.array_equal(icl[:, :3], icl_rt[:, :3]) or max(cl_err(icl, icl_rt)[:3]) < 1e-13   # T, E untouched
+
+
+def test_asynchronous_calls_and_deferred_result_copies(ctx):
+    """cb_set_option("async_calls") / ("async_outputs"): cb_evolve and cb_project only queue their work, Delta_p_l_k reaches the
+    host after cb_wait_outputs -- the results are the synchronous ones bit for bit, a batch's result copy may overlap the
+    next batch's kernels, and an integrator failure surfaces at the next blocking call with the reference's error id."""
+    hs = host_state("planck_massless_lensing", CASES["planck_massless_lensing"])
+    ref = run_gpu(ctx, hs)
+    ctx.set_bessel(hs)
+    try:
+        ctx.set_option("async_calls", 1)
+        ctx.set_option("async_outputs", 1)
+        bufs = [np.zeros((len(hs.q_int), len(hs.ls), hs.n_src)) for _ in range(2)]
+        dms = []
+        for it in range(2):                          # two "batches": the first one's copy is issued when the second evolves
+            dm = ctx.create_model(hs)
+            dms.append(dm)
+            ctx.evolve([hs], [dm], want_sources=False, want_stats=False)
+            ctx.project([hs], [dm], want_delta=True, out=[bufs[it]])
+            icl = ctx.cl([hs], [dm])[0]
+            assert np.array_equal(icl, ref["icl"])
+        ctx.wait_outputs()
+        for b in bufs:
+            assert np.array_equal(b, ref["delta"])
+        for dm in dms:
+            ctx.destroy_model(dm)
+        # a failing integration: cb_evolve itself returns 0 (queued), the next blocking call reports error 4
+        p = planck2018_params(lmax=300, lensing=False, massless=True)
+        p.Accuracy.IntTolBoost = 100.0
+        bad = HostState(p)
+        ctx.set_bessel(bad)
+        dm = ctx.create_model(bad)
+        ctx.evolve([bad], [dm], want_sources=False, want_stats=False)
+        ctx.project([bad], [dm], want_delta=False)
+        with pytest.raises(CAMBError) as e:
+            ctx.cl([bad], [dm])
+        assert e.value.code == 4
+        ctx.destroy_model(dm)
+    finally:
+        ctx.set_option("async_outputs", 0)
+        try:
+            ctx.set_option("async_calls", 0)
+        except CAMBError:
+            pass
+    ctx.set_bessel(hs)
+    assert np.array_equal(run_gpu(ctx, hs)["icl"], ref["icl"])     # the context is usable and synchronous again
