@@ -483,9 +483,9 @@ def main():
                              "traffic": None,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",
                              "record_bytes_per_launch": gather_bytes, "l2_gbs": gather_bytes / (los_ms * 1e-3) / 1e9,
-                             "note": "the working set is L2-resident: every 32-byte Bessel record comes from L2 (record_bytes_per_launch = "
-                                     "32 B x the (q, l, tau) terms of the reference's own limits); l2_gbs is that stream, which is what "
-                                     "bounds the kernel (DESIGN.md 4.3), not HBM",
+                             "note": "the working set is L2-resident: every 32-byte Bessel record comes from L1/L2 (record_bytes_per_launch = "
+                                     "32 B x the (q, l, tau) terms of the reference's own limits; l2_gbs = that stream per second); ncu: L2 "
+                                     "at 20 % of its throughput, the warps wait on the L1-miss turnaround (DESIGN.md 4.3); HBM is not the resource",
                              "ms_per_launch": los_ms, "share_of_step": t_los / tot},
             "stage_ms_per_step": {"evolve": ev_ms, "spline_k": t_spl / args.steps, "los": los_ms, "cl": t_cl / args.steps,
                                   "lens": t_lens / args.steps},

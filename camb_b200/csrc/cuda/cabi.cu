@@ -42,8 +42,8 @@ cudaError_t cb_evolve_tensor_launch(const DModel*, const DModeItem*, int n_items
                                     cudaStream_t, int* grid_out);
 // project.cu
 void cb_spline_k_launch(const DModel*, int, int, double* const*, cudaStream_t);
-size_t cb_los_smem(int, int, int);
-cudaError_t cb_los_launch(const DModel*, int, const DBessel&, int, int, size_t, int, cudaStream_t);
+size_t cb_los_smem(int, int, int, int);
+cudaError_t cb_los_launch(const DModel*, int, const DBessel&, int, int, int, int, cudaStream_t);
 void cb_bessel_transpose_launch(const double*, double*, int, int, int, cudaStream_t);
 // collective.cu (NCCL bound at run time)
 bool cb_nccl_unique_id(char* id128, std::string* err);
@@ -147,7 +147,7 @@ struct cb_ctx {
     struct DeferredCopy { void* dst; const void* src; size_t bytes; };
     std::vector<DeferredCopy> deferred;   // queued by cb_project, issued by the next cb_evolve / cb_wait_outputs (see flush_outputs)
     void* comm = nullptr; int comm_ranks = 1, comm_rank = 0;   // NCCL communicator of a k-sharded run (cb_comm_init)
-    int los_kernel = 1;            // 1: lanes on the multipoles (transposed table, coalesced rows); 0: the gather kernel
+    int los_kernel = 1;            // lanes on the multipoles: 1 rows by coalesced loads (default), 2 rows by bulk copies (TMA) into per-warp rings (measured slower); 0: the gather kernel
     cudaEvent_t stage_ev[4][2] = {};     // per-stage kernel brackets of the last calls (evolve, spline-k, LOS, C_l)
     DModel* h_models = nullptr;   size_t cap_h_models = 0;   // page-locked staging
     DModeItem* h_items = nullptr; size_t cap_h_items = 0;
@@ -1019,7 +1019,7 @@ int cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q, 
     CK(cudaEventRecord(ctx->stage_ev[1][1], ctx->stream));
     bool any_windows = false;
     for (int m = 0; m < n_models; m++) any_windows = any_windows || dm[m]->h.num_redshiftwindows > 0;
-    const size_t smem = cb_los_smem(max_nsrc, max_ntau, n_l);
+    const size_t smem = cb_los_smem(max_nsrc, max_ntau, n_l, 1);   // (the staged kernels; the windows kernel sizes its own)
     CK(cudaEventRecord(ctx->stage_ev[2][0], ctx->stream));
     if (max_nq == 0) {
         // an empty slice of the integration grid (a rank with no share of a q-sharded run): nothing to project
@@ -1030,7 +1030,7 @@ int cb_project(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const int* n_q, 
         cudaError_t le = cb_los_win_launch(ctx->d_models, n_models, ctx->bess, max_nq, max_ntau, ctx->stream);
         if (le != cudaSuccess) { ctx->err = std::string("LOS (windows): ") + cudaGetErrorString(le); return le == cudaErrorInvalidValue ? CB_ERR_UNSUPPORTED_PARAMS : CB_ERR_CUDA; }
     } else {
-        cudaError_t le = cb_los_launch(ctx->d_models, n_models, ctx->bess, max_nq, max_ntau, smem, ctx->los_kernel, ctx->stream);
+        cudaError_t le = cb_los_launch(ctx->d_models, n_models, ctx->bess, max_nq, max_nsrc, max_ntau, ctx->los_kernel, ctx->stream);
         if (le != cudaSuccess) { ctx->err = std::string("LOS: ") + cudaGetErrorString(le); return CB_ERR_CUDA; }
     }
     ctx->launches++;

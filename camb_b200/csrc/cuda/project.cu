@@ -268,13 +268,20 @@ cb_los_gather_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau
 // product as in the reference (J_l dtau, then Source J_l: cmbmain.f90:1720-1737); only the order of the sum over time
 // steps differs (warp-strided instead of sequential).
 // grid = (max n_q, n_models); dynamic smem: as cb_los_gather_kernel, the reduction buffer aliases the per-step arrays.
-template <int NSLOT>
-__global__ void __launch_bounds__(LOS_THREADS, 3)
-cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
+#ifndef LOS_UNROLL
+#define LOS_UNROLL 1   /* time steps per round of the main loop, loads first (1: 37.7 ms, 2: 46.4, 3/4 at one CTA per SM: 80 ms per 128 sets) */
+#endif
+#ifndef LOS_BLOCKS
+#define LOS_BLOCKS 3
+#endif
+#define LOS_TMA_STAGES 3   /* rows in flight per warp on the bulk-copy path */
+template <int NSLOT, bool TMA>
+__global__ void __launch_bounds__(LOS_THREADS, TMA ? 2 : LOS_BLOCKS)
+cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau, unsigned ring_off) {
     const DModel& M = models[blockIdx.y];
     const int iq = blockIdx.x;
     if (iq >= M.n_q) return;
-    extern __shared__ __align__(16) double sm[];
+    extern __shared__ __align__(128) double sm[];
     const int ntime = M.n_tau, nsrc = M.n_src, n_k = M.n_k, n_l = B.n_l;
     double* Source_q = sm;                       // [nsrc][ntime]
     double* left_weight = Source_q + (size_t)nsrc * max_n_tau;
@@ -382,27 +389,123 @@ cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau) {
         if (j < n_l && s_n1[j] >= 0 && (nsrc <= 2 || tensors || q < s_qmax_int[j])) { n1s[s] = s_n1[j]; n2s[s] = s_n2[j]; }
         acc[s][0] = 0; acc[s][1] = 0; acc[s][2] = 0;
     }
-    {
+    if constexpr (TMA) {
+        // Bulk-copy path (the TMA engine of sm_100a: cp.async.bulk + mbarrier).  Every warp keeps LOS_TMA_STAGES - 1 table
+        // rows in flight into its own ring of shared-memory stages -- one asynchronous copy per time step of exactly the
+        // records its active l's need, a contiguous piece of the row -- and computes from shared memory.  The loads do not
+        // pass through the L1 miss path, whose outstanding-sector capacity bounds the LDG version (ncu r02bh: 16 B per cycle
+        // per SM, long-scoreboard 10.5 cycles per issue, L2 at 20 % of its throughput).  Same terms, same order of the sums.
+        constexpr int D = LOS_TMA_STAGES;
+        constexpr unsigned ROWB = NSLOT * 32 * 32;                                   // bytes of one stage: a whole padded row
+        unsigned char* smem_b = reinterpret_cast<unsigned char*>(sm);
+        unsigned char* ring = smem_b + ring_off + (size_t)warp * D * ROWB;
+        unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_b + ring_off + (size_t)nwarp * D * ROWB) + warp * D;
+        int* jlo_s = reinterpret_cast<int*>(smem_b + ring_off + (size_t)nwarp * D * ROWB + sizeof(unsigned long long) * nwarp * D) + warp * D;
+        const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring), bars_sa = (unsigned)__cvta_generic_to_shared(bars);
+        if (lane == 0) {
+            for (int d = 0; d < D; d++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars_sa + 8u * d));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        const char* Htb = reinterpret_cast<const char*>(B.horner_t);
+        const size_t rowb = (size_t)32 * B.n_l_pad;
+        const int nlo = s_nlo, nhi = s_nhi;
+        const int cnt = nlo <= nhi && nlo + warp <= nhi ? (nhi - nlo - warp) / nwarp + 1 : 0;   // this warp's time steps
+        const bool three = nsrc > 2;
+        // the l range (record indices jlo..jhi) that takes part at time step n; jlo < 0: none
+        auto issue = [&](int i) {
+            const int n = nlo + warp + i * nwarp;
+            int lo = 0x7fffffff, hi = -1;
+#pragma unroll
+            for (int s = 0; s < NSLOT; s++)
+                if (n >= n1s[s] && n <= n2s[s]) { lo = min(lo, 32 * s + lane); hi = max(hi, 32 * s + lane); }
+            lo = __reduce_min_sync(FULL, lo);
+            hi = __reduce_max_sync(FULL, hi);
+            const int st = i % D;
+            if (lane == 0) {
+                jlo_s[st] = hi >= 0 ? lo : -1;
+                if (hi >= 0) {
+                    const unsigned bytes = 32u * (unsigned)(hi - lo + 1);
+                    const char* src = Htb + rowb * (size_t)(bes_index[n - 1] - 1) + 32 * (size_t)lo;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage was read by generic loads before
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bars_sa + 8u * st), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(ring_sa + ROWB * st), "l"(src), "r"(bytes), "r"(bars_sa + 8u * st) : "memory");
+                }
+            }
+        };
+        for (int i = 0; i < D - 1 && i < cnt; i++) issue(i);
+        __syncwarp();
+        unsigned phase_bits = 0;   // bit st = parity the next wait on stage st expects
+        for (int i = 0; i < cnt; i++) {
+            if (i + D - 1 < cnt) issue(i + D - 1);      // refills the stage consumed in the previous round (all lanes are past it)
+            __syncwarp();
+            const int st = i % D, n = nlo + warp + i * nwarp;
+            const int jlo = jlo_s[st];
+            if (jlo >= 0) {
+                const unsigned par = (phase_bits >> st) & 1u;
+                unsigned done = 0;
+                while (!done)
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(done) : "r"(bars_sa + 8u * st), "r"(par) : "memory");
+                phase_bits ^= 1u << st;
+                const double a2 = left_weight[n - 1], dt = dtau_s[n - 1];
+                const double S0 = Source_q[n - 1], S1 = Source_q[max_n_tau + n - 1];
+                const double S2 = three ? Source_q[2 * (size_t)max_n_tau + n - 1] : 0.0;
+                const unsigned char* stage = ring + (size_t)ROWB * st;
+#pragma unroll
+                for (int s = 0; s < NSLOT; s++) {
+                    if (n >= n1s[s] && n <= n2s[s]) {
+                        const double4 c = *reinterpret_cast<const double4*>(stage + 32 * (32 * s + lane - jlo));
+                        double J_l = c.x + a2 * (c.y + a2 * (c.z + a2 * c.w));
+                        J_l = J_l * dt;
+                        acc[s][0] = acc[s][0] + S0 * J_l;
+                        acc[s][1] = acc[s][1] + S1 * J_l;
+                        if (three) acc[s][2] = acc[s][2] + S2 * J_l;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    } else {
+        // Two time steps per round, every load of the round issued before the first multiply: an in-order warp otherwise
+        // has one row in flight at a time (ncu r02bh: 16 B per cycle per SM against an L2 that can deliver 4x that, 10.5
+        // cycles of long-scoreboard stall per issue).  The sum a lane forms for one l still runs over its time steps in
+        // the same order, so the result is unchanged bit for bit.
         const double* Ht = B.horner_t + 4 * (size_t)lane;
         const size_t row = (size_t)4 * B.n_l_pad;
         const int nlo = s_nlo, nhi = s_nhi;   // nlo > nhi: no l integrates at this q
         const bool three = nsrc > 2;
-#pragma unroll 2
-        for (int n = nlo <= nhi ? nlo + warp : nhi + 1; n <= nhi; n += nwarp) {
-            const double a2 = left_weight[n - 1], dt = dtau_s[n - 1];
-            const double S0 = Source_q[n - 1], S1 = Source_q[max_n_tau + n - 1];
-            const double S2 = three ? Source_q[2 * (size_t)max_n_tau + n - 1] : 0.0;
-            const double* R = Ht + row * (size_t)(bes_index[n - 1] - 1);
+        for (int n = nlo <= nhi ? nlo + warp : nhi + 1; n <= nhi; n += LOS_UNROLL * nwarp) {
+            double c[LOS_UNROLL][NSLOT][4];
+            bool on[LOS_UNROLL][NSLOT];
 #pragma unroll
-            for (int s = 0; s < NSLOT; s++) {
-                if (n >= n1s[s] && n <= n2s[s]) {
-                    double c0, c1, c2, c3;
-                    ld_horner(R + 128 * s, c0, c1, c2, c3);
-                    double J_l = c0 + a2 * (c1 + a2 * (c2 + a2 * c3));
-                    J_l = J_l * dt;
-                    acc[s][0] = acc[s][0] + S0 * J_l;
-                    acc[s][1] = acc[s][1] + S1 * J_l;
-                    if (three) acc[s][2] = acc[s][2] + S2 * J_l;
+            for (int u = 0; u < LOS_UNROLL; u++) {
+                const int nu = n + u * nwarp;
+                const bool live = nu <= nhi;
+                const double* R = Ht + row * (size_t)(bes_index[(live ? nu : n) - 1] - 1);
+#pragma unroll
+                for (int s = 0; s < NSLOT; s++) {
+                    on[u][s] = live && nu >= n1s[s] && nu <= n2s[s];
+                    if (on[u][s]) ld_horner(R + 128 * s, c[u][s][0], c[u][s][1], c[u][s][2], c[u][s][3]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < LOS_UNROLL; u++) {
+                const int nu = n + u * nwarp;
+                if (nu > nhi) break;
+                const double a2 = left_weight[nu - 1], dt = dtau_s[nu - 1];
+                const double S0 = Source_q[nu - 1], S1 = Source_q[max_n_tau + nu - 1];
+                const double S2 = three ? Source_q[2 * (size_t)max_n_tau + nu - 1] : 0.0;
+#pragma unroll
+                for (int s = 0; s < NSLOT; s++) {
+                    if (on[u][s]) {
+                        double J_l = c[u][s][0] + a2 * (c[u][s][1] + a2 * (c[u][s][2] + a2 * c[u][s][3]));
+                        J_l = J_l * dt;
+                        acc[s][0] = acc[s][0] + S0 * J_l;
+                        acc[s][1] = acc[s][1] + S1 * J_l;
+                        if (three) acc[s][2] = acc[s][2] + S2 * J_l;
+                    }
                 }
             }
         }
@@ -954,12 +1057,24 @@ void cb_spline_k_launch(const DModel* d_models, int n_models, int max_cols, doub
     cb_spline_k_kernel<<<grid, 128, 0, st>>>(d_models, n_models, d_scratch);
 }
 
-size_t cb_los_smem(int max_nsrc, int max_n_tau, int n_l) {
-    const size_t steps = sizeof(double) * 2 * (size_t)max_n_tau + sizeof(int) * (size_t)max_n_tau + 16;   // left_weight, dtau, bes_index
+static int los_nslot(int n_l) {
     int nslot = (n_l + 31) / 32;
-    if (nslot > 4) nslot = 6;                                                                             // the instantiated slot counts: 1, 2, 3, 4, 6
-    const size_t red = sizeof(double) * 3 * (LOS_THREADS / 32) * 32 * (size_t)nslot;                      // the reduction buffer aliases them
-    return sizeof(double) * (size_t)max_nsrc * max_n_tau + (steps > red ? steps : red);
+    return nslot > 4 ? 6 : (nslot < 1 ? 1 : nslot);   // the instantiated slot counts: 1, 2, 3, 4, 6
+}
+
+// Offset of the bulk-copy rings = size of what every variant needs: Source_q + max(per-step arrays, reduction buffer that aliases them)
+static size_t los_base_smem(int max_nsrc, int max_n_tau, int n_l) {
+    const size_t steps = sizeof(double) * 2 * (size_t)max_n_tau + sizeof(int) * (size_t)max_n_tau + 16;   // left_weight, dtau, bes_index
+    const size_t red = sizeof(double) * 3 * (LOS_THREADS / 32) * 32 * (size_t)los_nslot(n_l);
+    const size_t b = sizeof(double) * (size_t)max_nsrc * max_n_tau + (steps > red ? steps : red);
+    return (b + 127) & ~size_t(127);
+}
+
+// which: 0 gather kernel, 1 coalesced row loads (LDG), 2 bulk copies into per-warp rings (+ mbarriers + per-stage first record index)
+size_t cb_los_smem(int max_nsrc, int max_n_tau, int n_l, int which) {
+    size_t b = los_base_smem(max_nsrc, max_n_tau, n_l);
+    if (which == 2) b += (size_t)(LOS_THREADS / 32) * LOS_TMA_STAGES * ((size_t)los_nslot(n_l) * 1024 + sizeof(unsigned long long) + sizeof(int));
+    return b;
 }
 
 void cb_bessel_transpose_launch(const double* d_h, double* d_ht, int nxm1, int n_l, int n_l_pad, cudaStream_t st) {
@@ -968,22 +1083,32 @@ void cb_bessel_transpose_launch(const double* d_h, double* d_ht, int nxm1, int n
 }
 
 // which = 1: lanes on the multipoles (coalesced rows of the transposed table); 0: the gather kernel
-cudaError_t cb_los_launch(const DModel* d_models, int n_models, const DBessel& B, int max_n_q, int max_n_tau, size_t smem, int which,
+cudaError_t cb_los_launch(const DModel* d_models, int n_models, const DBessel& B, int max_n_q, int max_nsrc, int max_n_tau, int which,
                           cudaStream_t st) {
     dim3 grid(max_n_q, n_models);
-    const int nslot = (B.n_l + 31) / 32;
-#define CB_LOS_GO(K)                                                                                          \
+    const int nslot = los_nslot(B.n_l);
+    if (!B.horner_t) which = 0;
+    size_t smem = cb_los_smem(max_nsrc, max_n_tau, B.n_l, which);
+    if (which == 2 && smem > 113 * 1024) { which = 1; smem = cb_los_smem(max_nsrc, max_n_tau, B.n_l, 1); }   // two CTAs per SM or the LDG path
+    const unsigned ring_off = (unsigned)los_base_smem(max_nsrc, max_n_tau, B.n_l);
+#define CB_LOS_GO(K, ...)                                                                                     \
     do {                                                                                                      \
         cudaError_t e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
         if (e != cudaSuccess) return e;                                                                       \
-        K<<<grid, LOS_THREADS, smem, st>>>(d_models, B, max_n_tau);                                           \
+        K<<<grid, LOS_THREADS, smem, st>>>(d_models, B, max_n_tau, ##__VA_ARGS__);                            \
     } while (0)
-    if (which == 0 || !B.horner_t) CB_LOS_GO(cb_los_gather_kernel);
-    else if (nslot <= 1) CB_LOS_GO(cb_los_kernel<1>);
-    else if (nslot == 2) CB_LOS_GO(cb_los_kernel<2>);
-    else if (nslot == 3) CB_LOS_GO(cb_los_kernel<3>);
-    else if (nslot == 4) CB_LOS_GO(cb_los_kernel<4>);
-    else CB_LOS_GO(cb_los_kernel<6>);
+#define CB_LOS_N(N)                                                   \
+    do {                                                              \
+        if (which == 2) CB_LOS_GO((cb_los_kernel<N, true>), ring_off); \
+        else CB_LOS_GO((cb_los_kernel<N, false>), ring_off);           \
+    } while (0)
+    if (which == 0) CB_LOS_GO(cb_los_gather_kernel);
+    else if (nslot == 1) CB_LOS_N(1);
+    else if (nslot == 2) CB_LOS_N(2);
+    else if (nslot == 3) CB_LOS_N(3);
+    else if (nslot == 4) CB_LOS_N(4);
+    else CB_LOS_N(6);
+#undef CB_LOS_N
 #undef CB_LOS_GO
     return cudaGetLastError();
 }

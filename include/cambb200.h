@@ -262,8 +262,9 @@ long long cb_launch_count(const cb_ctx* ctx);
  * "async_model_upload" = 1: cb_model_create queues its host->device copies and returns; the caller keeps the cb_model arrays
  * alive and unchanged until the next cb_evolve / cb_project / cb_cl* call on the context returns (a Fortran host's
  * allocatables outlive cmbmain anyway).  Default 0: the arrays may be freed as soon as cb_model_create returns.
- * "los_kernel": 1 (default) loop B with the lanes on the multipoles (coalesced rows of the transposed Bessel table), 0 the
- * gather kernel (A/B runs).
+ * "los_kernel": 1 (default) loop B with the lanes on the multipoles (coalesced rows of the transposed Bessel table), 2 the
+ * same with the rows staged by bulk copies (cp.async.bulk + mbarrier) into per-warp shared-memory rings, 0 the gather
+ * kernel (A/B runs; DESIGN.md 4.3 has the measurements).
  * "async_outputs" = 1: cb_project does not copy Delta_p_l_k to the host before it returns: the copies are handed to a copy
  * stream when the next cb_evolve starts (so they travel under the next batch's kernels, and the small read-backs of cb_cl /
  * cb_lens_contrib do not queue behind them) or when cb_wait_outputs is called; the host arrays are complete after

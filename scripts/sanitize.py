@@ -31,6 +31,43 @@ def scalar(hs, lanes):
     print("ok", hs.n_src, lanes, flush=True)
 
 
+NEW_ONLY = "--round2-only" in sys.argv     # the kernels added in round 2 alone
+if NEW_ONLY:
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    hs = HostState(planck2018_params(lmax=150, lensing=True, massless=True))
+    ctx.build_bessel(hs, want_table=True)                      # bessel_table.cu
+    dm = ctx.create_model(hs, thermo_on_device=True)           # thermo_pack.cu
+    ctx.evolve([hs], [dm])                                     # register kernel (three layouts), stage loop
+    ctx.project([hs], [dm])                                    # lanes-on-l line-of-sight kernel on the device-built table
+    ctx.set_option("los_kernel", 0)
+    ctx.project([hs], [dm])                                    # the gather kernel
+    ctx.set_option("los_kernel", 1)
+    ctx.cl([hs], [dm])
+    ctx.destroy_model(dm)
+    pn = planck2018_params(lmax=150, lensing=True, massless=True, want_transfer=True)
+    zs = [6.0, 2.0, 0.8, 0.3, 0.0]
+    pn.transfer_PK_num_redshifts = len(zs)
+    for i, z in enumerate(zs):
+        pn.transfer_PK_redshifts[i] = z
+    pn.transfer_kmax = 0.5
+    hn = HostState(pn)
+    ctx.set_bessel(hn)
+    dm = ctx.create_model(hn)
+    ctx.evolve([hn], [dm])
+    q = np.asarray(hn.source_q())
+    ratio = 1.0 + 0.3 * np.outer(np.linspace(0.2, 1.0, len(zs)), np.tanh(q * 10.0))
+    ctx.make_nonlinear_sources(dm, ratio)                      # cb_nonlinear_sources_kernel
+    ctx.set_option("async_calls", 1); ctx.set_option("async_outputs", 1)
+    out = [np.zeros((len(hn.q_int), len(hn.ls), hn.n_src))]
+    ctx.project([hn], [dm], want_delta=True, out=out)
+    ctx.cl([hn], [dm])
+    ctx.wait_outputs()
+    ctx.set_option("async_outputs", 0); ctx.set_option("async_calls", 0)
+    ctx.destroy_model(dm)
+    ctx.close()
+    print("sanitize run complete (round 2 kernels)")
+    sys.exit(0)
 LENS_ONLY = "--lens-only" in sys.argv      # racecheck of the lensing kernels alone (the whole script takes > 10 min under racecheck)
 p = planck2018_params(lmax=150, lensing=True, massless=False, want_transfer=True)
 p.transfer_kmax = 0.5
