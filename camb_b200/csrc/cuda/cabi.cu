@@ -664,6 +664,7 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
     int cls_nv[CB_N_CLASSES] = {}, cls_maxl[CB_N_CLASSES] = {};
     std::vector<StagePiece> pieces;
     std::vector<size_t> item_off((size_t)n_models + 1, 0);
+    std::vector<int> src_nk((size_t)n_models, -1);
     {
         size_t tot = 0;
         for (int m = 0; m < n_models; m++) tot += (size_t)std::max(modes[m].n_k, 0);
@@ -693,6 +694,10 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
             CK(cudaMemsetAsync(d->d_src, 0, sizeof(double) * ns, ctx->stream));
             D.n_k = n_k; D.q_src = d->d_q_src; D.LinearSrc = d->d_src; D.ddSrc = d->d_dd;
         } else {
+            // loop A' (GetTransfer) on a model that already holds sources: the kernels of THIS call index TransferData by the
+            // transfer-only mode count; the model's own n_k (the source wavenumbers loop B splines over) comes back after
+            // the launch descriptors have been staged
+            src_nk[m] = d->d_src ? D.n_k : -1;
             D.n_k = n_k;
         }
         if (nz > 0) {
@@ -780,7 +785,10 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
     }
     int n_items = 0;
     for (int c = 0; c < CB_N_CLASSES; c++) n_items += (int)cls_items[c].size();
-    if (n_items == 0) return 0;
+    if (n_items == 0) {
+        for (int m = 0; m < n_models; m++) if (src_nk[m] >= 0) dm[m]->h.n_k = src_nk[m];
+        return 0;
+    }
     if (int e = stage_upload(ctx, pieces)) return e;
     std::vector<DModeItem> items;
     items.reserve(n_items);
@@ -791,6 +799,7 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
         items.insert(items.end(), cls_items[c].begin(), cls_items[c].end());
     }
     if (int e = push_models(ctx, n_models, dm)) return e;
+    for (int m = 0; m < n_models; m++) if (src_nk[m] >= 0) dm[m]->h.n_k = src_nk[m];
     if (int e = ensure(ctx, &ctx->d_items, &ctx->cap_items, (size_t)n_items)) return e;
     if ((size_t)n_items > ctx->cap_h_items) {
         if (ctx->h_items) cudaFreeHost(ctx->h_items);
@@ -886,12 +895,13 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
     for (int m = 0; m < n_models; m++) {
         cb_dmodel* d = dm[m];
         const DModel& D = d->h;
+        const size_t call_nk = (size_t)modes[m].n_k;   // the mode count of THIS call (a transfer-only call leaves D.n_k at the source count)
         if (LinearSrc && LinearSrc[m] && !modes[m].transfer_only)
-            CK(cudaMemcpyAsync(LinearSrc[m], d->d_src, sizeof(double) * (size_t)D.n_k * D.n_src * D.n_tau, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(LinearSrc[m], d->d_src, sizeof(double) * call_nk * D.n_src * D.n_tau, cudaMemcpyDeviceToHost, ctx->stream));
         if (TransferData && TransferData[m] && D.num_transfer_redshifts > 0)
-            CK(cudaMemcpyAsync(TransferData[m], d->d_transfer, sizeof(float) * (size_t)13 * D.n_k * D.num_transfer_redshifts, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(TransferData[m], d->d_transfer, sizeof(float) * (size_t)13 * call_nk * D.num_transfer_redshifts, cudaMemcpyDeviceToHost, ctx->stream));
         if (stats && stats[m])
-            CK(cudaMemcpyAsync(stats[m], d->d_stats, sizeof(long long) * 4 * (size_t)D.n_k, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(stats[m], d->d_stats, sizeof(long long) * 4 * call_nk, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
 #ifdef CB_TRACE

@@ -228,6 +228,23 @@ def sigma8_anchor_params(anchor, notebook=False):
     return p
 
 
+def nonlinear_lensing_transfer_settings(p):
+    """What `GetComputedPKRedshifts` asks of the transfer outputs when the sources are to be scaled for non-linear lensing
+    (CP%NonLinear = lens / both with DoLensing; fortran/results.f90:1039-1095): matter transfer to kmax >= 5 NL_Boost and
+    a ladder of max(2, 30 NL_Boost) redshifts z = 10 f^(3/2), f = 1 ... 0, ending at z = 0 (merged with the power-spectrum
+    redshifts, of which this helper keeps none).  Modifies and returns `p`."""
+    nl_boost = p.Accuracy.AccuracyBoost * p.Accuracy.NonlinSourceBoost
+    p.WantTransfer = 1
+    p.transfer_kmax = max(p.transfer_kmax, 5.0 * nl_boost)
+    n = max(2, int(round(30 * nl_boost)))
+    zmax = 15.0 if nl_boost >= 2.5 else 10.0
+    p.transfer_PK_num_redshifts = n
+    for i in range(n):
+        f = (n - 1 - i) / (n - 1)
+        p.transfer_PK_redshifts[i] = zmax * f * np.sqrt(f)
+    return p
+
+
 def splined_counts_anchor_params(anchor, lmax=4000):
     """The parameter set of the reference's sharp-window known-answer test (camb/tests/camb_test.py:1226-1241):
     CAMBparams() defaults + RECFAST 'planck' set + set_cosmology(H0=67.5, ombh2=0.022, omch2=0.122) (mnu 0.06) +

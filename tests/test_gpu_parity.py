@@ -657,3 +657,53 @@ def test_asynchronous_calls_and_deferred_result_copies(ctx):
             pass
     ctx.set_bessel(hs)
     assert np.array_equal(run_gpu(ctx, hs)["icl"], ref["icl"])     # the context is usable and synchronous again
+
+
+def test_nonlinear_lensing_chain_config2(ctx):
+    """BASELINE configs[1] with its non-linear lensing on (do_nonlinear = 3; halofit_version takahashi instead of the shipped
+    HMcode, which the stand-in host does not restate): transfer outputs at the 30-redshift ladder to kmax = 5
+    (GetComputedPKRedshifts, results.f90:1039-1095), HALOFIT ratios from those transfers on the host (camb_b200/nonlinear.py,
+    pinned to the reference's known answer in tests/test_sigma8_anchor.py), MakeNonlinearSources on the DEVICE-resident
+    sources, loops B and C.  Against the same chain on the CPU oracle: C_l to 1e-5 (the ratios themselves see the
+    device's transfer functions); and the lensing potential power is boosted at high l while T and E are untouched."""
+    from camb_b200.nonlinear import halofit_ratios
+    from camb_b200.workloads import nonlinear_lensing_transfer_settings
+
+    def build():
+        p = planck2018_params(lmax=2500, lensing=True, massless=True, want_transfer=True)
+        p.NonLinear = 3
+        return nonlinear_lensing_transfer_settings(p)
+    hs = host_state("planck_nonlinear_lensing", build)
+    m = hs.model
+    assert m.num_transfer_redshifts == 30 and m.n_src == 3
+    zs = [hs.params.transfer_PK_redshifts[i] for i in range(30)]
+    q = np.asarray(hs.source_q())
+    n_src_k = len(q)
+    # CPU: oracle transfers -> ratios -> oracle MakeNonlinearSources -> oracle B, C
+    src_o, tr1_o, _ = O.evolve(hs, nthreads=8)
+    _, tr2_o, _ = O.evolve(hs, transfer_only=True, nthreads=8)
+    ratio_o = halofit_ratios(hs, np.concatenate([tr1_o, tr2_o], axis=1), zs)[:, :n_src_k]
+    src_nl = O.make_nonlinear_sources(hs, q, src_o, ratio_o, min_kh=0.005)
+    dd = O.spline_k(q, src_nl)
+    icl_o = O.cl(hs, O.project(hs, q, src_nl, dd, nthreads=8))
+    icl_lin = O.cl(hs, O.project(hs, q, src_o, O.spline_k(q, src_o), nthreads=8))
+    # GPU: device transfers -> ratios -> cb_make_nonlinear_sources -> B, C
+    ctx.set_bessel(hs)
+    dm = ctx.create_model(hs, thermo_on_device=True)
+    try:
+        _, tr1, _ = ctx.evolve([hs], [dm], want_sources=False, want_stats=False)
+        _, tr2, _ = ctx.evolve([hs], [dm], transfer_only=True)
+        ratio = halofit_ratios(hs, np.concatenate([tr1[0], tr2[0]], axis=1), zs)[:, :n_src_k]
+        ctx.make_nonlinear_sources(dm, ratio, min_kh=0.005)
+        ctx.project([hs], [dm], want_delta=False)
+        icl = ctx.cl([hs], [dm])[0]
+    finally:
+        ctx.destroy_model(dm)
+    assert np.abs(ratio / ratio_o - 1).max() < 1e-5
+    errs = cl_err(icl, icl_o)
+    print("non-linear lensing chain: C_l errors", errs, "ratio range", ratio.min(), ratio.max())
+    assert max(errs) < CL_RTOL, errs
+    ls = np.asarray(hs.ls)
+    boost = icl_o[:, 3] / icl_lin[:, 3]
+    assert np.all(np.abs(icl_o[:, :3] / icl_lin[:, :3] - 1) < 1e-12)          # T, E, TE: linear sources
+    assert np.abs(boost[ls <= 100] - 1).max() < 0.01 and boost[ls >= 900].min() > 1.08, boost[::8]   # phi-phi: +10...15 % at l ~ 1000-2500

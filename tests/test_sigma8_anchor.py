@@ -164,3 +164,51 @@ def test_gpu_relative_velocity_matches_notebook():
     finally:
         ctx.close()
     print("gpu v_bc rms", _check_vbc(hs, np.concatenate([tr1[0], tr2[0]], axis=1)))
+
+
+# ---- Takahashi HALOFIT: P_nl(k/h = 0.379, z = 3.1) = 57.734 of the same reference test (camb/tests/camb_test.py:804, 825-829:
+# halofit_version = "takahashi", NonLinear_both, get_matter_power_spectrum(1e-4, 1, 20)[-1][-3], asserted there to 2 places).
+# The reference run has NonLinear_lens on while the transfers are computed, so GetComputedPKRedshifts raises the transfer
+# kmax to 5 (results.f90:1066-1067) -- with kmax = 1.2 the extrapolated tail moves n_eff by 0.06 and the answer by 7 %.
+# camb_b200/nonlinear.py (the stand-in for the host's NonLinearModel) on our transfers: 57.7341, i.e. 2e-6. ----
+PK_NONLINEAR_Z31 = 57.734
+
+
+def _halofit_params():
+    p = sigma8_anchor_params(ANCHOR)
+    p.transfer_kmax = 5.0
+    return p
+
+
+def _check_halofit(hs, tr):
+    from camb_b200.nonlinear import halofit_ratios, nonlinear_matter_power_interp
+    zs = [hs.params.transfer_PK_redshifts[i] for i in range(hs.params.transfer_PK_num_redshifts)]
+    ratio = halofit_ratios(hs, tr, zs)
+    _, pl = matter_power_interp(hs, tr, 1e-4, 1.0, 20)
+    _, pn = nonlinear_matter_power_interp(hs, tr, ratio, 1e-4, 1.0, 20)
+    assert abs(pl[0][-3] / ANCHOR["expected"]["pk_interp_z3.1_khindex-3_of_20"] - 1) < 1e-4
+    assert abs(pn[0][-3] / PK_NONLINEAR_Z31 - 1) < 8.7e-5, pn[0][-3]      # the reference asserts 2 decimal places: 0.005 / 57.734
+    assert np.all(ratio >= 0.98) and ratio[-1].max() > 2.0                # z = 0: strongly non-linear at the top of the k range
+    return pn[0][-3]
+
+
+def test_oracle_takahashi_halofit_matches_reference_value():
+    hs = host_state("halofit_anchor", _halofit_params)
+    _, tr1, _ = O.evolve(hs, nthreads=8)
+    _, tr2, _ = O.evolve(hs, transfer_only=True, nthreads=8)
+    print("oracle P_nl(k/h = 0.379, z = 3.1)", _check_halofit(hs, np.concatenate([tr1, tr2], axis=1)))
+
+
+@pytest.mark.gpu
+def test_gpu_takahashi_halofit_matches_reference_value():
+    from camb_b200.gpu import GpuContext
+    hs = host_state("halofit_anchor", _halofit_params)
+    ctx = GpuContext(0)
+    try:
+        dm = ctx.create_model(hs)
+        _, tr1, _ = ctx.evolve([hs], [dm], want_sources=False)
+        _, tr2, _ = ctx.evolve([hs], [dm], transfer_only=True)
+        ctx.destroy_model(dm)
+    finally:
+        ctx.close()
+    print("gpu P_nl(k/h = 0.379, z = 3.1)", _check_halofit(hs, np.concatenate([tr1[0], tr2[0]], axis=1)))
