@@ -707,3 +707,57 @@ def test_nonlinear_lensing_chain_config2(ctx):
     boost = icl_o[:, 3] / icl_lin[:, 3]
     assert np.all(np.abs(icl_o[:, :3] / icl_lin[:, :3] - 1) < 1e-12)          # T, E, TE: linear sources
     assert np.abs(boost[ls <= 100] - 1).max() < 0.01 and boost[ls >= 900].min() > 1.08, boost[::8]   # phi-phi: +10...15 % at l ~ 1000-2500
+
+
+def test_nonlinear_counts_chain_config4(ctx):
+    """BASELINE configs[3] (params_counts.ini) with its do_nonlinear = 3 (halofit_version takahashi for the shipped HMcode):
+    every source from the third on -- lensing potential, the two count windows, the two magnification sources -- is scaled by
+    MakeNonlinearSources on the device; loops B and C with the window terms and the Limber part follow.  Against the CPU
+    oracle doing the same: iCl and the full iCl_Array to 1e-5; the count auto-spectra grow at small scales."""
+    from camb_b200.nonlinear import halofit_ratios
+    from camb_b200.workloads import nonlinear_lensing_transfer_settings
+
+    def build():
+        p = params_counts_config4(lmax=400)
+        p.NonLinear = 3
+        p.transfer_high_precision = 0
+        return nonlinear_lensing_transfer_settings(p)
+    hs = host_state("counts_nonlinear", build)
+    m = hs.model
+    nz = m.num_transfer_redshifts
+    assert nz == 30 and m.num_redshiftwindows == 2 and hs.n_src == 7
+    zs = [hs.params.transfer_PK_redshifts[i] for i in range(nz)]
+    q = np.asarray(hs.source_q())
+    src_o, tr1_o, _ = O.evolve(hs, nthreads=8)
+    _, tr2_o, _ = O.evolve(hs, transfer_only=True, nthreads=8)
+    ratio_o = halofit_ratios(hs, np.concatenate([tr1_o, tr2_o], axis=1), zs)[:, :len(q)]
+    src_nl = O.make_nonlinear_sources(hs, q, src_o, ratio_o)
+
+    def oracle_cls(src):
+        dd = O.spline_k(q, src)
+        delta = O.project(hs, q, src, dd, nthreads=8)
+        limb_src, n1n2 = O.limber(hs, q, src, dd)
+        return O.cl_windows(hs, delta, limb_src, n1n2)
+    icl_o, arr_o = oracle_cls(src_nl)
+    _, arr_lin = oracle_cls(src_o)
+    ctx.set_bessel(hs)
+    dm = ctx.create_model(hs)
+    try:
+        _, tr1, _ = ctx.evolve([hs], [dm], want_sources=False, want_stats=False)
+        _, tr2, _ = ctx.evolve([hs], [dm], transfer_only=True)
+        ratio = halofit_ratios(hs, np.concatenate([tr1[0], tr2[0]], axis=1), zs)[:, :len(q)]
+        ctx.make_nonlinear_sources(dm, ratio)
+        ctx.project([hs], [dm], want_delta=False)
+        icl, arr = ctx.cl_windows([hs], [dm])
+        icl, arr = icl[0], arr[0]
+    finally:
+        ctx.destroy_model(dm)
+    diag = np.sqrt(np.abs(np.einsum("iil,jjl->ijl", arr_o, arr_o)))
+    diag[diag == 0] = 1
+    err = (np.abs(arr - arr_o) / diag).max()
+    print("non-linear counts chain: iCl_Array error", err, "iCl errors", cl_err(icl, icl_o))
+    assert err < CL_RTOL and max(cl_err(icl, icl_o)) < CL_RTOL
+    ls = np.asarray(hs.ls)
+    hi = ls >= 200
+    assert np.all(arr_o[3, 3][hi] > 1.02 * arr_lin[3, 3][hi]), (arr_o[3, 3] / arr_lin[3, 3])[::6]     # W1 x W1 (z = 0.3): non-linear growth
+    assert np.allclose(arr_o[0, 0], arr_lin[0, 0], rtol=1e-12)                                        # TT untouched
