@@ -274,6 +274,9 @@ cb_los_gather_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau
 #ifndef LOS_BLOCKS
 #define LOS_BLOCKS 3
 #endif
+#ifndef LOS_PREFETCH
+#define LOS_PREFETCH 0   /* rounds ahead that the rows are prefetched into L1 (0: off) */
+#endif
 #define LOS_TMA_STAGES 3   /* rows in flight per warp on the bulk-copy path */
 template <int NSLOT, bool TMA>
 __global__ void __launch_bounds__(LOS_THREADS, TMA ? 2 : LOS_BLOCKS)
@@ -479,6 +482,17 @@ cb_los_kernel(const DModel* __restrict__ models, DBessel B, int max_n_tau, unsig
         for (int n = nlo <= nhi ? nlo + warp : nhi + 1; n <= nhi; n += LOS_UNROLL * nwarp) {
             double c[LOS_UNROLL][NSLOT][4];
             bool on[LOS_UNROLL][NSLOT];
+#if LOS_PREFETCH
+            {   // the rows of the round after this one, requested now without a register or a scoreboard entry to wait on
+                const int np = n + LOS_PREFETCH * LOS_UNROLL * nwarp;
+                if (np <= nhi) {
+                    const double* Rp = Ht + row * (size_t)(bes_index[np - 1] - 1);
+#pragma unroll
+                    for (int s = 0; s < NSLOT; s++)
+                        if (np >= n1s[s] && np <= n2s[s]) asm volatile("prefetch.global.L1 [%0];" ::"l"(Rp + 128 * s));
+                }
+            }
+#endif
 #pragma unroll
             for (int u = 0; u < LOS_UNROLL; u++) {
                 const int nu = n + u * nwarp;
