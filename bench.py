@@ -40,8 +40,9 @@ WORKLOAD = "planck2018_lcdm_box_massless_nu_T+E+phi_lensed_to_lmax2500 (Max_l 27
 # one cosmology.  Every workload is a batch of `--batch` synthetic parameter sets per GPU per step.
 WORKLOADS = {
     "lcdm_massless": dict(name=WORKLOAD, lensing=True),
-    "config1_massive": dict(name="params_ini_box_one_massive_nu_T+E_lmax2500_keta6250_unlensed", lensing=False),
-    "config5_mnu_w0wa": dict(name="planck2018_box_mnu+w0wa_ppf_T+E_lmax2500_keta6250_unlensed", lensing=False),
+    # the massive-neutrino workloads run the general (shared-memory) evolve kernel, whose per-set time is best at 64 sets per step
+    "config1_massive": dict(name="params_ini_box_one_massive_nu_T+E_lmax2500_keta6250_unlensed", lensing=False, batch=64),
+    "config5_mnu_w0wa": dict(name="planck2018_box_mnu+w0wa_ppf_T+E_lmax2500_keta6250_unlensed", lensing=False, batch=64),
     "single_cosmology": dict(name="planck_2018_massless_nu_T+E+phi_lmax2500_lensed_one_cosmology", lensing=True),
 }
 
@@ -265,7 +266,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="lcdm_massless", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=env_int("CAMB_B200_BATCH", 128), help="parameter sets per GPU per step")
+    ap.add_argument("--batch", type=int, default=env_int("CAMB_B200_BATCH", 0),
+                    help="parameter sets per GPU per step (default: 128, or the workload's own default)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the one-cosmology latency measurement")
@@ -276,6 +278,8 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     wl = WORKLOADS[args.workload]
+    if args.batch <= 0:
+        args.batch = wl.get("batch", 128)
     if args.workload == "single_cosmology":
         args.batch = 1
     if args.impl == "reference":
