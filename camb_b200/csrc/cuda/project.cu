@@ -67,31 +67,96 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 }  // namespace
 
-// One thread per (source, time step) column: natural-spline second derivatives along k.
-// `u` is scratch of the same shape as dd.
-__global__ void cb_spline_k_kernel(const DModel* __restrict__ models, int n_models, double* const* __restrict__ scratch) {
+// One thread per (source, time step) column: natural-spline second derivatives along k (InitSourceInterpolation,
+// cmbmain.f90:1249-1265; forutils spline).  A column is n_k consecutive doubles and the columns of a warp's 32 threads are
+// n_k apart, so a thread-per-column walk touches 32 different lines per load; here a warp stages 32-wavenumber tiles of its
+// 32 columns through shared memory -- every global access is a 256-byte run of one column -- and each thread runs the
+// recurrence of ITS column on the staged tile (stride 33: conflict-free both ways).  Forward elimination writes the two
+// recurrence arrays (d2, u) tile by tile, back substitution reads them back the same way.  Same arithmetic, same order.
+// block = one warp (25 KB of tiles); grid = (ceil(columns / 32), n_models); `u` is scratch of the shape of dd.
+#define SPL_T 32
+__global__ void __launch_bounds__(32) cb_spline_k_kernel(const DModel* __restrict__ models, int n_models, double* const* __restrict__ scratch) {
+    __shared__ double tile_y[1][SPL_T][SPL_T + 1], tile_a[1][SPL_T][SPL_T + 1], tile_b[1][SPL_T][SPL_T + 1], xs[1][SPL_T + 2];
     const int m = blockIdx.y;
     const DModel& M = models[m];
     const int n_k = M.n_k, ncol = M.n_src * M.n_tau;
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= ncol) return;
+    const int warp = 0, lane = threadIdx.x & 31;
+    const int col0 = blockIdx.x * 32;                        // first column of this warp
+    if (col0 >= ncol) return;
+    const int ncw = min(32, ncol - col0);                    // columns this warp owns
+    const bool mine = lane < ncw;
     const double* x = M.q_src;
-    const double* y = M.LinearSrc + (size_t)n_k * col;
-    double* d2 = M.ddSrc + (size_t)n_k * col;
-    double* u = scratch[m] + (size_t)n_k * col;
-    double d1r = (y[1] - y[0]) / (x[1] - x[0]), d1l;
-    d2[0] = 0; u[0] = 0;
-    for (int i = 1; i < n_k - 1; i++) {
-        d1l = d1r;
-        d1r = (y[i + 1] - y[i]) / (x[i + 1] - x[i]);
-        double xxdiv = 1.0 / (x[i + 1] - x[i - 1]);
-        double sig = (x[i] - x[i - 1]) * xxdiv;
-        double xp = 1.0 / (sig * d2[i - 1] + 2.0);
-        d2[i] = (sig - 1.0) * xp;
-        u[i] = (6.0 * (d1r - d1l) * xxdiv - sig * u[i - 1]) * xp;
+    const double* Y = M.LinearSrc + (size_t)n_k * col0;
+    double* D2 = M.ddSrc + (size_t)n_k * col0;
+    double* U = scratch[m] + (size_t)n_k * col0;
+    double (*ty)[SPL_T + 1] = tile_y[warp];
+    double (*ta)[SPL_T + 1] = tile_a[warp];
+    double (*tb)[SPL_T + 1] = tile_b[warp];
+    double* xw = xs[warp];
+    // ---- forward elimination over i = 1 .. n_k-2; row 0: d2 = u = 0 ----
+    double y_prev = 0, y_cur = 0, d2_prev = 0, u_prev = 0, d1r = 0;   // per thread (its column)
+    for (int k0 = 0; k0 < n_k; k0 += SPL_T) {
+        const int len = min(SPL_T, n_k - k0);
+        // stage y[k0 .. k0+len] (one extra point for the i+1 difference) and x[k0-1 .. k0+len]
+        for (int c = 0; c < ncw; c++)
+            if (lane < len) ty[c][lane] = Y[(size_t)n_k * c + k0 + lane];
+        for (int j = lane; j < len + 2; j += 32) { const int kk = k0 - 1 + j; xw[j] = (kk >= 0 && kk < n_k) ? x[kk] : 0.0; }
+        __syncwarp();
+        // the i+1 point of the last row of the tile lives in the next tile: fetch it directly (one value per column)
+        double y_next_tile = 0;
+        if (mine && k0 + len < n_k) y_next_tile = Y[(size_t)n_k * lane + k0 + len];
+        if (mine) {
+            for (int j = 0; j < len; j++) {
+                const int i = k0 + j;
+                const double yi = ty[lane][j];
+                double a = 0, b = 0;
+                if (i == 0) { y_cur = yi; }
+                else {
+                    // entering row i: y_prev = y[i-1], y_cur = y[i]
+                    y_prev = y_cur; y_cur = yi;
+                    if (i == 1) d1r = (y_cur - y_prev) / (xw[j + 1] - xw[j]);
+                }
+                if (i >= 1 && i <= n_k - 2) {
+                    const double y_next = j + 1 < len ? ty[lane][j + 1] : y_next_tile;
+                    const double d1l = d1r;
+                    d1r = (y_next - y_cur) / (xw[j + 2] - xw[j + 1]);
+                    const double xxdiv = 1.0 / (xw[j + 2] - xw[j]);
+                    const double sig = (xw[j + 1] - xw[j]) * xxdiv;
+                    const double xp = 1.0 / (sig * d2_prev + 2.0);
+                    a = (sig - 1.0) * xp;
+                    b = (6.0 * (d1r - d1l) * xxdiv - sig * u_prev) * xp;
+                    d2_prev = a; u_prev = b;
+                }
+                ta[lane][j] = a; tb[lane][j] = b;
+            }
+        }
+        __syncwarp();
+        for (int c = 0; c < ncw; c++)
+            if (lane < len) { D2[(size_t)n_k * c + k0 + lane] = ta[c][lane]; U[(size_t)n_k * c + k0 + lane] = tb[c][lane]; }
+        __syncwarp();
     }
-    d2[n_k - 1] = 0.0;
-    for (int i = n_k - 2; i >= 0; i--) d2[i] = d2[i] * d2[i + 1] + u[i];
+    // ---- back substitution: d2[n_k-1] = 0; d2[i] = d2[i] d2[i+1] + u[i], i = n_k-2 .. 0 ----
+    double next = 0;   // d2[i+1] of this thread's column
+    for (int k1 = n_k; k1 > 0; k1 -= SPL_T) {
+        const int k0 = max(k1 - SPL_T, 0), len = k1 - k0;
+        for (int c = 0; c < ncw; c++)
+            if (lane < len) { ta[c][lane] = D2[(size_t)n_k * c + k0 + lane]; tb[c][lane] = U[(size_t)n_k * c + k0 + lane]; }
+        __syncwarp();
+        if (mine) {
+            for (int j = len - 1; j >= 0; j--) {
+                const int i = k0 + j;
+                double v;
+                if (i == n_k - 1) v = 0.0;
+                else v = ta[lane][j] * next + tb[lane][j];
+                ta[lane][j] = v;
+                next = v;
+            }
+        }
+        __syncwarp();
+        for (int c = 0; c < ncw; c++)
+            if (lane < len) D2[(size_t)n_k * c + k0 + lane] = ta[c][lane];
+        __syncwarp();
+    }
 }
 
 // The first mapping of loop B (kept for A/B runs, option "los_kernel" = 0): a warp owns one l, its lanes stride the time
@@ -1067,8 +1132,8 @@ void cb_cl_array_launch(const DModel* d_models, int n_models, const DBessel& B, 
 }
 
 void cb_spline_k_launch(const DModel* d_models, int n_models, int max_cols, double* const* d_scratch, cudaStream_t st) {
-    dim3 grid((max_cols + 127) / 128, n_models);
-    cb_spline_k_kernel<<<grid, 128, 0, st>>>(d_models, n_models, d_scratch);
+    dim3 grid((max_cols + 31) / 32, n_models);
+    cb_spline_k_kernel<<<grid, 32, 0, st>>>(d_models, n_models, d_scratch);
 }
 
 static int los_nslot(int n_l) {
