@@ -1,0 +1,7 @@
+#!/bin/bash
+OUT=gpurun_out; mkdir -p $OUT
+for rep in 1 2; do
+for lib in "" variants/libcambb200_split.so variants/libcambb200_split_cold.so; do
+  echo "lib=$lib"; CAMB_B200_LIB=$lib timeout 300 python scripts/evolve_only.py 128 2>&1 | tail -1
+done; done > $OUT/r02zx_split_ab.log 2>&1
+cat $OUT/r02zx_split_ab.log
