@@ -8,7 +8,10 @@ import bench
 from camb_b200 import lensing as L
 from camb_b200.gpu import GpuContext, group_by_l_sampling
 
-B = 64
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+if os.environ.get("NO_GC"):
+    import gc
+    gc.disable()
 ctx = GpuContext(0)
 hss = bench.build_batch(B, seed=20261017)
 groups = group_by_l_sampling(hss)
@@ -26,7 +29,7 @@ for bb in bufs:
         ctx.pin_array(a)
 pending = []
 rows = []
-for it in range(6):
+for it in range(10):
     T = {}
     def tick(name, t0):
         T[name] = T.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
@@ -51,5 +54,7 @@ for it in range(6):
 ctx.wait_outputs()
 med = {k: round(float(np.median([r[k] for r in rows[2:]])), 2) for k in rows[0]}
 calls = sum(v for k, v in med.items() if not k.endswith("_kernels"))
+for r in rows:
+    print({k: round(v, 1) for k, v in r.items()})
 print("per-iteration sum of calls:", [round(sum(v for k, v in r.items() if not k.endswith("_kernels")), 1) for r in rows])
 print("async_outputs", os.environ.get("ASYNC_OUT", "1"), med, "sum of calls %.1f ms -> %.1f sets/s" % (calls, 1e3 * B / calls))
