@@ -242,6 +242,7 @@ def one_cosmology_latency(ctx, reps=5):
     out = {}
     for label, opt in (("register_lane_groups", 1), ("mode_per_lane_tmem", 3), ("general_32_lanes", 0)):
         ctx.set_option("use_reg_kernel", opt)
+        ctx.set_option("reg_min_modes", 0)          # force the named kernel (the library's default routes few modes to the general one)
         best = 1e30
         for _ in range(reps + 1):
             torch.cuda.synchronize()
@@ -256,6 +257,7 @@ def one_cosmology_latency(ctx, reps=5):
             best = min(best, time.perf_counter() - t0)
         out[label] = 1e3 * best
     ctx.set_option("use_reg_kernel", 1)
+    ctx.set_option("reg_min_modes", -1)
     return out
 
 

@@ -133,6 +133,7 @@ struct cb_ctx {
     // 48-element classes, register kernel for the deep low-k hierarchies (equal throughput at >= 192 sets per call,
     // slower below: DESIGN.md section 4.1)
     int use_reg_kernel = 1;
+    int reg_min_modes = -1;   // launches with fewer lean modes take the general kernel (one mode per warp: latency); -1 = 8 per SM
     // asynchronous result copies (option "async_outputs"): Delta_p_l_k goes to the host on its own stream, behind the
     // kernel that produced it, while the next kernels run; cb_wait_outputs is the point where the host may read it
     cudaStream_t copy_stream = nullptr;
@@ -294,6 +295,7 @@ int cb_create(int device, cb_ctx** out) {
     cudaEventCreateWithFlags(&ctx->ev_copy_done, cudaEventDisableTiming);
     if (const char* e = getenv("CAMB_B200_LANES")) ctx->lanes_per_mode = atoi(e);
     if (const char* e = getenv("CAMB_B200_REG")) ctx->use_reg_kernel = atoi(e);
+    if (const char* e = getenv("CAMB_B200_REG_MIN_MODES")) ctx->reg_min_modes = atoi(e);
     if (const char* e = getenv("CAMB_B200_LOS")) ctx->los_kernel = atoi(e);
     if (const char* e = getenv("CAMB_B200_CLASS_LANES")) {   // tuning runs: lane width per slab-size class, e.g. "8,8,16,32,32"
         int i = 0;
@@ -762,11 +764,14 @@ int cb_evolve(cb_ctx* ctx, int n_models, cb_dmodel* const* dm, const cb_modes* m
         for (size_t i = 0; i < ord.size(); i++) sorted[i] = all_items[ord[i]];
         all_items.swap(sorted);
     }
+    // A launch of few modes is a latency problem, not a throughput one: the register kernel shares a warp between eight modes
+    // (31 ms for one cosmology), the general kernel gives every mode a warp of its own there (22 ms).
+    const bool few_modes = all_items.size() < (size_t)(ctx->reg_min_modes >= 0 ? ctx->reg_min_modes : 8 * ctx->n_sm);
     for (DModeItem& it : all_items) {
         const int ml = it.transfer_only >> 8;
         it.transfer_only &= 0xff;
         int c = 0;
-        int rc = (lean && ctx->use_reg_kernel) ? cb_reg_class(it.lmaxg, it.lmaxgpol, it.lmaxnr) : -1;
+        int rc = (lean && ctx->use_reg_kernel && !few_modes) ? cb_reg_class(it.lmaxg, it.lmaxgpol, it.lmaxnr) : -1;
         if (rc == 1 && ctx->use_reg_kernel == 2) rc = -1;   // experiment: the 16-lane layout's modes through the general kernel
         if (lean && ctx->use_reg_kernel == 3) {
             const int mc = cb_mpl_class(it.lmaxg, it.lmaxgpol, it.lmaxnr);
@@ -1327,6 +1332,7 @@ int cb_set_option(cb_ctx* ctx, const char* name, double value) {
     }
     if (!strcmp(name, "async_model_upload")) { ctx->async_model_upload = value != 0; return 0; }
     if (!strcmp(name, "use_reg_kernel")) { ctx->use_reg_kernel = (int)value; return 0; }
+    if (!strcmp(name, "reg_min_modes")) { ctx->reg_min_modes = (int)value; return 0; }
     if (!strcmp(name, "los_kernel")) { ctx->los_kernel = (int)value; return 0; }
     if (!strcmp(name, "async_calls")) {
         if (ctx->async_calls && value == 0) { CK(cudaStreamSynchronize(ctx->stream)); ctx->staged_pending = false; if (int e = deferred_error(ctx)) return e; }

@@ -259,6 +259,10 @@ long long cb_launch_count(const cb_ctx* ctx);
  * lane-group kernel (evolve_reg.cu) for every mode that fits one of its static layouts, 0 the general shared-memory kernel
  * (evolve.cu) only, 3 the mode-per-lane Tensor-Memory kernel (evolve_mpl.cu) for the 48-element classes.  Other models
  * always take the general kernel.
+ * "reg_min_modes": a cb_evolve call with fewer modes than this takes the general kernel whatever "use_reg_kernel" says (one
+ * mode per warp: the latency of one cosmology is 22 ms there, 31 ms with eight modes sharing a warp); -1 (default) = 8 per SM,
+ * 0 = never.  Environment CAMB_B200_REG_MIN_MODES sets the initial value (the test-suite sets 0 to keep its small cases on
+ * the register kernel).
  * "async_model_upload" = 1: cb_model_create queues its host->device copies and returns; the caller keeps the cb_model arrays
  * alive and unchanged until the next cb_evolve / cb_project / cb_cl* call on the context returns (a Fortran host's
  * allocatables outlive cmbmain anyway).  Default 0: the arrays may be freed as soon as cb_model_create returns.

@@ -5,6 +5,8 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the small parity cases must exercise the register-resident evolve kernel, not the few-modes (latency) route of cb_evolve
+os.environ.setdefault("CAMB_B200_REG_MIN_MODES", "0")
 for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)

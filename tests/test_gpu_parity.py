@@ -466,6 +466,27 @@ def test_evolve_kernel_variants_agree(ctx, path):
     assert same > 0.98
 
 
+def test_few_modes_route_to_the_general_kernel(ctx):
+    """cb_evolve sends a call with few modes (one cosmology: a latency problem) through the general one-mode-per-warp kernel
+    unless "reg_min_modes" says otherwise (the suite runs with 0: always the register kernel).  Both routes: identical step
+    statistics, sources equal to rounding, and the default route launches the general kernel (one slab class more)."""
+    hs = host_state("planck_massless_lensing", CASES["planck_massless_lensing"])
+    out = {}
+    for label, mm in (("register", 0), ("default", -1)):
+        ctx.set_option("reg_min_modes", mm)
+        try:
+            dm = ctx.create_model(hs)
+            src, _, st = ctx.evolve([hs], [dm])
+            out[label] = (np.array(src[0]), np.array(st[0]))
+            ctx.destroy_model(dm)
+        finally:
+            ctx.set_option("reg_min_modes", 0)
+    (s_r, st_r), (s_d, st_d) = out["register"], out["default"]
+    assert np.array_equal(st_r[:, 0], st_d[:, 0]) and np.array_equal(st_r[:, 1], st_d[:, 1])
+    scale = np.abs(s_r).max(axis=(0, 2), keepdims=True)
+    assert np.max(np.abs(s_r - s_d) / scale) < 1e-9
+
+
 def test_config5_mnu_w0wa_ragged_batch_parity(ctx):
     """BASELINE.json configs[4] as specified: synthetic LCDM + mnu + w0wa (PPF) parameter sets at lmax 2500,
     no lensing, evolved as ONE ragged batch; loops B and C per group of identical l sampling.  Every set against the oracle."""
