@@ -11,6 +11,7 @@ from camb_b200.workloads import (isocurvature_params, lensing_window_params, par
                                  tensor_params)
 
 ctx = GpuContext(0)
+ctx.set_option("reg_min_modes", 0)   # small cases must run the register kernel, not the few-modes route
 
 
 def scalar(hs, lanes):
