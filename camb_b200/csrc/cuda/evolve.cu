@@ -1276,6 +1276,9 @@ __device__ __forceinline__ void attempt_finish(const DModel& M, EVs& E, Ctl& C, 
 
 // Warps per block: two for the 8..32-lane groups, one for 4-lane groups (eight modes per warp) so that a block is
 // always eight modes or fewer and the slab classes of cabi.cu keep their meaning.
+#ifndef EVOLVE_FUSE_OUTPUT   /* 1: source / transfer output from the seventh stage evaluation of the step that lands on it */
+#define EVOLVE_FUSE_OUTPUT 1
+#endif
 #define WPB(G_) ((G_) >= 8 ? 2 : 1)
 #ifndef EVOLVE_MIN_BLOCKS
 #define EVOLVE_MIN_BLOCKS 6   /* 64 threads x 6 blocks: <= 168 registers per thread */
@@ -1383,6 +1386,16 @@ cb_evolve_kernel(const DModel* __restrict__ models, const DModeItem* __restrict_
                 out = t == 6 ? V.k2 : vec + (size_t)(t + 1) * nv;
                 tev = C.tau + c_dp_c[t] * h;
                 th = thbuf + (LEAN ? TH_LEAN : TH_FULL) * (t - 1);
+#if EVOLVE_FUSE_OUTPUT
+                // The seventh evaluation of a step that lands on an output time is `derivs` at the state and time the output
+                // evaluates it at again (y_new, x + h): run the output branch here, keep its result if the step is accepted.
+                if (t == 6 && C.trial_x == C.seg_end && !C.seg_switch && C.out_kind != OUT_NONE) {
+                    out_mode = C.out_kind;
+                    tev = C.trial_x;
+                    for (int i = lane; i < E.nvar; i += G) out[i] = 0;   // as before an output evaluation at t == 0
+                    __syncwarp(gm);
+                }
+#endif
             }
         }
         if (active) {
@@ -1406,7 +1419,24 @@ cb_evolve_kernel(const DModel* __restrict__ models, const DModeItem* __restrict_
                 }
             } else {
                 if (lane == 0) { C.nderivs++; C.neq_evals += E.neq; }
-                if (t == 6) attempt_finish<G>(models[C.model], E, C, V, nv, lane, gm, error_flag);
+                if (t == 6) {
+                    attempt_finish<G>(models[C.model], E, C, V, nv, lane, gm, error_flag);
+#if EVOLVE_FUSE_OUTPUT
+                    if (out_mode != OUT_NONE) {
+                        __syncwarp(gm);
+                        if (lane == 0 && C.phase == PH_OUTPUT) {   // accepted and on the output time: the evaluation above was the output's
+                            C.nderivs++;
+                            if (out_mode == OUT_SRC) {
+                                double* S = H.LinearSrc;
+                                const int n3 = H.n_src < 3 ? H.n_src : 3;
+                                for (int i = 0; i < n3; i++) S[C.q_ix + (size_t)H.n_k * (i + (size_t)H.n_src * (C.j - 1))] = srcs[i];
+                            } else C.itf++;
+                            C.stage = C.next_stage;
+                            C.phase = PH_NEXT_GOAL;
+                        }
+                    }
+#endif
+                }
             }
         }
         __syncwarp(gm);
