@@ -304,6 +304,31 @@ def test_batched_cosmologies_match_single_runs(ctx):
             ctx.destroy_model(dm)
 
 
+def test_bench_batch_matches_single_runs_and_oracle(ctx):
+    """The bench's batch (128 lensed-to-2500 parameter sets: 29 k modes, more than the 9 472 the register kernel holds
+    resident, so lane groups fetch second and third modes from the queue) against one-at-a-time launches of three of its
+    sets -- sources and integrator statistics bit for bit -- and one of them against the oracle."""
+    ps = synthetic_lcdm_batch(128, seed=20261017, lmax=2500, lensing=True, massless=True, lensed_to_lmax=True)
+    hss = [HostState(p) for p in ps]
+    dms = [ctx.create_model(hs) for hs in hss]
+    try:
+        src, _, st = ctx.evolve(hss, dms)
+        assert sum(len(s) for s in st) > 9472 * 2
+        for i in (0, 61, 127):
+            one_src, _, one_st = ctx.evolve([hss[i]], [dms[i]])
+            assert np.array_equal(one_st[0], st[i]), i
+            assert np.array_equal(one_src[0], src[i]), i
+        o_src, _, o_st = O.evolve(hss[61], nthreads=16)
+        same = (o_st[:, 0] == st[61][:, 0]).mean()
+        scale = np.abs(o_src).max(axis=(0, 2), keepdims=True)
+        err = float(np.max(np.abs(src[61] - o_src) / scale))
+        print("set 61 of the bench batch vs oracle: max source difference / peak", err, "identical derivs counts", same)
+        assert err < 1e-6 and same > 0.98
+    finally:
+        for dm in dms:
+            ctx.destroy_model(dm)
+
+
 def test_cl_properties_at_full_size(ctx):
     """Size-independent properties at BASELINE's full size (lmax 2500): C_l is linear in the
     primordial power and TE obeys Cauchy-Schwarz; rerunning is bit-reproducible."""
