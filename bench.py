@@ -295,7 +295,19 @@ def main():
         raise SystemExit("bench.py: no CUDA device; camb_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner with a plain printf when the communicator is created: stdout carries ONE JSON line, so
+        # file descriptor 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     ctx = GpuContext(local)
     B = args.batch
     lensing = wl["lensing"]
